@@ -1,0 +1,174 @@
+// TEST INFRASTRUCTURE ONLY -- not part of the shipped product path.
+//
+// A ctypes-friendly C ABI over the *unmodified* reference C++ objects (CPU mode).
+// It is compiled together with the reference's own sources, where they lie under
+// /root/reference/ModelOptimizations/DlQuantization/src, by oracle/Makefile into
+// oracle/_ref/libaimet_ref.so. Nothing from the reference is copied into this repo:
+// this file only includes the reference's public headers and forwards calls.
+//
+// Used by: tests/ (to pin the C restatement in oracle/qsim_oracle.c), the golden-vector
+// generator tests/golden/make_golden.py, and bench.py's cpu_baseline / --impl reference leg.
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <tuple>
+#include <vector>
+
+#include "DlQuantization/IQuantizationEncodingAnalyzer.hpp"
+#include "DlQuantization/ITensorQuantizationSim.h"
+#include "DlQuantization/Quantization.hpp"
+#include "DlQuantization/QuantizerFactory.hpp"
+#include "DlQuantization/TensorQuantizer.h"
+
+using namespace DlQuantization;
+
+namespace
+{
+struct Analyzer
+{
+    std::unique_ptr<IQuantizationEncodingAnalyzer<float>> impl;
+};
+
+void put(const TfEncoding& e, double* out5)
+{
+    out5[0] = e.min;
+    out5[1] = e.max;
+    out5[2] = e.delta;
+    out5[3] = e.offset;
+    out5[4] = e.bw;
+}
+}   // namespace
+
+extern "C"
+{
+// ---- encoding analyzers (TfEncodingAnalyzer / TfEnhancedEncodingAnalyzer via the reference factory) ----
+void* ref_analyzer_new(int quant_mode)
+{
+    auto* a = new Analyzer;
+    a->impl = getEncodingAnalyzerInstance<float>(static_cast<QuantizationMode>(quant_mode));
+    return a;
+}
+
+void ref_analyzer_free(void* h)
+{
+    delete static_cast<Analyzer*>(h);
+}
+
+void ref_analyzer_update(void* h, const float* data, size_t n)
+{
+    static_cast<Analyzer*>(h)->impl->updateStats(data, n, COMP_MODE_CPU);
+}
+
+void ref_analyzer_compute(void* h, int bw, int sym, int strict, int unsigned_sym, double* out5)
+{
+    TfEncoding e = static_cast<Analyzer*>(h)->impl->computeEncoding(bw, sym != 0, strict != 0, unsigned_sym != 0);
+    put(e, out5);
+}
+
+// returns the number of buckets written (512, or 0 if the PDF was never initialised)
+int ref_analyzer_histogram(void* h, double* x_left, double* pdf)
+{
+    auto hist = static_cast<Analyzer*>(h)->impl->getStatsHistogram();
+    int i     = 0;
+    for (auto& t: hist)
+    {
+        x_left[i] = std::get<0>(t);
+        pdf[i]    = std::get<1>(t);
+        ++i;
+    }
+    return i;
+}
+
+// ---- TensorQuantizationSim<float> ----
+void ref_fill_encoding_info(int bw, double enc_min, double enc_max, double* out5)
+{
+    auto sim = getTensorQuantizationSim<float>();
+    TfEncoding e;
+    sim->fillEncodingInfo(e, bw, enc_min, enc_max);
+    put(e, out5);
+}
+
+void ref_qdq(const float* in, size_t n, float* out, double enc_min, double enc_max, int bw, int round_mode)
+{
+    auto sim = getTensorQuantizationSim<float>();
+    sim->quantizeDequantizeTensor(in, n, out, enc_min, enc_max, bw, static_cast<RoundingMode>(round_mode), false);
+}
+
+void ref_quantize(const float* in, size_t n, float* out, double enc_min, double enc_max, int bw, int round_mode,
+                  int shift_to_signed)
+{
+    auto sim = getTensorQuantizationSim<float>();
+    sim->quantizeTensor(in, n, out, enc_min, enc_max, bw, static_cast<RoundingMode>(round_mode), false,
+                        shift_to_signed != 0);
+}
+
+void ref_qdq_per_channel(const float* in, size_t num_channel, size_t num_element, size_t num_element_per_channel,
+                         float* out, float* enc_min, float* enc_max, float* enc_delta, float* enc_offset,
+                         int round_mode)
+{
+    auto sim = getTensorQuantizationSim<float>();
+    sim->quantizeDequantizeTensorPerChannel(in, num_channel, num_element, num_element_per_channel, out, enc_min,
+                                            enc_max, enc_delta, enc_offset, static_cast<RoundingMode>(round_mode),
+                                            false);
+}
+
+// ---- TensorQuantizer facade ----
+void* ref_tq_new(int quant_mode, int round_mode)
+{
+    return new TensorQuantizer(static_cast<QuantizationMode>(quant_mode), static_cast<RoundingMode>(round_mode));
+}
+
+void ref_tq_free(void* h)
+{
+    delete static_cast<TensorQuantizer*>(h);
+}
+
+void ref_tq_set_flags(void* h, int strict, int unsigned_sym)
+{
+    auto* q = static_cast<TensorQuantizer*>(h);
+    q->setStrictSymmetric(strict != 0);
+    q->setUnsignedSymmetric(unsigned_sym != 0);
+}
+
+void ref_tq_update(void* h, const float* data, size_t n)
+{
+    static_cast<TensorQuantizer*>(h)->updateStats(data, n, false);
+}
+
+void ref_tq_compute(void* h, int bw, int sym, double* out5)
+{
+    put(static_cast<TensorQuantizer*>(h)->computeEncoding(bw, sym != 0), out5);
+}
+
+int ref_tq_is_valid(void* h)
+{
+    return static_cast<TensorQuantizer*>(h)->isEncodingValid ? 1 : 0;
+}
+
+void ref_tq_reset(void* h)
+{
+    static_cast<TensorQuantizer*>(h)->resetEncodingStats();
+}
+
+// returns 0 on success, 1 if the reference threw
+int ref_tq_partial(void* h, int bw, double* enc5, int sym, int unsigned_sym, int strict)
+{
+    TfEncoding e;
+    e.min    = enc5[0];
+    e.max    = enc5[1];
+    e.delta  = enc5[2];
+    e.offset = enc5[3];
+    e.bw     = static_cast<int>(enc5[4]);
+    try
+    {
+        static_cast<TensorQuantizer*>(h)->computePartialEncoding(bw, e, sym != 0, unsigned_sym != 0, strict != 0);
+    }
+    catch (const std::exception&)
+    {
+        return 1;
+    }
+    put(e, enc5);
+    return 0;
+}
+}   // extern "C"
