@@ -1,0 +1,91 @@
+"""ctypes binding of the C ABI declared in include/aimet_b200.h.
+
+The shared library is built in-tree by aimet_b200/_build.py (nvcc, sm_100a). There is no fallback of any kind: if the
+library is missing or cannot be loaded, importing this module raises, and every device entry point raises when CUDA
+reports an error (including "no device").
+"""
+import ctypes as C
+import os
+
+from . import _build
+
+_LIB = None
+
+
+class AbError(RuntimeError):
+    """A C-ABI call returned a negative ab_status."""
+
+
+class Encoding(C.Structure):
+    """ab_encoding == DlQuantization::TfEncoding (reference Quantization.hpp:113-120)."""
+    _fields_ = [("min", C.c_double), ("max", C.c_double), ("delta", C.c_double), ("offset", C.c_double),
+                ("bw", C.c_int)]
+
+
+PDF_SIZE = 512
+AB_OK, AB_ERR_INVALID, AB_ERR_CUDA, AB_ERR_UNSUPPORTED = 0, -1, -2, -3
+AB_F32, AB_BF16 = 0, 1
+
+_vp, _i64, _u64, _int, _dbl, _flt = C.c_void_p, C.c_int64, C.c_uint64, C.c_int, C.c_double, C.c_float
+_encp, _dblp, _fltp = C.POINTER(Encoding), C.POINTER(C.c_double), C.POINTER(C.c_float)
+
+# name -> (restype, argtypes); every symbol include/aimet_b200.h declares
+PROTOTYPES = {
+    "ab_last_error": (C.c_char_p, []),
+    "ab_version": (_int, []),
+    "ab_device_count": (_int, []),
+    "ab_stats_state_bytes": (C.c_size_t, []),
+    "ab_gate_min_max": (_int, [_dblp, _dblp]),
+    "ab_fill_encoding_info": (_int, [_int, _dbl, _dbl, _encp]),
+    "ab_tf_compute_encoding": (_int, [_int, _dbl, _dbl, _int, _int, _int, _encp]),
+    "ab_tf_analyzer_encoding": (_int, [_int, _dbl, _dbl, _int, _int, _int, _encp]),
+    "ab_compute_partial_encoding": (_int, [_int, _encp, _int, _int, _int]),
+    "ab_per_channel_params": (_int, [_dblp, _dblp, _int, _int, _fltp]),
+    "ab_qdq_per_tensor_fwd": (_int, [_vp, _vp, _i64, _int, _dbl, _dbl, _int, _int, _u64, _vp]),
+    "ab_qdq_per_tensor_fwd_dev": (_int, [_vp, _vp, _i64, _int, _vp, _int, _u64, _vp]),
+    "ab_quantize_to_grid": (_int, [_vp, _vp, _i64, _int, _dbl, _dbl, _int, _int, _int, _u64, _vp]),
+    "ab_qdq_per_channel_fwd": (_int, [_vp, _vp, _i64, _i64, _i64, _int, _vp, _int, _u64, _vp]),
+    "ab_qdq_ste_bwd": (_int, [_vp, _vp, _vp, _i64, _int, _flt, _flt, _vp]),
+    "ab_qdq_ste_bwd_per_channel": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _int, _vp, _vp, _vp]),
+    "ab_stats_reset": (_int, [_vp, _i64, _vp]),
+    "ab_stats_update": (_int, [_vp, _i64, _int, _int, _vp, _vp, _vp]),
+    "ab_stats_update_segmented": (_int, [_vp, _i64, _i64, _int, _int, _vp, _vp]),
+    "ab_compute_encodings": (_int, [_vp, _i64, _int, _int, _int, _int, _int, _vp, _vp, _vp]),
+    "ab_stats_init_range": (_int, [_vp, _i64, _vp, _vp]),
+    "ab_stats_fold_batches": (_int, [_vp, _i64, _vp, _vp, _i64, _vp]),
+}
+
+
+def lib_path():
+    return _build.LIB_PATH
+
+
+def load():
+    """dlopen libaimet_b200.so (once). Raises if it has not been built: there is no other implementation."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise ImportError(
+            f"{path} not found. Build it with `python -m aimet_b200._build` (needs nvcc); aimet_b200 has no "
+            "CPU or pure-PyTorch fallback.")
+    lib = C.CDLL(path)
+    for name, (restype, argtypes) in PROTOTYPES.items():
+        fn = getattr(lib, name)          # AttributeError here == the library is stale / incomplete
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _LIB = lib
+    return lib
+
+
+def check(rc):
+    if rc != AB_OK:
+        msg = load().ab_last_error().decode("utf-8", "replace")
+        if rc == AB_ERR_INVALID:
+            raise ValueError(msg)
+        raise AbError(f"aimet_b200 C-ABI call failed (status {rc}): {msg}")
+
+
+def call(name, *args):
+    check(getattr(load(), name)(*args))

@@ -1,0 +1,772 @@
+// Job 1 -- fused quantize-dequantize (QDQ), quantize-only and STE-backward kernels for sm_100a.
+//
+// All of these are pure streaming kernels bound by HBM bandwidth (8 B/element fp32 QDQ, 4 B/element bf16,
+// 12 / 6 B/element for the backward). Design:
+//   * 128-bit coalesced accesses (ld.global.nc.L1::no_allocate.v4 / st.global.L1::no_allocate.v4), kUnroll
+//     independent loads in flight per thread before any arithmetic, so one CTA keeps 16 KB of reads outstanding;
+//   * grid = min(tiles, resident CTAs per SM x 148 SMs), grid-stride over tiles: a whole number of waves;
+//   * exact IEEE arithmetic (see common.cuh) -- the ~25 ALU instructions per element stay well under the
+//     issue budget of a memory-bound kernel;
+//   * per-channel: the CTA's tile covers a contiguous range of channels whose {min,max,delta,offset} are staged in
+//     shared memory as float4 once per tile; the channel index is advanced incrementally, one integer division per
+//     128-bit vector rather than one per element.
+//
+// Reference semantics: DlQ/src/trim_functions.cpp:140-218, 697-709 (CPU path = parity target);
+// the reference's own GPU kernels are DlQ/src/trim_functions.cu:46-92.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "encoding_math.h"
+
+namespace ab
+{
+
+constexpr int kThreads = 256;
+constexpr int kUnroll  = 4;   // 128-bit vectors per thread per tile
+
+enum class Op
+{
+    kQdq,
+    kQuantize
+};
+
+struct TensorArgs
+{
+    Enc4 enc;            // used when enc_dev == nullptr
+    const float* enc_dev;   // optional device-resident {min,max,delta,offset}
+    float shift;         // quantize-only: subtracted from the grid value
+    uint64_t seed;
+};
+
+template <Op kOp, bool kStochastic>
+__device__ __forceinline__ float apply(float x, const Enc4& e, float shift, uint64_t seed, uint64_t idx)
+{
+    const float q = quantize_value<kStochastic>(x, e, seed, idx);
+    if (kOp == Op::kQdq)
+        return dequantize_value(q, e);
+    return __fsub_rn(q, shift);   // out[i] -= shift (DlQ/src/trim_functions.cpp:216)
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// per-tensor QDQ / quantize-only.  `in`/`out` are 16-byte aligned here (otherwise per_tensor_scalar_kernel runs).
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, Op kOp, bool kStochastic>
+__global__ void __launch_bounds__(kThreads) per_tensor_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                              int64_t count, TensorArgs args)
+{
+    constexpr int kV       = Elem<T>::kPerVec;
+    Enc4 e = args.enc;
+    if (args.enc_dev != nullptr)
+    {
+        const float4 p = *reinterpret_cast<const float4*>(args.enc_dev);
+        e              = Enc4 {p.x, p.y, p.z, p.w};
+    }
+    const int64_t num_vec   = count / kV;
+    const int64_t num_tiles = (num_vec + kThreads * kUnroll - 1) / (kThreads * kUnroll);
+
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+    {
+        const int64_t v0 = tile * (kThreads * kUnroll) + threadIdx.x;
+        uint4 raw[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+        {
+            const int64_t v = v0 + (int64_t) u * kThreads;
+            if (v < num_vec)
+                raw[u] = ldg_stream(reinterpret_cast<const uint4*>(in) + v);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+        {
+            const int64_t v = v0 + (int64_t) u * kThreads;
+            if (v < num_vec)
+            {
+                float f[kV];
+                Elem<T>::unpack(raw[u], f);
+#pragma unroll
+                for (int k = 0; k < kV; ++k)
+                    f[k] = apply<kOp, kStochastic>(f[k], e, args.shift, args.seed, (uint64_t) (v * kV + k));
+                stg_stream(reinterpret_cast<uint4*>(out) + v, Elem<T>::pack(f));
+            }
+        }
+    }
+    // scalar tail (< one vector), handled by the first threads of block 0
+    if (blockIdx.x == 0)
+    {
+        const int64_t i = num_vec * kV + threadIdx.x;
+        if (i < count)
+            Elem<T>::store(out + i,
+                           apply<kOp, kStochastic>(Elem<T>::load(in + i), e, args.shift, args.seed, (uint64_t) i));
+    }
+}
+
+// element-wise variant for tensors that are not 16-byte aligned
+template <typename T, Op kOp, bool kStochastic>
+__global__ void __launch_bounds__(kThreads) per_tensor_scalar_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                                     int64_t count, TensorArgs args)
+{
+    Enc4 e = args.enc;
+    if (args.enc_dev != nullptr)
+    {
+        const float4 p = *reinterpret_cast<const float4*>(args.enc_dev);
+        e              = Enc4 {p.x, p.y, p.z, p.w};
+    }
+    const int64_t stride = (int64_t) gridDim.x * kThreads;
+    for (int64_t i = (int64_t) blockIdx.x * kThreads + threadIdx.x; i < count; i += stride)
+        Elem<T>::store(out + i, apply<kOp, kStochastic>(Elem<T>::load(in + i), e, args.shift, args.seed, (uint64_t) i));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// per-channel QDQ.  channel(i) = (i / per_channel) % num_channel   (DlQ/src/trim_functions.cpp:703)
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kSmemChannels = 2048;   // float4 per channel -> 32 KB of shared memory
+
+struct ChannelArgs
+{
+    const float* params;   // device: [min | max | delta | offset], each num_channel long
+    int64_t num_channel;
+    int64_t per_channel;
+    uint64_t seed;
+};
+
+__device__ __forceinline__ Enc4 load_channel(const float* params, int64_t num_channel, int64_t c)
+{
+    return Enc4 {__ldg(params + c), __ldg(params + num_channel + c), __ldg(params + 2 * num_channel + c),
+                 __ldg(params + 3 * num_channel + c)};
+}
+
+template <typename T, bool kStochastic>
+__global__ void __launch_bounds__(kThreads) per_channel_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                               int64_t count, ChannelArgs args)
+{
+    constexpr int kV           = Elem<T>::kPerVec;
+    constexpr int kVecPerTile  = kThreads * kUnroll;
+    constexpr int64_t kTileLen = (int64_t) kVecPerTile * kV;
+    __shared__ float4 s_enc[kSmemChannels];
+
+    const int64_t num_vec   = count / kV;
+    const int64_t num_tiles = (count + kTileLen - 1) / kTileLen;
+    const int64_t C         = args.num_channel;
+    const int64_t L         = args.per_channel;
+
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+    {
+        const int64_t e0 = tile * kTileLen;
+        const int64_t e1 = min(e0 + kTileLen, count);
+        // un-wrapped channel counters of the first / last element of the tile
+        const int64_t g0     = e0 / L;
+        const int64_t g1     = (e1 - 1) / L;
+        const int64_t span   = g1 - g0 + 1;
+        const bool in_smem   = span <= kSmemChannels;
+        const int64_t c_base = g0 % C;
+        __syncthreads();   // previous tile's readers are done with s_enc
+        if (in_smem)
+        {
+            for (int64_t j = threadIdx.x; j < span; j += kThreads)
+            {
+                const Enc4 e = load_channel(args.params, C, (c_base + j) % C);
+                s_enc[j]     = make_float4(e.mn, e.mx, e.delta, e.offset);
+            }
+        }
+        __syncthreads();
+
+        const int64_t v0 = tile * kVecPerTile + threadIdx.x;
+        uint4 raw[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+        {
+            const int64_t v = v0 + (int64_t) u * kThreads;
+            if (v < num_vec)
+                raw[u] = ldg_stream(reinterpret_cast<const uint4*>(in) + v);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+        {
+            const int64_t v = v0 + (int64_t) u * kThreads;
+            if (v < num_vec)
+            {
+                float f[kV];
+                Elem<T>::unpack(raw[u], f);
+                const int64_t i0 = v * kV;
+                int64_t g        = i0 / L;          // one division per vector
+                int64_t rem      = i0 - g * L;
+                int64_t j        = g - g0;          // index into the staged channels
+                Enc4 e;
+                bool reload = true;
+#pragma unroll
+                for (int k = 0; k < kV; ++k)
+                {
+                    if (reload)
+                    {
+                        if (in_smem)
+                        {
+                            const float4 p = s_enc[j];
+                            e              = Enc4 {p.x, p.y, p.z, p.w};
+                        }
+                        else
+                            e = load_channel(args.params, C, (c_base + j) % C);
+                        reload = false;
+                    }
+                    f[k] = dequantize_value(quantize_value<kStochastic>(f[k], e, args.seed, (uint64_t) (i0 + k)), e);
+                    if (++rem == L)
+                    {
+                        rem = 0;
+                        ++j;
+                        reload = true;
+                    }
+                }
+                stg_stream(reinterpret_cast<uint4*>(out) + v, Elem<T>::pack(f));
+            }
+        }
+        // scalar tail of the whole tensor (only the last tile can have one)
+        if (e1 == count)
+        {
+            const int64_t i = num_vec * kV + threadIdx.x;
+            if (i < count)
+            {
+                const int64_t c = (i / L) % C;
+                const Enc4 e    = load_channel(args.params, C, c);
+                Elem<T>::store(out + i, dequantize_value(quantize_value<kStochastic>(Elem<T>::load(in + i), e,
+                                                                                      args.seed, (uint64_t) i),
+                                                         e));
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// STE backward: grad_in = grad * [min <= x <= max]   (quantsim_straight_through_grad.py:91-118)
+// The product with 1.0f / 0.0f (not a select) keeps torch's `grad * mask` semantics for inf / NaN gradients.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads) ste_bwd_kernel(const T* __restrict__ x, const T* __restrict__ grad,
+                                                           T* __restrict__ grad_in, int64_t count, float mn, float mx)
+{
+    constexpr int kV        = Elem<T>::kPerVec;
+    constexpr int kU        = 2;   // two tensors are read: keep the same bytes in flight as the forward
+    const int64_t num_vec   = count / kV;
+    const int64_t num_tiles = (num_vec + kThreads * kU - 1) / (kThreads * kU);
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+    {
+        const int64_t v0 = tile * (kThreads * kU) + threadIdx.x;
+        uint4 rx[kU], rg[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u)
+        {
+            const int64_t v = v0 + (int64_t) u * kThreads;
+            if (v < num_vec)
+            {
+                rx[u] = ldg_stream(reinterpret_cast<const uint4*>(x) + v);
+                rg[u] = ldg_stream(reinterpret_cast<const uint4*>(grad) + v);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u)
+        {
+            const int64_t v = v0 + (int64_t) u * kThreads;
+            if (v < num_vec)
+            {
+                float fx[kV], fg[kV];
+                Elem<T>::unpack(rx[u], fx);
+                Elem<T>::unpack(rg[u], fg);
+#pragma unroll
+                for (int k = 0; k < kV; ++k)
+                    fg[k] = __fmul_rn(fg[k], (mn <= fx[k] && fx[k] <= mx) ? 1.0f : 0.0f);
+                stg_stream(reinterpret_cast<uint4*>(grad_in) + v, Elem<T>::pack(fg));
+            }
+        }
+    }
+    if (blockIdx.x == 0)
+    {
+        const int64_t i = num_vec * kV + threadIdx.x;
+        if (i < count)
+        {
+            const float xv = Elem<T>::load(x + i);
+            Elem<T>::store(grad_in + i, __fmul_rn(Elem<T>::load(grad + i), (mn <= xv && xv <= mx) ? 1.0f : 0.0f));
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+    ste_bwd_per_channel_kernel(const T* __restrict__ x, const T* __restrict__ grad, T* __restrict__ grad_in,
+                               int64_t count, int64_t C, int64_t L, const float* __restrict__ mins,
+                               const float* __restrict__ maxs)
+{
+    constexpr int kV        = Elem<T>::kPerVec;
+    const int64_t num_vec   = count / kV;
+    const int64_t stride    = (int64_t) gridDim.x * kThreads;
+    for (int64_t v = (int64_t) blockIdx.x * kThreads + threadIdx.x; v < num_vec; v += stride)
+    {
+        const uint4 rx = ldg_stream(reinterpret_cast<const uint4*>(x) + v);
+        const uint4 rg = ldg_stream(reinterpret_cast<const uint4*>(grad) + v);
+        float fx[kV], fg[kV];
+        Elem<T>::unpack(rx, fx);
+        Elem<T>::unpack(rg, fg);
+        const int64_t i0 = v * kV;
+        int64_t g        = i0 / L;
+        int64_t rem      = i0 - g * L;
+        int64_t c        = g % C;
+        float mn = __ldg(mins + c), mx = __ldg(maxs + c);
+#pragma unroll
+        for (int k = 0; k < kV; ++k)
+        {
+            fg[k] = __fmul_rn(fg[k], (mn <= fx[k] && fx[k] <= mx) ? 1.0f : 0.0f);
+            if (++rem == L)
+            {
+                rem = 0;
+                c   = (c + 1 == C) ? 0 : c + 1;
+                mn = __ldg(mins + c), mx = __ldg(maxs + c);
+            }
+        }
+        stg_stream(reinterpret_cast<uint4*>(grad_in) + v, Elem<T>::pack(fg));
+    }
+    if (blockIdx.x == 0)
+    {
+        const int64_t i = num_vec * kV + threadIdx.x;
+        if (i < count)
+        {
+            const int64_t c = (i / L) % C;
+            const float xv  = Elem<T>::load(x + i);
+            Elem<T>::store(grad_in + i, __fmul_rn(Elem<T>::load(grad + i),
+                                                  (__ldg(mins + c) <= xv && xv <= __ldg(maxs + c)) ? 1.0f : 0.0f));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what)
+{
+    set_error("CUDA error %d (%s) in %s", (int) e, cudaGetErrorString(e), what);
+    return AB_ERR_CUDA;
+}
+
+int num_sms()
+{
+    static int cached[64] = {0};
+    int dev               = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64)
+        return 148;
+    if (cached[dev] == 0)
+    {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+template <typename K>
+static int grid_for(K kernel, int64_t tiles, int threads, size_t smem = 0)
+{
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm <= 0)
+        per_sm = 1;
+    const int64_t resident = (int64_t) per_sm * num_sms();
+    return (int) (tiles < 1 ? 1 : (tiles < resident ? tiles : resident));
+}
+
+static bool aligned16(const void* p)
+{
+    return (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
+}
+
+
+template <typename T, Op kOp>
+static int launch_per_tensor_typed(const T* in, T* out, int64_t count, const TensorArgs& a, bool stochastic,
+                                   cudaStream_t st)
+{
+    constexpr int kV      = Elem<T>::kPerVec;
+    const int64_t tiles   = (count / kV + kThreads * kUnroll - 1) / (kThreads * kUnroll);
+    if (stochastic)
+    {
+        auto k = per_tensor_kernel<T, kOp, true>;
+        k<<<grid_for(k, tiles, kThreads), kThreads, 0, st>>>(in, out, count, a);
+    }
+    else
+    {
+        auto k = per_tensor_kernel<T, kOp, false>;
+        k<<<grid_for(k, tiles, kThreads), kThreads, 0, st>>>(in, out, count, a);
+    }
+    AB_CUDA_CHECK(cudaGetLastError());
+    return AB_OK;
+}
+
+template <typename T, Op kOp>
+static int launch_scalar_typed(const T* in, T* out, int64_t count, const TensorArgs& a, bool stochastic,
+                               cudaStream_t st)
+{
+    const int64_t tiles = (count + kThreads - 1) / kThreads;
+    if (stochastic)
+    {
+        auto k = per_tensor_scalar_kernel<T, kOp, true>;
+        k<<<grid_for(k, tiles, kThreads), kThreads, 0, st>>>(in, out, count, a);
+    }
+    else
+    {
+        auto k = per_tensor_scalar_kernel<T, kOp, false>;
+        k<<<grid_for(k, tiles, kThreads), kThreads, 0, st>>>(in, out, count, a);
+    }
+    AB_CUDA_CHECK(cudaGetLastError());
+    return AB_OK;
+}
+
+template <Op kOp>
+static int launch_per_tensor(const void* in, void* out, int64_t count, int dtype, TensorArgs a, int round_mode,
+                             cudaStream_t st)
+{
+    if (count < 0 || (count > 0 && (in == nullptr || out == nullptr)))
+    {
+        set_error("null tensor pointer or negative count");
+        return AB_ERR_INVALID;
+    }
+    if (dtype != AB_F32 && dtype != AB_BF16)
+    {
+        set_error("unsupported dtype %d", dtype);
+        return AB_ERR_UNSUPPORTED;
+    }
+    if (round_mode != AB_ROUND_NEAREST && round_mode != AB_ROUND_STOCHASTIC)
+    {
+        set_error("Unknown rounding mode.");   // DlQ/src/trim_functions.cpp:162
+        return AB_ERR_INVALID;
+    }
+    if (count == 0)
+        return AB_OK;
+    const bool stochastic = round_mode == AB_ROUND_STOCHASTIC;
+    // A view that starts at an odd element offset (x[1:]) is contiguous but not 16-byte aligned: such tensors take the
+    // element-wise kernel (still coalesced, 4 / 2-byte accesses).
+    const bool vec = aligned16(in) && aligned16(out);
+    if (dtype == AB_F32)
+        return vec ? launch_per_tensor_typed<float, kOp>((const float*) in, (float*) out, count, a, stochastic, st)
+                   : launch_scalar_typed<float, kOp>((const float*) in, (float*) out, count, a, stochastic, st);
+    return vec ? launch_per_tensor_typed<__nv_bfloat16, kOp>((const __nv_bfloat16*) in, (__nv_bfloat16*) out, count, a,
+                                                             stochastic, st)
+               : launch_scalar_typed<__nv_bfloat16, kOp>((const __nv_bfloat16*) in, (__nv_bfloat16*) out, count, a,
+                                                         stochastic, st);
+}
+
+static Enc4 narrow(const ab_encoding& e)
+{
+    // the double encoding narrows to the tensor's float type at the call (DlQ/src/trim_functions.cpp:178)
+    return Enc4 {(float) e.min, (float) e.max, (float) e.delta, (float) e.offset};
+}
+
+}   // namespace ab
+
+using namespace ab;
+
+extern "C"
+{
+const char* ab_last_error(void)
+{
+    return g_error;
+}
+
+int ab_version(void)
+{
+    return 100;
+}
+
+int ab_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int ab_qdq_per_tensor_fwd(const void* in, void* out, int64_t count, int dtype, double enc_min, double enc_max,
+                          int bw, int round_mode, uint64_t seed, void* stream)
+{
+    ab_encoding e;
+    em::fill_encoding_info(bw, enc_min, enc_max, e);
+    TensorArgs a {narrow(e), nullptr, 0.0f, seed};
+    return launch_per_tensor<Op::kQdq>(in, out, count, dtype, a, round_mode, (cudaStream_t) stream);
+}
+
+int ab_qdq_per_tensor_fwd_dev(const void* in, void* out, int64_t count, int dtype, const float* enc4,
+                              int round_mode, uint64_t seed, void* stream)
+{
+    if (enc4 == nullptr || !aligned16(enc4))
+    {
+        set_error("enc4 must be a 16-byte aligned device pointer");
+        return AB_ERR_INVALID;
+    }
+    TensorArgs a {Enc4 {0, 0, 1, 0}, enc4, 0.0f, seed};
+    return launch_per_tensor<Op::kQdq>(in, out, count, dtype, a, round_mode, (cudaStream_t) stream);
+}
+
+int ab_quantize_to_grid(const void* in, void* out, int64_t count, int dtype, double enc_min, double enc_max, int bw,
+                        int round_mode, int shift_to_signed, uint64_t seed, void* stream)
+{
+    ab_encoding e;
+    em::fill_encoding_info(bw, enc_min, enc_max, e);
+    // `unsigned int shift = pow(2, bw - 1)` then `out[i] -= shift` in float (DlQ/src/trim_functions.cpp:206-216)
+    unsigned int shift = 0;
+    if (shift_to_signed)
+        shift = (unsigned int) em::pow2(e.bw - 1);
+    TensorArgs a {narrow(e), nullptr, (float) shift, seed};
+    return launch_per_tensor<Op::kQuantize>(in, out, count, dtype, a, round_mode, (cudaStream_t) stream);
+}
+
+int ab_qdq_per_channel_fwd(const void* in, void* out, int64_t num_channel, int64_t num_element,
+                           int64_t num_element_per_channel, int dtype, const float* params, int round_mode,
+                           uint64_t seed, void* stream)
+{
+    if (num_element < 0 || num_channel <= 0 || num_element_per_channel <= 0 || params == nullptr ||
+        (num_element > 0 && (in == nullptr || out == nullptr)))
+    {
+        set_error("invalid per-channel arguments");
+        return AB_ERR_INVALID;
+    }
+    if (dtype != AB_F32 && dtype != AB_BF16)
+    {
+        set_error("unsupported dtype %d", dtype);
+        return AB_ERR_UNSUPPORTED;
+    }
+    if (round_mode != AB_ROUND_NEAREST && round_mode != AB_ROUND_STOCHASTIC)
+    {
+        set_error("Unknown rounding mode.");
+        return AB_ERR_INVALID;
+    }
+    if (num_element == 0)
+        return AB_OK;
+    if (!aligned16(in) || !aligned16(out))
+    {
+        set_error("per-channel tensors must be 16-byte aligned");
+        return AB_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t) stream;
+    ChannelArgs a {params, num_channel, num_element_per_channel, seed};
+    const bool stochastic = round_mode == AB_ROUND_STOCHASTIC;
+    if (dtype == AB_F32)
+    {
+        const int64_t tiles = (num_element + (int64_t) kThreads * kUnroll * 4 - 1) / ((int64_t) kThreads * kUnroll * 4);
+        if (stochastic)
+        {
+            auto k = per_channel_kernel<float, true>;
+            k<<<grid_for(k, tiles, kThreads), kThreads, 0, st>>>((const float*) in, (float*) out, num_element, a);
+        }
+        else
+        {
+            auto k = per_channel_kernel<float, false>;
+            k<<<grid_for(k, tiles, kThreads), kThreads, 0, st>>>((const float*) in, (float*) out, num_element, a);
+        }
+    }
+    else
+    {
+        const int64_t tiles = (num_element + (int64_t) kThreads * kUnroll * 8 - 1) / ((int64_t) kThreads * kUnroll * 8);
+        if (stochastic)
+        {
+            auto k = per_channel_kernel<__nv_bfloat16, true>;
+            k<<<grid_for(k, tiles, kThreads), kThreads, 0, st>>>((const __nv_bfloat16*) in, (__nv_bfloat16*) out,
+                                                                 num_element, a);
+        }
+        else
+        {
+            auto k = per_channel_kernel<__nv_bfloat16, false>;
+            k<<<grid_for(k, tiles, kThreads), kThreads, 0, st>>>((const __nv_bfloat16*) in, (__nv_bfloat16*) out,
+                                                                 num_element, a);
+        }
+    }
+    AB_CUDA_CHECK(cudaGetLastError());
+    return AB_OK;
+}
+
+int ab_qdq_ste_bwd(const void* x, const void* grad, void* grad_in, int64_t count, int dtype, float enc_min,
+                   float enc_max, void* stream)
+{
+    if (count < 0 || (count > 0 && (x == nullptr || grad == nullptr || grad_in == nullptr)))
+    {
+        set_error("null tensor pointer or negative count");
+        return AB_ERR_INVALID;
+    }
+    if (dtype != AB_F32 && dtype != AB_BF16)
+    {
+        set_error("unsupported dtype %d", dtype);
+        return AB_ERR_UNSUPPORTED;
+    }
+    if (count == 0)
+        return AB_OK;
+    if (!aligned16(x) || !aligned16(grad) || !aligned16(grad_in))
+    {
+        set_error("STE tensors must be 16-byte aligned");
+        return AB_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t) stream;
+    if (dtype == AB_F32)
+    {
+        auto k              = ste_bwd_kernel<float>;
+        const int64_t tiles = (count / 4 + kThreads * 2 - 1) / (kThreads * 2);
+        k<<<grid_for(k, tiles, kThreads), kThreads, 0, st>>>((const float*) x, (const float*) grad, (float*) grad_in,
+                                                             count, enc_min, enc_max);
+    }
+    else
+    {
+        auto k              = ste_bwd_kernel<__nv_bfloat16>;
+        const int64_t tiles = (count / 8 + kThreads * 2 - 1) / (kThreads * 2);
+        k<<<grid_for(k, tiles, kThreads), kThreads, 0, st>>>((const __nv_bfloat16*) x, (const __nv_bfloat16*) grad,
+                                                             (__nv_bfloat16*) grad_in, count, enc_min, enc_max);
+    }
+    AB_CUDA_CHECK(cudaGetLastError());
+    return AB_OK;
+}
+
+int ab_qdq_ste_bwd_per_channel(const void* x, const void* grad, void* grad_in, int64_t num_channel,
+                               int64_t num_element, int64_t num_element_per_channel, int dtype,
+                               const float* enc_min, const float* enc_max, void* stream)
+{
+    if (num_element < 0 || num_channel <= 0 || num_element_per_channel <= 0 || enc_min == nullptr ||
+        enc_max == nullptr || (num_element > 0 && (x == nullptr || grad == nullptr || grad_in == nullptr)))
+    {
+        set_error("invalid per-channel arguments");
+        return AB_ERR_INVALID;
+    }
+    if (dtype != AB_F32 && dtype != AB_BF16)
+    {
+        set_error("unsupported dtype %d", dtype);
+        return AB_ERR_UNSUPPORTED;
+    }
+    if (num_element == 0)
+        return AB_OK;
+    if (!aligned16(x) || !aligned16(grad) || !aligned16(grad_in))
+    {
+        set_error("STE tensors must be 16-byte aligned");
+        return AB_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t) stream;
+    if (dtype == AB_F32)
+    {
+        auto k              = ste_bwd_per_channel_kernel<float>;
+        const int64_t tiles = (num_element / 4 + kThreads - 1) / kThreads;
+        k<<<grid_for(k, tiles, kThreads), kThreads, 0, st>>>((const float*) x, (const float*) grad, (float*) grad_in,
+                                                             num_element, num_channel, num_element_per_channel,
+                                                             enc_min, enc_max);
+    }
+    else
+    {
+        auto k              = ste_bwd_per_channel_kernel<__nv_bfloat16>;
+        const int64_t tiles = (num_element / 8 + kThreads - 1) / kThreads;
+        k<<<grid_for(k, tiles, kThreads), kThreads, 0, st>>>((const __nv_bfloat16*) x, (const __nv_bfloat16*) grad,
+                                                             (__nv_bfloat16*) grad_in, num_element, num_channel,
+                                                             num_element_per_channel, enc_min, enc_max);
+    }
+    AB_CUDA_CHECK(cudaGetLastError());
+    return AB_OK;
+}
+
+// ---- host helpers ---------------------------------------------------------------------------------------------
+int ab_gate_min_max(double* enc_min, double* enc_max)
+{
+    if (!enc_min || !enc_max)
+        return AB_ERR_INVALID;
+    em::gate_min_max(*enc_min, *enc_max);
+    return AB_OK;
+}
+
+int ab_fill_encoding_info(int bw, double enc_min, double enc_max, ab_encoding* out)
+{
+    if (!out)
+        return AB_ERR_INVALID;
+    em::fill_encoding_info(bw, enc_min, enc_max, *out);
+    return AB_OK;
+}
+
+int ab_tf_compute_encoding(int bw, double mn, double mx, int use_symmetric, int use_strict_symmetric,
+                           int use_unsigned_symmetric, ab_encoding* out)
+{
+    if (!out)
+        return AB_ERR_INVALID;
+    em::tf_encoding(bw, mn, mx, use_symmetric != 0, use_strict_symmetric != 0, use_unsigned_symmetric != 0, *out);
+    return AB_OK;
+}
+
+int ab_tf_analyzer_encoding(int bw, double run_min, double run_max, int use_symmetric, int use_strict_symmetric,
+                            int use_unsigned_symmetric, ab_encoding* out)
+{
+    if (!out)
+        return AB_ERR_INVALID;
+    em::tf_analyzer_encoding(bw, run_min, run_max, use_symmetric != 0, use_strict_symmetric != 0,
+                             use_unsigned_symmetric != 0, *out);
+    return AB_OK;
+}
+
+int ab_compute_partial_encoding(int bw, ab_encoding* e, int sym, int unsigned_sym, int strict)
+{
+    if (!e)
+        return AB_ERR_INVALID;
+    if (e->min == 0 && e->max == 0)
+    {
+        // computeMinMaxRangeFromDeltaOffset -- DlQ/src/quantization_utils.cpp:158-205
+        if (e->bw == 0)
+        {
+            set_error("Encodings must have a valid non-zero bitwidth");
+            return AB_ERR_INVALID;
+        }
+        if (e->delta == 0 && e->offset > 0)
+        {
+            set_error("Encoding must have a valid non-zero delta/offset if min and max are zero");
+            return AB_ERR_INVALID;
+        }
+        double steps = em::pow2((uint8_t) bw) - 1;
+        if (sym && strict)
+            steps -= 1;
+        e->min = e->offset * e->delta;
+        if (sym && ((e->min < 0.0) || !unsigned_sym))
+            e->max = e->delta * floor(steps / 2);
+        else
+            e->max = e->delta * steps + e->min;
+        if (e->max - e->min < em::kEpsilon)
+            em::gate_min_max(e->min, e->max);
+        return AB_OK;
+    }
+    if (e->delta == 0)
+    {
+        // computeDeltaAndOffsetFromMinMax -- DlQ/src/quantization_utils.cpp:207-228
+        if (e->bw == 0)
+        {
+            set_error("Encodings must have a valid non-zero bitwidth");
+            return AB_ERR_INVALID;
+        }
+        const ab_encoding orig = *e;
+        em::tf_encoding(bw, orig.min, orig.max, sym != 0, strict != 0, unsigned_sym != 0, *e);
+        e->min = orig.min;
+        e->max = orig.max;
+        return AB_OK;
+    }
+    set_error("Cannot determine how to compute partial encoding");   // DlQ/src/TensorQuantizer.cpp:341
+    return AB_ERR_INVALID;
+}
+
+int ab_per_channel_params(const double* enc_min, const double* enc_max, int num_channel, int bw, float* params)
+{
+    if (!enc_min || !enc_max || !params || num_channel <= 0)
+        return AB_ERR_INVALID;
+    double steps = em::pow2(bw) - 1;
+    if (enc_min[0] == -enc_max[0])   // decided from channel 0 only (ATQ:286-294)
+        steps -= 1;
+    const float steps_f = (float) steps;
+    for (int c = 0; c < num_channel; ++c)
+        em::per_channel_param(enc_min[c], enc_max[c], steps_f, params[c], params[num_channel + c],
+                              params[2 * num_channel + c], params[3 * num_channel + c]);
+    return AB_OK;
+}
+}   // extern "C"

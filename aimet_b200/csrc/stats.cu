@@ -1,0 +1,785 @@
+// Job 2 -- statistics kernels for sm_100a: min/max and the 512-bin histogram, accumulated into device-resident
+// per-quantizer state (ab_stats_state) with no host synchronisation.
+//
+// Reference semantics (CPU path = parity target): DlQ/src/math_functions.cpp:207-288 (InitializePdf, UpdatePdf),
+// :327-347 (GetMin/GetMax), :367-384 (GetHistogram_cpu); DlQ/src/TfEncodingAnalyzer.cpp:60-71.
+// The reference's own GPU path (math_functions.cu:52-64,125-211) does two thrust reductions with host round trips,
+// per-thread global-memory histograms on at most 32 blocks, a single-block reduce and a blocking copy per call.
+//
+// Design here
+//   minmax_kernel   : one streaming pass, 128-bit loads, per-thread fmin/fmax, warp-shuffle + block reduce, one
+//                     atomicMin/atomicMax per CTA on an order-preserving integer image of the float; the last CTA
+//                     (ticket) folds the batch result into the state. For tf_enhanced it exits immediately once the
+//                     histogram range is fixed, so the steady state is ONE pass over the data.
+//   hist_kernel     : persistent, one CTA per SM. Tiles of 16 KB are staged into a 6-deep shared-memory ring by the
+//                     TMA engine (cp.async.bulk + mbarrier complete_tx), so no registers or LSU issue slots are
+//                     spent on global loads. Bins are counted in a shared-memory histogram privatised PER LANE
+//                     (bin b of lane l lives at word b*32+l: bank == lane, so a warp's 32 atomics never conflict,
+//                     whatever the data distribution -- ReLU outputs put half the samples in one bin). The CTA then
+//                     reduces its 32 copies and flushes with at most 512 global atomics; the last CTA folds the
+//                     batch into the running PDF in double precision, exactly as UpdatePdf does.
+//   segmented kernel: one CTA per segment (= per output channel of a weight): min/max, range, histogram and PDF fold
+//                     for thousands of quantizers in ONE launch, replacing a Python loop of per-channel calls.
+#include "common.cuh"
+#include "encoding_math.h"
+
+namespace ab
+{
+namespace
+{
+
+constexpr int kBins = AB_PDF_SIZE;
+
+// ---- small helpers --------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_min(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// GetHistogram_cpu's bin index (DlQ/src/math_functions.cpp:375-376): round(x / bucket - offset) in float, then the
+// x86 float->int conversion (NaN / out of range -> INT_MIN, i.e. dropped). Returns -1 for "not counted".
+__device__ __forceinline__ int bin_index(float x, float bucket, float offset)
+{
+    const float r = round_half_away(__fsub_rn(__fdiv_rn(x, bucket), offset));
+    // r is an integer-valued float (or NaN / inf). In-range test done in float so NaN and inf fall out.
+    return (r >= 0.0f && r < (float) kBins) ? (int) r : -1;
+}
+
+struct Range
+{
+    float bucket, offset;
+    bool valid;   // false: uninitialised PDF and an all-zero batch -> nothing to count
+};
+
+// Range for this call: the frozen one, or (first non-zero batch) the one InitializePdf derives from the batch min/max.
+__device__ __forceinline__ Range resolve_range(const ab_stats_state* st, double* x_left0, double* bucket_d)
+{
+    Range r;
+    if (st->initialized)
+    {
+        r.bucket = st->bucket_size;
+        r.offset = st->pdf_offset;
+        r.valid  = true;
+        return r;
+    }
+    const float mn = ordered_to_float(st->batch_min_bits);
+    const float mx = ordered_to_float(st->batch_max_bits);
+    if (mn == 0 && mx == 0)   // DlQ/src/math_functions.cpp:254-259
+    {
+        r.bucket = 1.0f, r.offset = 0.0f, r.valid = false;
+        return r;
+    }
+    double x0, bd;
+    em::init_pdf_range(mn, mx, x0, bd, r.bucket, r.offset);
+    if (x_left0)
+        *x_left0 = x0, *bucket_d = bd;
+    r.valid = true;
+    return r;
+}
+
+// Fold one batch's counts into the running PDF (DlQ/src/math_functions.cpp:279-287). One thread per bin.
+__device__ __forceinline__ void fold_bin(double* pdf, uint32_t h, double cnt, int iterations)
+{
+    const double prob = (double) h / cnt;
+    *pdf              = __ddiv_rn(__dadd_rn(__dmul_rn(*pdf, (double) iterations), prob), (double) (iterations + 1));
+}
+
+constexpr int32_t kPosInfBits = 0x7f800000;                     // ordered image of +inf
+constexpr int32_t kNegInfBits = (int32_t) 0xff800000 ^ 0x7fffffff;   // ordered image of -inf
+
+// ---------------------------------------------------------------------------------------------------------------
+// reset
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void reset_kernel(ab_stats_state* states, int64_t count)
+{
+    const int64_t s = blockIdx.x;
+    if (s >= count)
+        return;
+    ab_stats_state* st = states + s;
+    for (int i = threadIdx.x; i < kBins; i += blockDim.x)
+    {
+        st->pdf[i]  = 0.0;
+        st->hist[i] = 0;
+    }
+    if (threadIdx.x == 0)
+    {
+        st->x_left0        = 0.0;
+        st->bucket_size_d  = 0.0;
+        st->run_min        = DBL_MAX;    // DlQ/src/TfEncodingAnalyzer.h:88-91
+        st->run_max        = -DBL_MAX;
+        st->bucket_size    = 0.0f;
+        st->pdf_offset     = 0.0f;
+        st->batch_min_bits = kPosInfBits;
+        st->batch_max_bits = kNegInfBits;
+        st->initialized    = 0;
+        st->stats_updated  = 0;
+        st->iterations     = 0;
+        st->ticket         = 0;
+        st->pad_[0] = st->pad_[1] = st->pad_[2] = st->pad_[3] = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// min / max pass
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kMmThreads = 256;
+constexpr int kMmUnroll  = 4;
+
+template <typename T>
+__device__ __forceinline__ void thread_minmax(const T* __restrict__ in, int64_t count, int64_t cta, int64_t num_cta,
+                                              float& lo, float& hi)
+{
+    constexpr int kV = Elem<T>::kPerVec;
+    lo               = INFINITY;    // float(+DBL_MAX) == +inf (DlQ/src/math_functions.cpp:341)
+    hi               = -INFINITY;
+    if ((reinterpret_cast<uintptr_t>(in) & 15u) == 0)
+    {
+        const int64_t num_vec   = count / kV;
+        const int64_t per_tile  = (int64_t) kMmThreads * kMmUnroll;
+        const int64_t num_tiles = (num_vec + per_tile - 1) / per_tile;
+        for (int64_t tile = cta; tile < num_tiles; tile += num_cta)
+        {
+            const int64_t v0 = tile * per_tile + threadIdx.x;
+            uint4 raw[kMmUnroll];
+#pragma unroll
+            for (int u = 0; u < kMmUnroll; ++u)
+            {
+                const int64_t v = v0 + (int64_t) u * kMmThreads;
+                if (v < num_vec)
+                    raw[u] = ldg_stream(reinterpret_cast<const uint4*>(in) + v);
+            }
+#pragma unroll
+            for (int u = 0; u < kMmUnroll; ++u)
+            {
+                const int64_t v = v0 + (int64_t) u * kMmThreads;
+                if (v < num_vec)
+                {
+                    float f[kV];
+                    Elem<T>::unpack(raw[u], f);
+#pragma unroll
+                    for (int k = 0; k < kV; ++k)
+                    {
+                        lo = fminf(lo, f[k]);   // fminf / fmaxf drop NaN, like std::min / std::max with a NaN 2nd arg
+                        hi = fmaxf(hi, f[k]);
+                    }
+                }
+            }
+        }
+        if (cta == 0)
+        {
+            const int64_t i = num_vec * kV + threadIdx.x;
+            if (i < count)
+            {
+                const float x = Elem<T>::load(in + i);
+                lo = fminf(lo, x), hi = fmaxf(hi, x);
+            }
+        }
+    }
+    else
+    {
+        for (int64_t i = cta * kMmThreads + threadIdx.x; i < count; i += num_cta * kMmThreads)
+        {
+            const float x = Elem<T>::load(in + i);
+            lo = fminf(lo, x), hi = fmaxf(hi, x);
+        }
+    }
+}
+
+__device__ __forceinline__ void block_minmax(float& lo, float& hi)
+{
+    __shared__ float s_lo[32], s_hi[32];
+    lo = warp_min(lo), hi = warp_max(hi);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0)
+        s_lo[warp] = lo, s_hi[warp] = hi;
+    __syncthreads();
+    if (warp == 0)
+    {
+        const int nw = (blockDim.x + 31) >> 5;
+        lo           = lane < nw ? s_lo[lane] : INFINITY;
+        hi           = lane < nw ? s_hi[lane] : -INFINITY;
+        lo = warp_min(lo), hi = warp_max(hi);
+    }
+}
+
+// quant_mode TF: fold into run_min / run_max.  TF_ENHANCED: leave the batch min/max in the scratch fields for
+// hist_kernel (which runs next on the same stream) -- and do nothing at all once the range is fixed.
+template <typename T>
+__global__ void __launch_bounds__(kMmThreads)
+    minmax_kernel(const T* __restrict__ in, int64_t count, int quant_mode, ab_stats_state* st)
+{
+    if (quant_mode == AB_QUANTIZATION_TF_ENHANCED && st->initialized)
+        return;
+    float lo, hi;
+    thread_minmax(in, count, blockIdx.x, gridDim.x, lo, hi);
+    block_minmax(lo, hi);
+    if (threadIdx.x == 0)
+    {
+        atomicMin(&st->batch_min_bits, float_to_ordered(lo));
+        atomicMax(&st->batch_max_bits, float_to_ordered(hi));
+        if (quant_mode == AB_QUANTIZATION_TF)
+        {
+            __threadfence();
+            const uint32_t t = atomicAdd(&st->ticket, 1u);
+            if (t == gridDim.x - 1)
+            {
+                __threadfence();
+                const double cur_min = (double) ordered_to_float(*(volatile int32_t*) &st->batch_min_bits);
+                const double cur_max = (double) ordered_to_float(*(volatile int32_t*) &st->batch_max_bits);
+                st->run_min          = em::smin(st->run_min, cur_min);   // DlQ/src/TfEncodingAnalyzer.cpp:69-70
+                st->run_max          = em::smax(st->run_max, cur_max);
+                st->stats_updated    = 1;
+                st->batch_min_bits   = kPosInfBits;
+                st->batch_max_bits   = kNegInfBits;
+                st->ticket           = 0;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// histogram pass (tf_enhanced): TMA-staged tiles, per-lane privatised shared-memory bins
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kHistThreads = 512;
+constexpr int kTileBytes   = 16384;
+constexpr int kStages      = 6;
+constexpr int kLaneCopies  = 32;
+constexpr size_t kHistSmem = (size_t) kStages * kTileBytes + (size_t) kBins * kLaneCopies * 4 + kStages * 8 + 64;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+    return (uint32_t) __cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA engine, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void count_sample(uint32_t* s_hist, int lane, float x, float bucket, float offset)
+{
+    const int b = bin_index(x, bucket, offset);
+    if (b >= 0)
+        atomicAdd(s_hist + b * kLaneCopies + lane, 1u);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kHistThreads, 1)
+    hist_kernel(const T* __restrict__ in, int64_t count, ab_stats_state* st, uint32_t* batch_log)
+{
+    constexpr int kV = Elem<T>::kPerVec;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* s_tiles  = smem;
+    uint32_t* s_hist  = reinterpret_cast<uint32_t*>(smem + (size_t) kStages * kTileBytes);
+    uint64_t* s_full  = reinterpret_cast<uint64_t*>(smem + (size_t) kStages * kTileBytes + (size_t) kBins * kLaneCopies * 4);
+    __shared__ double s_x_left0, s_bucket_d;
+    __shared__ uint32_t s_is_last;
+
+    const int tid  = threadIdx.x;
+    const int lane = tid & 31;
+
+    double x_left0 = 0, bucket_d = 0;
+    const Range rg = resolve_range(st, &x_left0, &bucket_d);   // every thread derives the same range
+
+    if (rg.valid)
+    {
+        for (int i = tid; i < kBins * kLaneCopies; i += kHistThreads)
+            s_hist[i] = 0;
+
+        const bool aligned      = (reinterpret_cast<uintptr_t>(in) & 15u) == 0;
+        const int64_t bytes     = aligned ? (count / kV) * 16 : 0;   // the 16-byte-granular body goes through TMA
+        const int64_t num_tiles = (bytes + kTileBytes - 1) / kTileBytes;
+        // tiles owned by this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+        const int64_t my_tiles = (num_tiles > blockIdx.x) ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+        if (tid == 0)
+        {
+            for (int s = 0; s < kStages; ++s)
+                mbar_init(s_full + s, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+
+        auto issue = [&](int64_t k) {   // thread 0 only
+            const int64_t tile = blockIdx.x + k * gridDim.x;
+            const int64_t off  = tile * kTileBytes;
+            const uint32_t nb  = (uint32_t) min((int64_t) kTileBytes, bytes - off);
+            const int s        = (int) (k % kStages);
+            mbar_expect_tx(s_full + s, nb);
+            tma_load_1d(s_tiles + (size_t) s * kTileBytes, reinterpret_cast<const uint8_t*>(in) + off, nb, s_full + s);
+        };
+        if (tid == 0)
+            for (int64_t k = 0; k < my_tiles && k < kStages; ++k)
+                issue(k);
+
+        for (int64_t k = 0; k < my_tiles; ++k)
+        {
+            const int s        = (int) (k % kStages);
+            const int64_t tile = blockIdx.x + k * gridDim.x;
+            const int nb       = (int) min((int64_t) kTileBytes, bytes - tile * kTileBytes);
+            mbar_wait(s_full + s, (uint32_t) ((k / kStages) & 1));
+            const uint4* src = reinterpret_cast<const uint4*>(s_tiles + (size_t) s * kTileBytes);
+#pragma unroll
+            for (int u = 0; u < kTileBytes / 16 / kHistThreads; ++u)
+            {
+                const int v = tid + u * kHistThreads;
+                if (v * 16 < nb)
+                {
+                    float f[kV];
+                    Elem<T>::unpack(src[v], f);
+#pragma unroll
+                    for (int e = 0; e < kV; ++e)
+                        count_sample(s_hist, lane, f[e], rg.bucket, rg.offset);
+                }
+            }
+            __syncthreads();   // every thread has finished reading stage s
+            if (tid == 0 && k + kStages < my_tiles)
+                issue(k + kStages);
+        }
+        // elements the TMA body did not cover: the sub-vector tail, or everything when the base is misaligned
+        const int64_t body = aligned ? (count / kV) * kV : 0;
+        for (int64_t i = body + (int64_t) blockIdx.x * kHistThreads + tid; i < count;
+             i += (int64_t) gridDim.x * kHistThreads)
+            count_sample(s_hist, lane, Elem<T>::load(in + i), rg.bucket, rg.offset);
+        __syncthreads();
+
+        // reduce the 32 lane copies of bin `tid` (rotated start: conflict-free) and flush
+        uint32_t sum = 0;
+#pragma unroll
+        for (int l = 0; l < kLaneCopies; ++l)
+            sum += s_hist[tid * kLaneCopies + ((l + tid) & (kLaneCopies - 1))];
+        if (sum)
+            atomicAdd(&st->hist[tid], sum);
+    }
+
+    // ---- last CTA folds the batch into the running PDF --------------------------------------------------------
+    __threadfence();
+    __syncthreads();
+    if (tid == 0)
+    {
+        const uint32_t t = atomicAdd(&st->ticket, 1u);
+        s_is_last        = (t == gridDim.x - 1);
+        if (s_is_last && rg.valid && !st->initialized)
+            s_x_left0 = x_left0, s_bucket_d = bucket_d;
+    }
+    __syncthreads();
+    if (!s_is_last)
+        return;
+    __threadfence();
+    const int iterations = st->iterations;
+    if (rg.valid)
+    {
+        const uint32_t h = *(volatile uint32_t*) &st->hist[tid];
+        fold_bin(&st->pdf[tid], h, (double) count, iterations);
+        st->hist[tid] = 0;
+        if (batch_log)
+            batch_log[tid] = h;
+    }
+    else if (batch_log)
+        batch_log[tid] = 0;
+    if (tid == 0)
+    {
+        if (batch_log)
+        {
+            // element count (0 when the batch was skipped, as the reference skips all-zero batches before init)
+            const uint64_t c       = rg.valid ? (uint64_t) count : 0;
+            batch_log[kBins]       = (uint32_t) c;
+            batch_log[kBins + 1]   = (uint32_t) (c >> 32);
+        }
+        if (rg.valid)
+        {
+            if (!st->initialized)
+            {
+                st->x_left0       = s_x_left0;
+                st->bucket_size_d = s_bucket_d;
+                st->bucket_size   = rg.bucket;
+                st->pdf_offset    = rg.offset;
+                st->initialized   = 1;
+            }
+            st->iterations = iterations + 1;
+        }
+        st->stats_updated  = 1;
+        st->batch_min_bits = kPosInfBits;
+        st->batch_max_bits = kNegInfBits;
+        st->ticket         = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// segmented statistics: one CTA per segment
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kSegThreads = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(kSegThreads)
+    segmented_kernel(const T* __restrict__ in, int64_t num_segments, int64_t seg_len, int quant_mode,
+                     ab_stats_state* states)
+{
+    __shared__ uint32_t s_hist[kBins];
+    __shared__ float s_lo, s_hi;
+    constexpr int kV = Elem<T>::kPerVec;
+
+    for (int64_t seg = blockIdx.x; seg < num_segments; seg += gridDim.x)
+    {
+        const T* x         = in + seg * seg_len;
+        ab_stats_state* st = states + seg;
+        const bool vec     = (reinterpret_cast<uintptr_t>(x) & 15u) == 0;
+        const int64_t nvec = vec ? seg_len / kV : 0;
+        const bool need_mm = (quant_mode == AB_QUANTIZATION_TF) || !st->initialized;
+
+        __syncthreads();   // previous segment's fold has finished with s_hist / s_lo / s_hi
+        if (need_mm)
+        {
+            float lo = INFINITY, hi = -INFINITY;
+            for (int64_t v = threadIdx.x; v < nvec; v += kSegThreads)
+            {
+                float f[kV];
+                Elem<T>::unpack(__ldg(reinterpret_cast<const uint4*>(x) + v), f);
+#pragma unroll
+                for (int k = 0; k < kV; ++k)
+                    lo = fminf(lo, f[k]), hi = fmaxf(hi, f[k]);
+            }
+            for (int64_t i = nvec * kV + threadIdx.x; i < seg_len; i += kSegThreads)
+            {
+                const float xv = Elem<T>::load(x + i);
+                lo = fminf(lo, xv), hi = fmaxf(hi, xv);
+            }
+            block_minmax(lo, hi);
+            if (threadIdx.x == 0)
+                s_lo = lo, s_hi = hi;
+        }
+        for (int i = threadIdx.x; i < kBins; i += kSegThreads)
+            s_hist[i] = 0;
+        __syncthreads();
+
+        if (quant_mode == AB_QUANTIZATION_TF)
+        {
+            if (threadIdx.x == 0)
+            {
+                st->run_min       = em::smin(st->run_min, (double) s_lo);
+                st->run_max       = em::smax(st->run_max, (double) s_hi);
+                st->stats_updated = 1;
+            }
+            continue;
+        }
+
+        // tf_enhanced
+        Range rg;
+        double x_left0 = 0, bucket_d = 0;
+        const bool was_init = st->initialized != 0;
+        if (was_init)
+        {
+            rg.bucket = st->bucket_size, rg.offset = st->pdf_offset, rg.valid = true;
+        }
+        else if (s_lo == 0 && s_hi == 0)
+        {
+            rg.bucket = 1.0f, rg.offset = 0.0f, rg.valid = false;
+        }
+        else
+        {
+            em::init_pdf_range(s_lo, s_hi, x_left0, bucket_d, rg.bucket, rg.offset);
+            rg.valid = true;
+        }
+        if (rg.valid)
+        {
+            for (int64_t v = threadIdx.x; v < nvec; v += kSegThreads)
+            {
+                float f[kV];
+                Elem<T>::unpack(__ldg(reinterpret_cast<const uint4*>(x) + v), f);
+#pragma unroll
+                for (int k = 0; k < kV; ++k)
+                {
+                    const int b = bin_index(f[k], rg.bucket, rg.offset);
+                    if (b >= 0)
+                        atomicAdd(s_hist + b, 1u);
+                }
+            }
+            for (int64_t i = nvec * kV + threadIdx.x; i < seg_len; i += kSegThreads)
+            {
+                const int b = bin_index(Elem<T>::load(x + i), rg.bucket, rg.offset);
+                if (b >= 0)
+                    atomicAdd(s_hist + b, 1u);
+            }
+            __syncthreads();
+            const int iterations = st->iterations;
+            for (int i = threadIdx.x; i < kBins; i += kSegThreads)
+                fold_bin(&st->pdf[i], s_hist[i], (double) seg_len, iterations);
+            __syncthreads();   // every thread has read st->iterations before it changes
+            if (threadIdx.x == 0)
+            {
+                if (!was_init)
+                {
+                    st->x_left0       = x_left0;
+                    st->bucket_size_d = bucket_d;
+                    st->bucket_size   = rg.bucket;
+                    st->pdf_offset    = rg.offset;
+                    st->initialized   = 1;
+                }
+                st->iterations = iterations + 1;
+            }
+        }
+        if (threadIdx.x == 0)
+            st->stats_updated = 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// range injection and ordered replay (multi-GPU exact merge)
+// ---------------------------------------------------------------------------------------------------------------
+// minmax: [count][2] floats = the batch min/max that fixes each quantizer's range; (0,0) leaves it uninitialised
+__global__ void init_range_kernel(ab_stats_state* states, int64_t count, const float* __restrict__ minmax)
+{
+    const int64_t s = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= count)
+        return;
+    ab_stats_state* st = states + s;
+    const float mn = minmax[2 * s], mx = minmax[2 * s + 1];
+    if (st->initialized || (mn == 0 && mx == 0))
+        return;
+    double x0, bd;
+    float bf, of;
+    em::init_pdf_range(mn, mx, x0, bd, bf, of);
+    st->x_left0       = x0;
+    st->bucket_size_d = bd;
+    st->bucket_size   = bf;
+    st->pdf_offset    = of;
+    st->initialized   = 1;
+}
+
+// One CTA per quantizer, one thread per bin. Replays pdf = (pdf*k + hist/cnt)/(k+1) over the batches in order.
+__global__ void __launch_bounds__(kBins)
+    fold_batches_kernel(ab_stats_state* states, int64_t count, const uint32_t* __restrict__ batch_log,
+                        const int64_t* __restrict__ batch_offsets, int64_t num_batches)
+{
+    const int64_t s = blockIdx.x;
+    if (s >= count)
+        return;
+    ab_stats_state* st = states + s;
+    const int b        = threadIdx.x;
+    double pdf         = 0.0;
+    int iterations     = 0;
+    bool seen          = false;
+    for (int64_t k = 0; k < num_batches; ++k)
+    {
+        const uint32_t* entry = batch_log + batch_offsets[k] + s * (kBins + 2);
+        const uint64_t cnt    = (uint64_t) entry[kBins] | ((uint64_t) entry[kBins + 1] << 32);
+        if (cnt == 0)
+            continue;
+        seen              = true;
+        const double prob = (double) entry[b] / (double) cnt;
+        pdf               = __ddiv_rn(__dadd_rn(__dmul_rn(pdf, (double) iterations), prob), (double) (iterations + 1));
+        ++iterations;
+    }
+    st->pdf[b] = pdf;
+    if (b == 0)
+    {
+        st->iterations = iterations;
+        if (seen)
+            st->stats_updated = 1;
+    }
+}
+
+template <typename K>
+int resident_grid(K kernel, int threads, size_t smem)
+{
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm <= 0)
+        per_sm = 1;
+    return per_sm * num_sms();
+}
+
+bool check_common(const void* in, int64_t count, int dtype, int quant_mode, const void* state)
+{
+    if (count < 0 || (count > 0 && in == nullptr) || state == nullptr)
+    {
+        set_error("null pointer or negative count");
+        return false;
+    }
+    if (dtype != AB_F32 && dtype != AB_BF16)
+    {
+        set_error("unsupported dtype %d", dtype);
+        return false;
+    }
+    if (quant_mode != AB_QUANTIZATION_TF && quant_mode != AB_QUANTIZATION_TF_ENHANCED)
+    {
+        set_error("unsupported quantization mode %d (only tf and tf_enhanced are on the hot path)", quant_mode);
+        return false;
+    }
+    return true;
+}
+
+template <typename T>
+int launch_update(const T* in, int64_t count, int quant_mode, ab_stats_state* st, uint32_t* batch_log,
+                  cudaStream_t stream)
+{
+    constexpr int kV = Elem<T>::kPerVec;
+    {
+        auto k              = minmax_kernel<T>;
+        const int64_t tiles = (count / kV + kMmThreads * kMmUnroll - 1) / (kMmThreads * kMmUnroll);
+        int grid            = resident_grid(k, kMmThreads, 0);
+        if (tiles < grid)
+            grid = tiles < 1 ? 1 : (int) tiles;
+        k<<<grid, kMmThreads, 0, stream>>>(in, count, quant_mode, st);
+        AB_CUDA_CHECK(cudaGetLastError());
+    }
+    if (quant_mode == AB_QUANTIZATION_TF_ENHANCED)
+    {
+        auto k = hist_kernel<T>;
+        static thread_local bool configured[2] = {false, false};
+        const int which                        = sizeof(T) == 4 ? 0 : 1;
+        if (!configured[which])
+        {
+            AB_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kHistSmem));
+            configured[which] = true;
+        }
+        const int64_t tiles = ((count / kV) * 16 + kTileBytes - 1) / kTileBytes;
+        int grid            = num_sms();
+        if (tiles < grid)
+            grid = tiles < 1 ? 1 : (int) tiles;
+        k<<<grid, kHistThreads, kHistSmem, stream>>>(in, count, st, batch_log);
+        AB_CUDA_CHECK(cudaGetLastError());
+    }
+    return AB_OK;
+}
+
+}   // namespace
+}   // namespace ab
+
+using namespace ab;
+
+extern "C"
+{
+size_t ab_stats_state_bytes(void)
+{
+    return sizeof(ab_stats_state);
+}
+
+int ab_stats_reset(ab_stats_state* states, int64_t count, void* stream)
+{
+    if (count < 0 || (count > 0 && states == nullptr))
+    {
+        set_error("null state pointer or negative count");
+        return AB_ERR_INVALID;
+    }
+    if (count == 0)
+        return AB_OK;
+    if (count > 0x7fffffff)
+    {
+        set_error("too many states in one call");
+        return AB_ERR_INVALID;
+    }
+    reset_kernel<<<(unsigned) count, 128, 0, (cudaStream_t) stream>>>(states, count);
+    AB_CUDA_CHECK(cudaGetLastError());
+    return AB_OK;
+}
+
+int ab_stats_update(const void* in, int64_t count, int dtype, int quant_mode, ab_stats_state* state,
+                    uint32_t* batch_log_entry, void* stream)
+{
+    if (!check_common(in, count, dtype, quant_mode, state))
+        return AB_ERR_INVALID;
+    if (dtype == AB_F32)
+        return launch_update((const float*) in, count, quant_mode, state, batch_log_entry, (cudaStream_t) stream);
+    return launch_update((const __nv_bfloat16*) in, count, quant_mode, state, batch_log_entry, (cudaStream_t) stream);
+}
+
+int ab_stats_update_segmented(const void* in, int64_t num_segments, int64_t segment_len, int dtype, int quant_mode,
+                              ab_stats_state* states, void* stream)
+{
+    if (num_segments < 0 || segment_len < 0)
+    {
+        set_error("negative segment count or length");
+        return AB_ERR_INVALID;
+    }
+    if (!check_common(in, num_segments * segment_len, dtype, quant_mode, states))
+        return AB_ERR_INVALID;
+    if (num_segments == 0)
+        return AB_OK;
+    cudaStream_t st = (cudaStream_t) stream;
+    if (dtype == AB_F32)
+    {
+        auto k   = segmented_kernel<float>;
+        int grid = resident_grid(k, kSegThreads, 0);
+        if (num_segments < grid)
+            grid = (int) num_segments;
+        k<<<grid, kSegThreads, 0, st>>>((const float*) in, num_segments, segment_len, quant_mode, states);
+    }
+    else
+    {
+        auto k   = segmented_kernel<__nv_bfloat16>;
+        int grid = resident_grid(k, kSegThreads, 0);
+        if (num_segments < grid)
+            grid = (int) num_segments;
+        k<<<grid, kSegThreads, 0, st>>>((const __nv_bfloat16*) in, num_segments, segment_len, quant_mode, states);
+    }
+    AB_CUDA_CHECK(cudaGetLastError());
+    return AB_OK;
+}
+
+int ab_stats_init_range(ab_stats_state* states, int64_t count, const float* minmax, void* stream)
+{
+    if (count < 0 || (count > 0 && (states == nullptr || minmax == nullptr)))
+    {
+        set_error("null pointer or negative count");
+        return AB_ERR_INVALID;
+    }
+    if (count == 0)
+        return AB_OK;
+    init_range_kernel<<<(unsigned) ((count + 127) / 128), 128, 0, (cudaStream_t) stream>>>(states, count, minmax);
+    AB_CUDA_CHECK(cudaGetLastError());
+    return AB_OK;
+}
+
+int ab_stats_fold_batches(ab_stats_state* states, int64_t count, const uint32_t* batch_log,
+                          const int64_t* batch_offsets, int64_t num_batches, void* stream)
+{
+    if (count < 0 || num_batches < 0 ||
+        (count > 0 && (states == nullptr || (num_batches > 0 && (batch_log == nullptr || batch_offsets == nullptr)))))
+    {
+        set_error("null pointer or negative count");
+        return AB_ERR_INVALID;
+    }
+    if (count == 0)
+        return AB_OK;
+    fold_batches_kernel<<<(unsigned) count, kBins, 0, (cudaStream_t) stream>>>(states, count, batch_log,
+                                                                               batch_offsets, num_batches);
+    AB_CUDA_CHECK(cudaGetLastError());
+    return AB_OK;
+}
+}   // extern "C"

@@ -1,0 +1,225 @@
+// Job 3 -- the tf_enhanced SQNR grid search on the device, batched over quantizers.
+//
+// Reference: TfEnhancedEncodingAnalyzer<float>::computeEncoding (DlQ/src/TfEnhancedEncodingAnalyzer.cpp:79-397): a
+// serial loop over <= 358 (asymmetric) or ~101 (symmetric) (delta, offset) candidates, each costing a pass over the
+// 512-bin PDF; ~0.6 ms per quantizer on a CPU core, x 26 560 weight channels for per-channel ResNet-50.
+//
+// Here: one CTA per quantizer, one thread per candidate. The PDF (4 KB of doubles) is staged in shared memory; every
+// thread evaluates its candidate's cost with the reference's exact mixed float/double arithmetic and its exact bin
+// order (tfe_math.h), so each cost is bit-identical to the CPU value. The winner is the lowest-index strict minimum
+// (`cost < bestCost`, :138), found with a (cost, index) block reduction -- NOT a reduction over bins, which would
+// change rounding. The epilogue also emits the fp32 kernel parameters fillEncodingInfo would derive, so a per-tensor
+// QDQ can follow on the same stream without a host round trip.
+#include "common.cuh"
+#include "tfe_math.h"
+
+namespace ab
+{
+namespace
+{
+
+constexpr int kSearchThreads = 384;   // >= 358 candidates
+
+struct SearchArgs
+{
+    int quant_mode, bw, sym, strict, unsigned_sym;
+};
+
+__device__ __forceinline__ void write_encoding(double* enc_out, float* qdq4_out, int64_t s, const ab_encoding& e,
+                                               bool valid)
+{
+    double* o = enc_out + s * 5;
+    o[0] = e.min, o[1] = e.max, o[2] = e.delta, o[3] = e.offset, o[4] = (double) e.bw;
+    if (qdq4_out)
+    {
+        float4 p = make_float4(0.f, 0.f, 1.f, 0.f);
+        if (valid)
+        {
+            ab_encoding full;
+            em::fill_encoding_info(e.bw, e.min, e.max, full);
+            p = make_float4((float) full.min, (float) full.max, (float) full.delta, (float) full.offset);
+        }
+        reinterpret_cast<float4*>(qdq4_out)[s] = p;
+    }
+}
+
+__global__ void __launch_bounds__(kSearchThreads)
+    compute_encodings_kernel(const ab_stats_state* __restrict__ states, int64_t count, SearchArgs a,
+                             double* __restrict__ enc_out, float* __restrict__ qdq4_out)
+{
+    __shared__ double s_pdf[AB_PDF_SIZE];
+    __shared__ float s_sym_deltas[tfe::kMaxSymDeltas];
+    __shared__ tfe::AsymSetup s_asym;
+    __shared__ float s_num_steps;
+    __shared__ int s_sym_offset, s_num_cand;
+    __shared__ double s_best_cost[kSearchThreads / 32];
+    __shared__ int s_best_idx[kSearchThreads / 32];
+
+    const int tid = threadIdx.x;
+    for (int64_t s = blockIdx.x; s < count; s += gridDim.x)
+    {
+        const ab_stats_state* st = states + s;
+        __syncthreads();   // previous quantizer is completely done with shared memory
+
+        if (a.quant_mode == AB_QUANTIZATION_TF)
+        {
+            if (tid == 0)
+            {
+                ab_encoding e = {0, 0, 0, 0, 0};
+                const bool ok = st->stats_updated != 0;
+                if (ok)
+                    em::tf_analyzer_encoding(a.bw, st->run_min, st->run_max, a.sym != 0, a.strict != 0,
+                                             a.unsigned_sym != 0, e);
+                write_encoding(enc_out, qdq4_out, s, e, ok);
+            }
+            continue;
+        }
+        if (!st->initialized)
+        {
+            if (tid == 0)
+            {
+                ab_encoding e = {0, 0, 0, 0, 0};
+                const bool ok = st->stats_updated != 0;
+                if (ok)
+                    tfe::all_zero_encoding(a.bw, e);   // only zeros seen so far (:85-100)
+                write_encoding(enc_out, qdq4_out, s, e, ok);
+            }
+            continue;
+        }
+
+        for (int i = tid; i < AB_PDF_SIZE; i += kSearchThreads)
+            s_pdf[i] = st->pdf[i];
+        __syncthreads();
+        const tfe::PdfView view {s_pdf, st->x_left0, st->bucket_size_d};
+
+        if (tid == 0)
+        {
+            float min_val, max_val;
+            tfe::find_range(view, min_val, max_val);
+            const float steps = tfe::num_steps_for(a.bw, a.sym != 0, a.strict != 0);
+            s_num_steps       = steps;
+            if (a.sym)
+            {
+                int off;
+                s_num_cand   = tfe::sym_candidates(min_val, max_val, steps, a.unsigned_sym != 0, s_sym_deltas, off);
+                s_sym_offset = off;
+            }
+            else
+            {
+                s_asym     = tfe::asym_setup(min_val, max_val, steps);
+                s_num_cand = tfe::kAsymCandidates;
+            }
+        }
+        __syncthreads();
+
+        double my_cost = INFINITY;
+        int my_idx     = INT_MAX;
+        float my_delta = -1.0f;
+        int my_offset  = -1;
+        if (tid < s_num_cand)
+        {
+            bool valid;
+            if (a.sym)
+            {
+                my_delta  = s_sym_deltas[tid];
+                my_offset = s_sym_offset;
+                valid     = true;
+            }
+            else
+                valid = tfe::asym_candidate(s_asym, tid, my_delta, my_offset);
+            if (valid)
+            {
+                const double c = tfe::cost(view, a.bw, my_delta, my_offset);
+                if (c < DBL_MAX)   // `cost < bestCost` with bestCost starting at DBL_MAX (:126,138); NaN never wins
+                {
+                    my_cost = c;
+                    my_idx  = tid;
+                }
+            }
+        }
+        // argmin over (cost, index): lowest cost, ties -> lowest index == the first strict minimum in push order
+        double bc = my_cost;
+        int bi    = my_idx;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            const double oc = __shfl_xor_sync(0xffffffffu, bc, o);
+            const int oi    = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (oc < bc || (oc == bc && oi < bi))
+                bc = oc, bi = oi;
+        }
+        if ((tid & 31) == 0)
+            s_best_cost[tid >> 5] = bc, s_best_idx[tid >> 5] = bi;
+        __syncthreads();
+        if (tid == 0)
+        {
+            for (int w = 1; w < kSearchThreads / 32; ++w)
+                if (s_best_cost[w] < bc || (s_best_cost[w] == bc && s_best_idx[w] < bi))
+                    bc = s_best_cost[w], bi = s_best_idx[w];
+            s_best_idx[0] = bi;
+        }
+        __syncthreads();
+        const int winner = s_best_idx[0];
+        if (winner == INT_MAX)
+        {
+            if (tid == 0)   // no candidate beat DBL_MAX: the reference keeps bestDelta = bestOffset = -1 (:121-122)
+            {
+                ab_encoding e;
+                tfe::finish(-1.0f, -1, s_num_steps, a.bw, e);
+                write_encoding(enc_out, qdq4_out, s, e, true);
+            }
+        }
+        else if (tid == winner)
+        {
+            ab_encoding e;
+            tfe::finish(my_delta, my_offset, s_num_steps, a.bw, e);
+            write_encoding(enc_out, qdq4_out, s, e, true);
+        }
+    }
+}
+
+}   // namespace
+}   // namespace ab
+
+using namespace ab;
+
+extern "C" int ab_compute_encodings(const ab_stats_state* states, int64_t count, int quant_mode, int bw,
+                                    int use_symmetric, int use_strict_symmetric, int use_unsigned_symmetric,
+                                    double* enc_out, float* qdq4_out, void* stream)
+{
+    if (count < 0 || (count > 0 && (states == nullptr || enc_out == nullptr)))
+    {
+        set_error("null pointer or negative count");
+        return AB_ERR_INVALID;
+    }
+    if (quant_mode != AB_QUANTIZATION_TF && quant_mode != AB_QUANTIZATION_TF_ENHANCED)
+    {
+        set_error("unsupported quantization mode %d", quant_mode);
+        return AB_ERR_INVALID;
+    }
+    if (bw < 1 || bw > 32)
+    {
+        set_error("bitwidth %d out of range", bw);
+        return AB_ERR_INVALID;
+    }
+    if (qdq4_out != nullptr && (reinterpret_cast<uintptr_t>(qdq4_out) & 15u) != 0)
+    {
+        set_error("qdq4_out must be 16-byte aligned");
+        return AB_ERR_INVALID;
+    }
+    if (count == 0)
+        return AB_OK;
+    SearchArgs a {quant_mode, bw, use_symmetric, use_strict_symmetric, use_unsigned_symmetric};
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, compute_encodings_kernel, kSearchThreads, 0) !=
+            cudaSuccess ||
+        per_sm <= 0)
+        per_sm = 1;
+    int64_t grid = (int64_t) per_sm * num_sms();
+    if (count < grid)
+        grid = count;
+    compute_encodings_kernel<<<(unsigned) grid, kSearchThreads, 0, (cudaStream_t) stream>>>(states, count, a, enc_out,
+                                                                                           qdq4_out);
+    AB_CUDA_CHECK(cudaGetLastError());
+    return AB_OK;
+}

@@ -1,0 +1,306 @@
+"""torch custom ops (namespace ``aimet_b200``) over the C ABI in include/aimet_b200.h.
+
+Every op hands raw device pointers and the current CUDA stream to libaimet_b200.so; torch is used only for device
+memory, streams and autograd plumbing. There is no CPU implementation registered for any of them: calling an op with
+a CPU tensor raises (the class-level API in tensor_quantizer_op.py stages host tensors onto the GPU first).
+
+Functional surface (schema strings below); autograd is registered for the two QDQ forwards with the reference's
+straight-through estimator (aimet_torch/v1/quantsim_straight_through_grad.py:91-118) as their backward.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+ROUND_NEAREST, ROUND_STOCHASTIC = 0, 1
+QUANTIZATION_TF, QUANTIZATION_TF_ENHANCED = 0, 1
+STATE_BYTES = None          # filled at import from ab_stats_state_bytes()
+LOG_WORDS = _lib.PDF_SIZE + 2
+
+_L = _lib.load()
+STATE_BYTES = int(_L.ab_stats_state_bytes())
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return _lib.AB_F32
+    if t.dtype == torch.bfloat16:
+        return _lib.AB_BF16
+    raise TypeError(f"aimet_b200 kernels take float32 or bfloat16 tensors, got {t.dtype}")
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("aimet_b200 has no CPU path: tensor must live on a CUDA device "
+                               "(reference analogue: 'Not compiled for GPU mode.' in the other direction)")
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+class _on_device:
+    """Make `t`'s device current for the duration of a C-ABI call (cheap no-op when it already is)."""
+
+    def __init__(self, t):
+        self.idx = t.device.index
+        self.prev = None
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if cur != self.idx:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+
+
+def _contig16(t: torch.Tensor) -> torch.Tensor:
+    """Contiguous and 16-byte aligned (the per-channel / STE kernels require it)."""
+    t = t.contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone(memory_format=torch.contiguous_format)
+    return t
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# implementations (CUDA)
+# ---------------------------------------------------------------------------------------------------------------------
+def qdq_per_tensor_impl(x, enc_min, enc_max, bw, round_mode, seed):
+    _require_cuda(x)
+    x = x.contiguous(memory_format=torch.contiguous_format) if not (
+        x.is_contiguous() or x.is_contiguous(memory_format=torch.channels_last)) else x
+    out = torch.empty_like(x)
+    with _on_device(x):
+        _lib.check(_L.ab_qdq_per_tensor_fwd(x.data_ptr(), out.data_ptr(), x.numel(), _dtype_code(x), float(enc_min),
+                                            float(enc_max), int(bw), int(round_mode), int(seed) & (2**64 - 1),
+                                            _stream(x)))
+    return out
+
+
+def qdq_per_tensor_dev_impl(x, enc4, round_mode, seed):
+    _require_cuda(x, enc4)
+    if enc4.dtype != torch.float32 or enc4.numel() < 4:
+        raise ValueError("enc4 must be a float32 CUDA tensor {min, max, delta, offset}")
+    x = x if (x.is_contiguous() or x.is_contiguous(memory_format=torch.channels_last)) else x.contiguous()
+    out = torch.empty_like(x)
+    with _on_device(x):
+        _lib.check(_L.ab_qdq_per_tensor_fwd_dev(x.data_ptr(), out.data_ptr(), x.numel(), _dtype_code(x),
+                                                enc4.data_ptr(), int(round_mode), int(seed) & (2**64 - 1),
+                                                _stream(x)))
+    return out
+
+
+def quantize_to_grid_impl(x, enc_min, enc_max, bw, round_mode, shift_to_signed, seed):
+    _require_cuda(x)
+    x = x if (x.is_contiguous() or x.is_contiguous(memory_format=torch.channels_last)) else x.contiguous()
+    out = torch.empty_like(x)
+    with _on_device(x):
+        _lib.check(_L.ab_quantize_to_grid(x.data_ptr(), out.data_ptr(), x.numel(), _dtype_code(x), float(enc_min),
+                                          float(enc_max), int(bw), int(round_mode), int(bool(shift_to_signed)),
+                                          int(seed) & (2**64 - 1), _stream(x)))
+    return out
+
+
+def qdq_per_channel_impl(x, params, num_channel, num_element_per_channel, round_mode, seed):
+    _require_cuda(x, params)
+    if params.dtype != torch.float32 or params.numel() != 4 * num_channel or not params.is_contiguous():
+        raise ValueError("params must be a contiguous float32 CUDA tensor of 4*num_channel values")
+    x = _contig16(x)
+    out = torch.empty_like(x, memory_format=torch.contiguous_format)
+    with _on_device(x):
+        _lib.check(_L.ab_qdq_per_channel_fwd(x.data_ptr(), out.data_ptr(), int(num_channel), x.numel(),
+                                             int(num_element_per_channel), _dtype_code(x), params.data_ptr(),
+                                             int(round_mode), int(seed) & (2**64 - 1), _stream(x)))
+    return out
+
+
+def ste_bwd_impl(x, grad, enc_min, enc_max):
+    _require_cuda(x, grad)
+    if x.dtype != grad.dtype or x.shape != grad.shape:
+        raise ValueError("x and grad must share dtype and shape")
+    if x.is_contiguous(memory_format=torch.channels_last) and grad.is_contiguous(memory_format=torch.channels_last) \
+            and not x.is_contiguous():
+        pass   # same physical layout on both: element-wise is layout agnostic
+    else:
+        x, grad = x.contiguous(), grad.contiguous()
+    if x.data_ptr() % 16:
+        x = x.clone()
+    if grad.data_ptr() % 16:
+        grad = grad.clone()
+    out = torch.empty_like(grad)
+    with _on_device(x):
+        _lib.check(_L.ab_qdq_ste_bwd(x.data_ptr(), grad.data_ptr(), out.data_ptr(), x.numel(), _dtype_code(x),
+                                     float(enc_min), float(enc_max), _stream(x)))
+    return out
+
+
+def ste_bwd_per_channel_impl(x, grad, enc_min, enc_max, num_channel, num_element_per_channel):
+    _require_cuda(x, grad, enc_min, enc_max)
+    if x.dtype != grad.dtype or x.shape != grad.shape:
+        raise ValueError("x and grad must share dtype and shape")
+    for e in (enc_min, enc_max):
+        if e.dtype != torch.float32 or e.numel() != num_channel or not e.is_contiguous():
+            raise ValueError("per-channel min/max must be contiguous float32 CUDA tensors of num_channel values")
+    x, grad = _contig16(x), _contig16(grad)
+    out = torch.empty_like(grad, memory_format=torch.contiguous_format)
+    with _on_device(x):
+        _lib.check(_L.ab_qdq_ste_bwd_per_channel(x.data_ptr(), grad.data_ptr(), out.data_ptr(), int(num_channel),
+                                                 x.numel(), int(num_element_per_channel), _dtype_code(x),
+                                                 enc_min.data_ptr(), enc_max.data_ptr(), _stream(x)))
+    return out
+
+
+def _state_ptr(states: torch.Tensor, index: int) -> int:
+    if states.dtype != torch.uint8 or not states.is_contiguous():
+        raise ValueError("state arena must be a contiguous uint8 CUDA tensor")
+    return states.data_ptr() + index * STATE_BYTES
+
+
+def stats_reset_impl(states, first, count):
+    _require_cuda(states)
+    with _on_device(states):
+        _lib.check(_L.ab_stats_reset(_state_ptr(states, first), int(count), _stream(states)))
+
+
+def stats_update_impl(x, states, index, quant_mode, batch_log, log_entry):
+    """One updateStats call for the quantizer whose record is `states[index]`."""
+    _require_cuda(x, states)
+    x = x if (x.is_contiguous() or x.is_contiguous(memory_format=torch.channels_last)) else x.contiguous()
+    log_ptr = None
+    if batch_log is not None:
+        _require_cuda(batch_log)
+        if batch_log.dtype != torch.int32 and batch_log.dtype != torch.uint32:
+            raise ValueError("batch_log must be a 32-bit integer CUDA tensor")
+        log_ptr = batch_log.data_ptr() + int(log_entry) * LOG_WORDS * 4
+    with _on_device(x):
+        _lib.check(_L.ab_stats_update(x.data_ptr(), x.numel(), _dtype_code(x), int(quant_mode),
+                                      _state_ptr(states, index), log_ptr, _stream(x)))
+
+
+def stats_update_segmented_impl(x, states, first, num_segments, segment_len, quant_mode):
+    _require_cuda(x, states)
+    x = x.contiguous()
+    if x.numel() != num_segments * segment_len:
+        raise ValueError("tensor size does not match num_segments * segment_len")
+    with _on_device(x):
+        _lib.check(_L.ab_stats_update_segmented(x.data_ptr(), int(num_segments), int(segment_len), _dtype_code(x),
+                                                int(quant_mode), _state_ptr(states, first), _stream(x)))
+
+
+def compute_encodings_impl(states, first, count, quant_mode, bw, sym, strict, unsigned_sym, want_qdq4=False):
+    """Returns (enc[count,5] float64 CUDA tensor, qdq4[count,4] float32 CUDA tensor or None)."""
+    _require_cuda(states)
+    enc = torch.empty((count, 5), dtype=torch.float64, device=states.device)
+    qdq4 = torch.empty((count, 4), dtype=torch.float32, device=states.device) if want_qdq4 else None
+    with _on_device(states):
+        _lib.check(_L.ab_compute_encodings(_state_ptr(states, first), int(count), int(quant_mode), int(bw),
+                                           int(bool(sym)), int(bool(strict)), int(bool(unsigned_sym)),
+                                           enc.data_ptr(), qdq4.data_ptr() if want_qdq4 else None, _stream(states)))
+    return enc, qdq4
+
+
+def stats_init_range_impl(states, first, count, minmax):
+    _require_cuda(states, minmax)
+    if minmax.dtype != torch.float32 or minmax.numel() != 2 * count or not minmax.is_contiguous():
+        raise ValueError("minmax must be a contiguous float32 CUDA tensor [count, 2]")
+    with _on_device(states):
+        _lib.check(_L.ab_stats_init_range(_state_ptr(states, first), int(count), minmax.data_ptr(),
+                                          _stream(states)))
+
+
+def stats_fold_batches_impl(states, first, count, batch_log, batch_offsets):
+    _require_cuda(states, batch_log, batch_offsets)
+    if batch_offsets.dtype != torch.int64 or not batch_offsets.is_contiguous():
+        raise ValueError("batch_offsets must be a contiguous int64 CUDA tensor")
+    with _on_device(states):
+        _lib.check(_L.ab_stats_fold_batches(_state_ptr(states, first), int(count), batch_log.data_ptr(),
+                                            batch_offsets.data_ptr(), batch_offsets.numel(), _stream(states)))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# host helpers (pure C, no device)
+# ---------------------------------------------------------------------------------------------------------------------
+def fill_encoding_info(bw, enc_min, enc_max):
+    e = _lib.Encoding()
+    _lib.check(_L.ab_fill_encoding_info(int(bw), float(enc_min), float(enc_max), C.byref(e)))
+    return e
+
+
+def per_channel_params(mins, maxs, bw):
+    """Host fp32 parameter block [min | max | delta | offset] for a list of per-channel (min, max) doubles."""
+    n = len(mins)
+    a = (C.c_double * n)(*mins)
+    b = (C.c_double * n)(*maxs)
+    out = torch.empty(4 * n, dtype=torch.float32)
+    _lib.check(_L.ab_per_channel_params(a, b, n, int(bw), C.cast(out.data_ptr(), C.POINTER(C.c_float))))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# registration as torch custom ops
+# ---------------------------------------------------------------------------------------------------------------------
+_LIBRARY = torch.library.Library("aimet_b200", "DEF")
+_LIBRARY.define("qdq_per_tensor(Tensor x, float enc_min, float enc_max, int bw, int round_mode=0, int seed=0) -> Tensor")
+_LIBRARY.define("qdq_per_tensor_dev(Tensor x, Tensor enc4, int round_mode=0, int seed=0) -> Tensor")
+_LIBRARY.define("quantize_to_grid(Tensor x, float enc_min, float enc_max, int bw, int round_mode=0, "
+                "bool shift_to_signed=False, int seed=0) -> Tensor")
+_LIBRARY.define("qdq_per_channel(Tensor x, Tensor params, int num_channel, int num_element_per_channel, "
+                "int round_mode=0, int seed=0) -> Tensor")
+_LIBRARY.define("ste_bwd(Tensor x, Tensor grad, float enc_min, float enc_max) -> Tensor")
+_LIBRARY.define("ste_bwd_per_channel(Tensor x, Tensor grad, Tensor enc_min, Tensor enc_max, int num_channel, "
+                "int num_element_per_channel) -> Tensor")
+_LIBRARY.define("stats_update(Tensor x, Tensor(a!) states, int index, int quant_mode) -> ()")
+_LIBRARY.define("stats_update_segmented(Tensor x, Tensor(a!) states, int first, int num_segments, int segment_len, "
+                "int quant_mode) -> ()")
+
+_LIBRARY.impl("qdq_per_tensor", qdq_per_tensor_impl, "CUDA")
+_LIBRARY.impl("qdq_per_tensor_dev", qdq_per_tensor_dev_impl, "CUDA")
+_LIBRARY.impl("quantize_to_grid", quantize_to_grid_impl, "CUDA")
+_LIBRARY.impl("qdq_per_channel", qdq_per_channel_impl, "CUDA")
+_LIBRARY.impl("ste_bwd", ste_bwd_impl, "CUDA")
+_LIBRARY.impl("ste_bwd_per_channel", ste_bwd_per_channel_impl, "CUDA")
+_LIBRARY.impl("stats_update", lambda x, states, index, quant_mode: stats_update_impl(x, states, index, quant_mode,
+                                                                                      None, 0), "CUDA")
+_LIBRARY.impl("stats_update_segmented", stats_update_segmented_impl, "CUDA")
+
+for _name in ("qdq_per_tensor", "qdq_per_tensor_dev", "quantize_to_grid", "qdq_per_channel"):
+    torch.library.register_fake(f"aimet_b200::{_name}", lambda x, *a, **k: torch.empty_like(x))
+for _name in ("ste_bwd", "ste_bwd_per_channel"):
+    torch.library.register_fake(f"aimet_b200::{_name}", lambda x, grad, *a, **k: torch.empty_like(grad))
+
+
+def _qdq_per_tensor_setup(ctx, inputs, output):
+    x, enc_min, enc_max = inputs[0], inputs[1], inputs[2]
+    ctx.save_for_backward(x)
+    # torch.tensor(python float) is float32: the reference compares against the fp32 image of the encoding range
+    ctx.range = (float(torch.tensor(enc_min, dtype=torch.float32)), float(torch.tensor(enc_max, dtype=torch.float32)))
+
+
+def _qdq_per_tensor_backward(ctx, grad):
+    (x,) = ctx.saved_tensors
+    return (torch.ops.aimet_b200.ste_bwd(x, grad, ctx.range[0], ctx.range[1]), None, None, None, None, None)
+
+
+def _qdq_per_channel_setup(ctx, inputs, output):
+    x, params, num_channel, per_channel = inputs[0], inputs[1], inputs[2], inputs[3]
+    ctx.save_for_backward(x, params)
+    ctx.geometry = (num_channel, per_channel)
+
+
+def _qdq_per_channel_backward(ctx, grad):
+    x, params = ctx.saved_tensors
+    c, per = ctx.geometry
+    # op-level autograd masks with the gated per-channel range the forward clamps to
+    g = torch.ops.aimet_b200.ste_bwd_per_channel(x, grad, params[:c].contiguous(), params[c:2 * c].contiguous(), c, per)
+    return (g, None, None, None, None, None)
+
+
+torch.library.register_autograd("aimet_b200::qdq_per_tensor", _qdq_per_tensor_backward,
+                                setup_context=_qdq_per_tensor_setup)
+torch.library.register_autograd("aimet_b200::qdq_per_channel", _qdq_per_channel_backward,
+                                setup_context=_qdq_per_channel_setup)

@@ -1,0 +1,113 @@
+"""Device-resident statistics records (ab_stats_state) and the arena that hands them out.
+
+The reference keeps one encoding-analyzer object per quantizer -- and one per *channel* for per-channel weights
+(aimet_torch/v1/tensor_quantizer.py:424,506: 26 560 of them for ResNet-50) -- in host memory. Here the records live
+in HBM, packed in large uint8 tensors, so that statistics kernels update them in place with no host round trip and a
+per-channel quantizer owns one contiguous block that a single segmented launch can update.
+"""
+import threading
+
+import numpy as np
+import torch
+
+from . import ops
+
+PDF_SIZE = 512
+
+# mirrors `ab_stats_state` in include/aimet_b200.h
+STATE_DTYPE = np.dtype([
+    ("pdf", "<f8", PDF_SIZE), ("hist", "<u4", PDF_SIZE), ("x_left0", "<f8"), ("bucket_size_d", "<f8"),
+    ("run_min", "<f8"), ("run_max", "<f8"), ("bucket_size", "<f4"), ("pdf_offset", "<f4"),
+    ("batch_min_bits", "<i4"), ("batch_max_bits", "<i4"), ("initialized", "<i4"), ("stats_updated", "<i4"),
+    ("iterations", "<i4"), ("ticket", "<u4"), ("pad", "<u4", 4)])
+assert STATE_DTYPE.itemsize == ops.STATE_BYTES, (STATE_DTYPE.itemsize, ops.STATE_BYTES)
+
+
+class StateBlock:
+    """`count` consecutive records inside one arena chunk."""
+
+    def __init__(self, owner, arena, first, count):
+        self._owner = owner
+        self.arena = arena          # uint8 CUDA tensor (the whole chunk)
+        self.first = first
+        self.count = count
+
+    @property
+    def device(self):
+        return self.arena.device
+
+    def reset(self):
+        ops.stats_reset_impl(self.arena, self.first, self.count)
+
+    def bytes_view(self) -> torch.Tensor:
+        return self.arena[self.first * ops.STATE_BYTES:(self.first + self.count) * ops.STATE_BYTES]
+
+    def read(self) -> np.ndarray:
+        """Synchronising copy of the records to the host, as a structured numpy array."""
+        return self.bytes_view().cpu().numpy().view(STATE_DTYPE)
+
+    def write(self, records: np.ndarray):
+        self.bytes_view().copy_(torch.from_numpy(records.view(np.uint8).reshape(-1)))
+
+    def histogram(self, i=0):
+        """[(xLeft, pdf)] * 512 as IQuantizationEncodingAnalyzer::getStatsHistogram returns it; [] if no range yet."""
+        rec = self.read()[i]
+        if not rec["initialized"]:
+            return []
+        x_left = rec["x_left0"] + np.arange(PDF_SIZE, dtype=np.float64) * rec["bucket_size_d"]
+        return list(zip(x_left.tolist(), rec["pdf"].tolist()))
+
+    def __del__(self):
+        owner = getattr(self, "_owner", None)
+        if owner is not None:
+            owner._release(self)
+
+
+class StateArena:
+    """Per-device pool of statistics records."""
+    CHUNK_STATES = 1024
+    _arenas = {}
+    _lock = threading.Lock()
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self._chunk = None
+        self._used = 0
+        self._free = {}        # count -> [(chunk, first)]
+
+    @classmethod
+    def for_device(cls, device) -> "StateArena":
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("aimet_b200 statistics live in CUDA memory: there is no CPU path")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        with cls._lock:
+            arena = cls._arenas.get(device)
+            if arena is None:
+                arena = cls._arenas[device] = StateArena(device)
+            return arena
+
+    def allocate(self, count: int) -> StateBlock:
+        with self._lock:
+            free = self._free.get(count)
+            if free:
+                chunk, first = free.pop()
+            else:
+                cap = 0 if self._chunk is None else self._chunk.numel() // ops.STATE_BYTES
+                if self._chunk is None or self._used + count > cap:
+                    n = max(count, self.CHUNK_STATES)
+                    self._chunk = torch.empty(n * ops.STATE_BYTES, dtype=torch.uint8, device=self.device)
+                    self._used = 0
+                chunk, first = self._chunk, self._used
+                self._used += count
+        block = StateBlock(self, chunk, first, count)
+        block.reset()
+        return block
+
+    def _release(self, block):
+        try:
+            with self._lock:
+                self._free.setdefault(block.count, []).append((block.arena, block.first))
+        except Exception:   # interpreter shutdown
+            pass

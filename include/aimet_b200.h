@@ -1,0 +1,226 @@
+/*
+ * aimet_b200 -- C ABI of the B200-native quantization-simulation hot path.
+ *
+ * This header is the drop-in boundary: every entry point replaces one call the
+ * reference's two Python-visible native modules make into ModelOptimizations/DlQuantization. All
+ * file:line citations are into the reference checkout (shayaanjamil-10xe/aimet, v1.35.0):
+ *   DlQ = ModelOptimizations/DlQuantization,  ATQ = TrainingExtensions/torch/src/AimetTensorQuantizer.cpp
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary
+ *   - `const void* in` / `void* out` are DEVICE pointers to contiguous fp32 (AB_F32) or bf16 (AB_BF16) data
+ *   - element counts are int64_t (the reference uses `int cnt`, which overflows at 2^31 elements)
+ *   - every device entry point enqueues work on `stream` (a cudaStream_t passed as void*) and returns
+ *     without synchronising; nothing allocates device memory: state and scratch are caller-owned
+ *   - return value: AB_OK (0) or a negative ab_status; ab_last_error() gives a thread-local message
+ *   - there is no CPU fallback: on a machine without a CUDA device every device entry point fails
+ *     with AB_ERR_CUDA
+ */
+#ifndef AIMET_B200_H_
+#define AIMET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AB_PDF_SIZE 512 /* DlQ/src/math_functions.hpp:80 (PDF_SIZE) */
+
+typedef enum
+{
+    AB_OK              = 0,
+    AB_ERR_INVALID     = -1, /* bad argument (the reference throws std::invalid_argument / runtime_error) */
+    AB_ERR_CUDA        = -2, /* CUDA runtime error, or no device */
+    AB_ERR_UNSUPPORTED = -3
+} ab_status;
+
+typedef enum
+{
+    AB_F32  = 0,
+    AB_BF16 = 1
+} ab_dtype;
+
+/* DlQ/include/DlQuantization/Quantization.hpp:76-80 */
+typedef enum
+{
+    AB_ROUND_NEAREST    = 0,
+    AB_ROUND_STOCHASTIC = 1
+} ab_round_mode;
+
+/* DlQ/include/DlQuantization/Quantization.hpp:83-107 (only the two schemes on the hot path) */
+typedef enum
+{
+    AB_QUANTIZATION_TF          = 0,
+    AB_QUANTIZATION_TF_ENHANCED = 1
+} ab_quant_mode;
+
+/* DlQ/include/DlQuantization/Quantization.hpp:113-120 (TfEncoding), same field order */
+typedef struct
+{
+    double min;
+    double max;
+    double delta;
+    double offset;
+    int bw;
+} ab_encoding;
+
+/* Per-quantizer statistics record, resident in DEVICE memory (one per tensor quantizer, or one per channel).
+ * It replaces the host-side state of TfEncodingAnalyzer (DlQ/src/TfEncodingAnalyzer.h:85-93: running min/max)
+ * and TfEnhancedEncodingAnalyzer (DlQ/src/math_functions.hpp:59-67: PDF{xLeft, pdf, iterations}).
+ * xLeft[i] is not stored: it is x_left0 + i * bucket_size_d, exactly as InitializePdf computes it
+ * (DlQ/src/math_functions.cpp:231-236). Plain old data, sizeof is a multiple of 16; zero bytes are NOT a valid initial
+ * state: use ab_stats_reset().
+ */
+typedef struct
+{
+    double pdf[AB_PDF_SIZE];    /* running mean of per-batch PDFs (math_functions.cpp:279-287) */
+    uint32_t hist[AB_PDF_SIZE]; /* scratch: the current batch's counts; zero between calls */
+    double x_left0;             /* xLeft[0] */
+    double bucket_size_d;       /* (max - min) / 512 in double (math_functions.cpp:222) */
+    double run_min;             /* TF scheme: running min over batches (TfEncodingAnalyzer.cpp:69) */
+    double run_max;             /* TF scheme: running max over batches (TfEncodingAnalyzer.cpp:70) */
+    float bucket_size;          /* float(xLeft[1] - xLeft[0]) (math_functions.cpp:265) */
+    float pdf_offset;           /* float(xLeft[0]) / bucket_size (math_functions.cpp:266-268) */
+    int32_t batch_min_bits;     /* scratch: order-preserving int image of the current batch's min */
+    int32_t batch_max_bits;     /* scratch: ... max */
+    int32_t initialized;        /* PDF range fixed (xLeft.size() != 0) */
+    int32_t stats_updated;      /* updateStats was called at least once (_statsUpdated) */
+    int32_t iterations;         /* PDF.iterations */
+    uint32_t ticket;            /* scratch: last-block election counter; zero between calls */
+    uint32_t pad_[4];           /* keeps sizeof a multiple of 16 */
+} ab_stats_state;
+
+const char* ab_last_error(void);
+/* library / device probes (host only) */
+int ab_version(void);
+int ab_device_count(void);
+size_t ab_stats_state_bytes(void); /* == sizeof(ab_stats_state) */
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Host helpers: encoding math in double, bit-identical to the reference's host code.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* gateMinMax: DlQ/src/quantization_utils.cpp:145-156 */
+int ab_gate_min_max(double* enc_min, double* enc_max);
+/* TensorQuantizationSim::fillEncodingInfo / generateScaleOffset: DlQ/src/TensorQuantizationSim.cpp:63-92 */
+int ab_fill_encoding_info(int bw, double enc_min, double enc_max, ab_encoding* out);
+/* getComputedEncodings (TF scheme, from a min/max pair): DlQ/src/quantization_utils.cpp:58-143 */
+int ab_tf_compute_encoding(int bw, double mn, double mx, int use_symmetric, int use_strict_symmetric,
+                           int use_unsigned_symmetric, ab_encoding* out);
+/* TfEncodingAnalyzer::computeEncoding (adds the include-zero / MIN_RANGE gating): DlQ/src/TfEncodingAnalyzer.cpp:81-101 */
+int ab_tf_analyzer_encoding(int bw, double run_min, double run_max, int use_symmetric, int use_strict_symmetric,
+                            int use_unsigned_symmetric, ab_encoding* out);
+/* TensorQuantizer::computePartialEncoding: DlQ/src/TensorQuantizer.cpp:327-343 -> quantization_utils.cpp:158-228.
+ * AB_ERR_INVALID where the reference throws. */
+int ab_compute_partial_encoding(int bw, ab_encoding* enc, int use_symmetric, int use_unsigned_symmetric,
+                                int use_strict_symmetric);
+/* The per-channel parameter preparation AimetTensorQuantizer::quantizeDequantizePerChannel does with torch fp32
+ * CPU ops (ATQ:236-299): gate, delta = (max-min)/steps, offset = rint(min/delta); the step count is decided from
+ * channel 0 only. Writes params[0..C) = min, [C..2C) = max, [2C..3C) = delta, [3C..4C) = offset (host memory). */
+int ab_per_channel_params(const double* enc_min, const double* enc_max, int num_channel, int bw, float* params);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Job 1: fused quantize-dequantize, quantize-only, and straight-through-estimator backward.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* ITensorQuantizationSim::quantizeDequantizeTensor (DlQ/src/TensorQuantizationSim.cpp:104-114 ->
+ * trim_functions.cpp:94-113,174-182 ; GPU twin trim_functions.cu:46-60,126-132).
+ * y = delta * (round(clamp(x, min, max) / delta - offset) + offset) with the encoding derived from
+ * (enc_min, enc_max, bw) by fillEncodingInfo. bf16: x is widened to fp32, y is rounded to bf16 (RNE), which is
+ * what the Python host does around the call (aimet_torch/v1/tensor_quantizer.py:1129-1136). */
+int ab_qdq_per_tensor_fwd(const void* in, void* out, int64_t count, int dtype, double enc_min, double enc_max,
+                          int bw, int round_mode, uint64_t seed, void* stream);
+
+/* Same kernel, but the four fp32 parameters {min, max, delta, offset} are read from DEVICE memory (`enc4`),
+ * so an encoding produced on the device (ab_compute_encodings) can be consumed without a host round trip. */
+int ab_qdq_per_tensor_fwd_dev(const void* in, void* out, int64_t count, int dtype, const float* enc4,
+                              int round_mode, uint64_t seed, void* stream);
+
+/* ITensorQuantizationSim::quantizeTensor (DlQ/src/TensorQuantizationSim.cpp:116-126 -> trim_functions.cpp:202-218;
+ * GPU twin trim_functions.cu:62-76,151-162): the integer grid value, stored in the float type, minus
+ * 2^(bw-1) when shift_to_signed. */
+int ab_quantize_to_grid(const void* in, void* out, int64_t count, int dtype, double enc_min, double enc_max, int bw,
+                        int round_mode, int shift_to_signed, uint64_t seed, void* stream);
+
+/* ITensorQuantizationSim::quantizeDequantizeTensorPerChannel (DlQ/src/TensorQuantizationSim.cpp:281-318 ->
+ * trim_functions.cpp:697-709 ; GPU twin trim_functions.cu:78-92,169-172).
+ * channel(i) = (i / num_element_per_channel) % num_channel. `params` is a DEVICE array of 4*num_channel floats
+ * laid out as ab_per_channel_params writes it. */
+int ab_qdq_per_channel_fwd(const void* in, void* out, int64_t num_channel, int64_t num_element,
+                           int64_t num_element_per_channel, int dtype, const float* params, int round_mode,
+                           uint64_t seed, void* stream);
+
+/* compute_dloss_by_dx (TrainingExtensions/torch/src/python/aimet_torch/v1/quantsim_straight_through_grad.py:91-118):
+ * grad_in = grad * [enc_min <= x <= enc_max]. x, grad, grad_in share `dtype`. */
+int ab_qdq_ste_bwd(const void* x, const void* grad, void* grad_in, int64_t count, int dtype, float enc_min,
+                   float enc_max, void* stream);
+/* per-channel variant: enc_min / enc_max are DEVICE arrays of num_channel floats */
+int ab_qdq_ste_bwd_per_channel(const void* x, const void* grad, void* grad_in, int64_t num_channel,
+                               int64_t num_element, int64_t num_element_per_channel, int dtype,
+                               const float* enc_min, const float* enc_max, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Job 2: statistics -- min/max and the 512-bin histogram, accumulated into device-resident state.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* (re)initialise `count` records: IQuantizationEncodingAnalyzer construction / resetEncodingStats (ATQ:85-92) */
+int ab_stats_reset(ab_stats_state* states, int64_t count, void* stream);
+
+/* One updateStats call on one quantizer (ATQ:94-126).
+ *  AB_QUANTIZATION_TF          : TfEncodingAnalyzer::updateStats (DlQ/src/TfEncodingAnalyzer.cpp:60-71): one pass,
+ *                                running min / max.
+ *  AB_QUANTIZATION_TF_ENHANCED : UpdatePdf (DlQ/src/math_functions.cpp:243-288): on the first non-zero batch a min/max
+ *                                pass fixes the histogram range (InitializePdf :207-241), then GetHistogram (:367-384)
+ *                                bins the batch and the counts are folded into the running PDF -- all inside ONE
+ *                                launch, with no host synchronisation.
+ * `batch_log_entry`, if not NULL, is a DEVICE array of AB_PDF_SIZE + 2 uint32 that also receives this batch's raw
+ * counts followed by the element count (low word, high word; 0 when the batch was skipped because the PDF was still
+ * uninitialised and the batch was all zeros). Used by the multi-GPU exact merge (ab_stats_fold_batches). */
+int ab_stats_update(const void* in, int64_t count, int dtype, int quant_mode, ab_stats_state* state,
+                    uint32_t* batch_log_entry, void* stream);
+
+/* updateStats on `num_segments` quantizers at once: segment s is in[s*segment_len .. (s+1)*segment_len) and updates
+ * states[s]. Replaces the per-channel Python loop (aimet_torch/v1/tensor_quantizer.py:567-570). */
+int ab_stats_update_segmented(const void* in, int64_t num_segments, int64_t segment_len, int dtype, int quant_mode,
+                              ab_stats_state* states, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Job 3: tf_enhanced grid search on the device.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* TfEnhancedEncodingAnalyzer::computeEncoding for `count` quantizers in one launch
+ * (DlQ/src/TfEnhancedEncodingAnalyzer.cpp:79-113, 115-144, 178-253, 256-291, 294-355, 358-397).
+ * enc_out   : DEVICE array of count * 5 doubles {min, max, delta, offset, bw}; all zero when no stats were seen
+ * qdq4_out  : optional DEVICE array of count * 4 floats: the {min, max, delta, offset} fp32 kernel parameters that
+ *             fillEncodingInfo(enc.min, enc.max, bw) yields (per-tensor QDQ, for ab_qdq_per_tensor_fwd_dev); may be NULL
+ * AB_QUANTIZATION_TF states are also accepted (then the encoding is TfEncodingAnalyzer::computeEncoding). */
+int ab_compute_encodings(const ab_stats_state* states, int64_t count, int quant_mode, int bw, int use_symmetric,
+                         int use_strict_symmetric, int use_unsigned_symmetric, double* enc_out, float* qdq4_out,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Multi-GPU exact merge (net-new). The reference's tf_enhanced result depends on the range
+ * fixed by the first non-zero batch and on a sequential running mean over batches, so ranks exchange integer
+ * per-batch histograms and replay them in global batch order.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* Fix the histogram range of `count` quantizers from given batch (min, max) pairs -- InitializePdf
+ * (DlQ/src/math_functions.cpp:207-241) on the device. minmax: DEVICE [count][2] floats; a (0, 0) pair, or a state
+ * whose range is already fixed, is left untouched (math_functions.cpp:254-259). */
+int ab_stats_init_range(ab_stats_state* states, int64_t count, const float* minmax, void* stream);
+
+/* Rebuild the running PDFs of `count` quantizers from logged batches, replaying
+ * pdf = (pdf*k + hist/cnt)/(k+1) (DlQ/src/math_functions.cpp:279-287) for k = 0 .. num_batches-1 in order.
+ * batch_log    : DEVICE uint32 buffer holding, for every batch, `count` consecutive entries of AB_PDF_SIZE + 2 words
+ *                as ab_stats_update writes them
+ * batch_offsets: DEVICE int64[num_batches], the word offset of batch k's first entry inside batch_log
+ * Entries whose element count is 0 are skipped, as the reference skips all-zero batches seen before the range is fixed. */
+int ab_stats_fold_batches(ab_stats_state* states, int64_t count, const uint32_t* batch_log,
+                          const int64_t* batch_offsets, int64_t num_batches, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AIMET_B200_H_ */

@@ -12,6 +12,7 @@
 #include <cstdint>
 #include <cstring>
 #include <memory>
+#include <random>
 #include <tuple>
 #include <vector>
 
@@ -170,5 +171,14 @@ int ref_tq_partial(void* h, int bw, double* enc5, int sym, int unsigned_sym, int
     }
     put(e, enc5);
     return 0;
+}
+// The input the reference's own fixture builds (DlQuantization/test/TestTensorQuantizer.cpp:92-103):
+// std::normal_distribution<float>(mean, stddev) driven by std::mt19937(seed). libstdc++-specific, hence generated here.
+void ref_kat_normal(unsigned seed, float mean, float stddev, unsigned n, float* out)
+{
+    std::normal_distribution<float> distribution(mean, stddev);
+    std::mt19937 generator(seed);
+    for (unsigned i = 0; i < n; i++)
+        out[i] = distribution(generator);
 }
 }   // extern "C"
