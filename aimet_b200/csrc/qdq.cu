@@ -43,7 +43,7 @@ struct TensorArgs
 template <Op kOp, bool kStochastic>
 __device__ __forceinline__ float apply(float x, const Enc4& e, float shift, uint64_t seed, uint64_t idx)
 {
-    const float q = quantize_value<kStochastic>(x, e, seed, idx);
+    const float q = quantize_value<kStochastic, kOp == Op::kQuantize>(x, e, seed, idx);
     if (kOp == Op::kQdq)
         return dequantize_value(q, e);
     return __fsub_rn(q, shift);   // out[i] -= shift (DlQ/src/trim_functions.cpp:216)

@@ -70,7 +70,7 @@ def _contig16(t: torch.Tensor) -> torch.Tensor:
 # ---------------------------------------------------------------------------------------------------------------------
 # implementations (CUDA)
 # ---------------------------------------------------------------------------------------------------------------------
-def qdq_per_tensor_impl(x, enc_min, enc_max, bw, round_mode, seed):
+def qdq_per_tensor_impl(x, enc_min, enc_max, bw, round_mode=0, seed=0):
     _require_cuda(x)
     x = x.contiguous(memory_format=torch.contiguous_format) if not (
         x.is_contiguous() or x.is_contiguous(memory_format=torch.channels_last)) else x
@@ -82,7 +82,7 @@ def qdq_per_tensor_impl(x, enc_min, enc_max, bw, round_mode, seed):
     return out
 
 
-def qdq_per_tensor_dev_impl(x, enc4, round_mode, seed):
+def qdq_per_tensor_dev_impl(x, enc4, round_mode=0, seed=0):
     _require_cuda(x, enc4)
     if enc4.dtype != torch.float32 or enc4.numel() < 4:
         raise ValueError("enc4 must be a float32 CUDA tensor {min, max, delta, offset}")
@@ -95,7 +95,7 @@ def qdq_per_tensor_dev_impl(x, enc4, round_mode, seed):
     return out
 
 
-def quantize_to_grid_impl(x, enc_min, enc_max, bw, round_mode, shift_to_signed, seed):
+def quantize_to_grid_impl(x, enc_min, enc_max, bw, round_mode=0, shift_to_signed=False, seed=0):
     _require_cuda(x)
     x = x if (x.is_contiguous() or x.is_contiguous(memory_format=torch.channels_last)) else x.contiguous()
     out = torch.empty_like(x)
@@ -106,7 +106,7 @@ def quantize_to_grid_impl(x, enc_min, enc_max, bw, round_mode, shift_to_signed, 
     return out
 
 
-def qdq_per_channel_impl(x, params, num_channel, num_element_per_channel, round_mode, seed):
+def qdq_per_channel_impl(x, params, num_channel, num_element_per_channel, round_mode=0, seed=0):
     _require_cuda(x, params)
     if params.dtype != torch.float32 or params.numel() != 4 * num_channel or not params.is_contiguous():
         raise ValueError("params must be a contiguous float32 CUDA tensor of 4*num_channel values")
