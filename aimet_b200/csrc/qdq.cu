@@ -52,17 +52,11 @@ __device__ __forceinline__ float apply(float x, const Enc4& e, float shift, uint
 // ---------------------------------------------------------------------------------------------------------------
 // per-tensor QDQ / quantize-only.  `in`/`out` are 16-byte aligned here (otherwise per_tensor_scalar_kernel runs).
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T, Op kOp, bool kStochastic>
-__global__ void __launch_bounds__(kThreads) per_tensor_kernel(const T* __restrict__ in, T* __restrict__ out,
-                                                              int64_t count, TensorArgs args)
+template <typename T, Op kOp, bool kStochastic, bool kFast>
+__device__ __forceinline__ void per_tensor_body(const T* __restrict__ in, T* __restrict__ out, int64_t count,
+                                                const Enc4& e, const Divisor& dv, float shift, uint64_t seed)
 {
-    constexpr int kV       = Elem<T>::kPerVec;
-    Enc4 e = args.enc;
-    if (args.enc_dev != nullptr)
-    {
-        const float4 p = *reinterpret_cast<const float4*>(args.enc_dev);
-        e              = Enc4 {p.x, p.y, p.z, p.w};
-    }
+    constexpr int kV        = Elem<T>::kPerVec;
     const int64_t num_vec   = count / kV;
     const int64_t num_tiles = (num_vec + kThreads * kUnroll - 1) / (kThreads * kUnroll);
 
@@ -87,7 +81,8 @@ __global__ void __launch_bounds__(kThreads) per_tensor_kernel(const T* __restric
                 Elem<T>::unpack(raw[u], f);
 #pragma unroll
                 for (int k = 0; k < kV; ++k)
-                    f[k] = apply<kOp, kStochastic>(f[k], e, args.shift, args.seed, (uint64_t) (v * kV + k));
+                    f[k] = kFast ? qdq_fast(f[k], e, dv)
+                                 : apply<kOp, kStochastic>(f[k], e, shift, seed, (uint64_t) (v * kV + k));
                 stg_stream(reinterpret_cast<uint4*>(out) + v, Elem<T>::pack(f));
             }
         }
@@ -97,9 +92,26 @@ __global__ void __launch_bounds__(kThreads) per_tensor_kernel(const T* __restric
     {
         const int64_t i = num_vec * kV + threadIdx.x;
         if (i < count)
-            Elem<T>::store(out + i,
-                           apply<kOp, kStochastic>(Elem<T>::load(in + i), e, args.shift, args.seed, (uint64_t) i));
+            Elem<T>::store(out + i, apply<kOp, kStochastic>(Elem<T>::load(in + i), e, shift, seed, (uint64_t) i));
     }
+}
+
+template <typename T, Op kOp, bool kStochastic>
+__global__ void __launch_bounds__(kThreads) per_tensor_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                              int64_t count, TensorArgs args)
+{
+    Enc4 e = args.enc;
+    if (args.enc_dev != nullptr)
+    {
+        const float4 p = *reinterpret_cast<const float4*>(args.enc_dev);
+        e              = Enc4 {p.x, p.y, p.z, p.w};
+    }
+    const Divisor dv = make_divisor(e.delta);
+    // Nearest-rounding QDQ with an ordinary grid takes the XU-free path; the choice is uniform over the launch.
+    if (kOp == Op::kQdq && !kStochastic && qdq_fast_ok(e, dv))
+        per_tensor_body<T, kOp, kStochastic, true>(in, out, count, e, dv, args.shift, args.seed);
+    else
+        per_tensor_body<T, kOp, kStochastic, false>(in, out, count, e, dv, args.shift, args.seed);
 }
 
 // element-wise variant for tensors that are not 16-byte aligned
@@ -121,7 +133,7 @@ __global__ void __launch_bounds__(kThreads) per_tensor_scalar_kernel(const T* __
 // ---------------------------------------------------------------------------------------------------------------
 // per-channel QDQ.  channel(i) = (i / per_channel) % num_channel   (DlQ/src/trim_functions.cpp:703)
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kSmemChannels = 2048;   // float4 per channel -> 32 KB of shared memory
+constexpr int kSmemChannels = 1024;   // staged {min,max,delta,offset} + reciprocal: 20 KB of shared memory
 
 struct ChannelArgs
 {
@@ -129,6 +141,7 @@ struct ChannelArgs
     int64_t num_channel;
     int64_t per_channel;
     uint64_t seed;
+    uint32_t div_mul, div_shift;   // n / per_channel == umulhi(n, div_mul) >> div_shift for n < 2^31 (per_channel > 1)
 };
 
 __device__ __forceinline__ Enc4 load_channel(const float* params, int64_t num_channel, int64_t c)
@@ -137,101 +150,167 @@ __device__ __forceinline__ Enc4 load_channel(const float* params, int64_t num_ch
                  __ldg(params + 3 * num_channel + c)};
 }
 
-template <typename T, bool kStochastic>
-__global__ void __launch_bounds__(kThreads) per_channel_kernel(const T* __restrict__ in, T* __restrict__ out,
-                                                               int64_t count, ChannelArgs args)
+// Fast kernel: element count < 2^31 so that all index arithmetic is 32-bit, nearest rounding.
+//   * the tile's channels are staged once, with their refined reciprocal, in shared memory;
+//   * one multiply-high replaces the integer division per 128-bit vector;
+//   * a vector that lies inside one channel (the common case) does a single 16-byte shared load and runs the straight-line
+//     fast QDQ; only vectors that straddle a channel boundary step element by element.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) per_channel_fast_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                                    uint32_t count, ChannelArgs args)
 {
-    constexpr int kV           = Elem<T>::kPerVec;
-    constexpr int kVecPerTile  = kThreads * kUnroll;
-    constexpr int64_t kTileLen = (int64_t) kVecPerTile * kV;
+    constexpr int kV               = Elem<T>::kPerVec;
+    constexpr uint32_t kVecPerTile = kThreads * kUnroll;
+    constexpr uint32_t kTileLen    = kVecPerTile * kV;
     __shared__ float4 s_enc[kSmemChannels];
+    __shared__ float s_rcp[kSmemChannels];
 
-    const int64_t num_vec   = count / kV;
-    const int64_t num_tiles = (count + kTileLen - 1) / kTileLen;
-    const int64_t C         = args.num_channel;
-    const int64_t L         = args.per_channel;
+    const uint32_t num_vec   = count / kV;
+    const uint32_t num_tiles = (count + kTileLen - 1) / kTileLen;
+    const uint32_t C         = (uint32_t) args.num_channel;
+    const uint32_t L         = (uint32_t) args.per_channel;
+    auto div_l               = [&](uint32_t n) { return L == 1 ? n : (__umulhi(n, args.div_mul) >> args.div_shift); };
 
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+    for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
     {
-        const int64_t e0 = tile * kTileLen;
-        const int64_t e1 = min(e0 + kTileLen, count);
-        // un-wrapped channel counters of the first / last element of the tile
-        const int64_t g0     = e0 / L;
-        const int64_t g1     = (e1 - 1) / L;
-        const int64_t span   = g1 - g0 + 1;
-        const bool in_smem   = span <= kSmemChannels;
-        const int64_t c_base = g0 % C;
-        __syncthreads();   // previous tile's readers are done with s_enc
-        if (in_smem)
-        {
-            for (int64_t j = threadIdx.x; j < span; j += kThreads)
+        const uint32_t e0   = tile * kTileLen;
+        const uint32_t e1   = min(e0 + kTileLen, count);
+        const uint32_t g0   = div_l(e0);            // un-wrapped channel counter of the tile's first element
+        const uint32_t span = div_l(e1 - 1) - g0 + 1;
+        const uint32_t c0   = g0 % C;
+        __syncthreads();   // previous tile's readers are done with the staged channels
+        bool ok = span <= kSmemChannels;
+        if (ok)
+            for (uint32_t j = threadIdx.x; j < span; j += kThreads)
             {
-                const Enc4 e = load_channel(args.params, C, (c_base + j) % C);
-                s_enc[j]     = make_float4(e.mn, e.mx, e.delta, e.offset);
+                const Enc4 e     = load_channel(args.params, C, (c0 + j) % C);
+                const Divisor dv = make_divisor(e.delta);
+                s_enc[j]         = make_float4(e.mn, e.mx, e.delta, e.offset);
+                s_rcp[j]         = dv.y;
+                ok               = ok && qdq_fast_ok(e, dv);
             }
-        }
-        __syncthreads();
+        const bool fast = __syncthreads_and(ok);   // every channel of the tile is staged and takes the fast arithmetic
 
-        const int64_t v0 = tile * kVecPerTile + threadIdx.x;
+        const uint32_t v0 = tile * kVecPerTile + threadIdx.x;
         uint4 raw[kUnroll];
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u)
         {
-            const int64_t v = v0 + (int64_t) u * kThreads;
+            const uint32_t v = v0 + u * kThreads;
             if (v < num_vec)
                 raw[u] = ldg_stream(reinterpret_cast<const uint4*>(in) + v);
         }
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u)
         {
-            const int64_t v = v0 + (int64_t) u * kThreads;
-            if (v < num_vec)
+            const uint32_t v = v0 + u * kThreads;
+            if (v >= num_vec)
+                continue;
+            float f[kV];
+            Elem<T>::unpack(raw[u], f);
+            const uint32_t i0 = v * kV;
+            const uint32_t g  = div_l(i0);
+            uint32_t rem      = i0 - g * L;
+            uint32_t j        = g - g0;
+            if (fast)
             {
-                float f[kV];
-                Elem<T>::unpack(raw[u], f);
-                const int64_t i0 = v * kV;
-                int64_t g        = i0 / L;          // one division per vector
-                int64_t rem      = i0 - g * L;
-                int64_t j        = g - g0;          // index into the staged channels
-                Enc4 e;
-                bool reload = true;
+                float4 p   = s_enc[j];
+                Enc4 e     = Enc4 {p.x, p.y, p.z, p.w};
+                Divisor dv = Divisor {p.z, s_rcp[j], true};
+                if (rem + kV <= L)
+                {
+#pragma unroll
+                    for (int k = 0; k < kV; ++k)
+                        f[k] = qdq_fast(f[k], e, dv);
+                }
+                else
+                {
+#pragma unroll
+                    for (int k = 0; k < kV; ++k)
+                    {
+                        f[k] = qdq_fast(f[k], e, dv);
+                        if (++rem == L && k + 1 < kV)
+                        {
+                            rem = 0;
+                            ++j;
+                            p  = s_enc[j];
+                            e  = Enc4 {p.x, p.y, p.z, p.w};
+                            dv = Divisor {p.z, s_rcp[j], true};
+                        }
+                    }
+                }
+            }
+            else
+            {
+                uint32_t c = (c0 + j) % C;
 #pragma unroll
                 for (int k = 0; k < kV; ++k)
                 {
-                    if (reload)
-                    {
-                        if (in_smem)
-                        {
-                            const float4 p = s_enc[j];
-                            e              = Enc4 {p.x, p.y, p.z, p.w};
-                        }
-                        else
-                            e = load_channel(args.params, C, (c_base + j) % C);
-                        reload = false;
-                    }
-                    f[k] = dequantize_value(quantize_value<kStochastic>(f[k], e, args.seed, (uint64_t) (i0 + k)), e);
+                    const Enc4 e = load_channel(args.params, C, c);
+                    f[k]         = dequantize_value(quantize_value<false>(f[k], e, 0, 0), e);
                     if (++rem == L)
                     {
                         rem = 0;
-                        ++j;
-                        reload = true;
+                        c   = (c + 1 == C) ? 0 : c + 1;
                     }
                 }
-                stg_stream(reinterpret_cast<uint4*>(out) + v, Elem<T>::pack(f));
             }
+            stg_stream(reinterpret_cast<uint4*>(out) + v, Elem<T>::pack(f));
         }
         // scalar tail of the whole tensor (only the last tile can have one)
         if (e1 == count)
         {
-            const int64_t i = num_vec * kV + threadIdx.x;
+            const uint32_t i = num_vec * kV + threadIdx.x;
             if (i < count)
             {
-                const int64_t c = (i / L) % C;
-                const Enc4 e    = load_channel(args.params, C, c);
-                Elem<T>::store(out + i, dequantize_value(quantize_value<kStochastic>(Elem<T>::load(in + i), e,
-                                                                                      args.seed, (uint64_t) i),
-                                                         e));
+                const Enc4 e = load_channel(args.params, C, div_l(i) % C);
+                Elem<T>::store(out + i, dequantize_value(quantize_value<false>(Elem<T>::load(in + i), e, 0, 0), e));
             }
+        }
+    }
+}
+
+// General kernel: 64-bit indexing, either rounding mode.
+template <typename T, bool kStochastic>
+__global__ void __launch_bounds__(kThreads) per_channel_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                               int64_t count, ChannelArgs args)
+{
+    constexpr int kV      = Elem<T>::kPerVec;
+    const int64_t num_vec = count / kV;
+    const int64_t C       = args.num_channel;
+    const int64_t L       = args.per_channel;
+    const int64_t stride  = (int64_t) gridDim.x * kThreads;
+    for (int64_t v = (int64_t) blockIdx.x * kThreads + threadIdx.x; v < num_vec; v += stride)
+    {
+        float f[kV];
+        Elem<T>::unpack(ldg_stream(reinterpret_cast<const uint4*>(in) + v), f);
+        const int64_t i0 = v * kV;
+        const int64_t g  = i0 / L;
+        int64_t rem      = i0 - g * L;
+        int64_t c        = g % C;
+        Enc4 e           = load_channel(args.params, C, c);
+#pragma unroll
+        for (int k = 0; k < kV; ++k)
+        {
+            f[k] = dequantize_value(quantize_value<kStochastic>(f[k], e, args.seed, (uint64_t) (i0 + k)), e);
+            if (++rem == L)
+            {
+                rem = 0;
+                c   = (c + 1 == C) ? 0 : c + 1;
+                e   = load_channel(args.params, C, c);
+            }
+        }
+        stg_stream(reinterpret_cast<uint4*>(out) + v, Elem<T>::pack(f));
+    }
+    if (blockIdx.x == 0)
+    {
+        const int64_t i = num_vec * kV + threadIdx.x;
+        if (i < count)
+        {
+            const Enc4 e = load_channel(args.params, C, (i / L) % C);
+            Elem<T>::store(out + i, dequantize_value(quantize_value<kStochastic>(Elem<T>::load(in + i), e, args.seed,
+                                                                                  (uint64_t) i),
+                                                     e));
         }
     }
 }
@@ -555,11 +634,42 @@ int ab_qdq_per_channel_fwd(const void* in, void* out, int64_t num_channel, int64
         return AB_ERR_INVALID;
     }
     cudaStream_t st = (cudaStream_t) stream;
-    ChannelArgs a {params, num_channel, num_element_per_channel, seed};
+    ChannelArgs a {params, num_channel, num_element_per_channel, seed, 0, 0};
     const bool stochastic = round_mode == AB_ROUND_STOCHASTIC;
+    const bool fast       = !stochastic && num_element < (int64_t) 0x7fffffff && num_channel < (int64_t) 0x7fffffff;
+    if (fast)
+    {
+        // CUTLASS-style fast divmod constants, exact for dividends below 2^31
+        const uint32_t d = (uint32_t) num_element_per_channel;
+        if (d > 1)
+        {
+            uint32_t lg = 0;
+            while ((1ull << lg) < d)
+                ++lg;
+            const uint32_t p = 31 + lg;
+            a.div_mul        = (uint32_t) (((1ull << p) + d - 1) / d);
+            a.div_shift      = p - 32;
+        }
+        if (dtype == AB_F32)
+        {
+            auto k              = per_channel_fast_kernel<float>;
+            const int64_t tiles = (num_element + (int64_t) kThreads * kUnroll * 4 - 1) / ((int64_t) kThreads * kUnroll * 4);
+            k<<<grid_for(k, tiles, kThreads), kThreads, 0, st>>>((const float*) in, (float*) out, (uint32_t) num_element, a);
+        }
+        else
+        {
+            auto k              = per_channel_fast_kernel<__nv_bfloat16>;
+            const int64_t tiles = (num_element + (int64_t) kThreads * kUnroll * 8 - 1) / ((int64_t) kThreads * kUnroll * 8);
+            k<<<grid_for(k, tiles, kThreads), kThreads, 0, st>>>((const __nv_bfloat16*) in, (__nv_bfloat16*) out,
+                                                                 (uint32_t) num_element, a);
+        }
+        AB_CUDA_CHECK(cudaGetLastError());
+        return AB_OK;
+    }
+    const int64_t es    = dtype == AB_F32 ? 4 : 8;
+    const int64_t tiles = (num_element / es + kThreads - 1) / kThreads;
     if (dtype == AB_F32)
     {
-        const int64_t tiles = (num_element + (int64_t) kThreads * kUnroll * 4 - 1) / ((int64_t) kThreads * kUnroll * 4);
         if (stochastic)
         {
             auto k = per_channel_kernel<float, true>;
@@ -573,7 +683,6 @@ int ab_qdq_per_channel_fwd(const void* in, void* out, int64_t num_channel, int64
     }
     else
     {
-        const int64_t tiles = (num_element + (int64_t) kThreads * kUnroll * 8 - 1) / ((int64_t) kThreads * kUnroll * 8);
         if (stochastic)
         {
             auto k = per_channel_kernel<__nv_bfloat16, true>;
