@@ -204,6 +204,18 @@ def compute_encodings_impl(states, first, count, quant_mode, bw, sym, strict, un
     return enc, qdq4
 
 
+def compute_encodings_into(states, first, count, quant_mode, bw, sym, strict, unsigned_sym, out):
+    """Same as compute_encodings_impl, but writes into `out` (float64 CUDA, [count, 5], contiguous): lets a caller
+    enqueue many searches and read them back with one copy."""
+    _require_cuda(states, out)
+    if out.dtype != torch.float64 or out.numel() != 5 * count or not out.is_contiguous():
+        raise ValueError("out must be a contiguous float64 CUDA tensor [count, 5]")
+    with _on_device(states):
+        _lib.check(_L.ab_compute_encodings(_state_ptr(states, first), int(count), int(quant_mode), int(bw),
+                                           int(bool(sym)), int(bool(strict)), int(bool(unsigned_sym)),
+                                           out.data_ptr(), None, _stream(states)))
+
+
 def stats_init_range_impl(states, first, count, minmax):
     _require_cuda(states, minmax)
     if minmax.dtype != torch.float32 or minmax.numel() != 2 * count or not minmax.is_contiguous():

@@ -1,0 +1,241 @@
+"""Host mirror of the reference's static-grid quantization wrapper.
+
+Reference: TrainingExtensions/torch/src/python/aimet_torch/v1/qc_quantize_op.py -- QcQuantizeOpMode :63-70,
+QcQuantizeWrapper :82-677, StaticGridQuantWrapper :679-924, SteGatingFuncForParameters :1314-1366.
+"""
+import enum
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from .. import libpymo
+from .defs import MAP_ROUND_MODE_TO_PYMO, QuantizationDataType, QuantScheme
+from .tensor_quantizer import (StaticGridPerChannelQuantizer, StaticGridPerTensorQuantizer, compute_dloss_by_dx)
+
+import os
+
+# reference :75-77: AIMET_TFE_USE_DOWNSAMPLING=1 strides the tensor handed to tf_enhanced statistics
+TF_ENHANCED_USE_DOWNSAMPLING = bool(int(os.environ.get("AIMET_TFE_USE_DOWNSAMPLING", "0")))
+TF_ENHANCED_OFFSET_FACTOR = 0
+TF_ENHANCED_STRIDE_FACTOR = 2
+
+_IGNORED_DTYPES = (torch.int, torch.int8, torch.int16, torch.int32, torch.int64, torch.bool, torch.uint8)
+
+
+class QcQuantizeOpMode(enum.Enum):
+    PASSTHROUGH = 1
+    ANALYSIS = 2
+    ACTIVE = 3
+    LEARN_ENCODINGS = 4
+
+
+def export_quantizer_encoding(quantizer) -> Optional[List[Dict]]:
+    """reference :1529-1545 + aimet_torch/utils.py:1156-1185 (create_encoding_dict)"""
+    if not quantizer.enabled:
+        return None
+    if quantizer.data_type == QuantizationDataType.int and quantizer.bitwidth == 32:
+        return None
+    encoding = quantizer.encoding
+
+    def to_dict(enc):
+        if not enc:
+            return None
+        return {"min": enc.min, "max": enc.max, "scale": enc.delta, "offset": int(enc.offset), "bitwidth": enc.bw,
+                "is_symmetric": str(quantizer.use_symmetric_encodings), "dtype": "int"}
+
+    if isinstance(encoding, list):
+        return [to_dict(e) for e in encoding]
+    d = to_dict(encoding)
+    return [d] if d else None
+
+
+class SteGatingFuncForParameters(torch.autograd.Function):
+    """Gates the parameter gradients with the straight-through estimator after the wrapped module's backward
+    (reference :1314-1366)."""
+
+    @staticmethod
+    def forward(ctx, quant_wrapper_ref, *quantized_inputs):   # pylint: disable=arguments-differ
+        ctx.quantization_wrapper_ref = quant_wrapper_ref
+        return quantized_inputs
+
+    @staticmethod
+    def backward(ctx, *output_grad):   # pylint: disable=arguments-differ
+        wrapper = ctx.quantization_wrapper_ref
+        for name, param in wrapper.get_named_parameters():
+            q = wrapper.param_quantizers[name]
+            if q.bitwidth == 32 or q.data_type == QuantizationDataType.float:
+                continue
+            if q.enabled and param.grad is not None:
+                if isinstance(q.encoding, list):
+                    param.grad = compute_dloss_by_dx(param, param.grad, [e.min for e in q.encoding],
+                                                     [e.max for e in q.encoding], q.channel_axis)
+                else:
+                    param.grad = compute_dloss_by_dx(param, param.grad, q.encoding.min, q.encoding.max)
+        return (None, *output_grad)
+
+
+class StaticGridQuantWrapper(nn.Module):
+    """Wraps one leaf module: quantizes its inputs, parameters and outputs around the wrapped forward."""
+
+    def __init__(self, module_to_wrap: nn.Module, weight_bw: int, activation_bw: int, round_mode, quant_scheme,
+                 is_output_quantized=True, is_symmetric=False, num_inputs=1, num_outputs=1,
+                 data_type: QuantizationDataType = QuantizationDataType.int):
+        super().__init__()
+        if isinstance(round_mode, str):
+            round_mode = MAP_ROUND_MODE_TO_PYMO[round_mode]
+        if isinstance(quant_scheme, str):
+            quant_scheme = QuantScheme.from_str(quant_scheme)
+        self._module_to_wrap = module_to_wrap
+        self._mode = QcQuantizeOpMode.ANALYSIS
+        self._quant_scheme = quant_scheme
+        self.output_quantizers = [StaticGridPerTensorQuantizer(activation_bw, round_mode, quant_scheme, is_symmetric,
+                                                               enabled_by_default=is_output_quantized,
+                                                               data_type=data_type) for _ in range(num_outputs)]
+        self.input_quantizers = [StaticGridPerTensorQuantizer(activation_bw, round_mode, quant_scheme, is_symmetric,
+                                                              enabled_by_default=False, data_type=data_type)
+                                 for _ in range(num_inputs)]
+        self.param_quantizers = {}
+        for name, _ in module_to_wrap.named_parameters():
+            self.param_quantizers[name] = StaticGridPerTensorQuantizer(weight_bw, round_mode, quant_scheme,
+                                                                       is_symmetric, enabled_by_default=True,
+                                                                       data_type=data_type)
+
+    # ---- accessors the reference exposes -------------------------------------------------------------------------
+    @property
+    def output_quantizer(self):
+        return self.output_quantizers[0]
+
+    @property
+    def input_quantizer(self):
+        return self.input_quantizers[0]
+
+    def get_original_module(self) -> nn.Module:
+        return self._module_to_wrap
+
+    def get_named_parameters(self):
+        return self._module_to_wrap.named_parameters()
+
+    def set_mode(self, mode: QcQuantizeOpMode):
+        self._mode = mode
+
+    def reset_encodings(self):
+        """reference :231-243"""
+        for q in self._all_quantizers():
+            q.reset_encoding_stats()
+
+    def _all_quantizers(self):
+        return list(self.input_quantizers) + list(self.param_quantizers.values()) + list(self.output_quantizers)
+
+    def enable_per_channel_quantization(self):
+        """reference :899-920"""
+        new = {}
+        for name, param in self._module_to_wrap.named_parameters():
+            q = self.param_quantizers[name]
+            axis = 0
+            if isinstance(self._module_to_wrap, (nn.ConvTranspose1d, nn.ConvTranspose2d, nn.ConvTranspose3d)) and \
+                    len(param.shape) > 1:
+                axis = 1
+            pcq = StaticGridPerChannelQuantizer(q.bitwidth, q.round_mode, q.quant_scheme, q.use_symmetric_encodings,
+                                                num_channels=param.shape[axis], enabled_by_default=q.enabled,
+                                                ch_axis=axis, data_type=q.data_type)
+            pcq.use_strict_symmetric = q.use_strict_symmetric
+            pcq.use_unsigned_symmetric = q.use_unsigned_symmetric
+            new[name] = pcq
+        self.param_quantizers = new
+
+    # ---- forward -------------------------------------------------------------------------------------------------
+    def forward(self, *inputs, **kwargs):
+        """reference :705-745"""
+        quantized_inputs = self._quantize_activation(self.input_quantizers, list(inputs))
+        shadow_params = self._quantize_dequantize_params()
+        quantized_inputs = SteGatingFuncForParameters.apply(self, *quantized_inputs)
+        quantized_inputs = [inp.clone() if isinstance(inp, torch.Tensor) and inp.requires_grad else inp
+                            for inp in quantized_inputs]
+        wrapped_output = self._module_to_wrap(*quantized_inputs, **kwargs)
+        self._restore_shadow_params(shadow_params)
+        is_seq = isinstance(wrapped_output, (list, tuple))
+        outputs = self._quantize_activation(self.output_quantizers, list(wrapped_output) if is_seq else [wrapped_output])
+        return outputs[0] if len(outputs) == 1 else outputs
+
+    def _restore_shadow_params(self, shadow_params):
+        for name, param in self.get_named_parameters():
+            if name in shadow_params:
+                param.data = shadow_params[name]
+
+    def _quantize_dequantize_params(self):
+        """reference :753-798. The reference clones every parameter and later copies it back in place; holding the
+        original tensor aside and re-pointing `.data` gives the same values with two fewer passes over the weights."""
+        shadow_params = {}
+        for name, param in self.get_named_parameters():
+            q = self.param_quantizers[name]
+            if q.enabled and q.bitwidth != 32:
+                shadow_params[name] = param.data
+                if self._module_to_wrap.training or q.encoding is None:
+                    q.reset_encoding_stats()
+                    q.update_encoding_stats(param.data)
+                    q.compute_encoding()
+                round_mode = q.round_mode if self.training else libpymo.RoundingMode.ROUND_NEAREST
+                param.data = q.quantize_dequantize(param.data, round_mode)
+        return shadow_params
+
+    def compute_encoding(self):
+        """reference :811-826"""
+        for q in self.input_quantizers:
+            q.compute_encoding()
+        for q in self.param_quantizers.values():
+            q.compute_encoding()
+        for q in self.output_quantizers:
+            q.compute_encoding()
+
+    @staticmethod
+    def should_perform_quant_dequant(tensor, tensor_quantizer) -> bool:
+        """reference :451-473"""
+        if not isinstance(tensor, torch.Tensor) or tensor.dtype in _IGNORED_DTYPES or \
+                (tensor_quantizer.is_const and torch.numel(tensor) == 1) or not tensor_quantizer.enabled:
+            tensor_quantizer.enabled = False
+            return False
+        return True
+
+    def _quantize_activation(self, tensor_quantizers, tensors_to_quantize):
+        """reference :837-897"""
+
+        def inner(t, index):
+            if isinstance(t, (list, tuple)):
+                return [inner(x, index) for x in t]
+            q = tensor_quantizers[index]
+            if not self.should_perform_quant_dequant(t, q):
+                return t
+            if self._mode is QcQuantizeOpMode.ANALYSIS and not q.is_encoding_frozen:
+                if TF_ENHANCED_USE_DOWNSAMPLING and q.quant_scheme == QuantScheme.post_training_tf_enhanced:
+                    flat = t.reshape(-1)
+                    q.update_encoding_stats(flat[TF_ENHANCED_OFFSET_FACTOR::TF_ENHANCED_STRIDE_FACTOR].contiguous())
+                else:
+                    q.update_encoding_stats(t)
+                return t
+            if self._mode is QcQuantizeOpMode.ACTIVE or (self._mode is QcQuantizeOpMode.ANALYSIS and
+                                                         q.is_encoding_frozen):
+                round_mode = q.round_mode if self.training else libpymo.RoundingMode.ROUND_NEAREST
+                return q.quantize_dequantize(t, round_mode)
+            return t
+
+        outputs = []
+        for index, t in enumerate(tensors_to_quantize):
+            assert len(tensor_quantizers) > index, f"Not enough tensor quantizers ({len(tensor_quantizers)}) allocated"
+            outputs.append(inner(t, index))
+        return outputs
+
+    # ---- export --------------------------------------------------------------------------------------------------
+    def export_param_encodings(self):
+        return {name: export_quantizer_encoding(q) for name, q in self.param_quantizers.items()}
+
+    def export_output_encodings(self):
+        return [export_quantizer_encoding(q) for q in self.output_quantizers]
+
+    def export_input_encodings(self):
+        return [export_quantizer_encoding(q) for q in self.input_quantizers]
+
+
+# names the reference exports for the same class
+QcQuantizeWrapper = StaticGridQuantWrapper
+QcPostTrainingWrapper = StaticGridQuantWrapper

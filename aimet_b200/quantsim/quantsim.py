@@ -1,0 +1,249 @@
+"""Host mirror of the reference's QuantizationSimModel on the static-grid (tf / tf_enhanced) path.
+
+Reference: TrainingExtensions/torch/src/python/aimet_torch/v1/quantsim.py -- __init__ :225-307,
+prepare_sim_for_compute_encodings :381-400, compute_layer_encodings_for_sim :403-423, compute_encodings :425-448,
+save_encodings_to_json / get_activation_param_encodings :680-729, export :486-575 (the `_torch.encodings` file; the
+ONNX-keyed twin needs the `onnx` package and an ONNX export, which are outside this path).
+"""
+import copy
+import json
+import os
+from collections import OrderedDict, defaultdict
+from contextlib import contextmanager
+from typing import Callable, Dict, List, Tuple
+
+import torch
+from torch import nn
+
+from . import config as qconfig
+from .defs import MAP_ROUND_MODE_TO_PYMO, QuantizationDataType, QuantScheme
+from .qc_quantize_op import QcQuantizeOpMode, StaticGridQuantWrapper
+
+ENCODING_VERSION = "0.6.1"   # reference aimet_common/quantsim.py:55-57
+_SUPPORTED_SCHEMES = (QuantScheme.post_training_tf, QuantScheme.post_training_tf_enhanced)
+unquantizable_modules = (nn.Identity,)
+
+
+@contextmanager
+def in_eval_mode(model: nn.Module):
+    was_training = {m: m.training for m in model.modules()}
+    model.eval()
+    try:
+        yield
+    finally:
+        for m, t in was_training.items():
+            m.training = t
+
+
+def _count_inout(model: nn.Module, dummy_input) -> Dict[nn.Module, Tuple[int, int]]:
+    """One forward with hooks: number of input / output tensors of each leaf (reference utils.get_inout_tensor_shape_per_module)."""
+    counts = {}
+    hooks = []
+
+    def hook(mod, inp, out):
+        n_in = len(inp) if isinstance(inp, (tuple, list)) else 1
+        n_out = len(out) if isinstance(out, (tuple, list)) else 1
+        counts[mod] = (n_in, n_out)
+
+    for m in model.modules():
+        if len(list(m.children())) == 0:
+            hooks.append(m.register_forward_hook(hook))
+    with in_eval_mode(model), torch.no_grad():
+        if isinstance(dummy_input, (tuple, list)):
+            model(*dummy_input)
+        else:
+            model(dummy_input)
+    for h in hooks:
+        h.remove()
+    return counts
+
+
+class QuantizationSimModel:
+    """Adds quantization-simulation wrappers to a model, calibrates them and exports the encodings."""
+
+    def __init__(self, model: nn.Module, dummy_input, quant_scheme="tf_enhanced", rounding_mode: str = "nearest",
+                 default_output_bw: int = 8, default_param_bw: int = 8, in_place: bool = False, config_file=None,
+                 default_data_type: QuantizationDataType = QuantizationDataType.int):
+        if isinstance(quant_scheme, str):
+            quant_scheme = QuantScheme.from_str(quant_scheme)
+        if quant_scheme not in _SUPPORTED_SCHEMES:
+            raise NotImplementedError(f"{quant_scheme} is outside the aimet_b200 hot path (tf / tf_enhanced only)")
+        if default_data_type != QuantizationDataType.int:
+            raise NotImplementedError("only integer quantization simulation is on the aimet_b200 hot path")
+        self.model = model if in_place else copy.deepcopy(model)
+        self._quant_scheme = quant_scheme
+        self._rounding_mode = rounding_mode
+        self._default_output_bw = default_output_bw
+        self._default_param_bw = default_param_bw
+        self._config = qconfig.load_config(config_file)
+
+        try:
+            ops = qconfig.build_op_graph(self.model)          # call-site graph, before the wrappers go in
+        except Exception as exc:   # pylint: disable=broad-except
+            raise RuntimeError(f"torch.fx could not trace the model ({exc}); the supergroup / model-input rules of the "
+                               "quantsim config need an op graph") from exc
+        inout = _count_inout(self.model, dummy_input)
+        self._wrappers: Dict[nn.Module, StaticGridQuantWrapper] = {}
+        self._add_quantization_wrappers(self.model, inout)
+        # bias parameters are never quantized (reference :290 exclude_param_from_quantization("bias"))
+        qconfig.configure(self.model, self._wrappers, self._config, ops)
+        for w in self._wrappers.values():
+            if "bias" in w.param_quantizers:
+                w.param_quantizers["bias"].enabled = False
+
+    # ---- model surgery -----------------------------------------------------------------------------------------
+    @staticmethod
+    def _is_quantizable_module(module: nn.Module) -> bool:
+        return type(module) != nn.Module and not isinstance(module, unquantizable_modules) and \
+            not isinstance(module, StaticGridQuantWrapper)   # pylint: disable=unidiomatic-typecheck
+
+    def _add_quantization_wrappers(self, module: nn.Module, inout):
+        for name, child in list(module.named_children()):
+            if isinstance(child, StaticGridQuantWrapper):
+                continue
+            if len(list(child.children())) == 0:
+                if self._is_quantizable_module(child) and child in inout:
+                    n_in, n_out = inout[child]
+                    w = StaticGridQuantWrapper(child, self._default_param_bw, self._default_output_bw,
+                                               MAP_ROUND_MODE_TO_PYMO[self._rounding_mode], self._quant_scheme,
+                                               num_inputs=n_in, num_outputs=n_out)
+                    self._wrappers[child] = w
+                    setattr(module, name, w)
+            else:
+                self._add_quantization_wrappers(child, inout)
+
+    def quant_wrappers(self):
+        """(name, wrapper) for every wrapper in the model (reference quant_wrappers())."""
+        for name, m in self.model.named_modules():
+            if isinstance(m, StaticGridQuantWrapper):
+                yield name, m
+
+    _get_qc_quantized_layers = lambda self, model=None: list(self.quant_wrappers())   # noqa: E731
+
+    # ---- calibration -------------------------------------------------------------------------------------------
+    @staticmethod
+    def prepare_sim_for_compute_encodings(sim: "QuantizationSimModel"):
+        for _, layer in sim.quant_wrappers():
+            layer.reset_encodings()
+            layer.set_mode(QcQuantizeOpMode.ANALYSIS)
+
+    @staticmethod
+    def compute_layer_encodings_for_sim(sim: "QuantizationSimModel"):
+        sim._compute_activation_encodings_batched()   # pylint: disable=protected-access
+        for _, layer in sim.quant_wrappers():
+            layer.compute_encoding()
+            layer.set_mode(QcQuantizeOpMode.ACTIVE)
+
+    def compute_encodings(self, forward_pass_callback: Callable, forward_pass_callback_args):
+        """Runs the user's calibration callback with every wrapper collecting statistics, then computes the encodings."""
+        QuantizationSimModel.prepare_sim_for_compute_encodings(self)
+        with in_eval_mode(self.model), torch.no_grad():
+            _ = forward_pass_callback(self.model, forward_pass_callback_args)
+        QuantizationSimModel.compute_layer_encodings_for_sim(self)
+
+    def _compute_activation_encodings_batched(self):
+        """All per-tensor grid searches are enqueued first and read back with ONE device->host copy (the reference does
+        one blocking native call per quantizer). Quantizers that are not backed by the native op are left to the
+        generic path in layer.compute_encoding()."""
+        from .. import libpymo, ops
+        from ..tensor_quantizer_op import AimetTensorQuantizer
+        from .tensor_quantizer import StaticGridPerTensorQuantizer
+        pending = []
+        for _, layer in self.quant_wrappers():
+            for q in layer.input_quantizers + list(layer.param_quantizers.values()) + layer.output_quantizers:
+                if not isinstance(q, StaticGridPerTensorQuantizer) or not q.enabled or q.is_encoding_frozen or \
+                        q.bitwidth == 32 or (q.encoding is not None and not q._stats_dirty):   # pylint: disable=protected-access
+                    continue
+                op = q._cppOp[0]   # pylint: disable=protected-access
+                if isinstance(op, AimetTensorQuantizer) and op._is_encoding_valid and op._block is not None:   # pylint: disable=protected-access
+                    pending.append((q, op))
+        if not pending:
+            return
+        by_device = defaultdict(list)
+        for q, op in pending:
+            by_device[op._block.device].append((q, op))   # pylint: disable=protected-access
+        for device, items in by_device.items():
+            out = torch.empty((len(items), 5), dtype=torch.float64, device=device)
+            for row, (q, op) in enumerate(items):
+                ops.compute_encodings_into(op._block.arena, op._block.first + op._index, 1, op._code, q.bitwidth,   # pylint: disable=protected-access
+                                           q.use_symmetric_encodings, q.use_strict_symmetric,
+                                           q.use_unsigned_symmetric, out[row:row + 1])
+            rows = out.cpu().tolist()
+            for (q, _), r in zip(items, rows):
+                q._encoding = [libpymo.TfEncoding._from_values(r[0], r[1], r[2], r[3], int(r[4]))]   # pylint: disable=protected-access
+                q.is_unsigned_symmetric = q.use_symmetric_encodings and q.use_unsigned_symmetric and \
+                    r[0] >= 0 and r[1] >= 0
+                q._stats_dirty = False   # pylint: disable=protected-access
+
+    # ---- export ------------------------------------------------------------------------------------------------
+    def get_activation_param_encodings(self):
+        """reference :692-729"""
+        activation_encodings = OrderedDict()
+        param_encodings = OrderedDict()
+        for module_name, module in self.quant_wrappers():
+            activation_encodings[module_name] = defaultdict(OrderedDict)
+            for i, encoding in enumerate(module.export_input_encodings()):
+                if not encoding:
+                    continue
+                activation_encodings[module_name]["input"][i] = encoding[0] if len(encoding) == 1 else encoding
+            for i, encoding in enumerate(module.export_output_encodings()):
+                if not encoding:
+                    continue
+                activation_encodings[module_name]["output"][i] = encoding[0] if len(encoding) == 1 else encoding
+            if not activation_encodings[module_name]:
+                del activation_encodings[module_name]
+            for param_name, encoding in module.export_param_encodings().items():
+                if not encoding:
+                    continue
+                param_encodings[f"{module_name}.{param_name}"] = encoding
+        return activation_encodings, param_encodings
+
+    def save_encodings_to_json(self, path: str, filename_prefix: str):
+        """reference :680-690"""
+        activation_encodings, param_encodings = self.get_activation_param_encodings()
+        encodings_dict = {"activation_encodings": activation_encodings, "param_encodings": param_encodings}
+        with open(os.path.join(path, filename_prefix + ".json"), "w") as f:
+            json.dump(encodings_dict, f, sort_keys=True, indent=4)
+
+    def export(self, path: str, filename_prefix: str, dummy_input=None, **_unused):
+        """Writes `<prefix>_torch.encodings` (torch-module-name keyed, reference :1000-1042 layout) and the original
+        model's state_dict with quantize-dequantized weights. The ONNX-tensor-name keyed `<prefix>.encodings` needs an
+        ONNX export and is not produced here."""
+        os.makedirs(path, exist_ok=True)
+        activation_encodings, param_encodings = self.get_activation_param_encodings()
+        torch_encodings = {"version": ENCODING_VERSION,
+                           "activation_encodings": activation_encodings,
+                           "param_encodings": param_encodings,
+                           "excluded_layers": [],
+                           "quantizer_args": {"activation_bitwidth": self._default_output_bw,
+                                              "param_bitwidth": self._default_param_bw,
+                                              "dtype": "int",
+                                              "is_symmetric": True,
+                                              "quant_scheme": self._quant_scheme.name,
+                                              "per_channel_quantization": qconfig._truthy(   # pylint: disable=protected-access
+                                                  self._config["defaults"].get("per_channel_quantization", "False"))}}
+        with open(os.path.join(path, filename_prefix + "_torch.encodings"), "w") as f:
+            json.dump(torch_encodings, f, sort_keys=True, indent=4)
+        torch.save(self.get_original_model(self.model, qdq_weights=True).state_dict(),
+                   os.path.join(path, filename_prefix + ".pth"))
+
+    @staticmethod
+    def get_original_model(model: nn.Module, qdq_weights: bool = False) -> nn.Module:
+        """A copy of the model with the wrappers removed (reference :1502-1526); optionally with QDQ'd weights."""
+        original = copy.deepcopy(model)
+
+        def strip(parent):
+            for name, child in list(parent.named_children()):
+                if isinstance(child, StaticGridQuantWrapper):
+                    if qdq_weights:
+                        from .. import libpymo
+                        for pname, param in child.get_named_parameters():
+                            q = child.param_quantizers[pname]
+                            if q.enabled and q.bitwidth != 32 and q.encoding is not None:
+                                param.data = q.quantize_dequantize(param.data, libpymo.RoundingMode.ROUND_NEAREST)
+                    setattr(parent, name, child.get_original_module())
+                else:
+                    strip(child)
+
+        strip(original)
+        return original

@@ -1,0 +1,390 @@
+"""Host mirror of the reference's static-grid tensor quantizers and their autograd functions.
+
+Reference: TrainingExtensions/torch/src/python/aimet_torch/v1/tensor_quantizer.py
+  StaticGridTensorQuantizer :143-421, StaticGridPerTensorQuantizer :408-480, StaticGridPerChannelQuantizer :483-570,
+  QuantizeDequantize :1098-1212, Quantize :1215-1282.
+Same attribute and method names, same state machine. What changes is underneath `_cppOp`:
+  * the native op is aimet_b200.AimetTensorQuantizer (sm_100a kernels, device-resident statistics);
+  * a per-channel quantizer owns ONE contiguous block of statistics records, so `update_encoding_stats` is one segmented
+    launch and `compute_encoding` one batched grid search + one device->host copy, instead of the reference's Python loop
+    of num_channels native calls each (:567-570, :296-299);
+  * bfloat16 tensors go to the kernels as they are (the reference only knows how to upcast float16).
+A different op class (anything with AimetTensorQuantizer's nine methods) can be injected with `op_factory`; the test suite
+uses that to drive this layer with the CPU oracle.
+"""
+import functools
+from typing import List, Optional, Tuple, Union
+
+import torch
+
+from .. import libpymo, ops
+from ..state import StateArena
+from ..tensor_quantizer_op import AimetTensorQuantizer
+from .defs import MAP_QUANT_SCHEME_TO_PYMO, QuantizationDataType, QuantScheme
+
+_DEFAULT_OP_FACTORY = AimetTensorQuantizer
+
+
+def set_default_op_factory(factory):
+    """Replace the class used for `_cppOp` objects (test hook). Returns the previous one."""
+    global _DEFAULT_OP_FACTORY
+    prev, _DEFAULT_OP_FACTORY = _DEFAULT_OP_FACTORY, factory
+    return prev
+
+
+def _is_native(op) -> bool:
+    return isinstance(op, AimetTensorQuantizer)
+
+
+class StaticGridTensorQuantizer:
+    """Simulates quantization for a tensor with a grid fixed by calibration (reference :143-421)."""
+
+    def __init__(self, bitwidth: int, round_mode, quant_scheme: QuantScheme, use_symmetric_encodings: bool,
+                 enabled_by_default: bool, data_type: QuantizationDataType = QuantizationDataType.int):
+        if data_type != QuantizationDataType.int:
+            raise NotImplementedError("float (fp16 / fp8) simulation is outside the aimet_b200 hot path")
+        self.round_mode = round_mode
+        self._quant_scheme = quant_scheme
+        self.use_symmetric_encodings = use_symmetric_encodings
+        self.use_strict_symmetric = False
+        self.use_unsigned_symmetric = False
+        self.is_unsigned_symmetric = False
+        self.bitwidth = bitwidth
+        self.enabled = enabled_by_default
+        self.data_type = data_type
+        self.is_const = False
+        self._encoding_min_max_fixed_vals = None
+        self._is_encoding_frozen = False
+        self._cppOp = None
+        self._encoding = None
+        self._stats_dirty = True      # statistics changed since the encoding was last computed
+        self._op_factory = _DEFAULT_OP_FACTORY
+
+    # ---- properties ----------------------------------------------------------------------------------------------
+    @property
+    def quant_scheme(self) -> QuantScheme:
+        return self._quant_scheme
+
+    @quant_scheme.setter
+    def quant_scheme(self, quant_scheme: QuantScheme):
+        # changing the scheme re-creates the native objects, which also clears their statistics (reference :236-249)
+        self._quant_scheme = quant_scheme
+        assert self._cppOp
+        self._cppOp = [self._op_factory(MAP_QUANT_SCHEME_TO_PYMO[quant_scheme]) for _ in self._cppOp]
+        self._block = None
+
+    @property
+    def is_encoding_frozen(self) -> bool:
+        return self._is_encoding_frozen
+
+    @property
+    def channel_axis(self):
+        return None
+
+    @property
+    def encoding(self):
+        return self._encoding
+
+    @encoding.setter
+    def encoding(self, encoding):
+        if self._is_encoding_frozen:
+            raise RuntimeError("Encoding can be set only when it is not frozen.")
+        self._encoding = encoding
+
+    @property
+    def encoding_min_max_fixed_vals(self) -> Optional[Tuple[float, float]]:
+        return self._encoding_min_max_fixed_vals
+
+    @encoding_min_max_fixed_vals.setter
+    def encoding_min_max_fixed_vals(self, min_max_vals: Tuple[float, float]):
+        assert isinstance(min_max_vals, tuple) and len(min_max_vals) == 2, "Min max vals must be a tuple of two values"
+        assert min_max_vals[0] < min_max_vals[1], f"Min value {min_max_vals[0]} is not less than max val {min_max_vals[1]}"
+        if self.quant_scheme != QuantScheme.post_training_tf:
+            self.quant_scheme = QuantScheme.post_training_tf
+        self._encoding_min_max_fixed_vals = min_max_vals
+
+    # ---- encodings -----------------------------------------------------------------------------------------------
+    def _collect_encodings(self):
+        """[(TfEncoding, is_valid)] for every native op: the generic, one-call-per-op route (reference :296-299)."""
+        return [op.getEncoding(self.bitwidth, self.use_symmetric_encodings, self.use_strict_symmetric,
+                               self.use_unsigned_symmetric) for op in self._cppOp]
+
+    def compute_encoding(self):
+        """reference :280-321. Recomputing from unchanged statistics returns the same encoding (the reference does it for
+        every parameter after calibration, 26 560 extra native calls for per-channel ResNet-50); that case is skipped."""
+        if self.enabled and not self._is_encoding_frozen:
+            if self._encoding and not self._stats_dirty:
+                return
+            self._stats_dirty = False
+            self._encoding = []
+            if self.bitwidth == 32:
+                self._encoding = None
+                return
+            for encoding, is_valid in self._collect_encodings():
+                if not is_valid:
+                    self.enabled = False
+                else:
+                    self._encoding.append(encoding)
+            self.is_unsigned_symmetric = self.use_symmetric_encodings and self.use_unsigned_symmetric and \
+                all(enc.min >= 0 and enc.max >= 0 for enc in self._encoding)
+            if not self.enabled and self._encoding:
+                raise AssertionError("At least one encoding for a multi-encoding quantizer is invalid.")
+
+    def quantize_dequantize(self, tensor: torch.Tensor, round_mode) -> torch.Tensor:
+        return QuantizeDequantize.apply(tensor, self, round_mode)
+
+    def quantize(self, tensor: torch.Tensor, round_mode) -> torch.Tensor:
+        return Quantize.apply(tensor, self, round_mode)
+
+    def reset_encoding_stats(self):
+        if not self._is_encoding_frozen:
+            self._reset_ops()
+            self._encoding = None
+            self._stats_dirty = True
+
+    def _reset_ops(self):
+        for op in self._cppOp:
+            op.resetEncodingStats()
+
+    def get_stats_histogram(self) -> List[List]:
+        if self._quant_scheme != QuantScheme.post_training_tf_enhanced:
+            raise RuntimeError("get_stats_histogram() can be invoked only when quantization scheme is TF-Enhanced.")
+        if not self._encoding:
+            raise RuntimeError("get_stats_histogram() can be invoked only when encoding is computed.")
+        return [op.getStatsHistogram() for op in self._cppOp]
+
+    def freeze_encoding(self):
+        if not self._encoding:
+            raise RuntimeError("Encoding can be frozen only when it is not None.")
+        self._is_encoding_frozen = True
+
+    def set_percentile_value(self, percentile_value: float):
+        for op in self._cppOp:
+            op.setPercentileValue(percentile_value)
+
+    # ---- pickling: native objects are re-created, statistics are dropped (reference :128-220) --------------------
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_cppOp"] = len(self._cppOp)
+        state.pop("_block", None)
+        state.pop("_op_factory", None)
+        return state
+
+    def __setstate__(self, state):
+        n = state.pop("_cppOp")
+        self.__dict__.update(state)
+        self._op_factory = _DEFAULT_OP_FACTORY
+        self._block = None
+        self._cppOp = [self._op_factory(MAP_QUANT_SCHEME_TO_PYMO[self._quant_scheme]) for _ in range(n)]
+
+
+class StaticGridPerTensorQuantizer(StaticGridTensorQuantizer):
+    """reference :408-480"""
+
+    def __init__(self, bitwidth, round_mode, quant_scheme, use_symmetric_encodings, enabled_by_default,
+                 data_type=QuantizationDataType.int):
+        super().__init__(bitwidth, round_mode, quant_scheme, use_symmetric_encodings, enabled_by_default, data_type)
+        self._cppOp = [self._op_factory(MAP_QUANT_SCHEME_TO_PYMO[quant_scheme])]
+        self._block = None
+
+    @property
+    def encoding(self):
+        return self._encoding[0] if self._encoding else None
+
+    @encoding.setter
+    def encoding(self, encoding):
+        if self._is_encoding_frozen:
+            raise RuntimeError("Encoding can be set only when it is not frozen.")
+        self._encoding = encoding if isinstance(encoding, list) and len(encoding) == 1 else [encoding]
+
+    def update_encoding_stats(self, tensor: torch.Tensor):
+        """reference :452-480"""
+        if self.enabled and not self._is_encoding_frozen:
+            if self.bitwidth == 32:
+                return
+            self._stats_dirty = True
+            if self.encoding_min_max_fixed_vals is not None:
+                tensor = torch.tensor([self.encoding_min_max_fixed_vals[0], self.encoding_min_max_fixed_vals[1]])
+            for op in self._cppOp:
+                if tensor.dtype == torch.float16:
+                    tensor = tensor.to(torch.float32)
+                op.updateStats(tensor, tensor.is_cuda)
+
+
+class StaticGridPerChannelQuantizer(StaticGridTensorQuantizer):
+    """reference :483-570"""
+
+    def __init__(self, bitwidth, round_mode, quant_scheme, use_symmetric_encodings, num_channels, enabled_by_default,
+                 ch_axis: int = 0, data_type=QuantizationDataType.int):
+        super().__init__(bitwidth, round_mode, quant_scheme, use_symmetric_encodings, enabled_by_default, data_type)
+        self._cppOp = [self._op_factory(MAP_QUANT_SCHEME_TO_PYMO[quant_scheme]) for _ in range(num_channels)]
+        self._ch_axis = ch_axis
+        self._block = None          # one contiguous block of statistics records shared by all channels (native ops)
+        self._params_cache = None
+
+    @property
+    def channel_axis(self) -> int:
+        return self._ch_axis
+
+    def _ensure_block(self, device):
+        if self._block is None or self._block.device != device:
+            self._block = StateArena.for_device(device).allocate(len(self._cppOp))
+            for i, op in enumerate(self._cppOp):
+                op._bind(self._block, i)   # pylint: disable=protected-access
+
+    def _reset_ops(self):
+        if self._block is not None and _is_native(self._cppOp[0]):
+            self._block.reset()
+            for op in self._cppOp:
+                op._is_encoding_valid = False   # pylint: disable=protected-access
+        else:
+            super()._reset_ops()
+
+    def update_encoding_stats(self, tensor: torch.Tensor):
+        """reference :537-570"""
+        if self.enabled and not self._is_encoding_frozen:
+            if self.bitwidth == 32:
+                return
+            self._stats_dirty = True
+            if self.encoding_min_max_fixed_vals is not None:
+                tensor = torch.tensor([self.encoding_min_max_fixed_vals[0], self.encoding_min_max_fixed_vals[1]])
+                for op in self._cppOp:
+                    op.updateStats(tensor, tensor.is_cuda)
+                return
+            if tensor.dtype == torch.float16:
+                tensor = tensor.to(torch.float32)
+            if _is_native(self._cppOp[0]) and tensor.is_cuda and tensor.dtype in (torch.float32, torch.bfloat16):
+                # all channels in one launch: channel-major contiguous view, one segment per channel
+                n_ch = len(self._cppOp)
+                moved = tensor if self._ch_axis == 0 else tensor.movedim(self._ch_axis, 0)
+                moved = moved.contiguous(memory_format=torch.contiguous_format)
+                self._ensure_block(tensor.device)
+                ops.stats_update_segmented_impl(moved, self._block.arena, self._block.first, n_ch,
+                                                moved.numel() // n_ch, self._cppOp[0]._code)   # pylint: disable=protected-access
+                for op in self._cppOp:
+                    op._is_encoding_valid = True   # pylint: disable=protected-access
+                return
+            for channel_idx, op in enumerate(self._cppOp):
+                tensor_slice = tensor.select(self._ch_axis, channel_idx).contiguous(memory_format=torch.contiguous_format)
+                op.updateStats(tensor_slice, tensor.is_cuda)
+
+    def _collect_encodings(self):
+        op0 = self._cppOp[0]
+        if _is_native(op0) and self._block is not None and all(op._block is self._block for op in self._cppOp):   # pylint: disable=protected-access
+            if not all(op._is_encoding_valid for op in self._cppOp):   # pylint: disable=protected-access
+                return [(libpymo.TfEncoding(), op._is_encoding_valid) for op in self._cppOp]   # pylint: disable=protected-access
+            enc, _ = ops.compute_encodings_impl(self._block.arena, self._block.first, len(self._cppOp), op0._code,   # pylint: disable=protected-access
+                                                self.bitwidth, self.use_symmetric_encodings, self.use_strict_symmetric,
+                                                self.use_unsigned_symmetric)
+            rows = enc.cpu().tolist()
+            return [(libpymo.TfEncoding._from_values(r[0], r[1], r[2], r[3], int(r[4])), True) for r in rows]   # pylint: disable=protected-access
+        return super()._collect_encodings()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# autograd functions
+# ---------------------------------------------------------------------------------------------------------------------
+def compute_dloss_by_dx(x, grad, encoding_min, encoding_max, ch_axis=0):
+    """Straight-through estimator, reference quantsim_straight_through_grad.py:91-118: grad * [min <= x <= max].
+    On CUDA tensors this is one fused kernel (3 tensors of traffic) instead of three element-wise torch kernels."""
+    if not x.is_cuda:
+        raise RuntimeError("aimet_b200 has no CPU path")
+    if isinstance(encoding_min, (list, tuple)):
+        mins = torch.tensor(encoding_min).to(x.device)       # float32, as torch.tensor(list of python floats) gives
+        maxs = torch.tensor(encoding_max).to(x.device)
+        if mins.numel() > 1:
+            n_ch = x.shape[ch_axis]
+            assert mins.numel() == n_ch
+            per_channel = 1
+            for d in x.shape[ch_axis + 1:]:
+                per_channel *= d
+            return ops.ste_bwd_per_channel_impl(x, grad, mins, maxs, n_ch, per_channel)
+        encoding_min, encoding_max = float(mins), float(maxs)
+    # torch.tensor(python float) is a 0-dim float32 tensor; compared with a lower-precision tensor it does not promote,
+    # i.e. the reference compares in x's dtype with the range rounded to that dtype
+    cmp_dtype = x.dtype if x.dtype in (torch.bfloat16, torch.float16) else torch.float32
+    lo = float(torch.tensor(float(encoding_min), dtype=torch.float32).to(cmp_dtype))
+    hi = float(torch.tensor(float(encoding_max), dtype=torch.float32).to(cmp_dtype))
+    if x.dtype == torch.float16:
+        return ops.ste_bwd_impl(x.float(), grad.float(), lo, hi).to(torch.float16)
+    return ops.ste_bwd_impl(x, grad, lo, hi)
+
+
+class QuantizeDequantize(torch.autograd.Function):
+    """reference :1098-1212"""
+
+    @staticmethod
+    def _per_tensor(tensor, tensor_quantizer, round_mode):
+        dtype = tensor.dtype
+        if dtype not in (torch.float32, torch.bfloat16):
+            tensor = tensor.to(torch.float32)
+        out = tensor_quantizer._cppOp[0].quantizeDequantize(tensor, tensor_quantizer.encoding, round_mode, tensor.is_cuda)   # pylint: disable=protected-access
+        return out.to(dtype)
+
+    @staticmethod
+    def _per_channel(tensor, tensor_quantizer, round_mode):
+        dtype = tensor.dtype
+        if dtype not in (torch.float32, torch.bfloat16):
+            tensor = tensor.to(torch.float32)
+        sizes = [*tensor.shape, 1]
+        num_channel = sizes[tensor_quantizer.channel_axis]
+        num_element = functools.reduce(lambda x, y: x * y, sizes)
+        num_element_per_channel = functools.reduce(lambda x, y: x * y, sizes[tensor_quantizer.channel_axis + 1:])
+        out = tensor_quantizer._cppOp[0].quantizeDequantizePerChannel(   # pylint: disable=protected-access
+            tensor, tensor_quantizer._encoding, num_channel, num_element, num_element_per_channel, round_mode,   # pylint: disable=protected-access
+            tensor.is_cuda)
+        return out.to(dtype)
+
+    @staticmethod
+    def forward(ctx, tensor, tensor_quantizer, round_mode):   # pylint: disable=arguments-differ
+        if tensor_quantizer.enabled and tensor_quantizer.bitwidth != 32:
+            if isinstance(tensor_quantizer, StaticGridPerChannelQuantizer):
+                out = QuantizeDequantize._per_channel(tensor, tensor_quantizer, round_mode)
+            else:
+                out = QuantizeDequantize._per_tensor(tensor, tensor_quantizer, round_mode)
+            ctx.save_for_backward(tensor)
+        else:
+            out = tensor
+        ctx.tensor_quantizer = tensor_quantizer
+        return out
+
+    @staticmethod
+    def backward(ctx, output_grad):   # pylint: disable=arguments-differ
+        q = ctx.tensor_quantizer
+        if q.enabled and q.data_type == QuantizationDataType.int and q.bitwidth != 32:
+            (tensor,) = ctx.saved_tensors
+            if isinstance(q, StaticGridPerChannelQuantizer):
+                # (the reference reads `.encoding.min` here, which only exists per tensor; the per-channel weights get
+                # their gradient gate from SteGatingFuncForParameters instead -- we gate consistently in both places)
+                grad = compute_dloss_by_dx(tensor, output_grad, [e.min for e in q.encoding],
+                                           [e.max for e in q.encoding], q.channel_axis)
+            else:
+                grad = compute_dloss_by_dx(tensor, output_grad, q.encoding.min, q.encoding.max, 0)
+        else:
+            grad = output_grad
+        return grad, None, None
+
+
+class Quantize(torch.autograd.Function):
+    """Quantize-only to the integer grid, reference :1215-1282."""
+
+    @staticmethod
+    def forward(ctx, tensor, tensor_quantizer, round_mode):   # pylint: disable=arguments-differ
+        assert tensor_quantizer.enabled, "Tensor quantizer must be enabled to perform quantize only."
+        assert tensor_quantizer.bitwidth != 32, "Tensor quantizer bitwidth must be < 32 to perform quantize only."
+        assert tensor_quantizer.encoding is not None, "Tensor quantizer encoding must be valid to perform quantize only."
+        shift_to_signed = not (tensor_quantizer.use_symmetric_encodings and tensor_quantizer.use_unsigned_symmetric)
+        if isinstance(tensor_quantizer, StaticGridPerChannelQuantizer):
+            outs = []
+            for index, op in enumerate(tensor_quantizer._cppOp):   # pylint: disable=protected-access
+                tensor_slice = tensor.select(tensor_quantizer.channel_axis, index).contiguous(
+                    memory_format=torch.contiguous_format)
+                outs.append(op.quantize(tensor_slice, tensor_quantizer._encoding[index], round_mode, tensor.is_cuda,   # pylint: disable=protected-access
+                                        shift_to_signed))
+            return torch.stack(tuple(outs), dim=tensor_quantizer.channel_axis)
+        return tensor_quantizer._cppOp[0].quantize(tensor, tensor_quantizer.encoding, round_mode, tensor.is_cuda,   # pylint: disable=protected-access
+                                                   shift_to_signed)
+
+    @staticmethod
+    def backward(ctx, _output_grad):   # pylint: disable=arguments-differ
+        raise AssertionError("Backward pass for quantize only not implemented")

@@ -1,0 +1,104 @@
+"""The host layer (aimet_b200.quantsim) against the reference's own Python + C++.
+
+The goldens in tests/golden/quantsim_*.json come from the reference's unmodified QuantizationSimModel running on the
+reference's unmodified C++ (make_quantsim_golden.py). Here the mirror runs the same models on the same seeded inputs
+with the CPU oracle injected as the native op, on CPU tensors, and must reproduce quantizer placement, every encoding
+(bit for bit: compared through the canonical JSON's sha256) and the quantized model's output.
+"""
+import hashlib
+import json
+import os
+
+import pytest
+import torch
+import torchvision
+
+from tests.conftest import GOLDEN
+
+CASES = {
+    "resnet18_default_tfe": (torchvision.models.resnet18, "default", "tf_enhanced", (4, 3, 64, 64)),
+    "resnet18_perchannel_tfe": (torchvision.models.resnet18, "per_channel", "tf_enhanced", (2, 3, 64, 64)),
+    "resnet18_default_tf": (torchvision.models.resnet18, "default", "tf", (4, 3, 64, 64)),
+    "mobilenet_v2_default_tfe": (torchvision.models.mobilenet_v2, "default", "tf_enhanced", (2, 3, 64, 64)),
+    "resnet50_perchannel_tfe": (torchvision.models.resnet50, "per_channel", "tf_enhanced", (2, 3, 64, 64)),
+}
+
+
+@pytest.fixture()
+def oracle_backend(oracle):
+    from aimet_b200.quantsim import tensor_quantizer
+    from tests.oracle_backend import OracleTensorQuantizer
+    prev = tensor_quantizer.set_default_op_factory(OracleTensorQuantizer)
+    yield
+    tensor_quantizer.set_default_op_factory(prev)
+
+
+def build_and_calibrate(name, device="cpu"):
+    from aimet_b200.quantsim import QuantizationSimModel
+    from aimet_b200.quantsim import config as qconfig
+    ctor, cfg, scheme, shape = CASES[name]
+    torch.manual_seed(0)
+    model = ctor().eval()
+    torch.manual_seed(1)
+    x = torch.randn(*shape)
+    x2 = torch.randn(*shape) * 1.5
+    model, x, x2 = model.to(device), x.to(device), x2.to(device)
+    sim = QuantizationSimModel(model, dummy_input=x, quant_scheme=scheme, default_output_bw=8, default_param_bw=8,
+                               config_file=qconfig.DEFAULT_CONFIG_PER_CHANNEL if cfg == "per_channel" else None)
+    structure = {}
+    for mname, w in sim.quant_wrappers():
+        structure[mname] = {
+            "type": type(w.get_original_module()).__name__,
+            "inputs": [bool(q.enabled) for q in w.input_quantizers],
+            "outputs": [bool(q.enabled) for q in w.output_quantizers],
+            "params": {k: [bool(q.enabled), bool(q.use_symmetric_encodings), type(q).__name__]
+                       for k, q in w.param_quantizers.items()},
+        }
+
+    def calib(m, _):
+        m(x)
+        m(x2)
+
+    sim.compute_encodings(calib, None)
+    with torch.no_grad():
+        out = sim.model(x)
+    return sim, structure, out
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_host_layer_reproduces_reference_python(oracle_backend, name):
+    golden = json.load(open(os.path.join(GOLDEN, f"quantsim_{name}.json")))
+    sim, structure, out = build_and_calibrate(name)
+    assert structure == golden["structure"]
+    act, par = sim.get_activation_param_encodings()
+    enc = {"activation_encodings": act, "param_encodings": par}
+    canonical = json.dumps(enc, sort_keys=True)
+    if "encodings" in golden:
+        mine = json.loads(canonical)
+        assert mine["activation_encodings"] == golden["encodings"]["activation_encodings"]
+        assert mine["param_encodings"] == golden["encodings"]["param_encodings"]
+    else:
+        assert json.loads(json.dumps(act, sort_keys=True)) == golden["activation_encodings"]
+        for k, v in golden["param_encodings_sample"].items():
+            assert json.loads(json.dumps(par[k][:3])) == v
+    assert hashlib.sha256(canonical.encode()).hexdigest() == golden["sha256"]
+    assert hashlib.sha256(out.numpy().tobytes()).hexdigest() == golden["output_sha256"]
+
+
+def test_export_files(oracle_backend, tmp_path):
+    sim, _, _ = build_and_calibrate("resnet18_default_tfe")
+    sim.save_encodings_to_json(str(tmp_path), "enc")
+    saved = json.load(open(tmp_path / "enc.json"))
+    assert set(saved) == {"activation_encodings", "param_encodings"}
+    entry = saved["param_encodings"]["conv1.weight"][0]
+    # reference create_encoding_dict (aimet_torch/utils.py:1156-1185): exactly these keys, is_symmetric as a string
+    assert set(entry) == {"min", "max", "scale", "offset", "bitwidth", "is_symmetric", "dtype"}
+    assert entry["is_symmetric"] == "True" and entry["dtype"] == "int" and isinstance(entry["offset"], int)
+    assert saved["activation_encodings"]["relu"]["output"]["0"]["is_symmetric"] == "False"
+    sim.export(str(tmp_path), "model")
+    exported = json.load(open(tmp_path / "model_torch.encodings"))
+    assert exported["version"] == "0.6.1"
+    assert exported["param_encodings"] == saved["param_encodings"]
+    assert os.path.exists(tmp_path / "model.pth")
+    # text form is json.dump(sort_keys=True, indent=4), as the reference writes it
+    assert open(tmp_path / "enc.json").read() == json.dumps(saved, sort_keys=True, indent=4)
