@@ -58,21 +58,40 @@ QUANTIZATION_ENTROPY = QuantizationMode.QUANTIZATION_ENTROPY
 ROUND_NEAREST, ROUND_STOCHASTIC = RoundingMode.ROUND_NEAREST, RoundingMode.ROUND_STOCHASTIC
 
 
+_ENCODING_EPOCH = [0]   # bumped by every write to any TfEncoding field: lets device-side caches of encodings stay valid
+
+
+def encoding_epoch() -> int:
+    return _ENCODING_EPOCH[0]
+
+
 class TfEncoding:
     """DlQuantization::TfEncoding (Quantization.hpp:113-120): read/write fields min, max, delta, offset, bw."""
     __slots__ = ("min", "max", "delta", "offset", "bw")
 
     def __init__(self):
-        self.min = 0.0
-        self.max = 0.0
-        self.delta = 0.0
-        self.offset = 0.0
-        self.bw = 0
+        _set = object.__setattr__
+        _set(self, "min", 0.0)
+        _set(self, "max", 0.0)
+        _set(self, "delta", 0.0)
+        _set(self, "offset", 0.0)
+        _set(self, "bw", 0)
+        _ENCODING_EPOCH[0] += 1
+
+    def __setattr__(self, name, value):
+        object.__setattr__(self, name, value)
+        _ENCODING_EPOCH[0] += 1
 
     @classmethod
     def _from_values(cls, mn, mx, delta, offset, bw):
-        e = cls()
-        e.min, e.max, e.delta, e.offset, e.bw = float(mn), float(mx), float(delta), float(offset), int(bw)
+        e = cls.__new__(cls)
+        _set = object.__setattr__
+        _set(e, "min", float(mn))
+        _set(e, "max", float(mx))
+        _set(e, "delta", float(delta))
+        _set(e, "offset", float(offset))
+        _set(e, "bw", int(bw))
+        _ENCODING_EPOCH[0] += 1
         return e
 
     @classmethod
@@ -86,7 +105,9 @@ class TfEncoding:
         return (self.min, self.max, self.delta, self.offset, self.bw)
 
     def __setstate__(self, s):
-        self.min, self.max, self.delta, self.offset, self.bw = s
+        for k, v in zip(self.__slots__, s):
+            object.__setattr__(self, k, v)
+        _ENCODING_EPOCH[0] += 1
 
     def __repr__(self):
         return (f"TfEncoding(min={self.min!r}, max={self.max!r}, delta={self.delta!r}, offset={self.offset!r}, "

@@ -21,6 +21,16 @@ LOG_WORDS = _lib.PDF_SIZE + 2
 _L = _lib.load()
 STATE_BYTES = int(_L.ab_stats_state_bytes())
 
+# kernel launches issued through this module, by kernel family (bench.py reports their sum as gpu_launches)
+LAUNCHES = {"qdq": 0, "quantize": 0, "qdq_per_channel": 0, "ste_bwd": 0, "minmax": 0, "hist": 0, "segmented": 0,
+            "search": 0, "reset": 0, "init_range": 0, "fold": 0}
+# when a list, stats_update_impl brackets its launches with CUDA events and appends (bytes, start, stop, quant_mode)
+STATS_TIMING = None
+
+
+def launches_total() -> int:
+    return sum(LAUNCHES.values())
+
 
 def _dtype_code(t: torch.Tensor) -> int:
     if t.dtype == torch.float32:
@@ -79,6 +89,7 @@ def qdq_per_tensor_impl(x, enc_min, enc_max, bw, round_mode=0, seed=0):
         _lib.check(_L.ab_qdq_per_tensor_fwd(x.data_ptr(), out.data_ptr(), x.numel(), _dtype_code(x), float(enc_min),
                                             float(enc_max), int(bw), int(round_mode), int(seed) & (2**64 - 1),
                                             _stream(x)))
+    LAUNCHES["qdq"] += 1
     return out
 
 
@@ -92,6 +103,7 @@ def qdq_per_tensor_dev_impl(x, enc4, round_mode=0, seed=0):
         _lib.check(_L.ab_qdq_per_tensor_fwd_dev(x.data_ptr(), out.data_ptr(), x.numel(), _dtype_code(x),
                                                 enc4.data_ptr(), int(round_mode), int(seed) & (2**64 - 1),
                                                 _stream(x)))
+    LAUNCHES["qdq"] += 1
     return out
 
 
@@ -103,6 +115,7 @@ def quantize_to_grid_impl(x, enc_min, enc_max, bw, round_mode=0, shift_to_signed
         _lib.check(_L.ab_quantize_to_grid(x.data_ptr(), out.data_ptr(), x.numel(), _dtype_code(x), float(enc_min),
                                           float(enc_max), int(bw), int(round_mode), int(bool(shift_to_signed)),
                                           int(seed) & (2**64 - 1), _stream(x)))
+    LAUNCHES["quantize"] += 1
     return out
 
 
@@ -116,6 +129,7 @@ def qdq_per_channel_impl(x, params, num_channel, num_element_per_channel, round_
         _lib.check(_L.ab_qdq_per_channel_fwd(x.data_ptr(), out.data_ptr(), int(num_channel), x.numel(),
                                              int(num_element_per_channel), _dtype_code(x), params.data_ptr(),
                                              int(round_mode), int(seed) & (2**64 - 1), _stream(x)))
+    LAUNCHES["qdq_per_channel"] += 1
     return out
 
 
@@ -136,6 +150,7 @@ def ste_bwd_impl(x, grad, enc_min, enc_max):
     with _on_device(x):
         _lib.check(_L.ab_qdq_ste_bwd(x.data_ptr(), grad.data_ptr(), out.data_ptr(), x.numel(), _dtype_code(x),
                                      float(enc_min), float(enc_max), _stream(x)))
+    LAUNCHES["ste_bwd"] += 1
     return out
 
 
@@ -152,6 +167,7 @@ def ste_bwd_per_channel_impl(x, grad, enc_min, enc_max, num_channel, num_element
         _lib.check(_L.ab_qdq_ste_bwd_per_channel(x.data_ptr(), grad.data_ptr(), out.data_ptr(), int(num_channel),
                                                  x.numel(), int(num_element_per_channel), _dtype_code(x),
                                                  enc_min.data_ptr(), enc_max.data_ptr(), _stream(x)))
+    LAUNCHES["ste_bwd"] += 1
     return out
 
 
@@ -165,6 +181,7 @@ def stats_reset_impl(states, first, count):
     _require_cuda(states)
     with _on_device(states):
         _lib.check(_L.ab_stats_reset(_state_ptr(states, first), int(count), _stream(states)))
+    LAUNCHES["reset"] += 1
 
 
 def stats_update_impl(x, states, index, quant_mode, batch_log, log_entry):
@@ -177,9 +194,19 @@ def stats_update_impl(x, states, index, quant_mode, batch_log, log_entry):
         if batch_log.dtype != torch.int32 and batch_log.dtype != torch.uint32:
             raise ValueError("batch_log must be a 32-bit integer CUDA tensor")
         log_ptr = batch_log.data_ptr() + int(log_entry) * LOG_WORDS * 4
+    timing = STATS_TIMING
     with _on_device(x):
+        if timing is not None:
+            start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            start.record()
         _lib.check(_L.ab_stats_update(x.data_ptr(), x.numel(), _dtype_code(x), int(quant_mode),
                                       _state_ptr(states, index), log_ptr, _stream(x)))
+        if timing is not None:
+            stop.record()
+            timing.append((x.numel() * x.element_size(), start, stop, int(quant_mode)))
+    LAUNCHES["minmax"] += 1
+    if int(quant_mode) == QUANTIZATION_TF_ENHANCED:
+        LAUNCHES["hist"] += 1
 
 
 def stats_update_segmented_impl(x, states, first, num_segments, segment_len, quant_mode):
@@ -190,6 +217,7 @@ def stats_update_segmented_impl(x, states, first, num_segments, segment_len, qua
     with _on_device(x):
         _lib.check(_L.ab_stats_update_segmented(x.data_ptr(), int(num_segments), int(segment_len), _dtype_code(x),
                                                 int(quant_mode), _state_ptr(states, first), _stream(x)))
+    LAUNCHES["segmented"] += 1
 
 
 def compute_encodings_impl(states, first, count, quant_mode, bw, sym, strict, unsigned_sym, want_qdq4=False):
@@ -201,6 +229,7 @@ def compute_encodings_impl(states, first, count, quant_mode, bw, sym, strict, un
         _lib.check(_L.ab_compute_encodings(_state_ptr(states, first), int(count), int(quant_mode), int(bw),
                                            int(bool(sym)), int(bool(strict)), int(bool(unsigned_sym)),
                                            enc.data_ptr(), qdq4.data_ptr() if want_qdq4 else None, _stream(states)))
+    LAUNCHES["search"] += 1
     return enc, qdq4
 
 
@@ -214,6 +243,7 @@ def compute_encodings_into(states, first, count, quant_mode, bw, sym, strict, un
         _lib.check(_L.ab_compute_encodings(_state_ptr(states, first), int(count), int(quant_mode), int(bw),
                                            int(bool(sym)), int(bool(strict)), int(bool(unsigned_sym)),
                                            out.data_ptr(), None, _stream(states)))
+    LAUNCHES["search"] += 1
 
 
 def stats_init_range_impl(states, first, count, minmax):
@@ -223,6 +253,7 @@ def stats_init_range_impl(states, first, count, minmax):
     with _on_device(states):
         _lib.check(_L.ab_stats_init_range(_state_ptr(states, first), int(count), minmax.data_ptr(),
                                           _stream(states)))
+    LAUNCHES["init_range"] += 1
 
 
 def stats_fold_batches_impl(states, first, count, batch_log, batch_offsets):
@@ -232,6 +263,7 @@ def stats_fold_batches_impl(states, first, count, batch_log, batch_offsets):
     with _on_device(states):
         _lib.check(_L.ab_stats_fold_batches(_state_ptr(states, first), int(count), batch_log.data_ptr(),
                                             batch_offsets.data_ptr(), batch_offsets.numel(), _stream(states)))
+    LAUNCHES["fold"] += 1
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -114,7 +114,10 @@ class StaticGridQuantWrapper(nn.Module):
         return self._module_to_wrap
 
     def get_named_parameters(self):
-        return self._module_to_wrap.named_parameters()
+        params = self._module_to_wrap._parameters   # pylint: disable=protected-access
+        if not self._module_to_wrap._modules:        # leaf module: its own parameters are all there is
+            return [(k, v) for k, v in params.items() if v is not None]
+        return list(self._module_to_wrap.named_parameters())
 
     def set_mode(self, mode: QcQuantizeOpMode):
         self._mode = mode
@@ -149,9 +152,10 @@ class StaticGridQuantWrapper(nn.Module):
         """reference :705-745"""
         quantized_inputs = self._quantize_activation(self.input_quantizers, list(inputs))
         shadow_params = self._quantize_dequantize_params()
-        quantized_inputs = SteGatingFuncForParameters.apply(self, *quantized_inputs)
-        quantized_inputs = [inp.clone() if isinstance(inp, torch.Tensor) and inp.requires_grad else inp
-                            for inp in quantized_inputs]
+        if torch.is_grad_enabled():
+            quantized_inputs = SteGatingFuncForParameters.apply(self, *quantized_inputs)
+            quantized_inputs = [inp.clone() if isinstance(inp, torch.Tensor) and inp.requires_grad else inp
+                                for inp in quantized_inputs]
         wrapped_output = self._module_to_wrap(*quantized_inputs, **kwargs)
         self._restore_shadow_params(shadow_params)
         is_seq = isinstance(wrapped_output, (list, tuple))

@@ -123,9 +123,40 @@ class QuantizationSimModel:
     # ---- calibration -------------------------------------------------------------------------------------------
     @staticmethod
     def prepare_sim_for_compute_encodings(sim: "QuantizationSimModel"):
+        sim._bind_activation_states()   # pylint: disable=protected-access
         for _, layer in sim.quant_wrappers():
             layer.reset_encodings()
             layer.set_mode(QcQuantizeOpMode.ANALYSIS)
+
+    def activation_quantizers(self):
+        """Enabled per-tensor activation quantizers in a deterministic (module, input/output, index) order."""
+        out = []
+        for _, layer in self.quant_wrappers():
+            for q in layer.input_quantizers + layer.output_quantizers:
+                if q.enabled and q.bitwidth != 32 and not q.is_encoding_frozen:
+                    out.append(q)
+        return out
+
+    def _bind_activation_states(self):
+        """Give all activation quantizers ONE contiguous block of device statistics records, so that range injection,
+        the ordered replay and the final grid search are single launches over the whole model."""
+        from ..state import StateArena
+        from ..tensor_quantizer_op import AimetTensorQuantizer
+        try:
+            device = next(self.model.parameters()).device
+        except StopIteration:
+            return
+        if device.type != "cuda":
+            return
+        quantizers = [q for q in self.activation_quantizers() if isinstance(q._cppOp[0], AimetTensorQuantizer)]   # pylint: disable=protected-access
+        if not quantizers:
+            return
+        block = getattr(self, "_act_block", None)
+        if block is None or block.count != len(quantizers) or block.device != device:
+            block = self._act_block = StateArena.for_device(device).allocate(len(quantizers))
+        for i, q in enumerate(quantizers):
+            q._cppOp[0]._bind(block, i)   # pylint: disable=protected-access
+        self._act_block_quantizers = quantizers
 
     @staticmethod
     def compute_layer_encodings_for_sim(sim: "QuantizationSimModel"):
@@ -164,7 +195,16 @@ class QuantizationSimModel:
             by_device[op._block.device].append((q, op))   # pylint: disable=protected-access
         for device, items in by_device.items():
             out = torch.empty((len(items), 5), dtype=torch.float64, device=device)
-            for row, (q, op) in enumerate(items):
+            first_q, first_op = items[0]
+            key = lambda q, op: (op._code, q.bitwidth, q.use_symmetric_encodings, q.use_strict_symmetric,   # noqa: E731
+                                 q.use_unsigned_symmetric)
+            contiguous = all(op._block is first_op._block and op._index == first_op._index + i and   # pylint: disable=protected-access
+                             key(q, op) == key(first_q, first_op) for i, (q, op) in enumerate(items))
+            if contiguous:
+                ops.compute_encodings_into(first_op._block.arena, first_op._block.first + first_op._index, len(items),   # pylint: disable=protected-access
+                                           first_op._code, first_q.bitwidth, first_q.use_symmetric_encodings,   # pylint: disable=protected-access
+                                           first_q.use_strict_symmetric, first_q.use_unsigned_symmetric, out)
+            for row, (q, op) in enumerate(items if not contiguous else []):
                 ops.compute_encodings_into(op._block.arena, op._block.first + op._index, 1, op._code, q.bitwidth,   # pylint: disable=protected-access
                                            q.use_symmetric_encodings, q.use_strict_symmetric,
                                            q.use_unsigned_symmetric, out[row:row + 1])

@@ -131,6 +131,8 @@ class StaticGridTensorQuantizer:
                 raise AssertionError("At least one encoding for a multi-encoding quantizer is invalid.")
 
     def quantize_dequantize(self, tensor: torch.Tensor, round_mode) -> torch.Tensor:
+        if not (torch.is_grad_enabled() and tensor.requires_grad):
+            return QuantizeDequantize.run(tensor, self, round_mode)
         return QuantizeDequantize.apply(tensor, self, round_mode)
 
     def quantize(self, tensor: torch.Tensor, round_mode) -> torch.Tensor:
@@ -201,6 +203,10 @@ class StaticGridPerTensorQuantizer(StaticGridTensorQuantizer):
         """reference :452-480"""
         if self.enabled and not self._is_encoding_frozen:
             if self.bitwidth == 32:
+                return
+            hook = getattr(self, "_calib_hook", None)
+            if hook is not None and self.encoding_min_max_fixed_vals is None:
+                hook(tensor)        # sharded calibration (aimet_b200.distributed) records / logs the call itself
                 return
             self._stats_dirty = True
             if self.encoding_min_max_fixed_vals is not None:
@@ -336,15 +342,19 @@ class QuantizeDequantize(torch.autograd.Function):
         return out.to(dtype)
 
     @staticmethod
-    def forward(ctx, tensor, tensor_quantizer, round_mode):   # pylint: disable=arguments-differ
+    def run(tensor, tensor_quantizer, round_mode):
+        """The forward computation without autograd bookkeeping."""
         if tensor_quantizer.enabled and tensor_quantizer.bitwidth != 32:
             if isinstance(tensor_quantizer, StaticGridPerChannelQuantizer):
-                out = QuantizeDequantize._per_channel(tensor, tensor_quantizer, round_mode)
-            else:
-                out = QuantizeDequantize._per_tensor(tensor, tensor_quantizer, round_mode)
+                return QuantizeDequantize._per_channel(tensor, tensor_quantizer, round_mode)
+            return QuantizeDequantize._per_tensor(tensor, tensor_quantizer, round_mode)
+        return tensor
+
+    @staticmethod
+    def forward(ctx, tensor, tensor_quantizer, round_mode):   # pylint: disable=arguments-differ
+        out = QuantizeDequantize.run(tensor, tensor_quantizer, round_mode)
+        if out is not tensor:
             ctx.save_for_backward(tensor)
-        else:
-            out = tensor
         ctx.tensor_quantizer = tensor_quantizer
         return out
 

@@ -79,8 +79,9 @@ class AimetTensorQuantizer:
     def quantizeDequantize(self, input, encoding, rounding_mode, use_cuda):   # pylint: disable=redefined-builtin
         """AimetTensorQuantizer.cpp:129-153: uses only encoding.min / max / bw."""
         t, orig = _to_device_tensor(input)
-        out = torch.ops.aimet_b200.qdq_per_tensor(t, float(encoding.min), float(encoding.max), int(encoding.bw),
-                                                  int(rounding_mode), _next_seed())
+        fn = torch.ops.aimet_b200.qdq_per_tensor if (t.requires_grad and torch.is_grad_enabled()) else \
+            ops.qdq_per_tensor_impl
+        out = fn(t, float(encoding.min), float(encoding.max), int(encoding.bw), int(rounding_mode), _next_seed())
         return _restore(out, input, orig)
 
     def quantize(self, input, encoding, rounding_mode, use_cuda, shift_to_signed):   # pylint: disable=redefined-builtin
@@ -95,8 +96,9 @@ class AimetTensorQuantizer:
         """AimetTensorQuantizer.cpp:256-307"""
         t, orig = _to_device_tensor(input)
         params = self._per_channel_params(encodings, t.device)
-        out = torch.ops.aimet_b200.qdq_per_channel(t, params, int(num_channel), int(num_element_per_channel),
-                                                   int(rounding_mode), _next_seed())
+        fn = torch.ops.aimet_b200.qdq_per_channel if (t.requires_grad and torch.is_grad_enabled()) else \
+            ops.qdq_per_channel_impl
+        out = fn(t, params, int(num_channel), int(num_element_per_channel), int(rounding_mode), _next_seed())
         return _restore(out, input, orig)
 
     def makeDeltaOffsetTensor(self, device, encodings):
@@ -120,12 +122,13 @@ class AimetTensorQuantizer:
 
     # ---- helpers ---------------------------------------------------------------------------------------------
     def _per_channel_params(self, encodings, device):
-        key = (device, tuple((e.min, e.max, e.bw) for e in encodings))
-        if self._pc_cache is not None and self._pc_cache[0] == key:
+        # valid while the very same list object is passed and no TfEncoding anywhere has been written since
+        key = (device, id(encodings), len(encodings), libpymo.encoding_epoch())
+        if self._pc_cache is not None and self._pc_cache[0] == key and self._pc_cache[2] is encodings:
             return self._pc_cache[1]
         host = ops.per_channel_params([e.min for e in encodings], [e.max for e in encodings], encodings[0].bw)
         dev = host.pin_memory().to(device, non_blocking=True) if torch.cuda.is_available() else host.to(device)
-        self._pc_cache = (key, dev)
+        self._pc_cache = (key, dev, encodings)
         return dev
 
 

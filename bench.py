@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""Headline benchmark (BASELINE.json): ResNet-50 QuantSim calibration img/s, plus the HBM roofline of the dominant kernel.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo: sm_100a kernels behind the reference's API
+  python bench.py --impl reference --steps K --warmup W    # the reference's own CPU implementation on the host cores
+
+Workload (BASELINE.json configs[1]): torchvision ResNet-50, random init (seed 0), W8A8, per-channel weights
+(default_config_per_channel), quant scheme tf_enhanced; one STEP = one calibration batch of 32 synthetic 3x224x224
+images through the quantsim model (fp32 forward with every wrapper collecting statistics). The timed region is a
+COMPLETE calibration job of K steps: reset -> K batches (the first one also derives the 26 560 per-channel weight
+encodings) -> (N > 1: NCCL merge of the per-rank statistics) -> grid search for every quantizer -> encodings on the host.
+value = images calibrated by all ranks / that time. N > 1 is weak scaling: every rank runs K batches.
+
+One JSON line on stdout (rank 0). See README / DESIGN.md for the key meanings.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BATCH = 32
+IMAGE = (3, 224, 224)
+CPU_BATCH = 4          # bounded sample for the CPU arms: images per step
+METRIC = "resnet50_quantsim_calibration_throughput"
+UNIT = "img/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=32)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-baseline-steps", type=int, default=2)
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# shared pieces
+# ---------------------------------------------------------------------------------------------------------------------
+def build_sim(device, op_factory=None):
+    import torch
+    import torchvision
+
+    from aimet_b200.quantsim import QuantizationSimModel, tensor_quantizer
+    from aimet_b200.quantsim import config as qconfig
+    prev = tensor_quantizer.set_default_op_factory(op_factory) if op_factory is not None else None
+    try:
+        torch.manual_seed(0)
+        model = torchvision.models.resnet50().eval().to(device)
+        dummy = torch.zeros((2,) + IMAGE, device=device)
+        sim = QuantizationSimModel(model, dummy_input=dummy, quant_scheme="tf_enhanced", default_output_bw=8,
+                                   default_param_bw=8, config_file=qconfig.DEFAULT_CONFIG_PER_CHANNEL, in_place=True)
+    finally:
+        if prev is not None:
+            tensor_quantizer.set_default_op_factory(prev)
+    return sim
+
+
+def synthetic_batch(global_index, batch, device="cpu", pin=False):
+    import torch
+    g = torch.Generator().manual_seed(1000 + global_index)
+    x = torch.randn((batch,) + IMAGE, generator=g)
+    if pin:
+        x = x.pin_memory()
+    return x.to(device) if device != "cpu" else x
+
+
+class ClockSampler:
+    """nvidia-smi in the background during the timed region (B200_PROFILING.md clocks line)."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:   # pylint: disable=broad-except
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:   # pylint: disable=broad-except
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1]))
+                    mx.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                     parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:   # pylint: disable=broad-except
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:   # pylint: disable=broad-except
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic_ratio():
+    """dram bytes / algorithmic bytes of the histogram kernel from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, "profiles", "hist_kernel_traffic.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["dram_bytes_per_launch"]) / float(d["algorithmic_bytes_per_launch"])
+        except Exception:   # pylint: disable=broad-except
+            pass
+    return None
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arms (the reference's own implementation on the host cores)
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_job(steps, warmup):
+    """A complete calibration job of `steps` batches of CPU_BATCH images on the host: torch CPU forward (all threads) and
+    the reference's C++ statistics / encodings (single-threaded, as the reference is). Returns (img/s, info)."""
+    import torch
+
+    from aimet_b200.quantsim import tensor_quantizer
+    from oracle import cpu_backend
+    factory = cpu_backend.best_cpu_backend()
+    sim = build_sim("cpu", factory)
+    prev = tensor_quantizer.set_default_op_factory(factory)
+    try:
+        batches = [synthetic_batch(b, CPU_BATCH) for b in range(max(steps, warmup))]
+        if warmup > 0:
+            # warm-up: forward passes only touch the allocator / thread pool; one tiny complete job primes everything
+            sim.compute_encodings(lambda m, _: [m(batches[i % len(batches)][:1]) for i in range(1)], None)
+        t0 = time.perf_counter()
+        sim.compute_encodings(lambda m, _: [m(batches[i]) for i in range(steps)], None)
+        act, par = sim.get_activation_param_encodings()
+        dt = time.perf_counter() - t0
+    finally:
+        tensor_quantizer.set_default_op_factory(prev)
+    info = {"kind": factory.KIND, "cores": torch.get_num_threads(),
+            "sample": f"complete calibration job of {steps} steps x {CPU_BATCH} images (ResNet-50 per-channel "
+                      f"tf_enhanced; includes the 26 560 weight-channel encodings and the final grid search); "
+                      f"torch CPU forward on {torch.get_num_threads()} threads, reference statistics single-threaded",
+            "num_activation_encodings": len(act), "num_param_encodings": len(par), "seconds": round(dt, 3)}
+    return steps * CPU_BATCH / dt, info
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    value, info = cpu_job(args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1000.0 * CPU_BATCH / value, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "ResNet-50 W8A8 per-channel weights, tf_enhanced calibration (BASELINE configs[1])",
+                       "images_per_step": CPU_BATCH, "note": "host CPU only; bounded sample of the same workload"},
+            "cpu_baseline": dict(info, value=round(value, 3), unit=UNIT),
+            "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: aimet_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.allow_tf32 = False          # the reference's forward is plain fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+    import aimet_b200  # noqa: F401
+    from aimet_b200 import ops
+    from aimet_b200.distributed import ShardedCalibrator
+
+    sim = build_sim(device)
+    steps, warmup = args.steps, args.warmup
+    # global batch index of this rank's i-th step: i * world + rank
+    dev_batches = [synthetic_batch(i * world + rank, BATCH, device) for i in range(steps)]
+    host_batches = [synthetic_batch(i * world + rank, BATCH, "cpu", pin=True) for i in range(steps)]
+
+    def job(batch_source, n):
+        def cb(model, _):
+            for i in range(n):
+                model(batch_source(i))
+        if world > 1:
+            ShardedCalibrator(sim).compute_encodings(cb, None)
+        else:
+            sim.compute_encodings(cb, None)
+        return sim.get_activation_param_encodings()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up: W steps of a complete job (cuDNN autotune, allocator, lazy module loading) ----
+    if warmup > 0:
+        job(lambda i: dev_batches[i % steps], warmup)
+    barrier()
+
+    # ---- timed: value (inputs resident in HBM) ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ops.launches_total()
+    ops.STATS_TIMING = []
+    barrier()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    act, par = job(lambda i: dev_batches[i], steps)
+    stop.record()
+    barrier()
+    ms = start.elapsed_time(stop)
+    timing, ops.STATS_TIMING = ops.STATS_TIMING, None
+    launches = ops.launches_total() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- timed: e2e (host buffers; H2D of every batch and D2H of the result inside the region) ----
+    barrier()
+    t0 = time.perf_counter()
+    act, par = job(lambda i: host_batches[i].to(device, non_blocking=True), steps)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+
+    # max over ranks
+    t = torch.tensor([ms, e2e_s * 1000.0], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = t.tolist()
+
+    # ---- roofline of the dominant kernel: tf_enhanced statistics (histogram) launches of the timed region ----
+    tot_bytes = tot_ms = 0.0
+    big_bytes = big_ms = 0.0
+    n_l = 0
+    for nbytes, e0, e1, mode in timing:
+        if mode != ops.QUANTIZATION_TF_ENHANCED:
+            continue
+        d = e0.elapsed_time(e1)
+        tot_bytes += nbytes
+        tot_ms += d
+        n_l += 1
+        if nbytes >= 32 * 2**20:
+            big_bytes += nbytes
+            big_ms += d
+    peak, peak_src = peak_hbm()
+    achieved = tot_bytes / tot_ms / 1e6 if tot_ms > 0 else 0.0
+    ratio = ncu_traffic_ratio()
+    roofline = {"bound": "hbm", "kernel": "hist_kernel<float> (+ the early-exit minmax_kernel launched with it)",
+                "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": round(ratio * tot_bytes / max(n_l, 1), 1) if ratio else None,
+                "algorithmic_bytes_per_launch": round(tot_bytes / max(n_l, 1), 1), "launches": n_l,
+                "avg_launch_us": round(1000.0 * tot_ms / max(n_l, 1), 2), "peak_source": peak_src,
+                "achieved_large_tensors": round(big_bytes / big_ms / 1e6, 1) if big_ms > 0 else None,
+                "note": "4 B/element x elements of every activation tensor handed to updateStats, divided by the "
+                        "CUDA-event time of those launches inside the timed region (events on the launching stream); "
+                        "achieved_large_tensors restricts to tensors >= 32 MB"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    images = BATCH * steps * world
+    value = images / (ms / 1000.0)
+    e2e = images / (e2e_ms / 1000.0)
+    enc_bytes = (sum(len(v.get("input", {})) + len(v.get("output", {})) for v in act.values()) +
+                 sum(len(v) for v in par.values())) * 5 * 8
+    line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": round(ms / steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "ResNet-50 W8A8 per-channel weights, tf_enhanced calibration (BASELINE configs[1])",
+                       "images_per_step": BATCH, "image": list(IMAGE), "global_images": images,
+                       "timed_region": "complete job: reset, K batches (incl. per-channel weight encodings), "
+                                       "merge (N>1), grid search, encodings on host",
+                       "l2": "activation working set per step (2.2 GB) exceeds the 126 MB L2; no flush needed",
+                       "num_activation_encodings": len(act), "num_param_tensors": len(par),
+                       "parallelism": f"batch-sharded x{world}"},
+            "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": BATCH * 3 * 224 * 224 * 4,
+                    "d2h_bytes_per_step": int(enc_bytes / steps)},
+            "gpu_launches": launches, "launches_by_kernel": dict(ops.LAUNCHES),
+            "roofline": roofline, "clocks": clocks}
+
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            v, info = cpu_job(args.cpu_baseline_steps, 1)
+            line["cpu_baseline"] = dict(info, value=round(v, 3), unit=UNIT)
+        except Exception as exc:   # pylint: disable=broad-except
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "error": str(exc)[:200]}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

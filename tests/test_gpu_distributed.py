@@ -1,0 +1,74 @@
+"""ShardedCalibrator end to end: two processes (ranks) sharing cuda:0 over the gloo backend calibrate a quantsim model
+on interleaved batches; the merged encodings must equal, byte for byte, a single-process run over all batches in order.
+(Real multi-GPU NCCL runs are exercised by bench.py --gpus N.)"""
+import json
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+WORLD = 2
+N_BATCH = 6
+
+
+def make_model_and_batches(scheme):
+    import torchvision
+    torch.manual_seed(0)
+    model = torchvision.models.resnet18().eval().cuda()
+    g = torch.Generator().manual_seed(7)
+    batches = [(torch.randn(2, 3, 64, 64, generator=g) * (1 + 0.2 * b)).cuda() for b in range(N_BATCH)]
+    batches[0][:] = 0.0      # the first global batch is all zeros: tf_enhanced ranges must come from batch 1 (rank 1)
+    return model, batches
+
+
+def encodings_json(sim):
+    act, par = sim.get_activation_param_encodings()
+    return json.dumps({"activation_encodings": act, "param_encodings": par}, sort_keys=True)
+
+
+def worker(rank, port, scheme, queue):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    try:
+        torch.backends.cudnn.deterministic = True
+        torch.backends.cudnn.benchmark = False
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        from aimet_b200.distributed import ShardedCalibrator
+        from aimet_b200.quantsim import QuantizationSimModel
+        model, batches = make_model_and_batches(scheme)
+        sim = QuantizationSimModel(model, dummy_input=batches[1], quant_scheme=scheme)
+        mine = batches[rank::WORLD]
+        ShardedCalibrator(sim).compute_encodings(lambda m, _: [m(x) for x in mine], None)
+        queue.put((rank, encodings_json(sim)))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("scheme", ["tf_enhanced", "tf"])
+def test_sharded_calibration_equals_single_process(scheme):
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    port = 29700 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=worker, args=(r, port, scheme, queue)) for r in range(WORLD)]
+    for p in procs:
+        p.start()
+    results = dict(queue.get(timeout=300) for _ in range(WORLD))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.benchmark = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from aimet_b200.quantsim import QuantizationSimModel
+    model, batches = make_model_and_batches(scheme)
+    sim = QuantizationSimModel(model, dummy_input=batches[1], quant_scheme=scheme)
+    sim.compute_encodings(lambda m, _: [m(x) for x in batches], None)
+    single = encodings_json(sim)
+    assert results[0] == results[1]
+    assert results[0] == single

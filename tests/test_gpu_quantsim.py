@@ -1,0 +1,80 @@
+"""End to end on the GPU: QuantizationSimModel driven by the CUDA ops vs the same host layer driven by the CPU oracle on
+the SAME device tensors (the model forward runs on the GPU in both, so every quantizer sees identical inputs).
+Encodings JSON must be identical, byte for byte; the quantized forward output must be bit-identical.
+"""
+import hashlib
+import json
+
+import pytest
+import torch
+import torchvision
+
+from tests.test_quantsim_host import CASES, build_and_calibrate
+
+pytestmark = pytest.mark.gpu
+
+
+def run(name, factory):
+    from aimet_b200.quantsim import tensor_quantizer
+    prev = tensor_quantizer.set_default_op_factory(factory)
+    try:
+        torch.backends.cudnn.deterministic = True
+        torch.backends.cudnn.benchmark = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        sim, structure, out = build_and_calibrate(name, device="cuda")
+        act, par = sim.get_activation_param_encodings()
+        return json.dumps({"activation_encodings": act, "param_encodings": par}, sort_keys=True), structure, out
+    finally:
+        tensor_quantizer.set_default_op_factory(prev)
+
+
+@pytest.mark.parametrize("name", ["resnet18_default_tfe", "resnet18_perchannel_tfe", "resnet18_default_tf",
+                                  "mobilenet_v2_default_tfe", "resnet50_perchannel_tfe"])
+def test_cuda_ops_and_oracle_give_identical_encodings_json(oracle, name):
+    from aimet_b200 import AimetTensorQuantizer
+    from tests.oracle_backend import OracleTensorQuantizer
+    json_native, struct_native, out_native = run(name, AimetTensorQuantizer)
+    json_oracle, struct_oracle, out_oracle = run(name, OracleTensorQuantizer)
+    assert struct_native == struct_oracle
+    if json_native != json_oracle:
+        a, b = json.loads(json_native), json.loads(json_oracle)
+        for sect in a:
+            for k in a[sect]:
+                assert a[sect][k] == b[sect][k], (sect, k)
+    assert hashlib.sha256(json_native.encode()).hexdigest() == hashlib.sha256(json_oracle.encode()).hexdigest()
+    assert torch.equal(out_native, out_oracle)
+
+
+def test_qat_step_forward_backward(oracle):
+    """MobileNet-v2-style QAT step (BASELINE config 3, small): train mode re-derives weight encodings every forward,
+    activations are QDQ'd, gradients pass the straight-through estimator. Checked against the oracle-backed host layer."""
+    from aimet_b200 import AimetTensorQuantizer
+    from aimet_b200.quantsim import QuantizationSimModel, tensor_quantizer
+    from tests.oracle_backend import OracleTensorQuantizer
+
+    def step(factory):
+        prev = tensor_quantizer.set_default_op_factory(factory)
+        try:
+            torch.backends.cudnn.deterministic = True
+            torch.manual_seed(0)
+            model = torch.nn.Sequential(torch.nn.Conv2d(3, 16, 3, padding=1), torch.nn.BatchNorm2d(16), torch.nn.ReLU(),
+                                        torch.nn.Conv2d(16, 8, 3, padding=1), torch.nn.ReLU(),
+                                        torch.nn.AdaptiveAvgPool2d(1), torch.nn.Flatten(), torch.nn.Linear(8, 4)).cuda()
+            x = torch.randn(8, 3, 16, 16, device="cuda")
+            sim = QuantizationSimModel(model, dummy_input=x, quant_scheme="tf_enhanced")
+            sim.compute_encodings(lambda m, _: m(x), None)
+            sim.model.train()
+            out = sim.model(x)
+            out.square().mean().backward()
+            grads = [p.grad.clone() for p in sim.model.parameters() if p.grad is not None]
+            return out.detach(), grads
+        finally:
+            tensor_quantizer.set_default_op_factory(prev)
+
+    out_n, grads_n = step(AimetTensorQuantizer)
+    out_o, grads_o = step(OracleTensorQuantizer)
+    assert torch.equal(out_n, out_o)
+    assert len(grads_n) == len(grads_o) > 0
+    for a, b in zip(grads_n, grads_o):
+        assert torch.equal(a, b)
