@@ -26,6 +26,17 @@ LAUNCHES = {"qdq": 0, "quantize": 0, "qdq_per_channel": 0, "ste_bwd": 0, "minmax
             "search": 0, "reset": 0, "init_range": 0, "fold": 0}
 # when a list, stats_update_impl brackets its launches with CUDA events and appends (bytes, start, stop, quant_mode)
 STATS_TIMING = None
+_EVENT_POOL = []
+
+
+def reserve_timing_events(n: int):
+    """Pre-create CUDA events so that timing a launch costs two cudaEventRecord calls and nothing else."""
+    while len(_EVENT_POOL) < n:
+        _EVENT_POOL.append(torch.cuda.Event(enable_timing=True))
+
+
+def _timing_event():
+    return _EVENT_POOL.pop() if _EVENT_POOL else torch.cuda.Event(enable_timing=True)
 
 
 def launches_total() -> int:
@@ -197,7 +208,7 @@ def stats_update_impl(x, states, index, quant_mode, batch_log, log_entry):
     timing = STATS_TIMING
     with _on_device(x):
         if timing is not None:
-            start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            start, stop = _timing_event(), _timing_event()
             start.record()
         _lib.check(_L.ab_stats_update(x.data_ptr(), x.numel(), _dtype_code(x), int(quant_mode),
                                       _state_ptr(states, index), log_ptr, _stream(x)))

@@ -255,6 +255,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     launches0 = ops.launches_total()
+    ops.reserve_timing_events(2 * 100 * steps + 64)
     ops.STATS_TIMING = []
     barrier()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
