@@ -730,14 +730,18 @@ bool check_common(const void* in, int64_t count, int dtype, int quant_mode, cons
 }
 
 template <typename T>
-int launch_update(const T* in, int64_t count, int quant_mode, ab_stats_state* st, uint32_t* batch_log,
+int launch_update(const T* in, int64_t count, int quant_mode, ab_stats_state* st, uint32_t* batch_log, int flags,
                   cudaStream_t stream)
 {
     constexpr int kV = Elem<T>::kPerVec;
+    if (!(quant_mode == AB_QUANTIZATION_TF_ENHANCED && (flags & AB_STATS_RANGE_FIXED)))
     {
         auto k              = minmax_kernel<T>;
         const int64_t tiles = (count / kV + kMmThreads * kMmUnroll - 1) / (kMmThreads * kMmUnroll);
-        int grid            = resident_grid(k, kMmThreads, 0);
+        static thread_local int resident = 0;   // occupancy query once per thread, not per call
+        if (resident == 0)
+            resident = resident_grid(k, kMmThreads, 0);
+        int grid = resident;
         if (tiles < grid)
             grid = tiles < 1 ? 1 : (int) tiles;
         k<<<grid, kMmThreads, 0, stream>>>(in, count, quant_mode, st);
@@ -795,13 +799,15 @@ int ab_stats_reset(ab_stats_state* states, int64_t count, void* stream)
 }
 
 int ab_stats_update(const void* in, int64_t count, int dtype, int quant_mode, ab_stats_state* state,
-                    uint32_t* batch_log_entry, void* stream)
+                    uint32_t* batch_log_entry, int flags, void* stream)
 {
     if (!check_common(in, count, dtype, quant_mode, state))
         return AB_ERR_INVALID;
     if (dtype == AB_F32)
-        return launch_update((const float*) in, count, quant_mode, state, batch_log_entry, (cudaStream_t) stream);
-    return launch_update((const __nv_bfloat16*) in, count, quant_mode, state, batch_log_entry, (cudaStream_t) stream);
+        return launch_update((const float*) in, count, quant_mode, state, batch_log_entry, flags,
+                             (cudaStream_t) stream);
+    return launch_update((const __nv_bfloat16*) in, count, quant_mode, state, batch_log_entry, flags,
+                         (cudaStream_t) stream);
 }
 
 int ab_stats_update_segmented(const void* in, int64_t num_segments, int64_t segment_len, int dtype, int quant_mode,

@@ -121,6 +121,13 @@ class ShardedCalibrator:
         self.first_block = StateArena.for_device(self.device).allocate(q_count * self.max_calls) if self.tfe else None
         self.log = None
         self.log_slots = 0
+        # every call of the current batch logs into a fixed staging area (constant addresses, so the step can live in a
+        # CUDA graph); `_end_batch` files it under the batch's slot
+        self.stage = torch.zeros((self.max_calls, q_count, LOG_WORDS), dtype=torch.int32, device=self.device) \
+            if self.tfe else None
+        self.staged_batch = -1
+        self.fixed = [False] * q_count
+        self.manual_batches = False
         self.ranges_fixed = not self.tfe
         self._pre = sim.model.register_forward_pre_hook(lambda m, a: self._begin_batch())
         for i, q in enumerate(self.quantizers):
@@ -134,10 +141,21 @@ class ShardedCalibrator:
         self.first_block = None
 
     def _begin_batch(self):
+        if self.manual_batches:
+            return
+        self._end_batch()
         if self.local_batch == 0 and not self.ranges_fixed:
             self._fix_ranges()
         self.local_batch += 1
         self.calls = [0] * len(self.quantizers)
+
+    def _end_batch(self):
+        """File the staged log of the batch that just ran under its slot."""
+        if self.tfe and self.ranges_fixed and self.local_batch >= 0 and self.staged_batch != self.local_batch:
+            first = self.local_batch * self.max_calls
+            self._ensure_log(first + self.max_calls)
+            self.log[first:first + self.max_calls].copy_(self.stage)
+            self.staged_batch = self.local_batch
 
     def _ensure_log(self, slots):
         if self.log is None or slots > self.log_slots:
@@ -168,10 +186,8 @@ class ShardedCalibrator:
                                   ops.QUANTIZATION_TF, None, 0)
             self.deferred[i].append(tensor.detach().clone())
             return
-        slot = self.local_batch * self.max_calls + call
-        self._ensure_log(slot + 1)
-        ops.stats_update_impl(tensor, self.block.arena, self.block.first + i, ops.QUANTIZATION_TF_ENHANCED, self.log,
-                              slot * len(self.quantizers) + i)
+        ops.stats_update_impl(tensor, self.block.arena, self.block.first + i, ops.QUANTIZATION_TF_ENHANCED, self.stage,
+                              call * len(self.quantizers) + i, ops.STATS_RANGE_FIXED if self.fixed[i] else 0)
 
     # -- exchange 1: ranges --------------------------------------------------------------------------------------
     def _fix_ranges(self):
@@ -186,13 +202,15 @@ class ShardedCalibrator:
         self.first_positions = first_call_positions(gathered)
         ops.stats_init_range_impl(self.block.arena, self.block.first, q_count, chosen)
         self.ranges_fixed = True
-        # now bin the tensors kept from local batch 0
-        self._ensure_log(self.max_calls)
+        self.fixed = ((chosen[:, 0] != 0) | (chosen[:, 1] != 0)).tolist()     # the one host read-back of the job
+        # now bin the tensors kept from local batch 0 (into the staging log, filed by _end_batch)
+        self.stage.zero_()
         for i, kept in enumerate(self.deferred):
             for call, tensor in enumerate(kept):
                 ops.stats_update_impl(tensor, self.block.arena, self.block.first + i, ops.QUANTIZATION_TF_ENHANCED,
-                                      self.log, call * q_count + i)
+                                      self.stage, call * q_count + i, ops.STATS_RANGE_FIXED if self.fixed[i] else 0)
         self.deferred = [[] for _ in range(q_count)]
+        self._end_batch()
 
     # -- exchange 2: statistics ------------------------------------------------------------------------------------
     def _merge(self):
@@ -217,6 +235,7 @@ class ShardedCalibrator:
         if not self.ranges_fixed:          # the callback ran a single batch (or none)
             if self.local_batch >= 0:
                 self._fix_ranges()
+        self._end_batch()
         local_batches = torch.tensor([self.local_batch + 1], device=self.device, dtype=torch.int64)
         if self.world > 1:
             _all_reduce(local_batches, dist.ReduceOp.MAX, self.group)
@@ -240,6 +259,38 @@ class ShardedCalibrator:
             q._cppOp[0]._is_encoding_valid = q._cppOp[0]._is_encoding_valid or n > 0   # pylint: disable=protected-access
 
     # -- public ----------------------------------------------------------------------------------------------------
+    def compute_encodings_for_batches(self, batches, cuda_graph: bool = True):
+        """Like compute_encodings with the callback `for x in batches: model(x)` over THIS rank's batches, with the
+        steady state replayed from a CUDA graph (see QuantizationSimModel.compute_encodings_for_batches)."""
+        from .quantsim.quantsim import QuantizationSimModel, in_eval_mode, run_batches
+        sim = self.sim
+        QuantizationSimModel.prepare_sim_for_compute_encodings(sim)
+        if not getattr(sim, "_act_block_quantizers", None):
+            raise RuntimeError("sharded calibration needs the model on a CUDA device")
+        self._install()
+        self.manual_batches = True
+        try:
+            def start_batch():
+                self.local_batch += 1
+                self.calls = [0] * len(self.quantizers)
+
+            def after_each(n):
+                if n == 0:
+                    if not self.ranges_fixed:
+                        self._fix_ranges()      # exchange 1, then bins the kept tensors of batch 0 and files them
+                else:
+                    self._end_batch()
+                start_batch()                   # the next forward (eager or replayed) belongs to the next batch
+
+            with in_eval_mode(sim.model), torch.no_grad():
+                start_batch()
+                n = run_batches(sim.model, batches, cuda_graph, after_each=after_each)
+                self.local_batch = n - 1        # after_each advanced one past the last batch
+            self._merge()
+        finally:
+            self._uninstall()
+        QuantizationSimModel.compute_layer_encodings_for_sim(sim)
+
     def compute_encodings(self, forward_pass_callback, forward_pass_callback_args):
         from .quantsim.quantsim import QuantizationSimModel, in_eval_mode
         sim = self.sim

@@ -36,6 +36,9 @@ def reserve_timing_events(n: int):
 
 
 def _timing_event():
+    if torch.cuda.is_current_stream_capturing():
+        # inside a CUDA-graph capture: an EXTERNAL event becomes an event-record node, re-recorded by every replay
+        return torch.cuda.Event(enable_timing=True, external=True)
     return _EVENT_POOL.pop() if _EVENT_POOL else torch.cuda.Event(enable_timing=True)
 
 
@@ -195,8 +198,12 @@ def stats_reset_impl(states, first, count):
     LAUNCHES["reset"] += 1
 
 
-def stats_update_impl(x, states, index, quant_mode, batch_log, log_entry):
-    """One updateStats call for the quantizer whose record is `states[index]`."""
+STATS_RANGE_FIXED = 1
+
+
+def stats_update_impl(x, states, index, quant_mode, batch_log, log_entry, flags=0):
+    """One updateStats call for the quantizer whose record is `states[index]`. flags=STATS_RANGE_FIXED: the caller has
+    read back that the histogram range is fixed, so the (immediately exiting) min/max launch is skipped."""
     _require_cuda(x, states)
     x = x if (x.is_contiguous() or x.is_contiguous(memory_format=torch.channels_last)) else x.contiguous()
     log_ptr = None
@@ -211,13 +218,17 @@ def stats_update_impl(x, states, index, quant_mode, batch_log, log_entry):
             start, stop = _timing_event(), _timing_event()
             start.record()
         _lib.check(_L.ab_stats_update(x.data_ptr(), x.numel(), _dtype_code(x), int(quant_mode),
-                                      _state_ptr(states, index), log_ptr, _stream(x)))
+                                      _state_ptr(states, index), log_ptr, int(flags), _stream(x)))
         if timing is not None:
             stop.record()
-            timing.append((x.numel() * x.element_size(), start, stop, int(quant_mode)))
-    LAUNCHES["minmax"] += 1
+            timing.append((x.numel() * x.element_size(), start, stop, int(quant_mode),
+                           torch.cuda.is_current_stream_capturing()))
     if int(quant_mode) == QUANTIZATION_TF_ENHANCED:
         LAUNCHES["hist"] += 1
+        if not flags & STATS_RANGE_FIXED:
+            LAUNCHES["minmax"] += 1
+    else:
+        LAUNCHES["minmax"] += 1
 
 
 def stats_update_segmented_impl(x, states, first, num_segments, segment_len, quant_mode):

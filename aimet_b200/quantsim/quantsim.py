@@ -58,6 +58,58 @@ def _count_inout(model: nn.Module, dummy_input) -> Dict[nn.Module, Tuple[int, in
     return counts
 
 
+EAGER_BATCHES = 2   # batch 0 derives encodings / fixes ranges; batch 1 refreshes every host-side cache; then capture
+LAST_GRAPH_INFO = {"captured_launches": 0, "replays": 0}   # bookkeeping of the most recent run_batches (for bench.py)
+
+
+def run_batches(model, batches, cuda_graph: bool, after_first=None, after_each=None, device=None):
+    """Run `model` over `batches`; with `cuda_graph`, every batch from the third on that has the first one's shape is a
+    replay of one captured forward. Returns the number of batches run."""
+    if device is None:
+        try:
+            device = next(model.parameters()).device
+        except StopIteration:
+            device = None
+    from .. import ops
+    graph = static_in = None
+    shape = dtype = None
+    n = 0
+    LAST_GRAPH_INFO.update(captured_launches=0, replays=0)
+    for b in batches:
+        on_device = b if (device is None or b.device == device) else None
+        if n == 0:
+            x = on_device if on_device is not None else b.to(device, non_blocking=True)
+            model(x)
+            shape, dtype = tuple(x.shape), x.dtype
+            if after_each is not None:
+                after_each(0)
+            if after_first is not None:
+                after_first()
+        elif cuda_graph and n >= EAGER_BATCHES and device is not None and device.type == "cuda" and \
+                tuple(b.shape) == shape and b.dtype == dtype:
+            if graph is None:
+                static_in = torch.empty(shape, dtype=dtype, device=device)
+                static_in.copy_(b, non_blocking=True)
+                torch.cuda.current_stream(device).synchronize()
+                graph = torch.cuda.CUDAGraph()
+                before = ops.launches_total()
+                with torch.cuda.graph(graph):
+                    model(static_in)
+                LAST_GRAPH_INFO["captured_launches"] = ops.launches_total() - before
+            else:
+                static_in.copy_(b, non_blocking=True)
+            graph.replay()
+            LAST_GRAPH_INFO["replays"] += 1
+            if after_each is not None:
+                after_each(n)
+        else:
+            model(on_device if on_device is not None else b.to(device, non_blocking=True))
+            if after_each is not None:
+                after_each(n)
+        n += 1
+    return n
+
+
 class QuantizationSimModel:
     """Adds quantization-simulation wrappers to a model, calibrates them and exports the encodings."""
 
@@ -171,6 +223,30 @@ class QuantizationSimModel:
         with in_eval_mode(self.model), torch.no_grad():
             _ = forward_pass_callback(self.model, forward_pass_callback_args)
         QuantizationSimModel.compute_layer_encodings_for_sim(self)
+
+    def compute_encodings_for_batches(self, batches, cuda_graph: bool = True):
+        """compute_encodings for the common case where the calibration callback is `for x in batches: model(x)`.
+
+        Knowing the loop lets the steady state be captured in a CUDA graph: the first batch runs eagerly (it fixes the
+        histogram ranges and derives the weight encodings, which needs host decisions); from the second batch on one
+        forward -- wrapped modules, statistics kernels, weight QDQ -- is recorded once and replayed per batch, so the
+        host cost of ~130 Python wrappers and ~250 launches per step disappears. Statistics are device-resident and all
+        their control flow is on the device, which is what makes the step capturable. Results are identical to
+        compute_encodings(). `batches`: iterable of CUDA tensors, or pinned host tensors (copied per step)."""
+        QuantizationSimModel.prepare_sim_for_compute_encodings(self)
+        with in_eval_mode(self.model), torch.no_grad():
+            run_batches(self.model, batches, cuda_graph, after_first=self._learn_fixed_ranges)
+        QuantizationSimModel.compute_layer_encodings_for_sim(self)
+
+    def _learn_fixed_ranges(self):
+        """One read-back after the first batch: which activation records have their histogram range fixed (so that the
+        min/max launch is skipped from now on, and is not baked into a captured graph)."""
+        block = getattr(self, "_act_block", None)
+        if block is None:
+            return
+        rec = block.read()
+        for q, initialized in zip(self._act_block_quantizers, rec["initialized"].tolist()):
+            q._cppOp[0]._range_fixed = bool(initialized)   # pylint: disable=protected-access
 
     def _compute_activation_encodings_batched(self):
         """All per-tensor grid searches are enqueued first and read back with ONE device->host copy (the reference does

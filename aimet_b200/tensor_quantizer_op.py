@@ -41,10 +41,13 @@ class AimetTensorQuantizer:
         self._block = None            # StateBlock with one record, allocated on first use
         self._index = 0
         self._pc_cache = None         # (key, device tensor) for the per-channel parameter block
+        self._range_fixed = False     # host knowledge that the device record's histogram range is fixed
+        self._probe = None            # (pinned int32 tensor, event) of an in-flight read-back of `initialized`
 
     # ---- wiring used by the batched host layer (aimet_b200.quantsim): share one contiguous block per weight -------
     def _bind(self, block, index):
         self._block, self._index = block, index
+        self._range_fixed, self._probe = False, None
 
     def _ensure_state(self, device):
         if self._block is None or self._block.device != device:
@@ -54,6 +57,7 @@ class AimetTensorQuantizer:
     def resetEncodingStats(self):
         """AimetTensorQuantizer.cpp:85-92"""
         self._is_encoding_valid = False
+        self._range_fixed, self._probe = False, None
         if self._block is not None:
             ops.stats_reset_impl(self._block.arena, self._block.first + self._index, 1)
 
@@ -62,7 +66,33 @@ class AimetTensorQuantizer:
         t, _ = _to_device_tensor(input)
         self._is_encoding_valid = True
         self._ensure_state(t.device)
-        ops.stats_update_impl(t, self._block.arena, self._block.first + self._index, self._code, None, 0)
+        ops.stats_update_impl(t, self._block.arena, self._block.first + self._index, self._code, None, 0,
+                              ops.STATS_RANGE_FIXED if self._range_fixed else 0)
+        if self._code == ops.QUANTIZATION_TF_ENHANCED and not self._range_fixed:
+            self._poll_range_fixed()
+
+    _INITIALIZED_WORD = 6192 // 4      # ab_stats_state.initialized as an int32 index into the record
+
+    def _poll_range_fixed(self):
+        """Learn, without ever blocking, that the record's range got fixed: a 4-byte asynchronous read-back of the
+        `initialized` flag into pinned memory, looked at on a later call once its event has completed."""
+        if self._probe is not None:
+            flag, event = self._probe
+            if not event.query():
+                return
+            self._probe = None
+            if int(flag[0]) == 1:
+                self._range_fixed = True
+                return
+        if torch.cuda.is_current_stream_capturing():
+            return
+        rec = self._block.arena[(self._block.first + self._index) * ops.STATE_BYTES:
+                                (self._block.first + self._index + 1) * ops.STATE_BYTES].view(torch.int32)
+        flag = torch.empty(1, dtype=torch.int32, pin_memory=True)
+        flag.copy_(rec[self._INITIALIZED_WORD:self._INITIALIZED_WORD + 1], non_blocking=True)
+        event = torch.cuda.Event()
+        event.record(torch.cuda.current_stream(self._block.device))
+        self._probe = (flag, event)
 
     def getEncoding(self, bitwidth, use_symmetric_encodings, use_strict_symmetric, use_unsigned_symmetric):
         """AimetTensorQuantizer.cpp:180-192 -> (TfEncoding, is_valid)"""
@@ -126,6 +156,8 @@ class AimetTensorQuantizer:
         key = (device, id(encodings), len(encodings), libpymo.encoding_epoch())
         if self._pc_cache is not None and self._pc_cache[0] == key and self._pc_cache[2] is encodings:
             return self._pc_cache[1]
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("per-channel parameters changed while a CUDA graph was being captured")
         host = ops.per_channel_params([e.min for e in encodings], [e.max for e in encodings], encodings[0].bw)
         dev = host.pin_memory().to(device, non_blocking=True) if torch.cuda.is_available() else host.to(device)
         self._pc_cache = (key, dev, encodings)

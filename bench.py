@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="do not replay the steady state from a CUDA graph")
     ap.add_argument("--cpu-baseline-steps", type=int, default=2)
     return ap.parse_args()
 
@@ -216,7 +217,7 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
-    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.benchmark = os.environ.get("BENCH_CUDNN_BENCHMARK", "1") == "1"
     torch.backends.cudnn.allow_tf32 = False          # the reference's forward is plain fp32
     torch.backends.cuda.matmul.allow_tf32 = False
 
@@ -230,14 +231,24 @@ def run_ours(args):
     dev_batches = [synthetic_batch(i * world + rank, BATCH, device) for i in range(steps)]
     host_batches = [synthetic_batch(i * world + rank, BATCH, "cpu", pin=True) for i in range(steps)]
 
-    def job(batch_source, n):
-        def cb(model, _):
-            for i in range(n):
-                model(batch_source(i))
-        if world > 1:
-            ShardedCalibrator(sim).compute_encodings(cb, None)
+    use_graph = os.environ.get("BENCH_CUDA_GRAPH", "1") == "1" and not args.eager
+
+    def job(batch_source, n, eager=False):
+        """One complete calibration job over n batches through the public API."""
+        if eager or not use_graph:
+            def cb(model, _):
+                for i in range(n):
+                    model(batch_source(i))
+            if world > 1:
+                ShardedCalibrator(sim).compute_encodings(cb, None)
+            else:
+                sim.compute_encodings(cb, None)
         else:
-            sim.compute_encodings(cb, None)
+            batches = (batch_source(i) for i in range(n))
+            if world > 1:
+                ShardedCalibrator(sim).compute_encodings_for_batches(batches, cuda_graph=True)
+            else:
+                sim.compute_encodings_for_batches(batches, cuda_graph=True)
         return sim.get_activation_param_encodings()
 
     def barrier():
@@ -254,19 +265,33 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = ops.launches_total()
-    ops.reserve_timing_events(2 * 100 * steps + 64)
-    ops.STATS_TIMING = []
+    launches0 = dict(ops.LAUNCHES)
     barrier()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.nvtx.range_push("timed")          # lets `ncu --nvtx --nvtx-include "timed/"` see only the timed region
     start.record()
     act, par = job(lambda i: dev_batches[i], steps)
     stop.record()
+    torch.cuda.nvtx.range_pop()
     barrier()
     ms = start.elapsed_time(stop)
-    timing, ops.STATS_TIMING = ops.STATS_TIMING, None
-    launches = ops.launches_total() - launches0
+    from aimet_b200.quantsim import quantsim as _qs
+    graph_info = dict(_qs.LAST_GRAPH_INFO)
+    eager_batches = min(steps, 2) if use_graph else steps
+    launched = {k: ops.LAUNCHES[k] - launches0[k] for k in ops.LAUNCHES}
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- the same job once more with CUDA events around every statistics call (roofline of the dominant kernel) ----
+    # In graph mode the events are external event-record nodes inside the captured step, so what is read afterwards are
+    # the device-side durations of the statistics launches of the LAST replayed step of this job.
+    ops.reserve_timing_events(2 * 100 * steps + 64)
+    ops.STATS_TIMING = []
+    per_step0 = dict(ops.LAUNCHES)
+    job(lambda i: dev_batches[i], steps)
+    barrier()
+    timing, ops.STATS_TIMING = ops.STATS_TIMING, None
+    # launches of one captured (replayed) step = launches issued while capturing = total of this job minus the eager ones
+    job_launches = {k: ops.LAUNCHES[k] - per_step0[k] for k in ops.LAUNCHES}
 
     # ---- timed: e2e (host buffers; H2D of every batch and D2H of the result inside the region) ----
     barrier()
@@ -286,7 +311,8 @@ def run_ours(args):
     tot_bytes = tot_ms = 0.0
     big_bytes = big_ms = 0.0
     n_l = 0
-    for nbytes, e0, e1, mode in timing:
+    steady = [t for t in timing if t[4]] if use_graph and any(t[4] for t in timing) else timing
+    for nbytes, e0, e1, mode, _captured in steady:
         if mode != ops.QUANTIZATION_TF_ENHANCED:
             continue
         d = e0.elapsed_time(e1)
@@ -299,21 +325,25 @@ def run_ours(args):
     peak, peak_src = peak_hbm()
     achieved = tot_bytes / tot_ms / 1e6 if tot_ms > 0 else 0.0
     ratio = ncu_traffic_ratio()
-    roofline = {"bound": "hbm", "kernel": "hist_kernel<float> (+ the early-exit minmax_kernel launched with it)",
+    roofline = {"bound": "hbm", "kernel": "hist_kernel<float>",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "traffic": round(ratio * tot_bytes / max(n_l, 1), 1) if ratio else None,
                 "algorithmic_bytes_per_launch": round(tot_bytes / max(n_l, 1), 1), "launches": n_l,
                 "avg_launch_us": round(1000.0 * tot_ms / max(n_l, 1), 2), "peak_source": peak_src,
                 "achieved_large_tensors": round(big_bytes / big_ms / 1e6, 1) if big_ms > 0 else None,
                 "note": "4 B/element x elements of every activation tensor handed to updateStats, divided by the "
-                        "CUDA-event time of those launches inside the timed region (events on the launching stream); "
-                        "achieved_large_tensors restricts to tensors >= 32 MB"}
+                        "CUDA-event time of those launches (events on the launching stream; in CUDA-graph mode: "
+                        "external event nodes inside the replayed step, read for the last step of an instrumented "
+                        "repeat of the timed job); achieved_large_tensors restricts to tensors >= 32 MB"}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
+    # kernels of ours that ran in the timed region: launches issued from Python (a captured launch counts once, for the
+    # replay that follows the capture) + the captured step's launches for every further replay of the graph
+    gpu_launches = sum(launched.values()) + graph_info["captured_launches"] * max(graph_info["replays"] - 1, 0)
     images = BATCH * steps * world
     value = images / (ms / 1000.0)
     e2e = images / (e2e_ms / 1000.0)
@@ -331,7 +361,8 @@ def run_ours(args):
                        "parallelism": f"batch-sharded x{world}"},
             "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": BATCH * 3 * 224 * 224 * 4,
                     "d2h_bytes_per_step": int(enc_bytes / steps)},
-            "gpu_launches": launches, "launches_by_kernel": dict(ops.LAUNCHES),
+            "gpu_launches": gpu_launches, "launches_by_kernel": launched,
+            "cuda_graph": dict(graph_info, enabled=bool(use_graph)),
             "roofline": roofline, "clocks": clocks}
 
     if world == 1 and not args.no_cpu_baseline:

@@ -173,13 +173,16 @@ int ab_stats_reset(ab_stats_state* states, int64_t count, void* stream);
  *                                running min / max.
  *  AB_QUANTIZATION_TF_ENHANCED : UpdatePdf (DlQ/src/math_functions.cpp:243-288): on the first non-zero batch a min/max
  *                                pass fixes the histogram range (InitializePdf :207-241), then GetHistogram (:367-384)
- *                                bins the batch and the counts are folded into the running PDF -- all inside ONE
- *                                launch, with no host synchronisation.
+ *                                bins the batch and the counts are folded into the running PDF -- all on the device,
+ *                                with no host synchronisation (two launches; one once the range is fixed).
  * `batch_log_entry`, if not NULL, is a DEVICE array of AB_PDF_SIZE + 2 uint32 that also receives this batch's raw
  * counts followed by the element count (low word, high word; 0 when the batch was skipped because the PDF was still
- * uninitialised and the batch was all zeros). Used by the multi-GPU exact merge (ab_stats_fold_batches). */
+ * uninitialised and the batch was all zeros). Used by the multi-GPU exact merge (ab_stats_fold_batches).
+ * `flags`: AB_STATS_RANGE_FIXED -- the caller KNOWS (from an earlier read-back of `initialized`) that this record's
+ * histogram range is fixed, so the min/max kernel, which would exit immediately, is not even launched. */
+#define AB_STATS_RANGE_FIXED 1
 int ab_stats_update(const void* in, int64_t count, int dtype, int quant_mode, ab_stats_state* state,
-                    uint32_t* batch_log_entry, void* stream);
+                    uint32_t* batch_log_entry, int flags, void* stream);
 
 /* updateStats on `num_segments` quantizers at once: segment s is in[s*segment_len .. (s+1)*segment_len) and updates
  * states[s]. Replaces the per-channel Python loop (aimet_torch/v1/tensor_quantizer.py:567-570). */

@@ -72,3 +72,46 @@ def test_sharded_calibration_equals_single_process(scheme):
     single = encodings_json(sim)
     assert results[0] == results[1]
     assert results[0] == single
+
+
+def graph_worker(rank, port, queue):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    try:
+        torch.backends.cudnn.deterministic = True
+        torch.backends.cudnn.benchmark = False
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        from aimet_b200.distributed import ShardedCalibrator
+        from aimet_b200.quantsim import QuantizationSimModel
+        model, batches = make_model_and_batches("tf_enhanced")
+        batches = batches + [b * 0.9 for b in batches[1:]] + [batches[2] * 1.1]     # 12 global batches, 6 per rank
+        sim = QuantizationSimModel(model, dummy_input=batches[1], quant_scheme="tf_enhanced")
+        ShardedCalibrator(sim).compute_encodings_for_batches(batches[rank::WORLD], cuda_graph=True)
+        queue.put((rank, encodings_json(sim)))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_cuda_graph_calibration_equals_single_process():
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    port = 29900 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=graph_worker, args=(r, port, queue)) for r in range(WORLD)]
+    for p in procs:
+        p.start()
+    results = dict(queue.get(timeout=300) for _ in range(WORLD))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.benchmark = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from aimet_b200.quantsim import QuantizationSimModel
+    model, batches = make_model_and_batches("tf_enhanced")
+    batches = batches + [b * 0.9 for b in batches[1:]] + [batches[2] * 1.1]
+    sim = QuantizationSimModel(model, dummy_input=batches[1], quant_scheme="tf_enhanced")
+    sim.compute_encodings(lambda m, _: [m(x) for x in batches], None)
+    assert results[0] == results[1] == encodings_json(sim)

@@ -78,3 +78,33 @@ def test_qat_step_forward_backward(oracle):
     assert len(grads_n) == len(grads_o) > 0
     for a, b in zip(grads_n, grads_o):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("name", ["resnet18_default_tfe", "resnet18_perchannel_tfe", "resnet18_default_tf"])
+def test_cuda_graph_calibration_equals_eager(name):
+    """compute_encodings_for_batches replays the steady-state step from a CUDA graph; its encodings must be identical
+    to the eager compute_encodings over the same batches."""
+    from aimet_b200.quantsim import QuantizationSimModel
+    from aimet_b200.quantsim import config as qconfig
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.benchmark = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ctor, cfg, scheme, shape = CASES[name]
+    g = torch.Generator().manual_seed(3)
+    batches = [(torch.randn(*shape, generator=g) * (1 + 0.1 * i)).cuda() for i in range(6)]
+    results = []
+    for graphed in (False, True):
+        torch.manual_seed(0)
+        model = ctor().eval().cuda()
+        sim = QuantizationSimModel(model, dummy_input=batches[0], quant_scheme=scheme,
+                                   config_file=qconfig.DEFAULT_CONFIG_PER_CHANNEL if cfg == "per_channel" else None)
+        if graphed:
+            sim.compute_encodings_for_batches(batches, cuda_graph=True)
+            from aimet_b200.quantsim import quantsim as qs
+            assert qs.LAST_GRAPH_INFO["replays"] == 4 and qs.LAST_GRAPH_INFO["captured_launches"] > 0
+        else:
+            sim.compute_encodings(lambda m, _: [m(x) for x in batches], None)
+        act, par = sim.get_activation_param_encodings()
+        results.append(json.dumps({"a": act, "p": par}, sort_keys=True))
+    assert results[0] == results[1]
