@@ -231,7 +231,10 @@ def run_ours(args):
     dev_batches = [synthetic_batch(i * world + rank, BATCH, device) for i in range(steps)]
     host_batches = [synthetic_batch(i * world + rank, BATCH, "cpu", pin=True) for i in range(steps)]
 
-    use_graph = os.environ.get("BENCH_CUDA_GRAPH", "1") == "1" and not args.eager
+    # Replaying the steady-state step from a CUDA graph is implemented and verified (tests/test_gpu_quantsim.py), but for
+    # ONE job of a few dozen steps capturing the ~700-kernel step costs more than the host time it saves, so the default
+    # measures the plain eager path; BENCH_CUDA_GRAPH=1 switches it on.
+    use_graph = os.environ.get("BENCH_CUDA_GRAPH", "0") == "1" and not args.eager
 
     def job(batch_source, n, eager=False):
         """One complete calibration job over n batches through the public API."""
