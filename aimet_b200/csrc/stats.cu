@@ -256,7 +256,8 @@ constexpr int kTileBytes     = 32768;
 constexpr int kStages        = 4;
 constexpr int kLaneCopies    = 32;
 constexpr int kVecPerThread  = kTileBytes / 16 / (kConsumerWarps * 32);
-constexpr size_t kHistSmem   = (size_t) kStages * kTileBytes + (size_t) kBins * kLaneCopies * 4 + 2 * kStages * 8 + 64;
+constexpr int kHistWords     = (kBins + 1) * kLaneCopies;   // + the dump row for dropped samples
+constexpr size_t kHistSmem   = (size_t) kStages * kTileBytes + (size_t) kHistWords * 4 + 2 * kStages * 8 + 64;
 static_assert(kVecPerThread * kConsumerWarps * 32 * 16 == kTileBytes, "tile must divide evenly over the consumers");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p)
@@ -299,15 +300,18 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                  : "memory");
 }
 
-// The per-sample work of the histogram, 14 instructions with none on the XU pipe. With M = 1.5 * 2^23:
-//   v = x / bucket - offset            (exact IEEE quotient via the hoisted reciprocal, then an exact subtraction)
-//   t = v + M  (round-to-nearest-even) for -0.5 < v < 511.5 the float t is M + rint(v), so bits(t) - bits(M) = rint(v);
-//                                      for every other v -- too small, too large, +-inf, NaN -- the UNSIGNED difference
-//                                      is >= 512, so one compare does the reference's `index >= 0 && index < 512` and
-//                                      its NaN / out-of-range drop (x86 cvttss2si gives INT_MIN for those)
-//   d = v - (t - M)                    C round() is half-away-from-zero: RNE differs only at ties it rounded down,
-//                                      where d == +0.5 exactly -> add one. The mirror case v == -0.5 (RNE gives bin 0,
-//                                      round() gives -1) is excluded explicitly.
+// The per-sample work of the histogram: 12 instructions, none on the XU pipe, no branch. With M = 1.5 * 2^23:
+//   v = x / bucket - offset            exact IEEE quotient via the hoisted reciprocal, then an exact subtraction
+//   w = RZ(v + 0.5);  t = RD(w + M)    t == M + floor(v + 0.5) == M + round_half_away(v) for every v > -0.5 (see
+//                                      round_half_away_small); the ulp of t is 1, so bits(t) - bits(M) IS the bin
+//   u = bits(t) - bits(M), unsigned    every v outside [-0.5, 511.5) -- too small, too large, +-inf, NaN -- gives
+//                                      u >= 512: one unsigned min implements the reference's
+//                                      `index >= 0 && index < 512` and its NaN / out-of-range drop (x86 cvttss2si
+//                                      yields INT_MIN for those)
+//   v == -0.5 exactly                  C round() gives -1 (dropped), floor(v + 0.5) gives 0: sent to the dump row too
+// Dropped samples increment row 512 of the privatised histogram (never read), which keeps the atomic unconditional.
+constexpr int kDumpBin = kBins;
+
 struct Binner
 {
     Divisor dv;
@@ -315,23 +319,22 @@ struct Binner
     bool fast;
     __device__ __forceinline__ void count(uint32_t* s_hist_lane, float x) const
     {
+        uint32_t u;
         if (fast)
         {
             constexpr float kMagic = 12582912.0f;
             const float v          = __fsub_rn(div_fast(x, dv), offset);
-            const float t          = __fadd_rn(v, kMagic);
-            const float d          = __fsub_rn(v, __fsub_rn(t, kMagic));
-            uint32_t idx           = __float_as_uint(t) - __float_as_uint(kMagic);
-            idx += (d == 0.5f) ? 1u : 0u;
-            if (idx < (uint32_t) kBins && v != -0.5f)
-                atomicAdd(s_hist_lane + idx * kLaneCopies, 1u);
+            const float t          = __fadd_rd(__fadd_rz(v, 0.5f), kMagic);
+            u                      = __float_as_uint(t) - __float_as_uint(kMagic);
+            u                      = (v == -0.5f) ? (uint32_t) kDumpBin : u;
+            u                      = min(u, (uint32_t) kDumpBin);
         }
         else
         {
             const int b = bin_index(x, dv.d, offset);
-            if (b >= 0)
-                atomicAdd(s_hist_lane + b * kLaneCopies, 1u);
+            u           = b >= 0 ? (uint32_t) b : (uint32_t) kDumpBin;
         }
+        atomicAdd(s_hist_lane + u * kLaneCopies, 1u);
     }
 };
 
@@ -375,7 +378,7 @@ __global__ void __launch_bounds__(kHistThreads, 1)
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_tiles  = smem;
     uint32_t* s_hist  = reinterpret_cast<uint32_t*>(smem + (size_t) kStages * kTileBytes);
-    uint64_t* s_full  = reinterpret_cast<uint64_t*>(smem + (size_t) kStages * kTileBytes + (size_t) kBins * kLaneCopies * 4);
+    uint64_t* s_full  = reinterpret_cast<uint64_t*>(smem + (size_t) kStages * kTileBytes + (size_t) kHistWords * 4);
     uint64_t* s_empty = s_full + kStages;
     __shared__ double s_x_left0, s_bucket_d;
     __shared__ uint32_t s_is_last;
@@ -384,30 +387,40 @@ __global__ void __launch_bounds__(kHistThreads, 1)
     const int lane = tid & 31;
     const int warp = tid >> 5;
 
+    // ---- prologue, ordered for latency: the first tiles are requested from HBM before anything else happens (a TMA load
+    // does not depend on the histogram range), then the state is read and the bins are zeroed while they are in flight.
+    const bool aligned      = (reinterpret_cast<uintptr_t>(in) & 15u) == 0;
+    const int64_t bytes     = aligned ? (count / kV) * 16 : 0;   // the 16-byte-granular body goes through TMA
+    const int64_t num_tiles = (bytes + kTileBytes - 1) / kTileBytes;
+    // tiles owned by this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+    const int64_t my_tiles = (num_tiles > blockIdx.x) ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    auto issue_tile = [&](int64_t k) {
+        const int s       = (int) (k % kStages);
+        const int64_t off = (blockIdx.x + k * gridDim.x) * (int64_t) kTileBytes;
+        const uint32_t nb = (uint32_t) min((int64_t) kTileBytes, bytes - off);
+        mbar_expect_tx(s_full + s, nb);
+        tma_load_1d(s_tiles + (size_t) s * kTileBytes, reinterpret_cast<const uint8_t*>(in) + off, nb, s_full + s);
+    };
+    if (warp == kConsumerWarps && lane == 0)
+    {
+        for (int s = 0; s < kStages; ++s)
+        {
+            mbar_init(s_full + s, 1);
+            mbar_init(s_empty + s, kConsumerWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int64_t k = 0; k < my_tiles && k < kStages; ++k)
+            issue_tile(k);
+    }
+
     double x_left0 = 0, bucket_d = 0;
     const Range rg = resolve_range(st, &x_left0, &bucket_d);   // every thread derives the same range
 
     if (rg.valid)
     {
-        for (int i = tid; i < kBins * kLaneCopies; i += kHistThreads)
-            s_hist[i] = 0;
-
-        const bool aligned      = (reinterpret_cast<uintptr_t>(in) & 15u) == 0;
-        const int64_t bytes     = aligned ? (count / kV) * 16 : 0;   // the 16-byte-granular body goes through TMA
-        const int64_t num_tiles = (bytes + kTileBytes - 1) / kTileBytes;
-        // tiles owned by this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
-        const int64_t my_tiles = (num_tiles > blockIdx.x) ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-
-        if (tid == 0)
-        {
-            for (int s = 0; s < kStages; ++s)
-            {
-                mbar_init(s_full + s, 1);
-                mbar_init(s_empty + s, kConsumerWarps);
-            }
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
+        for (int i = tid; i < kHistWords / 4; i += kHistThreads)
+            reinterpret_cast<uint4*>(s_hist)[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();   // barriers initialised, bins zeroed
 
         Binner binner;
         binner.dv     = make_divisor(rg.bucket);
@@ -417,18 +430,13 @@ __global__ void __launch_bounds__(kHistThreads, 1)
 
         if (warp == kConsumerWarps)
         {
-            // ---- producer warp: one lane feeds the ring ----
+            // ---- producer warp: one lane keeps the ring full ----
             if (lane == 0)
-                for (int64_t k = 0; k < my_tiles; ++k)
+                for (int64_t k = kStages; k < my_tiles; ++k)
                 {
                     const int s = (int) (k % kStages);
-                    if (k >= kStages)
-                        mbar_wait(s_empty + s, (uint32_t) (((k / kStages) - 1) & 1));   // consumers released the slot
-                    const int64_t off = (blockIdx.x + k * gridDim.x) * (int64_t) kTileBytes;
-                    const uint32_t nb = (uint32_t) min((int64_t) kTileBytes, bytes - off);
-                    mbar_expect_tx(s_full + s, nb);
-                    tma_load_1d(s_tiles + (size_t) s * kTileBytes, reinterpret_cast<const uint8_t*>(in) + off, nb,
-                                s_full + s);
+                    mbar_wait(s_empty + s, (uint32_t) (((k / kStages) - 1) & 1));   // consumers released the slot
+                    issue_tile(k);
                 }
         }
         else
@@ -467,6 +475,13 @@ __global__ void __launch_bounds__(kHistThreads, 1)
             if (sum)
                 atomicAdd(&st->hist[tid], sum);
         }
+    }
+    else if (warp == kConsumerWarps && lane == 0)
+    {
+        // nothing to count (no range yet and an all-zero batch), but the tiles requested in the prologue must land before
+        // this CTA's shared memory is released
+        for (int64_t k = 0; k < my_tiles && k < kStages; ++k)
+            mbar_wait(s_full + k, 0);
     }
 
     // ---- last CTA folds the batch into the running PDF --------------------------------------------------------

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(kSearchThreads)
             continue;
         }
 
-        for (int i = tid; i < AB_PDF_SIZE; i += kSearchThreads)
+        for (int i = tid; i < AB_PDF_SIZE; i += blockDim.x)
             s_pdf[i] = st->pdf[i];
         __syncthreads();
         const tfe::PdfView view {s_pdf, st->x_left0, st->bucket_size_d};
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kSearchThreads)
         __syncthreads();
         if (tid == 0)
         {
-            for (int w = 1; w < kSearchThreads / 32; ++w)
+            for (int w = 1; w < (int) blockDim.x / 32; ++w)
                 if (s_best_cost[w] < bc || (s_best_cost[w] == bc && s_best_idx[w] < bi))
                     bc = s_best_cost[w], bi = s_best_idx[w];
             s_best_idx[0] = bi;
@@ -210,16 +210,17 @@ extern "C" int ab_compute_encodings(const ab_stats_state* states, int64_t count,
     if (count == 0)
         return AB_OK;
     SearchArgs a {quant_mode, bw, use_symmetric, use_strict_symmetric, use_unsigned_symmetric};
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, compute_encodings_kernel, kSearchThreads, 0) !=
-            cudaSuccess ||
+    // one thread per candidate: 358 asymmetric, ~101 symmetric (tfe_math.h) -- the symmetric search (all weights) runs
+    // with a third of the threads, i.e. three times as many quantizers resident per SM
+    const int threads = (quant_mode == AB_QUANTIZATION_TF_ENHANCED && use_symmetric) ? 128 : kSearchThreads;
+    int per_sm        = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, compute_encodings_kernel, threads, 0) != cudaSuccess ||
         per_sm <= 0)
         per_sm = 1;
     int64_t grid = (int64_t) per_sm * num_sms();
     if (count < grid)
         grid = count;
-    compute_encodings_kernel<<<(unsigned) grid, kSearchThreads, 0, (cudaStream_t) stream>>>(states, count, a, enc_out,
-                                                                                           qdq4_out);
+    compute_encodings_kernel<<<(unsigned) grid, threads, 0, (cudaStream_t) stream>>>(states, count, a, enc_out, qdq4_out);
     AB_CUDA_CHECK(cudaGetLastError());
     return AB_OK;
 }

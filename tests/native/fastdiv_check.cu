@@ -87,15 +87,17 @@ __global__ void check_div(uint64_t seed, int iters, unsigned long long* bad_div,
 #pragma unroll
             for (int j = 0; j < 4; ++j)
             {
-                const float x  = xs[j] * (((g >> 7) & 1) ? 1.0f : 1.0f / 128.0f);
+                float x = xs[j] * (((g >> 7) & 1) ? 1.0f : 1.0f / 128.0f);
+                if (((g >> 9) & 3) == 0)      // construct quotients that land exactly on k +- 0.5 relative to the offset
+                    x = (offset + (float) ((int) ((g >> 11) % 516) - 2) + (((g >> 21) & 1) ? 0.5f : -0.5f)) * d;
                 const float r  = round_half_away(__fsub_rn(__fdiv_rn(x, d), offset));
                 const int slow = (r >= 0.0f && r < 512.0f) ? (int) r : -1;
                 const float v  = __fsub_rn(div_fast(x, dv), offset);
-                const float t  = __fadd_rn(v, kMagic);
-                const float dd = __fsub_rn(v, __fsub_rn(t, kMagic));
+                const float t  = __fadd_rd(__fadd_rz(v, 0.5f), kMagic);
                 uint32_t idx   = __float_as_uint(t) - __float_as_uint(kMagic);
-                idx += (dd == 0.5f) ? 1u : 0u;
-                const int fast = (idx < 512u && v != -0.5f) ? (int) idx : -1;
+                idx            = (v == -0.5f) ? 512u : idx;
+                idx            = min(idx, 512u);
+                const int fast = idx < 512u ? (int) idx : -1;
                 if (slow != fast)
                     ++nb;
             }
