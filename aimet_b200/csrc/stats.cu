@@ -94,6 +94,20 @@ __device__ __forceinline__ void fold_bin(double* pdf, uint32_t h, double cnt, in
     *pdf              = __ddiv_rn(__dadd_rn(__dmul_rn(*pdf, (double) iterations), prob), (double) (iterations + 1));
 }
 
+// Fold the batch parked in hist[write_parity ^ 1] (see ab_stats_state.pending). `lane` / `lanes`: the calling threads
+// split the 512 bins among themselves; the caller orders this before any later write of `pending` / `iterations`.
+__device__ __forceinline__ void fold_pending(ab_stats_state* st, int lane, int lanes)
+{
+    const int pp         = st->write_parity ^ 1;
+    const int iterations = st->iterations;
+    const double cnt     = st->pending_count;
+    for (int b = lane; b < kBins; b += lanes)
+    {
+        fold_bin(&st->pdf[b], st->hist[pp][b], cnt, iterations);
+        st->hist[pp][b] = 0;
+    }
+}
+
 constexpr int32_t kPosInfBits = 0x7f800000;                     // ordered image of +inf
 constexpr int32_t kNegInfBits = (int32_t) 0xff800000 ^ 0x7fffffff;   // ordered image of -inf
 
@@ -108,11 +122,15 @@ __global__ void reset_kernel(ab_stats_state* states, int64_t count)
     ab_stats_state* st = states + s;
     for (int i = threadIdx.x; i < kBins; i += blockDim.x)
     {
-        st->pdf[i]  = 0.0;
-        st->hist[i] = 0;
+        st->pdf[i]     = 0.0;
+        st->hist[0][i] = 0;
+        st->hist[1][i] = 0;
     }
     if (threadIdx.x == 0)
     {
+        st->pending_count  = 0.0;
+        st->pending        = 0;
+        st->write_parity   = 0;
         st->x_left0        = 0.0;
         st->bucket_size_d  = 0.0;
         st->run_min        = DBL_MAX;    // DlQ/src/TfEncodingAnalyzer.h:88-91
@@ -251,7 +269,7 @@ __global__ void __launch_bounds__(kMmThreads)
 // histogram pass (tf_enhanced): TMA-staged tiles, warp-specialised, per-lane privatised shared-memory bins
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kConsumerWarps = 16;
-constexpr int kHistThreads   = (kConsumerWarps + 1) * 32;   // + one producer warp that only drives the TMA engine
+constexpr int kHistThreads   = (kConsumerWarps + 2) * 32;   // + a producer warp (drives the TMA engine) + a housekeeping warp
 constexpr int kTileBytes     = 32768;
 constexpr int kStages        = 4;
 constexpr int kLaneCopies    = 32;
@@ -386,6 +404,8 @@ __global__ void __launch_bounds__(kHistThreads, 1)
     const int tid  = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
+    constexpr int kProducerWarp = kConsumerWarps;
+    constexpr int kKeeperWarp   = kConsumerWarps + 1;
 
     // ---- prologue, ordered for latency: the first tiles are requested from HBM before anything else happens (a TMA load
     // does not depend on the histogram range), then the state is read and the bins are zeroed while they are in flight.
@@ -401,7 +421,7 @@ __global__ void __launch_bounds__(kHistThreads, 1)
         mbar_expect_tx(s_full + s, nb);
         tma_load_1d(s_tiles + (size_t) s * kTileBytes, reinterpret_cast<const uint8_t*>(in) + off, nb, s_full + s);
     };
-    if (warp == kConsumerWarps && lane == 0)
+    if (warp == kProducerWarp && lane == 0)
     {
         for (int s = 0; s < kStages; ++s)
         {
@@ -414,7 +434,14 @@ __global__ void __launch_bounds__(kHistThreads, 1)
     }
 
     double x_left0 = 0, bucket_d = 0;
-    const Range rg = resolve_range(st, &x_left0, &bucket_d);   // every thread derives the same range
+    const Range rg   = resolve_range(st, &x_left0, &bucket_d);   // every thread derives the same range
+    // stable for the whole launch: only the last CTA, after every CTA has taken its ticket, changes them
+    const int parity      = st->write_parity;
+    const bool had_pending = st->pending != 0;
+    const int iterations0 = st->iterations;
+    // With a batch log (multi-GPU exact merge) the batch is folded and logged at the end of this launch; otherwise its
+    // counts stay parked in hist[parity] and the NEXT call on this record folds them while it streams its own data.
+    const bool lazy = batch_log == nullptr;
 
     if (rg.valid)
     {
@@ -428,7 +455,7 @@ __global__ void __launch_bounds__(kHistThreads, 1)
         binner.fast   = binner.dv.fast;
         uint32_t* s_hist_lane = s_hist + lane;
 
-        if (warp == kConsumerWarps)
+        if (warp == kProducerWarp)
         {
             // ---- producer warp: one lane keeps the ring full ----
             if (lane == 0)
@@ -438,6 +465,23 @@ __global__ void __launch_bounds__(kHistThreads, 1)
                     mbar_wait(s_empty + s, (uint32_t) (((k / kStages) - 1) & 1));   // consumers released the slot
                     issue_tile(k);
                 }
+        }
+        else if (warp == kKeeperWarp)
+        {
+            // ---- housekeeping warps: fold the previous batch of this record while the consumers stream. Every CTA's
+            // keeper takes a 32-bin slice (one independent load / divide / store per lane), so the whole fold is one
+            // memory round trip off the critical path; `iterations` / `pending` are updated by the last CTA. ----
+            if (had_pending)
+            {
+                const int pp     = parity ^ 1;
+                const double cnt = st->pending_count;
+                for (int b = blockIdx.x * 32 + lane; b < kBins; b += gridDim.x * 32)
+                {
+                    fold_bin(&st->pdf[b], st->hist[pp][b], cnt, iterations0);
+                    st->hist[pp][b] = 0;
+                }
+                __threadfence();   // ordered before this CTA's ticket, hence before the last CTA's bookkeeping
+            }
         }
         else
         {
@@ -473,10 +517,10 @@ __global__ void __launch_bounds__(kHistThreads, 1)
             for (int l = 0; l < kLaneCopies; ++l)
                 sum += s_hist[tid * kLaneCopies + ((l + tid) & (kLaneCopies - 1))];
             if (sum)
-                atomicAdd(&st->hist[tid], sum);
+                atomicAdd(&st->hist[parity][tid], sum);
         }
     }
-    else if (warp == kConsumerWarps && lane == 0)
+    else if (warp == kProducerWarp && lane == 0)
     {
         // nothing to count (no range yet and an all-zero batch), but the tiles requested in the prologue must land before
         // this CTA's shared memory is released
@@ -484,8 +528,9 @@ __global__ void __launch_bounds__(kHistThreads, 1)
             mbar_wait(s_full + k, 0);
     }
 
-    // ---- last CTA folds the batch into the running PDF --------------------------------------------------------
-    __threadfence();
+    // ---- election of the last CTA ------------------------------------------------------------------------------------
+    if (!lazy)
+        __threadfence();   // the last CTA will READ the flushed counts in this very launch
     __syncthreads();
     if (tid == 0)
     {
@@ -497,31 +542,58 @@ __global__ void __launch_bounds__(kHistThreads, 1)
     __syncthreads();
     if (!s_is_last)
         return;
+
+    if (lazy)
+    {
+        // Only bookkeeping here: a handful of scalar stores by one thread. The 512-bin fold is the next call's business.
+        if (tid == 0)
+        {
+            if (rg.valid)
+            {
+                if (!st->initialized)
+                {
+                    st->x_left0       = s_x_left0;
+                    st->bucket_size_d = s_bucket_d;
+                    st->bucket_size   = rg.bucket;
+                    st->pdf_offset    = rg.offset;
+                    st->initialized   = 1;
+                }
+                if (had_pending)
+                    st->iterations = iterations0 + 1;   // the keepers folded the previous batch during this launch
+                st->pending_count = (double) count;
+                st->pending       = 1;
+                st->write_parity  = parity ^ 1;
+            }
+            st->stats_updated  = 1;
+            st->batch_min_bits = kPosInfBits;
+            st->batch_max_bits = kNegInfBits;
+            st->ticket         = 0;
+        }
+        return;
+    }
+
+    // ---- logging mode: fold this batch now and write its raw counts to the log ------------------------------------------
     __threadfence();
-    const int iterations = st->iterations;
+    const int iterations = iterations0 + ((had_pending && rg.valid) ? 1 : 0);   // the keepers folded a parked batch first
     if (tid < kBins)
     {
         if (rg.valid)
         {
-            const uint32_t h = *(volatile uint32_t*) &st->hist[tid];
+            const uint32_t h = *(volatile uint32_t*) &st->hist[parity][tid];
             fold_bin(&st->pdf[tid], h, (double) count, iterations);
-            st->hist[tid] = 0;
-            if (batch_log)
-                batch_log[tid] = h;
+            st->hist[parity][tid] = 0;
+            batch_log[tid]        = h;
         }
-        else if (batch_log)
+        else
             batch_log[tid] = 0;
     }
     __syncthreads();   // every thread has read st->iterations / st->initialized before they change
     if (tid == 0)
     {
-        if (batch_log)
-        {
-            // element count (0 when the batch was skipped, as the reference skips all-zero batches before init)
-            const uint64_t c     = rg.valid ? (uint64_t) count : 0;
-            batch_log[kBins]     = (uint32_t) c;
-            batch_log[kBins + 1] = (uint32_t) (c >> 32);
-        }
+        // element count (0 when the batch was skipped, as the reference skips all-zero batches before init)
+        const uint64_t c     = rg.valid ? (uint64_t) count : 0;
+        batch_log[kBins]     = (uint32_t) c;
+        batch_log[kBins + 1] = (uint32_t) (c >> 32);
         if (rg.valid)
         {
             if (!st->initialized)
@@ -533,6 +605,7 @@ __global__ void __launch_bounds__(kHistThreads, 1)
                 st->initialized   = 1;
             }
             st->iterations = iterations + 1;
+            st->pending    = 0;
         }
         st->stats_updated  = 1;
         st->batch_min_bits = kPosInfBits;
@@ -564,6 +637,17 @@ __global__ void __launch_bounds__(kSegThreads)
         const bool need_mm = (quant_mode == AB_QUANTIZATION_TF) || !st->initialized;
 
         __syncthreads();   // previous segment's fold has finished with s_hist / s_lo / s_hi
+        if (st->pending)   // a batch parked by hist_kernel: fold it before this call's own batch
+        {
+            fold_pending(st, threadIdx.x, kSegThreads);
+            __syncthreads();
+            if (threadIdx.x == 0)
+            {
+                st->iterations = st->iterations + 1;
+                st->pending    = 0;
+            }
+            __syncthreads();
+        }
         if (need_mm)
         {
             float lo = INFINITY, hi = -INFINITY;
@@ -706,9 +790,12 @@ __global__ void __launch_bounds__(kBins)
         pdf               = __ddiv_rn(__dadd_rn(__dmul_rn(pdf, (double) iterations), prob), (double) (iterations + 1));
         ++iterations;
     }
-    st->pdf[b] = pdf;
+    st->pdf[b]     = pdf;
+    st->hist[0][b] = 0;
+    st->hist[1][b] = 0;
     if (b == 0)
     {
+        st->pending    = 0;
         st->iterations = iterations;
         if (seen)
             st->stats_updated = 1;
@@ -775,7 +862,7 @@ int launch_update(const T* in, int64_t count, int quant_mode, ab_stats_state* st
         const int64_t tiles = ((count / kV) * 16 + kTileBytes - 1) / kTileBytes;
         int grid            = num_sms();
         if (tiles < grid)
-            grid = tiles < 1 ? 1 : (int) tiles;
+            grid = tiles < 16 ? 16 : (int) tiles;   // >= 16 CTAs: their keeper warps fold 512 parked bins in one pass
         k<<<grid, kHistThreads, kHistSmem, stream>>>(in, count, st, batch_log);
         AB_CUDA_CHECK(cudaGetLastError());
     }

@@ -87,8 +87,21 @@ __global__ void __launch_bounds__(kSearchThreads)
             continue;
         }
 
-        for (int i = tid; i < AB_PDF_SIZE; i += blockDim.x)
-            s_pdf[i] = st->pdf[i];
+        {
+            // a batch still parked in hist[write_parity ^ 1] (ab_stats_state.pending) is folded on the fly:
+            // pdf = (pdf * k + hist / cnt) / (k + 1), the reference's running mean (DlQ/src/math_functions.cpp:279-287)
+            const bool pending = st->pending != 0;
+            const int pp       = st->write_parity ^ 1;
+            const int k        = st->iterations;
+            const double cnt   = st->pending_count;
+            for (int i = tid; i < AB_PDF_SIZE; i += blockDim.x)
+            {
+                double p = st->pdf[i];
+                if (pending)
+                    p = __ddiv_rn(__dadd_rn(__dmul_rn(p, (double) k), (double) st->hist[pp][i] / cnt), (double) (k + 1));
+                s_pdf[i] = p;
+            }
+        }
         __syncthreads();
         const tfe::PdfView view {s_pdf, st->x_left0, st->bucket_size_d};
 

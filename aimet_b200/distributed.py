@@ -26,7 +26,7 @@ import torch.distributed as dist
 
 from . import ops
 from .quantsim.defs import QuantScheme
-from .state import StateArena
+from .state import StateArena, field_index
 
 LOG_WORDS = ops.LOG_WORDS
 
@@ -193,8 +193,7 @@ class ShardedCalibrator:
     def _fix_ranges(self):
         q_count = len(self.quantizers)
         rec = self.first_block.bytes_view().view(torch.float64).view(q_count * self.max_calls, -1)
-        # run_min / run_max are the 3rd and 4th double after pdf[512] and hist[512] (see include/aimet_b200.h)
-        base = (512 * 8 + 512 * 4) // 8 + 2
+        base = field_index("run_min", 8)          # run_min, run_max are adjacent doubles (include/aimet_b200.h)
         table = rec[:, base:base + 2].to(torch.float32).view(q_count, self.max_calls, 2)
         # an un-updated record holds (+DBL_MAX, -DBL_MAX) -> (+inf, -inf) in float32: "call did not happen"
         gathered = _all_gather(table, self.group) if self.world > 1 else table.unsqueeze(0)
@@ -217,7 +216,7 @@ class ShardedCalibrator:
         q_count = len(self.quantizers)
         if not self.tfe:
             rec = self.block.bytes_view().view(torch.float64).view(q_count, -1)
-            base = (512 * 8 + 512 * 4) // 8 + 2
+            base = field_index("run_min", 8)
             mins, maxs = rec[:, base].clone(), rec[:, base + 1].clone()
             updated = torch.tensor([float(q._cppOp[0]._is_encoding_valid) for q in self.quantizers],   # pylint: disable=protected-access
                                    device=self.device, dtype=torch.float64)
@@ -228,7 +227,7 @@ class ShardedCalibrator:
             rec[:, base] = mins
             rec[:, base + 1] = maxs
             flags = self.block.bytes_view().view(torch.int32).view(q_count, -1)
-            flags[:, 1549] = updated.to(torch.int32)       # ab_stats_state.stats_updated (byte 6196)
+            flags[:, field_index("stats_updated", 4)] = updated.to(torch.int32)
             for q, u in zip(self.quantizers, updated.tolist()):
                 q._cppOp[0]._is_encoding_valid = bool(u)   # pylint: disable=protected-access
             return

@@ -16,11 +16,34 @@ PDF_SIZE = 512
 
 # mirrors `ab_stats_state` in include/aimet_b200.h
 STATE_DTYPE = np.dtype([
-    ("pdf", "<f8", PDF_SIZE), ("hist", "<u4", PDF_SIZE), ("x_left0", "<f8"), ("bucket_size_d", "<f8"),
-    ("run_min", "<f8"), ("run_max", "<f8"), ("bucket_size", "<f4"), ("pdf_offset", "<f4"),
+    ("pdf", "<f8", PDF_SIZE), ("hist", "<u4", (2, PDF_SIZE)), ("x_left0", "<f8"), ("bucket_size_d", "<f8"),
+    ("run_min", "<f8"), ("run_max", "<f8"), ("pending_count", "<f8"), ("bucket_size", "<f4"), ("pdf_offset", "<f4"),
     ("batch_min_bits", "<i4"), ("batch_max_bits", "<i4"), ("initialized", "<i4"), ("stats_updated", "<i4"),
-    ("iterations", "<i4"), ("ticket", "<u4"), ("pad", "<u4", 4)])
+    ("iterations", "<i4"), ("ticket", "<u4"), ("pending", "<i4"), ("write_parity", "<i4"), ("pad", "<u4", 4)])
 assert STATE_DTYPE.itemsize == ops.STATE_BYTES, (STATE_DTYPE.itemsize, ops.STATE_BYTES)
+
+
+def field_index(name: str, word_bytes: int) -> int:
+    """Index of a scalar field inside one record viewed as an array of `word_bytes`-wide words."""
+    offset = STATE_DTYPE.fields[name][1]
+    assert offset % word_bytes == 0
+    return offset // word_bytes
+
+
+def fold_pending(records: np.ndarray) -> np.ndarray:
+    """Host twin of the device-side lazy fold (ab_stats_state.pending): returns records in which a parked batch has been
+    folded into the PDF with the reference's formula pdf = (pdf*k + hist/cnt)/(k+1) (math_functions.cpp:279-287)."""
+    out = records.copy()
+    for r in out:
+        if r["pending"]:
+            pp = int(r["write_parity"]) ^ 1
+            k = int(r["iterations"])
+            prob = r["hist"][pp].astype(np.float64) / np.float64(r["pending_count"])
+            r["pdf"] = (r["pdf"] * np.float64(k) + prob) / np.float64(k + 1)
+            r["hist"][pp] = 0
+            r["iterations"] = k + 1
+            r["pending"] = 0
+    return out
 
 
 class StateBlock:
@@ -42,9 +65,13 @@ class StateBlock:
     def bytes_view(self) -> torch.Tensor:
         return self.arena[self.first * ops.STATE_BYTES:(self.first + self.count) * ops.STATE_BYTES]
 
-    def read(self) -> np.ndarray:
-        """Synchronising copy of the records to the host, as a structured numpy array."""
+    def read_raw(self) -> np.ndarray:
+        """Synchronising copy of the records to the host, as a structured numpy array, exactly as they sit in HBM."""
         return self.bytes_view().cpu().numpy().view(STATE_DTYPE)
+
+    def read(self) -> np.ndarray:
+        """Like read_raw, with any batch still parked in `hist` folded into the PDF (what the reference's state holds)."""
+        return fold_pending(self.read_raw())
 
     def write(self, records: np.ndarray):
         self.bytes_view().copy_(torch.from_numpy(records.view(np.uint8).reshape(-1)))

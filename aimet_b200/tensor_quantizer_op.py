@@ -16,7 +16,7 @@ import torch
 
 from . import libpymo
 from . import ops
-from .state import StateArena
+from .state import StateArena, field_index
 
 
 def _to_device_tensor(t: torch.Tensor):
@@ -71,7 +71,7 @@ class AimetTensorQuantizer:
         if self._code == ops.QUANTIZATION_TF_ENHANCED and not self._range_fixed:
             self._poll_range_fixed()
 
-    _INITIALIZED_WORD = 6192 // 4      # ab_stats_state.initialized as an int32 index into the record
+    _INITIALIZED_WORD = field_index("initialized", 4)      # ab_stats_state.initialized as an int32 index
 
     def _poll_range_fixed(self):
         """Learn, without ever blocking, that the record's range got fixed: a 4-byte asynchronous read-back of the

@@ -236,9 +236,10 @@ def run_ours(args):
     # measures the plain eager path; BENCH_CUDA_GRAPH=1 switches it on.
     use_graph = os.environ.get("BENCH_CUDA_GRAPH", "0") == "1" and not args.eager
 
-    def job(batch_source, n, eager=False):
+    def job(batch_source, n, graph=None):
         """One complete calibration job over n batches through the public API."""
-        if eager or not use_graph:
+        graph = use_graph if graph is None else graph
+        if not graph:
             def cb(model, _):
                 for i in range(n):
                     model(batch_source(i))
@@ -285,12 +286,14 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- the same job once more with CUDA events around every statistics call (roofline of the dominant kernel) ----
-    # In graph mode the events are external event-record nodes inside the captured step, so what is read afterwards are
-    # the device-side durations of the statistics launches of the LAST replayed step of this job.
+    # The eager step is host-bound, so an event pair around a launch would also time the GPU waiting for the host to
+    # enqueue it. This repeat therefore replays the steady-state step from a CUDA graph in which the event pairs are
+    # external event-record nodes: what is read afterwards are DEVICE-side durations of the statistics launches of the
+    # last replayed step -- same kernels, same tensors, same order as the timed job.
     ops.reserve_timing_events(2 * 100 * steps + 64)
     ops.STATS_TIMING = []
     per_step0 = dict(ops.LAUNCHES)
-    job(lambda i: dev_batches[i], steps)
+    job(lambda i: dev_batches[i], steps, graph=steps > 2)
     barrier()
     timing, ops.STATS_TIMING = ops.STATS_TIMING, None
     # launches of one captured (replayed) step = launches issued while capturing = total of this job minus the eager ones
@@ -314,7 +317,7 @@ def run_ours(args):
     tot_bytes = tot_ms = 0.0
     big_bytes = big_ms = 0.0
     n_l = 0
-    steady = [t for t in timing if t[4]] if use_graph and any(t[4] for t in timing) else timing
+    steady = [t for t in timing if t[4]] if any(t[4] for t in timing) else timing
     for nbytes, e0, e1, mode, _captured in steady:
         if mode != ops.QUANTIZATION_TF_ENHANCED:
             continue

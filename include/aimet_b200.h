@@ -75,21 +75,27 @@ typedef struct
  */
 typedef struct
 {
-    double pdf[AB_PDF_SIZE];    /* running mean of per-batch PDFs (math_functions.cpp:279-287) */
-    uint32_t hist[AB_PDF_SIZE]; /* scratch: the current batch's counts; zero between calls */
-    double x_left0;             /* xLeft[0] */
-    double bucket_size_d;       /* (max - min) / 512 in double (math_functions.cpp:222) */
-    double run_min;             /* TF scheme: running min over batches (TfEncodingAnalyzer.cpp:69) */
-    double run_max;             /* TF scheme: running max over batches (TfEncodingAnalyzer.cpp:70) */
-    float bucket_size;          /* float(xLeft[1] - xLeft[0]) (math_functions.cpp:265) */
-    float pdf_offset;           /* float(xLeft[0]) / bucket_size (math_functions.cpp:266-268) */
-    int32_t batch_min_bits;     /* scratch: order-preserving int image of the current batch's min */
-    int32_t batch_max_bits;     /* scratch: ... max */
-    int32_t initialized;        /* PDF range fixed (xLeft.size() != 0) */
-    int32_t stats_updated;      /* updateStats was called at least once (_statsUpdated) */
-    int32_t iterations;         /* PDF.iterations */
-    uint32_t ticket;            /* scratch: last-block election counter; zero between calls */
-    uint32_t pad_[4];           /* keeps sizeof a multiple of 16 */
+    double pdf[AB_PDF_SIZE];       /* running mean of per-batch PDFs (math_functions.cpp:279-287) */
+    uint32_t hist[2][AB_PDF_SIZE]; /* raw counts of the latest batch(es); see `pending` */
+    double x_left0;                /* xLeft[0] */
+    double bucket_size_d;          /* (max - min) / 512 in double (math_functions.cpp:222) */
+    double run_min;                /* TF scheme: running min over batches (TfEncodingAnalyzer.cpp:69) */
+    double run_max;                /* TF scheme: running max over batches (TfEncodingAnalyzer.cpp:70) */
+    double pending_count;          /* element count of the batch whose counts still await their fold */
+    float bucket_size;             /* float(xLeft[1] - xLeft[0]) (math_functions.cpp:265) */
+    float pdf_offset;              /* float(xLeft[0]) / bucket_size (math_functions.cpp:266-268) */
+    int32_t batch_min_bits;        /* scratch: order-preserving int image of the current batch's min */
+    int32_t batch_max_bits;        /* scratch: ... max */
+    int32_t initialized;           /* PDF range fixed (xLeft.size() != 0) */
+    int32_t stats_updated;         /* updateStats was called at least once (_statsUpdated) */
+    int32_t iterations;            /* PDF.iterations (batches already folded into pdf) */
+    uint32_t ticket;               /* scratch: last-block election counter; zero between calls */
+    int32_t pending;               /* 1: hist[write_parity ^ 1] holds a batch that is NOT yet folded into pdf. The
+                                      histogram kernel leaves the fold (pdf = (pdf*k + hist/cnt)/(k+1)) of batch k to the
+                                      next call on this record, where it overlaps the streaming of batch k+1 instead of
+                                      sitting on the kernel's tail; every reader folds it on the fly. */
+    int32_t write_parity;          /* which hist[] buffer the next batch's counts go to */
+    uint32_t pad_[4];              /* keeps sizeof a multiple of 16 */
 } ab_stats_state;
 
 const char* ab_last_error(void);

@@ -38,7 +38,7 @@ def test_header_symbols_are_exported(lib):
 
 def test_state_layout_matches_header(lib):
     from aimet_b200.state import STATE_DTYPE
-    assert lib.ab_stats_state_bytes() == STATE_DTYPE.itemsize == 6224
+    assert lib.ab_stats_state_bytes() == STATE_DTYPE.itemsize == 8288
     assert STATE_DTYPE.itemsize % 16 == 0
 
 
