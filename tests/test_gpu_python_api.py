@@ -1,0 +1,124 @@
+"""The drop-in classes (aimet_b200.AimetTensorQuantizer, aimet_b200.libpymo.*) used the way the reference's tests use
+the originals (TrainingExtensions/torch/test/python/test_tensor_quantizer.py, DlQuantization/test/python/
+test_tensor_quantizer.py), checked against the oracle."""
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_aimet_tensor_quantizer_methods(oracle):
+    from aimet_b200 import AimetTensorQuantizer, libpymo
+    from oracle.bindings import OracleTfe
+    q = AimetTensorQuantizer(libpymo.QuantizationMode.QUANTIZATION_TF_ENHANCED)
+    enc, valid = q.getEncoding(8, False, False, False)
+    assert valid is False                                                   # no stats yet (ATQ:180-192)
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal((4, 16, 8, 8)) * 2).astype(np.float32)
+    q.updateStats(torch.from_numpy(x).cuda(), True)
+    o = OracleTfe(oracle)
+    o.update(x.reshape(-1))
+    enc, valid = q.getEncoding(8, False, False, False)
+    assert valid and (enc.min, enc.max, enc.delta, enc.offset, enc.bw) == o.compute(8)
+    hist = q.getStatsHistogram()
+    assert len(hist) == 512                                                 # test_tensor_quantizer.py:60-92
+    assert np.array_equal(np.array(hist)[:, 1], o.histogram()[1])
+    y = q.quantizeDequantize(torch.from_numpy(x).cuda(), enc, libpymo.RoundingMode.ROUND_NEAREST, True)
+    assert y.shape == x.shape
+    assert np.array_equal(y.cpu().numpy().reshape(-1), oracle.qdq(x.reshape(-1), enc.min, enc.max, 8))
+    g = q.quantize(torch.from_numpy(x).cuda(), enc, libpymo.RoundingMode.ROUND_NEAREST, True, True)
+    assert np.array_equal(g.cpu().numpy().reshape(-1), oracle.quantize(x.reshape(-1), enc.min, enc.max, 8, True))
+    # a CPU tensor is staged to the GPU and comes back on the CPU (the reference's use_cuda=False call sites)
+    y_cpu = q.quantizeDequantize(torch.from_numpy(x), enc, libpymo.RoundingMode.ROUND_NEAREST, False)
+    assert y_cpu.device.type == "cpu" and torch.equal(y_cpu, y.cpu())
+    delta, offset = q.makeDeltaOffsetTensor(torch.device("cuda"), [enc, enc])
+    assert delta.tolist() == [np.float32(enc.delta)] * 2 and offset.tolist() == [enc.offset] * 2
+    q.resetEncodingStats()
+    assert q.getEncoding(8, False, False, False)[1] is False
+    q.setPercentileValue(99.0)                                               # no-op outside the percentile scheme
+    # channels_last input keeps its memory format (ATQ:140 suggest_memory_format)
+    xc = torch.from_numpy(x).cuda().contiguous(memory_format=torch.channels_last)
+    yc = q.quantizeDequantize(xc, enc, libpymo.RoundingMode.ROUND_NEAREST, True)
+    assert yc.is_contiguous(memory_format=torch.channels_last) and torch.equal(yc, y)
+    with pytest.raises(ValueError):
+        q.quantizeDequantize(xc, enc, 7, True)                               # "Unknown rounding mode."
+
+
+def test_libpymo_tensor_quantizer(oracle):
+    from aimet_b200 import libpymo
+    from oracle.bindings import OracleTf
+    tq = libpymo.TensorQuantizer(libpymo.QuantizationMode.QUANTIZATION_TF, libpymo.RoundingMode.ROUND_NEAREST)
+    assert tq.isEncodingValid is False
+    rng = np.random.default_rng(1)
+    x = (rng.standard_normal((2, 3, 5, 7)) * 3).astype(np.float32)          # nd-array shapes (test_tensor_quantizer.py)
+    tq.updateStats(x, False)
+    enc = tq.computeEncoding(8, False)
+    assert tq.isEncodingValid is True
+    o = OracleTf(oracle)
+    o.update(x.reshape(-1))
+    assert (enc.min, enc.max, enc.delta, enc.offset, enc.bw) == o.compute(8)
+    out = np.zeros_like(x)
+    tq.quantizeDequantize(x, out, enc.min, enc.max, 8, False)
+    assert np.array_equal(out.reshape(-1), oracle.qdq(x.reshape(-1), enc.min, enc.max, 8))
+    tq.setStrictSymmetric(True)                                              # setters reset the statistics
+    assert tq.isEncodingValid is False and tq.getStrictSymmetric() is True
+    tq.updateStats(x, False)
+    enc = tq.computeEncoding(8, True)
+    assert (enc.min, enc.max, enc.delta, enc.offset) == o.compute(8, True, True, False)[:4]
+    with pytest.raises(AssertionError):
+        tq.getStatsHistogram()                                               # TF analyzer keeps no histogram
+    # partial encodings (DlQ/test/TestTensorQuantizer.cpp:173-247)
+    e = libpymo.TfEncoding()
+    e.min, e.max, e.bw = -1.0, 2.0, 8
+    tq.computePartialEncoding(8, e, False, False, False)
+    exp = oracle.partial_encoding(8, (-1.0, 2.0, 0.0, 0.0, 8), False, False, False)[1]
+    assert (e.min, e.max, e.delta, e.offset) == exp[:4]
+    bad = libpymo.TfEncoding()
+    bad.min, bad.max, bad.delta, bad.offset, bad.bw = -1.0, 1.0, 0.1, -10.0, 8
+    with pytest.raises(RuntimeError):
+        tq.computePartialEncoding(8, bad, False, False, False)
+
+
+def test_encoding_analyzer_and_sim_for_python(oracle):
+    from aimet_b200 import libpymo
+    from oracle.bindings import OracleTfe
+    a = libpymo.EncodingAnalyzerForPython(libpymo.QuantizationMode.QUANTIZATION_TF_ENHANCED)
+    assert a.computeEncoding(8, False, False, False)[1] is False
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal(10000).astype(np.float32)
+    a.updateStats(x, False)
+    enc, valid = a.computeEncoding(8, False, False, False)
+    o = OracleTfe(oracle)
+    o.update(x)
+    assert valid and (enc.min, enc.max, enc.delta, enc.offset) == o.compute(8)[:4]
+    sim = libpymo.TensorQuantizationSimForPython()
+    y = sim.quantizeDequantize(x.reshape(100, 100), enc, libpymo.RoundingMode.ROUND_NEAREST, 8, False)
+    assert y.shape == (100, 100) and np.array_equal(y.reshape(-1), oracle.qdq(x, enc.min, enc.max, 8))
+    y2 = sim.quantizeDequantize(x, enc, libpymo.RoundingMode.ROUND_NEAREST, False)
+    assert np.array_equal(y2, y.reshape(-1))
+
+
+def test_quantizer_pickle_round_trip():
+    """Quantizers pickle without their native objects and re-create them (tensor_quantizer.py:128-220)."""
+    from aimet_b200 import libpymo
+    from aimet_b200.quantsim import QuantScheme, StaticGridPerChannelQuantizer, StaticGridPerTensorQuantizer
+    q = StaticGridPerTensorQuantizer(8, libpymo.RoundingMode.ROUND_NEAREST, QuantScheme.post_training_tf_enhanced, False,
+                                     True)
+    x = torch.randn(1000, device="cuda")
+    q.update_encoding_stats(x)
+    q.compute_encoding()
+    q2 = pickle.loads(pickle.dumps(q))
+    assert (q2.encoding.min, q2.encoding.max) == (q.encoding.min, q.encoding.max) and q2.enabled
+    assert torch.equal(q2.quantize_dequantize(x, libpymo.RoundingMode.ROUND_NEAREST),
+                       q.quantize_dequantize(x, libpymo.RoundingMode.ROUND_NEAREST))
+    pc = StaticGridPerChannelQuantizer(8, libpymo.RoundingMode.ROUND_NEAREST, QuantScheme.post_training_tf, True, 4, True)
+    w = torch.randn(4, 3, 3, 3, device="cuda")
+    pc.update_encoding_stats(w)
+    pc.compute_encoding()
+    pc2 = pickle.loads(pickle.dumps(pc))
+    assert len(pc2.encoding) == 4 and len(pc2._cppOp) == 4
+    assert torch.equal(pc2.quantize_dequantize(w, libpymo.RoundingMode.ROUND_NEAREST),
+                       pc.quantize_dequantize(w, libpymo.RoundingMode.ROUND_NEAREST))
