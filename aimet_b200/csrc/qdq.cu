@@ -81,8 +81,9 @@ __device__ __forceinline__ void per_tensor_body(const T* __restrict__ in, T* __r
                 Elem<T>::unpack(raw[u], f);
 #pragma unroll
                 for (int k = 0; k < kV; ++k)
-                    f[k] = kFast ? qdq_fast(f[k], e, dv)
-                                 : apply<kOp, kStochastic>(f[k], e, shift, seed, (uint64_t) (v * kV + k));
+                    f[k] = !kFast               ? apply<kOp, kStochastic>(f[k], e, shift, seed, (uint64_t) (v * kV + k))
+                           : kOp == Op::kQdq    ? qdq_fast(f[k], e, dv)
+                                                : __fsub_rn(quantize_fast(f[k], e, dv), shift);
                 stg_stream(reinterpret_cast<uint4*>(out) + v, Elem<T>::pack(f));
             }
         }
@@ -107,8 +108,8 @@ __global__ void __launch_bounds__(kThreads) per_tensor_kernel(const T* __restric
         e              = Enc4 {p.x, p.y, p.z, p.w};
     }
     const Divisor dv = make_divisor(e.delta);
-    // Nearest-rounding QDQ with an ordinary grid takes the XU-free path; the choice is uniform over the launch.
-    if (kOp == Op::kQdq && !kStochastic && qdq_fast_ok(e, dv))
+    // Nearest rounding with an ordinary grid takes the XU-free path; the choice is uniform over the launch.
+    if (!kStochastic && qdq_fast_ok(e, dv))
         per_tensor_body<T, kOp, kStochastic, true>(in, out, count, e, dv, args.shift, args.seed);
     else
         per_tensor_body<T, kOp, kStochastic, false>(in, out, count, e, dv, args.shift, args.seed);
@@ -178,6 +179,17 @@ __global__ void __launch_bounds__(kThreads) per_channel_fast_kernel(const T* __r
         const uint32_t g0   = div_l(e0);            // un-wrapped channel counter of the tile's first element
         const uint32_t span = div_l(e1 - 1) - g0 + 1;
         const uint32_t c0   = g0 % C;
+        // the tile's data is requested first: the loads do not depend on the channel parameters, so their latency
+        // overlaps the parameter staging below instead of following it
+        const uint32_t v0 = tile * kVecPerTile + threadIdx.x;
+        uint4 raw[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+        {
+            const uint32_t v = v0 + u * kThreads;
+            if (v < num_vec)
+                raw[u] = ldg_stream(reinterpret_cast<const uint4*>(in) + v);
+        }
         __syncthreads();   // previous tile's readers are done with the staged channels
         bool ok = span <= kSmemChannels;
         if (ok)
@@ -191,15 +203,6 @@ __global__ void __launch_bounds__(kThreads) per_channel_fast_kernel(const T* __r
             }
         const bool fast = __syncthreads_and(ok);   // every channel of the tile is staged and takes the fast arithmetic
 
-        const uint32_t v0 = tile * kVecPerTile + threadIdx.x;
-        uint4 raw[kUnroll];
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u)
-        {
-            const uint32_t v = v0 + u * kThreads;
-            if (v < num_vec)
-                raw[u] = ldg_stream(reinterpret_cast<const uint4*>(in) + v);
-        }
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u)
         {

@@ -341,11 +341,10 @@ struct Binner
         if (fast)
         {
             constexpr float kMagic = 12582912.0f;
-            const float v          = __fsub_rn(div_fast(x, dv), offset);
+            float v                = __fsub_rn(div_fast(x, dv), offset);
+            v                      = (v == -0.5f) ? -1.0f : v;   // round(-0.5) = -1: dropped, like every v in [-1.5, -0.5)
             const float t          = __fadd_rd(__fadd_rz(v, 0.5f), kMagic);
-            u                      = __float_as_uint(t) - __float_as_uint(kMagic);
-            u                      = (v == -0.5f) ? (uint32_t) kDumpBin : u;
-            u                      = min(u, (uint32_t) kDumpBin);
+            u                      = min(__float_as_uint(t) - __float_as_uint(kMagic), (uint32_t) kDumpBin);
         }
         else
         {

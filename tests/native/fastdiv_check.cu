@@ -78,6 +78,10 @@ __global__ void check_div(uint64_t seed, int iters, unsigned long long* bad_div,
                 const float fast = qdq_fast(xs[j], e, dv);
                 if (__float_as_uint(slow) != __float_as_uint(fast) && !(slow == 0.0f && fast == 0.0f))
                     ++nq;
+                // quantize-only: bit-exact INCLUDING the sign of zero, also for +-0 inputs
+                const float xq = ((g >> (13 + j)) & 15) == 0 ? copysignf(0.0f, xs[j]) : xs[j];
+                if (__float_as_uint(quantize_value<false, true>(xq, e, 0, 0)) != __float_as_uint(quantize_fast(xq, e, dv)))
+                    ++nq;
             }
         }
         // histogram bin: fast formulation vs round(x / bucket - offset) with the x86 drop rules
@@ -92,11 +96,10 @@ __global__ void check_div(uint64_t seed, int iters, unsigned long long* bad_div,
                     x = (offset + (float) ((int) ((g >> 11) % 516) - 2) + (((g >> 21) & 1) ? 0.5f : -0.5f)) * d;
                 const float r  = round_half_away(__fsub_rn(__fdiv_rn(x, d), offset));
                 const int slow = (r >= 0.0f && r < 512.0f) ? (int) r : -1;
-                const float v  = __fsub_rn(div_fast(x, dv), offset);
+                float v        = __fsub_rn(div_fast(x, dv), offset);
+                v              = (v == -0.5f) ? -1.0f : v;
                 const float t  = __fadd_rd(__fadd_rz(v, 0.5f), kMagic);
-                uint32_t idx   = __float_as_uint(t) - __float_as_uint(kMagic);
-                idx            = (v == -0.5f) ? 512u : idx;
-                idx            = min(idx, 512u);
+                const uint32_t idx = min(__float_as_uint(t) - __float_as_uint(kMagic), 512u);
                 const int fast = idx < 512u ? (int) idx : -1;
                 if (slow != fast)
                     ++nb;
