@@ -23,8 +23,14 @@
 namespace ab
 {
 
-constexpr int kThreads = 256;
-constexpr int kUnroll  = 4;   // 128-bit vectors per thread per tile
+#ifndef AB_QDQ_THREADS
+#define AB_QDQ_THREADS 256
+#endif
+#ifndef AB_QDQ_UNROLL
+#define AB_QDQ_UNROLL 4
+#endif
+constexpr int kThreads = AB_QDQ_THREADS;
+constexpr int kUnroll  = AB_QDQ_UNROLL;   // 128-bit vectors per thread per tile
 
 enum class Op
 {
@@ -151,47 +157,55 @@ __device__ __forceinline__ Enc4 load_channel(const float* params, int64_t num_ch
                  __ldg(params + 3 * num_channel + c)};
 }
 
-// Fast kernel: element count < 2^31 so that all index arithmetic is 32-bit, nearest rounding.
+// Fast kernel (nearest rounding, channel length < 2^31 - 2^16). Any element count: only the tile base is 64-bit, and its
+// one 64-bit division per tile is done by a single thread while the tile's data is already in flight.
 //   * the tile's channels are staged once, with their refined reciprocal, in shared memory;
-//   * one multiply-high replaces the integer division per 128-bit vector;
+//   * inside the tile all index arithmetic is 32-bit and one multiply-high replaces the division per 128-bit vector;
 //   * a vector that lies inside one channel (the common case) does a single 16-byte shared load and runs the straight-line
 //     fast QDQ; only vectors that straddle a channel boundary step element by element.
 template <typename T>
 __global__ void __launch_bounds__(kThreads) per_channel_fast_kernel(const T* __restrict__ in, T* __restrict__ out,
-                                                                    uint32_t count, ChannelArgs args)
+                                                                    int64_t count, ChannelArgs args)
 {
     constexpr int kV               = Elem<T>::kPerVec;
     constexpr uint32_t kVecPerTile = kThreads * kUnroll;
     constexpr uint32_t kTileLen    = kVecPerTile * kV;
     __shared__ float4 s_enc[kSmemChannels];
     __shared__ float s_rcp[kSmemChannels];
+    __shared__ uint32_t s_rem0, s_c0;
 
-    const uint32_t num_vec   = count / kV;
-    const uint32_t num_tiles = (count + kTileLen - 1) / kTileLen;
-    const uint32_t C         = (uint32_t) args.num_channel;
-    const uint32_t L         = (uint32_t) args.per_channel;
-    auto div_l               = [&](uint32_t n) { return L == 1 ? n : (__umulhi(n, args.div_mul) >> args.div_shift); };
+    const int64_t num_vec   = count / kV;
+    const int64_t num_tiles = (count + kTileLen - 1) / kTileLen;
+    const uint32_t C        = (uint32_t) args.num_channel;
+    const uint32_t L        = (uint32_t) args.per_channel;
+    auto div_l              = [&](uint32_t n) { return L == 1 ? n : (__umulhi(n, args.div_mul) >> args.div_shift); };
 
-    for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
     {
-        const uint32_t e0   = tile * kTileLen;
-        const uint32_t e1   = min(e0 + kTileLen, count);
-        const uint32_t g0   = div_l(e0);            // un-wrapped channel counter of the tile's first element
-        const uint32_t span = div_l(e1 - 1) - g0 + 1;
-        const uint32_t c0   = g0 % C;
+        const int64_t e0       = tile * kTileLen;
+        const uint32_t tile_n  = (uint32_t) min((int64_t) kTileLen, count - e0);
         // the tile's data is requested first: the loads do not depend on the channel parameters, so their latency
         // overlaps the parameter staging below instead of following it
-        const uint32_t v0 = tile * kVecPerTile + threadIdx.x;
+        const int64_t v0 = tile * kVecPerTile + threadIdx.x;
         uint4 raw[kUnroll];
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u)
         {
-            const uint32_t v = v0 + u * kThreads;
+            const int64_t v = v0 + (int64_t) u * kThreads;
             if (v < num_vec)
                 raw[u] = ldg_stream(reinterpret_cast<const uint4*>(in) + v);
         }
-        __syncthreads();   // previous tile's readers are done with the staged channels
-        bool ok = span <= kSmemChannels;
+        __syncthreads();   // previous tile's readers are done with the staged channels and s_rem0 / s_c0
+        if (threadIdx.x == 0)
+        {
+            const int64_t g0 = e0 / (int64_t) L;      // un-wrapped channel counter of the tile's first element
+            s_rem0           = (uint32_t) (e0 - g0 * (int64_t) L);
+            s_c0             = (uint32_t) (g0 % (int64_t) C);
+        }
+        __syncthreads();
+        const uint32_t rem0 = s_rem0, c0 = s_c0;
+        const uint32_t span = div_l(rem0 + tile_n - 1) + 1;   // channels the tile touches (rem0 + tile_n < 2^31)
+        bool ok             = span <= kSmemChannels;
         if (ok)
             for (uint32_t j = threadIdx.x; j < span; j += kThreads)
             {
@@ -206,15 +220,14 @@ __global__ void __launch_bounds__(kThreads) per_channel_fast_kernel(const T* __r
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u)
         {
-            const uint32_t v = v0 + u * kThreads;
+            const int64_t v = v0 + (int64_t) u * kThreads;
             if (v >= num_vec)
                 continue;
             float f[kV];
             Elem<T>::unpack(raw[u], f);
-            const uint32_t i0 = v * kV;
-            const uint32_t g  = div_l(i0);
-            uint32_t rem      = i0 - g * L;
-            uint32_t j        = g - g0;
+            const uint32_t off = (threadIdx.x + u * kThreads) * kV + rem0;   // position counted from the first channel's start
+            uint32_t j         = div_l(off);
+            uint32_t rem       = off - j * L;
             if (fast)
             {
                 float4 p   = s_enc[j];
@@ -245,7 +258,7 @@ __global__ void __launch_bounds__(kThreads) per_channel_fast_kernel(const T* __r
             }
             else
             {
-                uint32_t c = (c0 + j) % C;
+                uint32_t c = (uint32_t) (((uint64_t) c0 + j) % C);
 #pragma unroll
                 for (int k = 0; k < kV; ++k)
                 {
@@ -261,12 +274,12 @@ __global__ void __launch_bounds__(kThreads) per_channel_fast_kernel(const T* __r
             stg_stream(reinterpret_cast<uint4*>(out) + v, Elem<T>::pack(f));
         }
         // scalar tail of the whole tensor (only the last tile can have one)
-        if (e1 == count)
+        if (e0 + tile_n == count)
         {
-            const uint32_t i = num_vec * kV + threadIdx.x;
+            const int64_t i = num_vec * kV + threadIdx.x;
             if (i < count)
             {
-                const Enc4 e = load_channel(args.params, C, div_l(i) % C);
+                const Enc4 e = load_channel(args.params, C, (int64_t) ((i / (int64_t) L) % (int64_t) C));
                 Elem<T>::store(out + i, dequantize_value(quantize_value<false>(Elem<T>::load(in + i), e, 0, 0), e));
             }
         }
@@ -639,7 +652,8 @@ int ab_qdq_per_channel_fwd(const void* in, void* out, int64_t num_channel, int64
     cudaStream_t st = (cudaStream_t) stream;
     ChannelArgs a {params, num_channel, num_element_per_channel, seed, 0, 0};
     const bool stochastic = round_mode == AB_ROUND_STOCHASTIC;
-    const bool fast       = !stochastic && num_element < (int64_t) 0x7fffffff && num_channel < (int64_t) 0x7fffffff;
+    const bool fast       = !stochastic && num_element_per_channel < (int64_t) 0x7fff0000 &&
+                      num_channel < (int64_t) 0x7fffffff;
     if (fast)
     {
         // CUTLASS-style fast divmod constants, exact for dividends below 2^31
@@ -657,14 +671,14 @@ int ab_qdq_per_channel_fwd(const void* in, void* out, int64_t num_channel, int64
         {
             auto k              = per_channel_fast_kernel<float>;
             const int64_t tiles = (num_element + (int64_t) kThreads * kUnroll * 4 - 1) / ((int64_t) kThreads * kUnroll * 4);
-            k<<<grid_for(k, tiles, kThreads), kThreads, 0, st>>>((const float*) in, (float*) out, (uint32_t) num_element, a);
+            k<<<grid_for(k, tiles, kThreads), kThreads, 0, st>>>((const float*) in, (float*) out, num_element, a);
         }
         else
         {
             auto k              = per_channel_fast_kernel<__nv_bfloat16>;
             const int64_t tiles = (num_element + (int64_t) kThreads * kUnroll * 8 - 1) / ((int64_t) kThreads * kUnroll * 8);
             k<<<grid_for(k, tiles, kThreads), kThreads, 0, st>>>((const __nv_bfloat16*) in, (__nv_bfloat16*) out,
-                                                                 (uint32_t) num_element, a);
+                                                                 num_element, a);
         }
         AB_CUDA_CHECK(cudaGetLastError());
         return AB_OK;

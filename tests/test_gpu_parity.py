@@ -461,3 +461,34 @@ def test_large_tensor_properties(ops, oracle):
     ops.stats_update_impl(x, tf.arena, tf.first, ops.QUANTIZATION_TF, None, 0)
     r = tf.read()[0]
     assert (r["run_min"], r["run_max"]) == (mn, mx)
+
+
+def test_per_channel_more_than_2_31_elements(ops, oracle):
+    """The reference's `int` element counts overflow at 2^31 elements; the C ABI takes int64_t and the fast per-channel
+    kernel keeps only the tile base in 64 bits. Spot-checked against the oracle at the start, across 2^31 and at the end."""
+    c = 2050
+    per = (2**31 + 2**20) // c + 3            # ragged channel length, total just above 2^31
+    n = c * per
+    assert n > 2**31
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+    chunk = 2**28
+    for s in range(0, n, chunk):
+        x[s:s + chunk] = torch.randn(min(chunk, n - s), device="cuda", generator=g).to(torch.bfloat16)
+    rng = np.random.default_rng(3)
+    mins = -rng.uniform(0.5, 3.0, c)
+    maxs = rng.uniform(0.5, 3.0, c)
+    params = ops.per_channel_params(list(mins), list(maxs), 8)
+    out = ops.qdq_per_channel_impl(x, params.cuda(), c, per, 0, 0)
+    p = oracle.per_channel_prepare(mins, maxs, 8)
+    for start in (0, per - 100, 2**31 - 5000, 2**31 + 12345, n - 7000):
+        stop = min(start + 6000, n)
+        idx = np.arange(start, stop, dtype=np.int64)
+        ch = (idx // per) % c
+        xs = x[start:stop].float().cpu().numpy()
+        exp = np.empty_like(xs)
+        for cc in np.unique(ch):
+            m = ch == cc
+            exp[m] = oracle.qdq_per_channel(xs[m], 1, int(m.sum()), *[np.ascontiguousarray(a[cc:cc + 1]) for a in p])
+        got = out[start:stop].float().cpu().numpy()
+        assert np.array_equal(got, torch.from_numpy(exp).to(torch.bfloat16).float().numpy()), start
