@@ -197,7 +197,7 @@ def run_reference_arm(args):
             "cpu_baseline": dict(info, value=round(value, 3), unit=UNIT),
             "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -377,13 +377,27 @@ def run_ours(args):
             line["cpu_baseline"] = dict(info, value=round(v, 3), unit=UNIT)
         except Exception as exc:   # pylint: disable=broad-except
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "error": str(exc)[:200]}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line goes to the real stdout; everything else this process (or NCCL, cuDNN ...) prints went to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    # C libraries print to fd 1 too (e.g. "NCCL version ..." on the first collective): keep stdout clean for the JSON line
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference_arm(args)
     else:
