@@ -2,6 +2,6 @@
 from .defs import MAP_QUANT_SCHEME_TO_PYMO, MAP_ROUND_MODE_TO_PYMO, QuantizationDataType, QuantScheme  # noqa: F401
 from .qc_quantize_op import (QcPostTrainingWrapper, QcQuantizeOpMode, QcQuantizeWrapper,  # noqa: F401
                              StaticGridQuantWrapper, SteGatingFuncForParameters)
-from .quantsim import QuantizationSimModel  # noqa: F401
+from .quantsim import QuantizationSimModel, load_checkpoint, save_checkpoint  # noqa: F401
 from .tensor_quantizer import (Quantize, QuantizeDequantize, StaticGridPerChannelQuantizer,  # noqa: F401
                                StaticGridPerTensorQuantizer, StaticGridTensorQuantizer, compute_dloss_by_dx)

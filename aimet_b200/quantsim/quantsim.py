@@ -143,6 +143,12 @@ class QuantizationSimModel:
             if "bias" in w.param_quantizers:
                 w.param_quantizers["bias"].enabled = False
 
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state.pop("_act_block", None)               # device-resident statistics are not part of a checkpoint
+        state.pop("_act_block_quantizers", None)
+        return state
+
     # ---- model surgery -----------------------------------------------------------------------------------------
     @staticmethod
     def _is_quantizable_module(module: nn.Module) -> bool:
@@ -321,6 +327,34 @@ class QuantizationSimModel:
         with open(os.path.join(path, filename_prefix + ".json"), "w") as f:
             json.dump(encodings_dict, f, sort_keys=True, indent=4)
 
+    def load_encodings(self, encodings, strict: bool = True, partial: bool = True, requires_grad=None,
+                       allow_overwrite: bool = True):
+        """reference :1696-1757 -- `encodings`: the dictionary (or the path of the JSON file) that save_encodings_to_json /
+        export wrote: {'activation_encodings': {module: {'input'|'output': {idx: enc}}}, 'param_encodings': {name: [enc]}}.
+        After loading, every wrapper is in ACTIVE mode and quantize-dequantizes with the loaded encodings."""
+        if isinstance(encodings, (str, os.PathLike)):
+            with open(encodings) as f:
+                encodings = json.load(f)
+        param_encodings = encodings.get("param_encodings", {})
+        activation_encodings = encodings.get("activation_encodings", {})
+        if not param_encodings and not activation_encodings:
+            raise RuntimeError("no encodings to load")
+        wrappers = dict(self.quant_wrappers())
+        if strict:
+            known = set(wrappers) | {f"{m}.{p}" for m, w in wrappers.items() for p in w.param_quantizers}
+            missing = (set(param_encodings) | set(activation_encodings)) - known
+            if missing:
+                raise RuntimeError("Encoding dictionary contains modules/parameters that doesn't exist in the model: " +
+                                   ", ".join(sorted(missing)))
+        for name, wrapper in wrappers.items():
+            own = {p: param_encodings.get(f"{name}.{p}") for p in wrapper.param_quantizers}
+            wrapper.import_param_encodings({k: v for k, v in own.items() if v}, strict, partial, requires_grad,
+                                           allow_overwrite)
+            act = activation_encodings.get(name, {})
+            wrapper.import_input_encodings(act.get("input", {}), strict, partial, requires_grad, allow_overwrite)
+            wrapper.import_output_encodings(act.get("output", {}), strict, partial, requires_grad, allow_overwrite)
+            wrapper.set_mode(QcQuantizeOpMode.ACTIVE)
+
     def export(self, path: str, filename_prefix: str, dummy_input=None, **_unused):
         """Writes `<prefix>_torch.encodings` (torch-module-name keyed, reference :1000-1042 layout) and the original
         model's state_dict with quantize-dequantized weights. The ONNX-tensor-name keyed `<prefix>.encodings` needs an
@@ -363,3 +397,17 @@ class QuantizationSimModel:
 
         strip(original)
         return original
+
+
+def save_checkpoint(quant_sim_model: QuantizationSimModel, file_path: str):
+    """Pickle the whole sim (reference :2216-2228); quantizers drop their native objects and statistics, keep encodings."""
+    import pickle
+    with open(file_path, "wb") as f:
+        pickle.dump(quant_sim_model, f)
+
+
+def load_checkpoint(file_path: str) -> QuantizationSimModel:
+    """reference :2231-2240"""
+    import pickle
+    with open(file_path, "rb") as f:
+        return pickle.load(f)

@@ -102,3 +102,31 @@ def test_export_files(oracle_backend, tmp_path):
     assert os.path.exists(tmp_path / "model.pth")
     # text form is json.dump(sort_keys=True, indent=4), as the reference writes it
     assert open(tmp_path / "enc.json").read() == json.dumps(saved, sort_keys=True, indent=4)
+
+
+def test_load_encodings_and_checkpoint_round_trip(oracle_backend, tmp_path):
+    """Encodings written by one sim load into a fresh one (reference load_encodings, v1/quantsim.py:1696-1757) and give
+    the same quantized forward; a pickled checkpoint (save_checkpoint / load_checkpoint) does too."""
+    from aimet_b200.quantsim import QuantizationSimModel, load_checkpoint, save_checkpoint
+    sim, _, out = build_and_calibrate("resnet18_perchannel_tfe")
+    sim.save_encodings_to_json(str(tmp_path), "enc")
+    ctor, _, scheme, shape = CASES["resnet18_perchannel_tfe"]
+    from aimet_b200.quantsim import config as qconfig
+    torch.manual_seed(0)
+    model = ctor().eval()
+    torch.manual_seed(1)
+    x = torch.randn(*shape)
+    fresh = QuantizationSimModel(model, dummy_input=x, quant_scheme=scheme, config_file=qconfig.DEFAULT_CONFIG_PER_CHANNEL)
+    fresh.load_encodings(str(tmp_path / "enc.json"))
+    with torch.no_grad():
+        assert torch.equal(fresh.model(x), out)
+    a1, p1 = sim.get_activation_param_encodings()
+    a2, p2 = fresh.get_activation_param_encodings()
+    assert json.dumps(a1, sort_keys=True) == json.dumps(a2, sort_keys=True)
+    assert json.dumps(p1, sort_keys=True) == json.dumps(p2, sort_keys=True)
+    with pytest.raises(RuntimeError):
+        fresh.load_encodings({"param_encodings": {"no.such.weight": p1["conv1.weight"]}, "activation_encodings": {}})
+    save_checkpoint(sim, str(tmp_path / "sim.ckpt"))
+    restored = load_checkpoint(str(tmp_path / "sim.ckpt"))
+    with torch.no_grad():
+        assert torch.equal(restored.model(x), out)
