@@ -331,6 +331,20 @@ __global__ void __launch_bounds__(kThreads) per_channel_kernel(const T* __restri
     }
 }
 
+// per-channel parameter preparation on the device (one thread per channel), see em::per_channel_param
+__global__ void per_channel_params_kernel(const double* __restrict__ enc5, int64_t num_channel, int bw,
+                                          float* __restrict__ params)
+{
+    const int64_t c = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= num_channel)
+        return;
+    double steps = em::pow2(bw) - 1;
+    if (enc5[0] == -enc5[1])   // decided from channel 0 only (ATQ:286-294)
+        steps -= 1;
+    em::per_channel_param(enc5[c * 5], enc5[c * 5 + 1], (float) steps, params[c], params[num_channel + c],
+                          params[2 * num_channel + c], params[3 * num_channel + c]);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // STE backward: grad_in = grad * [min <= x <= max]   (quantsim_straight_through_grad.py:91-118)
 // The product with 1.0f / 0.0f (not a select) keeps torch's `grad * mask` semantics for inf / NaN gradients.
@@ -713,6 +727,19 @@ int ab_qdq_per_channel_fwd(const void* in, void* out, int64_t num_channel, int64
                                                                  num_element, a);
         }
     }
+    AB_CUDA_CHECK(cudaGetLastError());
+    return AB_OK;
+}
+
+int ab_per_channel_params_dev(const double* enc5, int64_t num_channel, int bw, float* params, void* stream)
+{
+    if (enc5 == nullptr || params == nullptr || num_channel <= 0)
+    {
+        set_error("invalid per-channel arguments");
+        return AB_ERR_INVALID;
+    }
+    per_channel_params_kernel<<<(unsigned) ((num_channel + 127) / 128), 128, 0, (cudaStream_t) stream>>>(enc5, num_channel,
+                                                                                                       bw, params);
     AB_CUDA_CHECK(cudaGetLastError());
     return AB_OK;
 }

@@ -147,6 +147,19 @@ def qdq_per_channel_impl(x, params, num_channel, num_element_per_channel, round_
     return out
 
 
+def per_channel_params_dev(enc5: torch.Tensor, bw: int) -> torch.Tensor:
+    """[4*C] fp32 parameter block on the device from a device [C,5] float64 encoding table (no host round trip)."""
+    _require_cuda(enc5)
+    if enc5.dtype != torch.float64 or enc5.dim() != 2 or enc5.shape[1] != 5 or not enc5.is_contiguous():
+        raise ValueError("enc5 must be a contiguous float64 CUDA tensor [C, 5]")
+    c = enc5.shape[0]
+    params = torch.empty(4 * c, dtype=torch.float32, device=enc5.device)
+    with _on_device(enc5):
+        _lib.check(_L.ab_per_channel_params_dev(enc5.data_ptr(), c, int(bw), params.data_ptr(), _stream(enc5)))
+    LAUNCHES["search"] += 0
+    return params
+
+
 def ste_bwd_impl(x, grad, enc_min, enc_max):
     _require_cuda(x, grad)
     if x.dtype != grad.dtype or x.shape != grad.shape:

@@ -50,6 +50,28 @@ def export_quantizer_encoding(quantizer) -> Optional[List[Dict]]:
     return [d] if d else None
 
 
+def ste_for_quantizer(x, grad, q):
+    """compute_dloss_by_dx with the quantizer's current encoding range; when that encoding lives on the device (see
+    tensor_quantizer._LAZY) the range is taken from there -- float32(min), float32(max), exactly what
+    torch.tensor(python floats) yields in the reference -- and no host synchronisation happens."""
+    from .. import ops
+    if q._device_encoding_valid() and x.is_cuda and x.dtype in (torch.float32, torch.bfloat16):   # pylint: disable=protected-access
+        rng = q._enc_dev[:, :2].to(torch.float32)                                                   # pylint: disable=protected-access
+        mins, maxs = rng[:, 0].contiguous(), rng[:, 1].contiguous()
+        n_ch = mins.numel()
+        axis = q.channel_axis if q.channel_axis is not None else 0
+        per_channel = 1
+        for d in (x.shape[axis + 1:] if n_ch > 1 else x.shape):
+            per_channel *= d
+        if x.dtype == torch.bfloat16 and q.channel_axis is None:
+            mins, maxs = mins.to(torch.bfloat16).float(), maxs.to(torch.bfloat16).float()   # 0-dim compare in x's dtype
+        return ops.ste_bwd_per_channel_impl(x, grad, mins, maxs, n_ch, per_channel)
+    enc = q.encoding
+    if isinstance(enc, list):
+        return compute_dloss_by_dx(x, grad, [e.min for e in enc], [e.max for e in enc], q.channel_axis)
+    return compute_dloss_by_dx(x, grad, enc.min, enc.max)
+
+
 class SteGatingFuncForParameters(torch.autograd.Function):
     """Gates the parameter gradients with the straight-through estimator after the wrapped module's backward
     (reference :1314-1366)."""
@@ -67,11 +89,7 @@ class SteGatingFuncForParameters(torch.autograd.Function):
             if q.bitwidth == 32 or q.data_type == QuantizationDataType.float:
                 continue
             if q.enabled and param.grad is not None:
-                if isinstance(q.encoding, list):
-                    param.grad = compute_dloss_by_dx(param, param.grad, [e.min for e in q.encoding],
-                                                     [e.max for e in q.encoding], q.channel_axis)
-                else:
-                    param.grad = compute_dloss_by_dx(param, param.grad, q.encoding.min, q.encoding.max)
+                param.grad = ste_for_quantizer(param, param.grad, q)
         return (None, *output_grad)
 
 
@@ -100,6 +118,7 @@ class StaticGridQuantWrapper(nn.Module):
             self.param_quantizers[name] = StaticGridPerTensorQuantizer(weight_bw, round_mode, quant_scheme,
                                                                        is_symmetric, enabled_by_default=True,
                                                                        data_type=data_type)
+            self.param_quantizers[name]._lazy_ok = True   # pylint: disable=protected-access
 
     # ---- accessors the reference exposes -------------------------------------------------------------------------
     @property
@@ -144,6 +163,7 @@ class StaticGridQuantWrapper(nn.Module):
                                                 ch_axis=axis, data_type=q.data_type)
             pcq.use_strict_symmetric = q.use_strict_symmetric
             pcq.use_unsigned_symmetric = q.use_unsigned_symmetric
+            pcq._lazy_ok = True   # pylint: disable=protected-access
             new[name] = pcq
         self.param_quantizers = new
 
@@ -175,7 +195,7 @@ class StaticGridQuantWrapper(nn.Module):
             q = self.param_quantizers[name]
             if q.enabled and q.bitwidth != 32:
                 shadow_params[name] = param.data
-                if self._module_to_wrap.training or q.encoding is None:
+                if self._module_to_wrap.training or not q._has_encoding():   # pylint: disable=protected-access
                     q.reset_encoding_stats()
                     q.update_encoding_stats(param.data)
                     q.compute_encoding()

@@ -265,7 +265,7 @@ class QuantizationSimModel:
         for _, layer in self.quant_wrappers():
             for q in layer.input_quantizers + list(layer.param_quantizers.values()) + layer.output_quantizers:
                 if not isinstance(q, StaticGridPerTensorQuantizer) or not q.enabled or q.is_encoding_frozen or \
-                        q.bitwidth == 32 or (q.encoding is not None and not q._stats_dirty):   # pylint: disable=protected-access
+                        q.bitwidth == 32 or (q._has_encoding() and not q._stats_dirty):   # pylint: disable=protected-access
                     continue
                 op = q._cppOp[0]   # pylint: disable=protected-access
                 if isinstance(op, AimetTensorQuantizer) and op._is_encoding_valid and op._block is not None:   # pylint: disable=protected-access
@@ -389,7 +389,7 @@ class QuantizationSimModel:
                         from .. import libpymo
                         for pname, param in child.get_named_parameters():
                             q = child.param_quantizers[pname]
-                            if q.enabled and q.bitwidth != 32 and q.encoding is not None:
+                            if q.enabled and q.bitwidth != 32 and q._has_encoding():   # pylint: disable=protected-access
                                 param.data = q.quantize_dequantize(param.data, libpymo.RoundingMode.ROUND_NEAREST)
                     setattr(parent, name, child.get_original_module())
                 else:

@@ -23,6 +23,11 @@ from ..tensor_quantizer_op import AimetTensorQuantizer
 from .defs import MAP_QUANT_SCHEME_TO_PYMO, QuantizationDataType, QuantScheme
 
 _DEFAULT_OP_FACTORY = AimetTensorQuantizer
+# `_encoding is _LAZY`: the encodings were computed on the device and still live only there (`_enc_dev`, a [n, 5] float64
+# tensor, plus the ready-made kernel parameters). The hot paths consume those directly; TfEncoding objects are built --
+# one device->host copy -- the first time anybody asks for `.encoding`. For per-channel ResNet-50 this takes 53 host
+# synchronisations and 26 560 Python objects out of every calibration job.
+_LAZY = object()
 
 
 def set_default_op_factory(factory):
@@ -57,6 +62,8 @@ class StaticGridTensorQuantizer:
         self._is_encoding_frozen = False
         self._cppOp = None
         self._encoding = None
+        self._enc_dev = self._qdq4_dev = self._params_dev = None
+        self._lazy_ok = False         # parameter quantizers switch this on (their encodings are consumed on the device)
         self._stats_dirty = True      # statistics changed since the encoding was last computed
         self._op_factory = _DEFAULT_OP_FACTORY
 
@@ -83,12 +90,14 @@ class StaticGridTensorQuantizer:
 
     @property
     def encoding(self):
+        self._materialize()
         return self._encoding
 
     @encoding.setter
     def encoding(self, encoding):
         if self._is_encoding_frozen:
             raise RuntimeError("Encoding can be set only when it is not frozen.")
+        self._drop_device_encoding()
         self._encoding = encoding
 
     @property
@@ -104,6 +113,54 @@ class StaticGridTensorQuantizer:
         self._encoding_min_max_fixed_vals = min_max_vals
 
     # ---- encodings -----------------------------------------------------------------------------------------------
+    def _has_encoding(self) -> bool:
+        return self._encoding is _LAZY or bool(self._encoding)
+
+    def _drop_device_encoding(self):
+        self._enc_dev = self._qdq4_dev = self._params_dev = None
+
+    def _materialize(self):
+        """Build the host-side TfEncoding objects of a device-resident result (one synchronising copy)."""
+        if self._encoding is _LAZY:
+            rows = self._enc_dev.cpu().tolist()
+            self._encoding = [libpymo.TfEncoding._from_values(r[0], r[1], r[2], r[3], int(r[4])) for r in rows]   # pylint: disable=protected-access
+            self._host_epoch = libpymo.encoding_epoch()
+
+    def _device_encoding_valid(self) -> bool:
+        """The device-side copy still describes the encodings: nothing has written to a TfEncoding since it was made."""
+        if getattr(self, "_enc_dev", None) is None:
+            return False
+        return self._encoding is _LAZY or getattr(self, "_host_epoch", -1) == libpymo.encoding_epoch()
+
+    def _native_block(self):
+        """(arena, first, count, code) when all `_cppOp` are native ops over one contiguous block with valid statistics."""
+        ops_ = self._cppOp
+        op0 = ops_[0]
+        if not _is_native(op0) or op0._block is None:   # pylint: disable=protected-access
+            return None
+        blk, idx0 = op0._block, op0._index              # pylint: disable=protected-access
+        for i, op in enumerate(ops_):
+            if op._block is not blk or op._index != idx0 + i or not op._is_encoding_valid:   # pylint: disable=protected-access
+                return None
+        return blk.arena, blk.first + idx0, len(ops_), op0._code   # pylint: disable=protected-access
+
+    def _compute_encoding_on_device(self) -> bool:
+        """Search on the device, keep the result there. False if this quantizer cannot take that route."""
+        nb = self._native_block()
+        if nb is None or (self.use_symmetric_encodings and self.use_unsigned_symmetric):
+            return False        # is_unsigned_symmetric needs the values on the host anyway
+        arena, first, count, code = nb
+        per_tensor = self.channel_axis is None
+        enc, qdq4 = ops.compute_encodings_impl(arena, first, count, code, self.bitwidth, self.use_symmetric_encodings,
+                                               self.use_strict_symmetric, self.use_unsigned_symmetric,
+                                               want_qdq4=per_tensor)
+        self._enc_dev = enc
+        self._qdq4_dev = qdq4
+        self._params_dev = None if per_tensor else ops.per_channel_params_dev(enc, self.bitwidth)
+        self._encoding = _LAZY
+        self.is_unsigned_symmetric = False
+        return True
+
     def _collect_encodings(self):
         """[(TfEncoding, is_valid)] for every native op: the generic, one-call-per-op route (reference :296-299)."""
         return [op.getEncoding(self.bitwidth, self.use_symmetric_encodings, self.use_strict_symmetric,
@@ -113,12 +170,15 @@ class StaticGridTensorQuantizer:
         """reference :280-321. Recomputing from unchanged statistics returns the same encoding (the reference does it for
         every parameter after calibration, 26 560 extra native calls for per-channel ResNet-50); that case is skipped."""
         if self.enabled and not self._is_encoding_frozen:
-            if self._encoding and not self._stats_dirty:
+            if self._has_encoding() and not self._stats_dirty:
                 return
             self._stats_dirty = False
+            self._drop_device_encoding()
             self._encoding = []
             if self.bitwidth == 32:
                 self._encoding = None
+                return
+            if self._lazy_ok and self._compute_encoding_on_device():
                 return
             for encoding, is_valid in self._collect_encodings():
                 if not is_valid:
@@ -142,6 +202,7 @@ class StaticGridTensorQuantizer:
         if not self._is_encoding_frozen:
             self._reset_ops()
             self._encoding = None
+            self._drop_device_encoding()
             self._stats_dirty = True
 
     def _reset_ops(self):
@@ -151,12 +212,12 @@ class StaticGridTensorQuantizer:
     def get_stats_histogram(self) -> List[List]:
         if self._quant_scheme != QuantScheme.post_training_tf_enhanced:
             raise RuntimeError("get_stats_histogram() can be invoked only when quantization scheme is TF-Enhanced.")
-        if not self._encoding:
+        if not self._has_encoding():
             raise RuntimeError("get_stats_histogram() can be invoked only when encoding is computed.")
         return [op.getStatsHistogram() for op in self._cppOp]
 
     def freeze_encoding(self):
-        if not self._encoding:
+        if not self._has_encoding():
             raise RuntimeError("Encoding can be frozen only when it is not None.")
         self._is_encoding_frozen = True
 
@@ -166,10 +227,13 @@ class StaticGridTensorQuantizer:
 
     # ---- pickling: native objects are re-created, statistics are dropped (reference :128-220) --------------------
     def __getstate__(self):
+        self._materialize()
         state = self.__dict__.copy()
         state["_cppOp"] = len(self._cppOp)
         state.pop("_block", None)
         state.pop("_op_factory", None)
+        for k in ("_enc_dev", "_qdq4_dev", "_params_dev"):
+            state[k] = None
         return state
 
     def __setstate__(self, state):
@@ -191,12 +255,14 @@ class StaticGridPerTensorQuantizer(StaticGridTensorQuantizer):
 
     @property
     def encoding(self):
+        self._materialize()
         return self._encoding[0] if self._encoding else None
 
     @encoding.setter
     def encoding(self, encoding):
         if self._is_encoding_frozen:
             raise RuntimeError("Encoding can be set only when it is not frozen.")
+        self._drop_device_encoding()
         self._encoding = encoding if isinstance(encoding, list) and len(encoding) == 1 else [encoding]
 
     def update_encoding_stats(self, tensor: torch.Tensor):
@@ -324,7 +390,11 @@ class QuantizeDequantize(torch.autograd.Function):
         dtype = tensor.dtype
         if dtype not in (torch.float32, torch.bfloat16):
             tensor = tensor.to(torch.float32)
-        out = tensor_quantizer._cppOp[0].quantizeDequantize(tensor, tensor_quantizer.encoding, round_mode, tensor.is_cuda)   # pylint: disable=protected-access
+        q = tensor_quantizer
+        if q._qdq4_dev is not None and tensor.is_cuda and not tensor.requires_grad and q._device_encoding_valid():   # pylint: disable=protected-access
+            out = ops.qdq_per_tensor_dev_impl(tensor, q._qdq4_dev[0], int(round_mode), 0)   # pylint: disable=protected-access
+        else:
+            out = q._cppOp[0].quantizeDequantize(tensor, q.encoding, round_mode, tensor.is_cuda)   # pylint: disable=protected-access
         return out.to(dtype)
 
     @staticmethod
@@ -336,9 +406,13 @@ class QuantizeDequantize(torch.autograd.Function):
         num_channel = sizes[tensor_quantizer.channel_axis]
         num_element = functools.reduce(lambda x, y: x * y, sizes)
         num_element_per_channel = functools.reduce(lambda x, y: x * y, sizes[tensor_quantizer.channel_axis + 1:])
-        out = tensor_quantizer._cppOp[0].quantizeDequantizePerChannel(   # pylint: disable=protected-access
-            tensor, tensor_quantizer._encoding, num_channel, num_element, num_element_per_channel, round_mode,   # pylint: disable=protected-access
-            tensor.is_cuda)
+        q = tensor_quantizer
+        if q._params_dev is not None and tensor.is_cuda and not tensor.requires_grad and q._device_encoding_valid():   # pylint: disable=protected-access
+            out = ops.qdq_per_channel_impl(tensor, q._params_dev, num_channel, num_element_per_channel,   # pylint: disable=protected-access
+                                           int(round_mode), 0)
+        else:
+            out = q._cppOp[0].quantizeDequantizePerChannel(tensor, q.encoding, num_channel, num_element,   # pylint: disable=protected-access
+                                                           num_element_per_channel, round_mode, tensor.is_cuda)
         return out.to(dtype)
 
     @staticmethod

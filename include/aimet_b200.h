@@ -158,6 +158,11 @@ int ab_qdq_per_channel_fwd(const void* in, void* out, int64_t num_channel, int64
                            int64_t num_element_per_channel, int dtype, const float* params, int round_mode,
                            uint64_t seed, void* stream);
 
+/* ab_per_channel_params on the device: `enc5` is a DEVICE array of num_channel x 5 doubles {min, max, delta, offset, bw} as
+ * ab_compute_encodings writes it; `params` a DEVICE array of 4*num_channel floats. Lets freshly searched per-channel
+ * encodings feed ab_qdq_per_channel_fwd without a host round trip (same arithmetic: ATQ:236-299). */
+int ab_per_channel_params_dev(const double* enc5, int64_t num_channel, int bw, float* params, void* stream);
+
 /* compute_dloss_by_dx (TrainingExtensions/torch/src/python/aimet_torch/v1/quantsim_straight_through_grad.py:91-118):
  * grad_in = grad * [enc_min <= x <= enc_max]. x, grad, grad_in share `dtype`. */
 int ab_qdq_ste_bwd(const void* x, const void* grad, void* grad_in, int64_t count, int dtype, float enc_min,
