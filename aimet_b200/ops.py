@@ -23,7 +23,7 @@ STATE_BYTES = int(_L.ab_stats_state_bytes())
 
 # kernel launches issued through this module, by kernel family (bench.py reports their sum as gpu_launches)
 LAUNCHES = {"qdq": 0, "quantize": 0, "qdq_per_channel": 0, "ste_bwd": 0, "minmax": 0, "hist": 0, "segmented": 0,
-            "search": 0, "reset": 0, "init_range": 0, "fold": 0}
+            "search": 0, "reset": 0, "init_range": 0, "fold": 0, "lg_fwd": 0, "lg_bwd": 0}
 # when a list, stats_update_impl brackets its launches with CUDA events and appends (bytes, start, stop, quant_mode)
 STATS_TIMING = None
 _EVENT_POOL = []
@@ -299,6 +299,125 @@ def stats_fold_batches_impl(states, first, count, batch_log, batch_offsets):
         _lib.check(_L.ab_stats_fold_batches(_state_ptr(states, first), int(count), batch_log.data_ptr(),
                                             batch_offsets.data_ptr(), batch_offsets.numel(), _stream(states)))
     LAUNCHES["fold"] += 1
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# range learning (learned grid): fused forward / backward of the reference's QuantizeDequantizeFunc
+# ---------------------------------------------------------------------------------------------------------------------
+LG_ASYMMETRIC, LG_SIGNED_SYMMETRIC, LG_UNSIGNED_SYMMETRIC = 0, 1, 2
+LG_GATE = 1
+_LG_WORKSPACES = {}
+
+
+def lg_symmetry_mode(use_symmetric_encodings: bool, is_unsigned_symmetric: bool) -> int:
+    """The branch get_computed_encodings takes (reference v1/quantsim_straight_through_grad.py:145-158)."""
+    if use_symmetric_encodings and not is_unsigned_symmetric:
+        return LG_SIGNED_SYMMETRIC
+    return LG_UNSIGNED_SYMMETRIC if use_symmetric_encodings else LG_ASYMMETRIC
+
+
+def _lg_workspace(device, num_channel):
+    """Zero-filled scratch, one per (device, stream): the kernels leave it zeroed, so it is reused launch after launch."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    need = int(_L.ab_lg_workspace_bytes(int(num_channel)))
+    ws = _LG_WORKSPACES.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(max(need, 4096), dtype=torch.uint8, device=device)
+        _LG_WORKSPACES[key] = ws
+    return ws
+
+
+def _lg_geometry(x, enc_min, ch_axis):
+    c = enc_min.numel()
+    if c == 1:
+        return 1, 1, x.numel()
+    if x.shape[ch_axis] != c:
+        raise ValueError(f"encoding has {c} channels, tensor has {x.shape[ch_axis]} along axis {ch_axis}")
+    outer = 1
+    for d in x.shape[:ch_axis]:
+        outer *= d
+    inner = x.numel() // (outer * c) if outer * c else 0
+    return outer, c, inner
+
+
+def _lg_check(x, enc_min, enc_max, bw):
+    _require_cuda(x, enc_min, enc_max)
+    if int(bw) >= 32:
+        raise RuntimeError(f"Invalid bitwidth: {bw}")   # calculate_forward_pass (:207-208)
+    if not (x.dtype == enc_min.dtype == enc_max.dtype):
+        # same message as calculate_forward_pass (:199-202)
+        raise RuntimeError("Data type mismatch. Expected the input and encoding min & max to be of same dtype."
+                           f"Got {x.dtype} input, {enc_min.dtype} encoding_min, and {enc_max.dtype} encoding_max")
+    if enc_min.numel() != enc_max.numel() or not enc_min.is_contiguous() or not enc_max.is_contiguous():
+        raise ValueError("encoding min / max must be contiguous tensors of equal length")
+
+
+def lg_qdq_fwd_impl(x, enc_min, enc_max, bw, sym_mode, strict=False, ch_axis=0, gate=False):
+    """Fused learned-grid forward. With gate=True, enc_min / enc_max are first clamped IN PLACE (apply_gating_logic)."""
+    _lg_check(x, enc_min, enc_max, bw)
+    per_tensor = enc_min.numel() == 1
+    if not (x.is_contiguous() or (per_tensor and x.is_contiguous(memory_format=torch.channels_last))):
+        x = x.contiguous()
+    outer, c, inner = _lg_geometry(x, enc_min, ch_axis)
+    out = torch.empty_like(x)
+    with _on_device(x):
+        ws = None if per_tensor else _lg_workspace(x.device, c).data_ptr()
+        _lib.check(_L.ab_lg_qdq_fwd(x.data_ptr(), out.data_ptr(), outer, c, inner, _dtype_code(x), enc_min.data_ptr(),
+                                    enc_max.data_ptr(), int(bw), int(sym_mode), int(bool(strict)),
+                                    LG_GATE if gate else 0, ws, _stream(x)))
+    LAUNCHES["lg_fwd"] += 1 if per_tensor else 2
+    return out
+
+
+def lg_qdq_bwd_impl(x, grad, enc_min, enc_max, bw, sym_mode, strict=False, ch_axis=0, need_grad_x=True,
+                    need_grad_enc=True):
+    """Fused learned-grid backward: (grad_x or None, grad_min or None, grad_max or None)."""
+    _lg_check(x, enc_min, enc_max, bw)
+    _require_cuda(grad)
+    if grad.dtype != x.dtype or grad.shape != x.shape:
+        raise ValueError("x and grad must share dtype and shape")
+    per_tensor = enc_min.numel() == 1
+    if per_tensor and x.is_contiguous(memory_format=torch.channels_last) and \
+            grad.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous():
+        pass
+    else:
+        x, grad = x.contiguous(), grad.contiguous()
+    outer, c, inner = _lg_geometry(x, enc_min, ch_axis)
+    gx = torch.empty_like(grad) if need_grad_x else None
+    gmin = torch.empty_like(enc_min) if need_grad_enc else None
+    gmax = torch.empty_like(enc_max) if need_grad_enc else None
+    with _on_device(x):
+        ws = _lg_workspace(x.device, c)
+        _lib.check(_L.ab_lg_qdq_bwd(x.data_ptr(), grad.data_ptr(), gx.data_ptr() if need_grad_x else None, outer, c,
+                                    inner, _dtype_code(x), enc_min.data_ptr(), enc_max.data_ptr(), int(bw),
+                                    int(sym_mode), int(bool(strict)), gmin.data_ptr() if need_grad_enc else None,
+                                    gmax.data_ptr() if need_grad_enc else None, ws.data_ptr(), _stream(x)))
+    LAUNCHES["lg_bwd"] += 1 if per_tensor else 2
+    return gx, gmin, gmax
+
+
+class LearnedGridQdq(torch.autograd.Function):
+    """Drop-in for the reference's QuantizeDequantizeFunc (v1/tensor_quantizer.py:854-963): same inputs, same three
+    gradients, one kernel each way; only x and a copy of (min, max) are kept for the backward."""
+
+    @staticmethod
+    def forward(ctx, x, enc_min, enc_max, bw, sym_mode, strict, ch_axis, gate=False):
+        y = lg_qdq_fwd_impl(x, enc_min, enc_max, bw, sym_mode, strict, ch_axis, gate=gate)
+        ctx.config = (bw, sym_mode, strict, ch_axis)
+        # the reference saves clones too: a reused module clamps the parameters again before the backward (:905-911)
+        ctx.save_for_backward(x, enc_min.detach().clone(), enc_max.detach().clone())
+        return y
+
+    @staticmethod
+    def backward(ctx, grad):
+        x, enc_min, enc_max = ctx.saved_tensors
+        bw, sym_mode, strict, ch_axis = ctx.config
+        need_x = ctx.needs_input_grad[0]
+        need_enc = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        if not (need_x or need_enc):
+            return (None,) * 8
+        gx, gmin, gmax = lg_qdq_bwd_impl(x, grad, enc_min, enc_max, bw, sym_mode, strict, ch_axis, need_x, need_enc)
+        return gx, gmin, gmax, None, None, None, None, None
 
 
 # ---------------------------------------------------------------------------------------------------------------------

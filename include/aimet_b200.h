@@ -215,6 +215,44 @@ int ab_compute_encodings(const ab_stats_state* states, int64_t count, int quant_
                          void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Range learning ("learned grid" QAT): fused forward and backward of QuantizeDequantizeFunc
+ * (TrainingExtensions/torch/src/python/aimet_torch/v1/tensor_quantizer.py:854-963), i.e. of
+ * get_computed_encodings / calculate_forward_pass / asymmetric_gradients / symmetric_gradients
+ * (v1/quantsim_straight_through_grad.py:121-346) and, with AB_LG_GATE, of set_encoding_min_max_gating_threshold
+ * (v1/tensor_quantizer.py:1347-1359).
+ *
+ * The tensor is viewed as [outer][num_channel][inner] (per-tensor: num_channel == 1), channel(i) = (i / inner) %
+ * num_channel, which is broadcast_to_tensor (quantsim_straight_through_grad.py:70-92) for any channel axis.
+ * enc_min / enc_max (and grad_min / grad_max) are DEVICE arrays of num_channel elements of the tensor's own `dtype`
+ * (the reference requires tensor and encoding parameters to share a dtype, :199-202). Arithmetic follows the
+ * reference's dtype rule: fp32 tensors in fp32; bf16 tensors in bf16 (every operation rounded) below 16 bit and in fp32
+ * from 16 bit up (:211-214).
+ * ---------------------------------------------------------------------------------------------------------- */
+enum ab_lg_symmetry
+{
+    AB_LG_ASYMMETRIC         = 0,
+    AB_LG_SIGNED_SYMMETRIC   = 1, /* use_symmetric_encodings and not is_unsigned_symmetric */
+    AB_LG_UNSIGNED_SYMMETRIC = 2
+};
+#define AB_LG_GATE 1 /* flags: clamp (min, max) in place first, as LearnedGridQuantWrapper.apply_gating_logic does */
+
+/* bytes of device scratch ab_lg_qdq_fwd (per-channel only) and ab_lg_qdq_bwd need for `num_channel` channels. The
+ * caller zero-fills it ONCE; the kernels leave it zeroed again. One workspace per stream. */
+int64_t ab_lg_workspace_bytes(int64_t num_channel);
+
+/* y = (clamp(round_half_even(x / delta) - offset, 0, num_steps) + offset) * delta with (delta, offset, num_steps) derived
+ * on the device from (enc_min, enc_max). `workspace` may be NULL when num_channel == 1. */
+int ab_lg_qdq_fwd(const void* in, void* out, int64_t outer, int64_t num_channel, int64_t inner, int dtype,
+                  void* enc_min, void* enc_max, int bw, int sym_mode, int use_strict_symmetric, int flags,
+                  void* workspace, void* stream);
+
+/* grad_in = grad * mask (skipped when grad_in is NULL) and, unless grad_min / grad_max are NULL, the gradients of the
+ * loss with respect to enc_min / enc_max. `in` is the forward's input, enc_min / enc_max the values the forward used. */
+int ab_lg_qdq_bwd(const void* in, const void* grad, void* grad_in, int64_t outer, int64_t num_channel, int64_t inner,
+                  int dtype, const void* enc_min, const void* enc_max, int bw, int sym_mode, int use_strict_symmetric,
+                  void* grad_min, void* grad_max, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Multi-GPU exact merge (net-new). The reference's tf_enhanced result depends on the range
  * fixed by the first non-zero batch and on a sequential running mean over batches, so ranks exchange integer
  * per-batch histograms and replay them in global batch order.

@@ -1,0 +1,236 @@
+"""GPU parity of the fused range-learning kernels (ab_lg_qdq_fwd / ab_lg_qdq_bwd) against
+ (1) the goldens produced by the reference's unmodified QuantizeDequantizeFunc (tests/golden/range_learning.npz) and
+ (2) the CPU oracle (oracle/range_learning.py, itself pinned to those goldens) on larger seeded inputs.
+
+Bars: gated (min, max), the dequantized output y and grad_x are BIT-EXACT (they are element-wise); grad_min / grad_max
+contain a sum over the tensor, which the kernel accumulates in double while torch.sum uses an fp32 tree, so they are
+compared to a tolerance proportional to the summed magnitude: 2^-20 * sum(|terms|) in fp32 (about four ulps of the
+largest partial sum) and one bf16 ulp of the result (2^-7 relative) plus the same absolute slack in bf16.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import range_learning as rl
+from tests.conftest import GOLDEN
+from tests.golden.make_range_learning_cases import CASES
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from aimet_b200 import ops as o
+    return o
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(GOLDEN, "range_learning.npz"))
+
+
+def bits_equal(a, b):
+    a, b = a.detach().cpu(), b.detach().cpu()
+    if a.dtype != b.dtype or a.shape != b.shape:
+        return False
+    if a.dtype == torch.bfloat16:
+        ai, bi = a.view(torch.int16), b.view(torch.int16)
+    else:
+        ai, bi = a.view(torch.int32), b.view(torch.int32)
+    nan = torch.isnan(a) & torch.isnan(b)
+    return bool(((ai == bi) | nan).all())
+
+
+def terms_magnitude(saved, grad, mode):
+    """sum over the reduced dims of |summand| for both sums of the backward (fp64), per channel."""
+    x, xq, mask = saved["x"].double(), saved["x_quant"].double(), saved["mask"]
+    delta, offset, g = saved["delta"].double(), saved["offset"].double(), grad.double()
+    if mode == rl.ASYMMETRIC:
+        t1 = ((xq + offset - x * mask / delta) * g).abs()
+        t2 = (delta * g * (~mask)).abs()
+    else:
+        t1 = ((xq + offset) * g).abs()
+        t2 = (mask * (x / delta) * g).abs()
+    per_channel = delta.numel() > 1
+    if per_channel and x.dim() == 1:
+        return t1, t2
+    dims = [d for d in range(x.dim()) if not (per_channel and d == saved["ch_axis"])]
+    return t1.nan_to_num(posinf=0).sum(dim=dims), t2.nan_to_num(posinf=0).sum(dim=dims)
+
+
+def grad_tolerance(saved, grad, mode, enc_min, enc_max, bw, strict, dtype):
+    """Propagate 2^-20 relative slack on each sum through the closing formulas."""
+    m1, m2 = terms_magnitude(saved, grad, mode)
+    rel = 2.0 ** -20
+    n = 2 ** bw - 1 - (1 if (mode != rl.ASYMMETRIC and strict) else 0)
+    mn, mx = enc_min.double().cpu(), enc_max.double().cpu()
+    if mode == rl.ASYMMETRIC:
+        a = rel * m1 / n
+        b = rel * m2 * n / (mx - mn) ** 2
+        tol_min, tol_max = a + mx.abs() * b, a + mn.abs() * b
+    else:
+        tol_min = tol_max = rel * (m1 + m2) / (n // 2)
+    return tol_min.reshape(-1), tol_max.reshape(-1)
+
+
+def close(a, ref, tol, dtype):
+    a, ref = a.detach().double().cpu().reshape(-1), ref.detach().double().cpu().reshape(-1)
+    slack = tol + 1e-30
+    if dtype == torch.bfloat16:
+        slack = slack + ref.abs() * 2.0 ** -7 + tol * 2 ** 13   # bf16 sums: every closing op rounds to 8 bits
+    return bool(((a - ref).abs() <= slack).all())
+
+
+def run_cuda(ops, x, grad, mn, mx, bw, mode, strict, axis, gate):
+    xd, gd = x.cuda(), grad.cuda()
+    mnd, mxd = mn.clone().cuda(), mx.clone().cuda()
+    y = ops.lg_qdq_fwd_impl(xd, mnd, mxd, bw, mode, strict, axis, gate=gate)
+    gx, gmin, gmax = ops.lg_qdq_bwd_impl(xd, gd, mnd, mxd, bw, mode, strict, axis)
+    torch.cuda.synchronize()
+    return y, gx, gmin, gmax, mnd, mxd
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_kernels_match_reference_goldens(ops, gold, case):
+    name, shape, dtype, bw, sym, strict, unsigned, axis, _, _ = case
+    dt = torch.float32 if dtype == "fp32" else torch.bfloat16
+    get = lambda k: torch.from_numpy(gold[f"{name}.{k}"]).to(dt)   # noqa: E731
+    mode = rl.symmetry_mode(sym, unsigned)
+    ax = 0 if axis is None else axis
+    y, gx, gmin, gmax, mnd, mxd = run_cuda(ops, get("x"), get("grad"), get("min_in"), get("max_in"), bw, mode, strict,
+                                           ax, gate=True)
+    assert bits_equal(mnd, get("min_gated")) and bits_equal(mxd, get("max_gated"))
+    assert bits_equal(y, get("y"))
+    assert bits_equal(gx, get("grad_x"))
+    _, saved = rl.forward(get("x"), get("min_gated"), get("max_gated"), bw, mode, strict, ax)
+    tmin, tmax = grad_tolerance(saved, get("grad"), mode, get("min_gated"), get("max_gated"), bw, strict, dt)
+    assert close(gmin, get("grad_min"), tmin, dt)
+    assert close(gmax, get("grad_max"), tmax, dt)
+
+
+SEEDED = [
+    # shape, dtype, bw, mode, strict, axis (None = per tensor)
+    ((1 << 20) + 37, torch.float32, 8, rl.ASYMMETRIC, False, None),
+    ((3, 64, 56, 56), torch.float32, 4, rl.ASYMMETRIC, False, None),
+    ((1 << 20) + 5, torch.float32, 8, rl.SIGNED_SYMMETRIC, False, None),
+    ((1 << 19), torch.float32, 8, rl.SIGNED_SYMMETRIC, True, None),
+    ((1 << 19) + 1, torch.float32, 16, rl.ASYMMETRIC, False, None),
+    ((1 << 19) + 3, torch.float32, 8, rl.UNSIGNED_SYMMETRIC, False, None),
+    ((1 << 20) + 24, torch.bfloat16, 8, rl.ASYMMETRIC, False, None),
+    ((1 << 20) + 24, torch.bfloat16, 4, rl.SIGNED_SYMMETRIC, False, None),
+    ((1 << 19) + 8, torch.bfloat16, 16, rl.ASYMMETRIC, False, None),
+    ((64, 3, 7, 7), torch.float32, 8, rl.SIGNED_SYMMETRIC, False, 0),
+    ((2048, 512), torch.float32, 8, rl.SIGNED_SYMMETRIC, False, 0),
+    ((512, 2048), torch.float32, 4, rl.ASYMMETRIC, False, 0),
+    ((128, 256, 3, 3), torch.float32, 8, rl.SIGNED_SYMMETRIC, False, 1),
+    ((16, 40, 5), torch.float32, 8, rl.ASYMMETRIC, False, 1),
+    ((1000,), torch.float32, 8, rl.ASYMMETRIC, False, 0),
+    ((3001,), torch.float32, 8, rl.SIGNED_SYMMETRIC, False, 0),
+    ((96, 33, 3), torch.bfloat16, 8, rl.SIGNED_SYMMETRIC, False, 0),
+    ((40, 130), torch.bfloat16, 4, rl.ASYMMETRIC, False, 0),
+    ((2000,), torch.bfloat16, 8, rl.ASYMMETRIC, False, 0),
+]
+
+
+def seeded_inputs(idx, shape, dtype, mode, axis):
+    g = torch.Generator().manual_seed(77 + idx)
+    shape = (shape,) if isinstance(shape, int) else shape
+    x = torch.randn(shape, generator=g) * 1.3 + (0.4 if mode == rl.ASYMMETRIC else 0.0)
+    grad = torch.randn(shape, generator=g)
+    c = 1 if axis is None else shape[axis]
+    scale = 0.5 + torch.rand(c, generator=g)
+    mn = (-2.0 * scale) if mode != rl.UNSIGNED_SYMMETRIC else torch.zeros(c)
+    mx = 2.5 * scale if mode == rl.ASYMMETRIC else 2.0 * scale
+    flat = x.view(-1)
+    flat[::1013] = 0.0
+    flat[5::2027] = 40.0       # saturates high
+    flat[7::2029] = -40.0      # saturates low
+    return x.to(dtype), grad.to(dtype), mn.to(dtype), mx.to(dtype)
+
+
+@pytest.mark.parametrize("idx", range(len(SEEDED)))
+def test_kernels_match_oracle_on_seeded_inputs(ops, idx):
+    shape, dtype, bw, mode, strict, axis = SEEDED[idx]
+    x, grad, mn, mx = seeded_inputs(idx, shape, dtype, mode, axis)
+    ax = 0 if axis is None else axis
+    mn_ref, mx_ref = mn.clone(), mx.clone()
+    rl.gate(mn_ref, mx_ref)
+    y_ref, saved = rl.forward(x, mn_ref, mx_ref, bw, mode, strict, ax)
+    gx_ref, gmin_ref, gmax_ref = rl.backward(grad, saved)
+    y, gx, gmin, gmax, mnd, mxd = run_cuda(ops, x, grad, mn, mx, bw, mode, strict, ax, gate=True)
+    assert bits_equal(mnd, mn_ref) and bits_equal(mxd, mx_ref)
+    assert bits_equal(y, y_ref)
+    assert bits_equal(gx, gx_ref.to(dtype))
+    tmin, tmax = grad_tolerance(saved, grad, mode, mn_ref, mx_ref, bw, strict, dtype)
+    assert close(gmin, gmin_ref, tmin, dtype)
+    assert close(gmax, gmax_ref, tmax, dtype)
+
+
+def test_non_finite_inputs_and_unaligned_views(ops):
+    g = torch.Generator().manual_seed(5)
+    base = torch.randn(70001, generator=g)
+    base[::97] = float("nan")
+    base[1::193] = float("inf")
+    base[2::211] = float("-inf")
+    base[3::89] = -0.0
+    x = base[1:]          # 4-byte aligned only
+    grad = torch.randn(70001, generator=g)[1:]
+    mn, mx = torch.tensor([-1.5]), torch.tensor([2.0])
+    for mode in (rl.ASYMMETRIC, rl.SIGNED_SYMMETRIC):
+        y_ref, saved = rl.forward(x, mn, mx, 8, mode)
+        gx_ref, _, _ = rl.backward(grad, saved)
+        xd = base.cuda()[1:]
+        gd = torch.cat([torch.zeros(1), grad]).cuda()[1:]
+        assert xd.data_ptr() % 16 != 0
+        y = ops.lg_qdq_fwd_impl(xd, mn.cuda(), mx.cuda(), 8, mode)
+        gx, gmin, gmax = ops.lg_qdq_bwd_impl(xd, gd, mn.cuda(), mx.cuda(), 8, mode)
+        assert bits_equal(y, y_ref)
+        assert bits_equal(gx, gx_ref)
+        assert torch.isnan(gmin).all() and torch.isnan(gmax).all()   # a NaN input poisons the sums, as in the reference
+
+
+def test_workspace_is_rearmed_and_optional_outputs(ops):
+    x, grad, mn, mx = seeded_inputs(3, (64, 3, 7, 7), torch.float32, rl.SIGNED_SYMMETRIC, 0)
+    xd, gd, mnd, mxd = x.cuda(), grad.cuda(), mn.cuda(), mx.cuda()
+    first = ops.lg_qdq_bwd_impl(xd, gd, mnd, mxd, 8, rl.SIGNED_SYMMETRIC)
+    second = ops.lg_qdq_bwd_impl(xd, gd, mnd, mxd, 8, rl.SIGNED_SYMMETRIC)
+    assert bits_equal(first[0], second[0])
+    assert torch.allclose(first[1], second[1], rtol=1e-6, atol=1e-7) and torch.allclose(first[2], second[2], rtol=1e-6,
+                                                                                       atol=1e-7)
+    only_x = ops.lg_qdq_bwd_impl(xd, gd, mnd, mxd, 8, rl.SIGNED_SYMMETRIC, need_grad_enc=False)
+    assert only_x[1] is None and bits_equal(only_x[0], first[0])
+    only_enc = ops.lg_qdq_bwd_impl(xd, gd, mnd, mxd, 8, rl.SIGNED_SYMMETRIC, need_grad_x=False)
+    assert only_enc[0] is None and torch.allclose(only_enc[1], first[1], rtol=1e-6, atol=1e-7)
+    # per-tensor after per-channel on the same workspace
+    pt = ops.lg_qdq_bwd_impl(xd, gd, mnd[:1].clone(), mxd[:1].clone(), 8, rl.SIGNED_SYMMETRIC)
+    _, saved = rl.forward(x, mn[:1], mx[:1], 8, rl.SIGNED_SYMMETRIC)
+    _, gmin_ref, gmax_ref = rl.backward(grad, saved)
+    assert torch.allclose(pt[2].cpu(), gmax_ref, rtol=1e-4, atol=1e-5)
+
+
+def test_autograd_function_and_errors(ops):
+    x, grad, mn, mx = seeded_inputs(1, (8, 16, 12, 12), torch.float32, rl.ASYMMETRIC, None)
+    xd = x.cuda().requires_grad_(True)
+    pmin, pmax = torch.nn.Parameter(mn.cuda()), torch.nn.Parameter(mx.cuda())
+    y = ops.LearnedGridQdq.apply(xd, pmin, pmax, 8, rl.ASYMMETRIC, False, 0, True)
+    y.backward(grad.cuda())
+    mn_ref, mx_ref = mn.clone(), mx.clone()
+    rl.gate(mn_ref, mx_ref)
+    y_ref, saved = rl.forward(x, mn_ref, mx_ref, 8, rl.ASYMMETRIC)
+    gx_ref, gmin_ref, gmax_ref = rl.backward(grad, saved)
+    assert bits_equal(y, y_ref) and bits_equal(xd.grad, gx_ref)
+    assert torch.allclose(pmin.grad.cpu(), gmin_ref, rtol=1e-4, atol=1e-4)
+    assert torch.allclose(pmax.grad.cpu(), gmax_ref, rtol=1e-4, atol=1e-4)
+    # frozen encodings: only grad_x is produced
+    xd2 = x.cuda().requires_grad_(True)
+    y2 = ops.LearnedGridQdq.apply(xd2, pmin.detach(), pmax.detach(), 8, rl.ASYMMETRIC, False, 0, False)
+    y2.backward(grad.cuda())
+    assert bits_equal(xd2.grad, gx_ref)
+    with pytest.raises(RuntimeError):   # dtype mismatch, as calculate_forward_pass raises
+        ops.lg_qdq_fwd_impl(x.cuda().bfloat16(), mn.cuda(), mx.cuda(), 8, rl.ASYMMETRIC)
+    with pytest.raises(RuntimeError):   # bitwidth 32
+        ops.lg_qdq_fwd_impl(x.cuda(), mn.cuda(), mx.cuda(), 32, rl.ASYMMETRIC)
+    with pytest.raises(RuntimeError):   # no CPU path
+        ops.lg_qdq_fwd_impl(x, mn, mx, 8, rl.ASYMMETRIC)
