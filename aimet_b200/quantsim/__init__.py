@@ -5,3 +5,5 @@ from .qc_quantize_op import (QcPostTrainingWrapper, QcQuantizeOpMode, QcQuantize
 from .quantsim import QuantizationSimModel, load_checkpoint, save_checkpoint  # noqa: F401
 from .tensor_quantizer import (Quantize, QuantizeDequantize, StaticGridPerChannelQuantizer,  # noqa: F401
                                StaticGridPerTensorQuantizer, StaticGridTensorQuantizer, compute_dloss_by_dx)
+from .learned_grid import (LearnedGridQuantWrapper, LearnedGridTensorQuantizer,  # noqa: F401
+                           set_encoding_min_max_gating_threshold)

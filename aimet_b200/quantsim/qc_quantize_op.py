@@ -36,7 +36,8 @@ def export_quantizer_encoding(quantizer) -> Optional[List[Dict]]:
         return None
     if quantizer.data_type == QuantizationDataType.int and quantizer.bitwidth == 32:
         return None
-    encoding = quantizer.encoding
+    # a learned-grid quantizer exports its effective encoding (reference get_encoding_by_quantizer :1514-1526)
+    encoding = quantizer.get_effective_encoding() if hasattr(quantizer, "get_effective_encoding") else quantizer.encoding
 
     def to_dict(enc):
         if not enc:

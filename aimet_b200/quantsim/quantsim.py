@@ -17,10 +17,14 @@ from torch import nn
 
 from . import config as qconfig
 from .defs import MAP_ROUND_MODE_TO_PYMO, QuantizationDataType, QuantScheme
+from .learned_grid import LearnedGridQuantWrapper, construct_and_initialize_trainable_wrapper
 from .qc_quantize_op import QcQuantizeOpMode, StaticGridQuantWrapper
 
 ENCODING_VERSION = "0.6.1"   # reference aimet_common/quantsim.py:55-57
-_SUPPORTED_SCHEMES = (QuantScheme.post_training_tf, QuantScheme.post_training_tf_enhanced)
+_RANGE_LEARNING_SCHEMES = (QuantScheme.training_range_learning_with_tf_init,
+                           QuantScheme.training_range_learning_with_tf_enhanced_init)
+_SUPPORTED_SCHEMES = (QuantScheme.post_training_tf, QuantScheme.post_training_tf_enhanced) + _RANGE_LEARNING_SCHEMES
+_WRAPPER_TYPES = (StaticGridQuantWrapper, LearnedGridQuantWrapper)
 unquantizable_modules = (nn.Identity,)
 
 
@@ -119,7 +123,8 @@ class QuantizationSimModel:
         if isinstance(quant_scheme, str):
             quant_scheme = QuantScheme.from_str(quant_scheme)
         if quant_scheme not in _SUPPORTED_SCHEMES:
-            raise NotImplementedError(f"{quant_scheme} is outside the aimet_b200 hot path (tf / tf_enhanced only)")
+            raise NotImplementedError(f"{quant_scheme} is outside the aimet_b200 hot path (tf / tf_enhanced and the "
+                                      "range-learning schemes initialised from them)")
         if default_data_type != QuantizationDataType.int:
             raise NotImplementedError("only integer quantization simulation is on the aimet_b200 hot path")
         self.model = model if in_place else copy.deepcopy(model)
@@ -153,11 +158,11 @@ class QuantizationSimModel:
     @staticmethod
     def _is_quantizable_module(module: nn.Module) -> bool:
         return type(module) != nn.Module and not isinstance(module, unquantizable_modules) and \
-            not isinstance(module, StaticGridQuantWrapper)   # pylint: disable=unidiomatic-typecheck
+            not isinstance(module, _WRAPPER_TYPES)   # pylint: disable=unidiomatic-typecheck
 
     def _add_quantization_wrappers(self, module: nn.Module, inout):
         for name, child in list(module.named_children()):
-            if isinstance(child, StaticGridQuantWrapper):
+            if isinstance(child, _WRAPPER_TYPES):
                 continue
             if len(list(child.children())) == 0:
                 if self._is_quantizable_module(child) and child in inout:
@@ -173,7 +178,7 @@ class QuantizationSimModel:
     def quant_wrappers(self):
         """(name, wrapper) for every wrapper in the model (reference quant_wrappers())."""
         for name, m in self.model.named_modules():
-            if isinstance(m, StaticGridQuantWrapper):
+            if isinstance(m, _WRAPPER_TYPES):
                 yield name, m
 
     _get_qc_quantized_layers = lambda self, model=None: list(self.quant_wrappers())   # noqa: E731
@@ -181,6 +186,9 @@ class QuantizationSimModel:
     # ---- calibration -------------------------------------------------------------------------------------------
     @staticmethod
     def prepare_sim_for_compute_encodings(sim: "QuantizationSimModel"):
+        if any(isinstance(layer, LearnedGridQuantWrapper) for _, layer in sim.quant_wrappers()):
+            raise RuntimeError("the wrappers have already been replaced by range-learning wrappers; their encodings are "
+                               "trainable parameters now and are not re-calibrated")
         sim._bind_activation_states()   # pylint: disable=protected-access
         for _, layer in sim.quant_wrappers():
             layer.reset_encodings()
@@ -190,6 +198,8 @@ class QuantizationSimModel:
         """Enabled per-tensor activation quantizers in a deterministic (module, input/output, index) order."""
         out = []
         for _, layer in self.quant_wrappers():
+            if not isinstance(layer, StaticGridQuantWrapper):
+                continue
             for q in layer.input_quantizers + layer.output_quantizers:
                 if q.enabled and q.bitwidth != 32 and not q.is_encoding_frozen:
                     out.append(q)
@@ -222,6 +232,30 @@ class QuantizationSimModel:
         for _, layer in sim.quant_wrappers():
             layer.compute_encoding()
             layer.set_mode(QcQuantizeOpMode.ACTIVE)
+        sim.replace_wrappers_for_quantize_dequantize()
+
+    def replace_wrappers_for_quantize_dequantize(self):
+        """Range-learning schemes: every static-grid wrapper becomes a LearnedGridQuantWrapper whose (min, max) parameters
+        start from the encodings just computed (reference :764-845)."""
+        if self._quant_scheme not in _RANGE_LEARNING_SCHEMES:
+            return
+        try:
+            device = next(self.model.parameters()).device
+        except StopIteration:
+            device = torch.device("cpu")
+
+        def replace(parent):
+            for name, child in list(parent.named_children()):
+                if isinstance(child, StaticGridQuantWrapper):
+                    new = construct_and_initialize_trainable_wrapper(
+                        child, device, self._default_param_bw, self._default_output_bw, self._rounding_mode,
+                        self._quant_scheme)
+                    self._wrappers[child.get_original_module()] = new
+                    setattr(parent, name, new)
+                elif not isinstance(child, LearnedGridQuantWrapper):
+                    replace(child)
+
+        replace(self.model)
 
     def compute_encodings(self, forward_pass_callback: Callable, forward_pass_callback_args):
         """Runs the user's calibration callback with every wrapper collecting statistics, then computes the encodings."""
@@ -384,7 +418,17 @@ class QuantizationSimModel:
 
         def strip(parent):
             for name, child in list(parent.named_children()):
-                if isinstance(child, StaticGridQuantWrapper):
+                if isinstance(child, LearnedGridQuantWrapper):
+                    if qdq_weights:
+                        with torch.no_grad():
+                            for pname, param in child.get_named_parameters():
+                                q = child.param_quantizers[pname]
+                                if q.enabled and q.bitwidth != 32:
+                                    param.data = q.quantize_dequantize(param.data,
+                                                                       getattr(child, pname + "_encoding_min"),
+                                                                       getattr(child, pname + "_encoding_max"))
+                    setattr(parent, name, child.get_original_module())
+                elif isinstance(child, StaticGridQuantWrapper):
                     if qdq_weights:
                         from .. import libpymo
                         for pname, param in child.get_named_parameters():

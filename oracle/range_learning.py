@@ -25,8 +25,8 @@ def symmetry_mode(use_symmetric, is_unsigned_symmetric):
 
 def gate(enc_min, enc_max):
     """set_encoding_min_max_gating_threshold (v1/tensor_quantizer.py:1347-1359), in place, in the parameters' dtype."""
-    zero = torch.zeros((), dtype=enc_min.dtype)
-    eps = torch.tensor(1e-5, dtype=enc_min.dtype)
+    zero = torch.zeros((), dtype=enc_min.dtype, device=enc_min.device)   # constant_like: same dtype AND device
+    eps = torch.tensor(1e-5, dtype=enc_min.dtype, device=enc_min.device)
     with torch.no_grad():
         enc_min.clamp_(max=zero)
         enc_max.clamp_(min=zero)
@@ -38,7 +38,7 @@ def _grid(enc_min, enc_max, bw, mode, strict):
     n = 2 ** bw - 1
     if mode != ASYMMETRIC and strict:
         n -= 1
-    like = dict(dtype=enc_min.dtype)
+    like = dict(dtype=enc_min.dtype, device=enc_min.device)
     steps = torch.tensor(n, **like)
     if mode == SIGNED_SYMMETRIC:
         delta = enc_max / torch.tensor(math.floor(n / 2), **like)

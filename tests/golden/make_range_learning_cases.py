@@ -39,3 +39,25 @@ def make_inputs(idx, shape, dtype, axis, dist, enc):
         flat[8], flat[9] = 1e30, -1e30
     dt = torch.float32 if dtype == "fp32" else torch.bfloat16
     return x.to(dt), grad.to(dt), mn.to(dt), mx.to(dt)
+
+
+# ---- whole-sim cases (tests/golden/make_range_learning_sim_golden.py) -------------------------------------------------
+# name: (torchvision architecture, quantsim config file or None, initialisation scheme, input shape)
+SIM_CASES = {
+    "resnet18_default_tf": ("resnet18", None, "tf", (2, 3, 64, 64)),
+    "resnet18_perchannel_tfe": ("resnet18", "default_config_per_channel.json", "tf_enhanced", (2, 3, 64, 64)),
+}
+
+
+def sim_model(arch):
+    import torchvision
+    torch.manual_seed(0)
+    return getattr(torchvision.models, arch)().eval()
+
+
+def sim_inputs(shape):
+    torch.manual_seed(1)
+    x = torch.randn(*shape)
+    x2 = torch.randn(*shape) * 1.5
+    target = torch.randn(shape[0], 1000)
+    return x, x2, target

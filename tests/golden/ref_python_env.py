@@ -75,9 +75,16 @@ class RoundingMode(enum.IntEnum):
 
 
 class TfEncoding:
+    """Stand-in for the pybind11 struct (PyModelOptimizations.cpp:172-178): double min/max/delta/offset, int bw. Like
+    pybind11's def_readwrite, assignment converts (a 0-dim tensor becomes a Python float)."""
+
     def __init__(self):
-        self.min = self.max = self.delta = self.offset = 0.0
-        self.bw = 0
+        self.__dict__.update(min=0.0, max=0.0, delta=0.0, offset=0.0, bw=0)
+
+    def __setattr__(self, key, value):
+        if key not in ("min", "max", "delta", "offset", "bw"):
+            raise AttributeError(key)
+        self.__dict__[key] = int(value) if key == "bw" else float(value)
 
 
 import aimet_common.py_libpymo as _py  # noqa: E402  (the reference's own pure-python enum definitions)
