@@ -33,5 +33,15 @@ for _ in range(3):
         ops.qdq_per_channel_impl(xb, params, 2048, n // 2048, 0, 0)
     if "ste" in which:
         ops.ste_bwd_impl(x, g, -4.0, 8.0)
+    if "lg" in which:   # range learning: per-tensor asymmetric fp32 / bf16, per-channel symmetric fp32
+        mn1, mx1 = torch.tensor([-3.0], device=dev), torch.tensor([4.0], device=dev)
+        ops.lg_qdq_fwd_impl(x, mn1, mx1, 8, ops.LG_ASYMMETRIC, False, 0, gate=True)
+        ops.lg_qdq_bwd_impl(x, g, mn1, mx1, 8, ops.LG_ASYMMETRIC)
+        ops.lg_qdq_fwd_impl(xb, mn1.bfloat16(), mx1.bfloat16(), 8, ops.LG_ASYMMETRIC, False, 0, gate=True)
+        ops.lg_qdq_bwd_impl(xb, g.bfloat16(), mn1.bfloat16(), mx1.bfloat16(), 8, ops.LG_ASYMMETRIC)
+        mnc, mxc = torch.full((2048,), -4.0, device=dev), torch.full((2048,), 4.0, device=dev)
+        xc, gc = x.view(2048, -1), g.view(2048, -1)
+        ops.lg_qdq_fwd_impl(xc, mnc, mxc, 8, ops.LG_SIGNED_SYMMETRIC, False, 0, gate=True)
+        ops.lg_qdq_bwd_impl(xc, gc, mnc, mxc, 8, ops.LG_SIGNED_SYMMETRIC)
 torch.cuda.synchronize()
 print("ok")
