@@ -824,7 +824,7 @@ bool check_common(const void* in, int64_t count, int dtype, int quant_mode, cons
     }
     if (quant_mode != AB_QUANTIZATION_TF && quant_mode != AB_QUANTIZATION_TF_ENHANCED)
     {
-        set_error("unsupported quantization mode %d (only tf and tf_enhanced are on the hot path)", quant_mode);
+        set_error("unsupported quantization mode %d (tf, tf_enhanced and percentile are on the hot path)", quant_mode);
         return false;
     }
     return true;
@@ -899,9 +899,16 @@ int ab_stats_reset(ab_stats_state* states, int64_t count, void* stream)
     return AB_OK;
 }
 
+// the percentile analyzer keeps exactly the tf_enhanced statistics (PercentileEncodingAnalyzer.cpp:69-75 -> UpdatePdf)
+static inline int stats_mode(int quant_mode)
+{
+    return quant_mode == AB_QUANTIZATION_PERCENTILE ? AB_QUANTIZATION_TF_ENHANCED : quant_mode;
+}
+
 int ab_stats_update(const void* in, int64_t count, int dtype, int quant_mode, ab_stats_state* state,
                     uint32_t* batch_log_entry, int flags, void* stream)
 {
+    quant_mode = stats_mode(quant_mode);
     if (!check_common(in, count, dtype, quant_mode, state))
         return AB_ERR_INVALID;
     if (dtype == AB_F32)
@@ -919,6 +926,7 @@ int ab_stats_update_segmented(const void* in, int64_t num_segments, int64_t segm
         set_error("negative segment count or length");
         return AB_ERR_INVALID;
     }
+    quant_mode = stats_mode(quant_mode);
     if (!check_common(in, num_segments * segment_len, dtype, quant_mode, states))
         return AB_ERR_INVALID;
     if (num_segments == 0)

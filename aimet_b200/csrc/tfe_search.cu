@@ -11,6 +11,7 @@
 // change rounding. The epilogue also emits the fp32 kernel parameters fillEncodingInfo would derive, so a per-tensor
 // QDQ can follow on the same stream without a host round trip.
 #include "common.cuh"
+#include "percentile_math.h"
 #include "tfe_math.h"
 
 namespace ab
@@ -23,6 +24,7 @@ constexpr int kSearchThreads = 384;   // >= 358 candidates
 struct SearchArgs
 {
     int quant_mode, bw, sym, strict, unsigned_sym;
+    float percentile;   // AB_QUANTIZATION_PERCENTILE only
 };
 
 __device__ __forceinline__ void write_encoding(double* enc_out, float* qdq4_out, int64_t s, const ab_encoding& e,
@@ -48,6 +50,7 @@ __global__ void __launch_bounds__(kSearchThreads)
                              double* __restrict__ enc_out, float* __restrict__ qdq4_out)
 {
     __shared__ double s_pdf[AB_PDF_SIZE];
+    __shared__ double s_cdf[AB_PDF_SIZE];
     __shared__ float s_sym_deltas[tfe::kMaxSymDeltas];
     __shared__ tfe::AsymSetup s_asym;
     __shared__ float s_num_steps;
@@ -81,7 +84,13 @@ __global__ void __launch_bounds__(kSearchThreads)
                 ab_encoding e = {0, 0, 0, 0, 0};
                 const bool ok = st->stats_updated != 0;
                 if (ok)
-                    tfe::all_zero_encoding(a.bw, e);   // only zeros seen so far (:85-100)
+                {
+                    // only zeros seen so far (TfEnhancedEncodingAnalyzer.cpp:85-100, PercentileEncodingAnalyzer.cpp:91-105)
+                    if (a.quant_mode == AB_QUANTIZATION_PERCENTILE)
+                        pct::all_zero_encoding(a.bw, a.sym != 0 && a.strict != 0, e);
+                    else
+                        tfe::all_zero_encoding(a.bw, e);
+                }
                 write_encoding(enc_out, qdq4_out, s, e, ok);
             }
             continue;
@@ -104,6 +113,20 @@ __global__ void __launch_bounds__(kSearchThreads)
         }
         __syncthreads();
         const tfe::PdfView view {s_pdf, st->x_left0, st->bucket_size_d};
+
+        if (a.quant_mode == AB_QUANTIZATION_PERCENTILE)
+        {
+            // The cumulative sum is sequential in the reference (cdf[i] += cdf[i - 1]) and so it is here: one thread,
+            // 512 dependent double additions, ~2 us -- with one CTA per quantizer that is still thousands of
+            // quantizers per millisecond.
+            if (tid == 0)
+            {
+                ab_encoding e;
+                pct::encoding(view, s_cdf, a.percentile, a.bw, a.sym != 0, a.strict != 0, a.unsigned_sym != 0, e);
+                write_encoding(enc_out, qdq4_out, s, e, true);
+            }
+            continue;
+        }
 
         if (tid == 0)
         {
@@ -196,16 +219,18 @@ __global__ void __launch_bounds__(kSearchThreads)
 
 using namespace ab;
 
-extern "C" int ab_compute_encodings(const ab_stats_state* states, int64_t count, int quant_mode, int bw,
-                                    int use_symmetric, int use_strict_symmetric, int use_unsigned_symmetric,
-                                    double* enc_out, float* qdq4_out, void* stream)
+namespace
+{
+int launch_search(const ab_stats_state* states, int64_t count, int quant_mode, float percentile, int bw, int use_symmetric,
+                  int use_strict_symmetric, int use_unsigned_symmetric, double* enc_out, float* qdq4_out, void* stream)
 {
     if (count < 0 || (count > 0 && (states == nullptr || enc_out == nullptr)))
     {
         set_error("null pointer or negative count");
         return AB_ERR_INVALID;
     }
-    if (quant_mode != AB_QUANTIZATION_TF && quant_mode != AB_QUANTIZATION_TF_ENHANCED)
+    if (quant_mode != AB_QUANTIZATION_TF && quant_mode != AB_QUANTIZATION_TF_ENHANCED &&
+        quant_mode != AB_QUANTIZATION_PERCENTILE)
     {
         set_error("unsupported quantization mode %d", quant_mode);
         return AB_ERR_INVALID;
@@ -222,7 +247,7 @@ extern "C" int ab_compute_encodings(const ab_stats_state* states, int64_t count,
     }
     if (count == 0)
         return AB_OK;
-    SearchArgs a {quant_mode, bw, use_symmetric, use_strict_symmetric, use_unsigned_symmetric};
+    SearchArgs a {quant_mode, bw, use_symmetric, use_strict_symmetric, use_unsigned_symmetric, percentile};
     // one thread per candidate: 358 asymmetric, ~101 symmetric (tfe_math.h) -- the symmetric search (all weights) runs
     // with a third of the threads, i.e. three times as many quantizers resident per SM
     const int threads = (quant_mode == AB_QUANTIZATION_TF_ENHANCED && use_symmetric) ? 128 : kSearchThreads;
@@ -236,4 +261,26 @@ extern "C" int ab_compute_encodings(const ab_stats_state* states, int64_t count,
     compute_encodings_kernel<<<(unsigned) grid, threads, 0, (cudaStream_t) stream>>>(states, count, a, enc_out, qdq4_out);
     AB_CUDA_CHECK(cudaGetLastError());
     return AB_OK;
+}
+}   // namespace
+
+extern "C" int ab_compute_encodings(const ab_stats_state* states, int64_t count, int quant_mode, int bw,
+                                    int use_symmetric, int use_strict_symmetric, int use_unsigned_symmetric,
+                                    double* enc_out, float* qdq4_out, void* stream)
+{
+    if (quant_mode == AB_QUANTIZATION_PERCENTILE)
+    {
+        set_error("the percentile scheme needs its percentile: call ab_compute_encodings_percentile");
+        return AB_ERR_INVALID;
+    }
+    return launch_search(states, count, quant_mode, 100.0f, bw, use_symmetric, use_strict_symmetric,
+                         use_unsigned_symmetric, enc_out, qdq4_out, stream);
+}
+
+extern "C" int ab_compute_encodings_percentile(const ab_stats_state* states, int64_t count, float percentile, int bw,
+                                               int use_symmetric, int use_strict_symmetric, int use_unsigned_symmetric,
+                                               double* enc_out, float* qdq4_out, void* stream)
+{
+    return launch_search(states, count, AB_QUANTIZATION_PERCENTILE, percentile, bw, use_symmetric, use_strict_symmetric,
+                         use_unsigned_symmetric, enc_out, qdq4_out, stream);
 }

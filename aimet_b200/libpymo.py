@@ -115,15 +115,21 @@ class TfEncoding:
 
 
 def scheme_code(quant_scheme) -> int:
-    """Map a QuantizationMode to the C ABI's ab_quant_mode. Only tf and tf_enhanced are on the hot path; the reference's
-    factory (QuantizerFactory.cpp:72-103) falls back to the TF analyzer for anything it does not know, range learning
-    included, and so do we. Percentile / MSE / entropy are out of scope."""
+    """Map a QuantizationMode to the kind of statistics the C ABI keeps for it (ab_quant_mode). tf, tf_enhanced and
+    percentile are on the hot path; percentile keeps the tf_enhanced statistics (PercentileEncodingAnalyzer.cpp:69-75)
+    and differs only in how the encoding is closed (see is_percentile). The reference's factory
+    (QuantizerFactory.cpp:72-103) falls back to the TF analyzer for anything it does not know, range learning included,
+    and so do we. MSE / entropy are out of scope."""
     mode = QuantizationMode(int(quant_scheme))
-    if mode == QuantizationMode.QUANTIZATION_TF_ENHANCED:
+    if mode in (QuantizationMode.QUANTIZATION_TF_ENHANCED, QuantizationMode.QUANTIZATION_PERCENTILE):
         return ops.QUANTIZATION_TF_ENHANCED
     if mode in (QuantizationMode.QUANTIZATION_TF, QuantizationMode.QUANTIZATION_RANGE_LEARNING):
         return ops.QUANTIZATION_TF
-    raise NotImplementedError(f"{mode.name} is outside the aimet_b200 hot path (tf / tf_enhanced only)")
+    raise NotImplementedError(f"{mode.name} is outside the aimet_b200 hot path (tf / tf_enhanced / percentile only)")
+
+
+def is_percentile(quant_scheme) -> bool:
+    return QuantizationMode(int(quant_scheme)) == QuantizationMode.QUANTIZATION_PERCENTILE
 
 
 def _default_device() -> torch.device:
@@ -145,6 +151,7 @@ class _Analyzer:
         self._scheme = QuantizationMode(int(quant_scheme))
         self._code = scheme_code(self._scheme)
         self._slot = None
+        self.percentile = 100.0   # PercentileEncodingAnalyzer.h:100
 
     def reset(self):
         if self._slot is not None:
@@ -159,7 +166,8 @@ class _Analyzer:
         if self._slot is None:
             return TfEncoding()   # no statistics at all: the zero encoding
         enc, _ = ops.compute_encodings_impl(self._slot.arena, self._slot.first, 1, self._code, bw, sym, strict,
-                                            unsigned_sym)
+                                            unsigned_sym,
+                                            percentile=self.percentile if is_percentile(self._scheme) else None)
         v = enc[0].tolist()
         return TfEncoding._from_values(v[0], v[1], v[2], v[3], int(v[4]))
 
@@ -244,7 +252,7 @@ class TensorQuantizer:
     def resetEncodingStats(self):
         self._valid_stats = False
         self.isEncodingValid = False
-        self._analyzer = _Analyzer(self._quant_scheme)
+        self._analyzer = _Analyzer(self._quant_scheme)   # a new analyzer: the percentile is back at its default too
 
     # -- statistics / encodings ---------------------------------------------------------------------------------
     def updateStats(self, tensor, use_cuda):
@@ -268,13 +276,13 @@ class TensorQuantizer:
         return self._analyzer.histogram()
 
     def setPercentileValue(self, percentile):
-        # only meaningful for the percentile scheme (TensorQuantizer.cpp:240-247), which is out of scope
+        # only meaningful for the percentile scheme (TensorQuantizer.cpp:239-246); lives in the analyzer, as there
         if self._quant_scheme == QuantizationMode.QUANTIZATION_PERCENTILE:
-            self._percentile = float(percentile)
+            self._analyzer.percentile = float(percentile)
 
     def getPercentileValue(self):
         if self._quant_scheme == QuantizationMode.QUANTIZATION_PERCENTILE:
-            return self._percentile
+            return self._analyzer.percentile
         raise RuntimeError("Percentile Value only exists in case of percentile quant scheme.")
 
     def computePartialEncoding(self, bw, encoding, use_symmetric_encodings, use_unsigned_symmetric,

@@ -255,30 +255,39 @@ def stats_update_segmented_impl(x, states, first, num_segments, segment_len, qua
     LAUNCHES["segmented"] += 1
 
 
-def compute_encodings_impl(states, first, count, quant_mode, bw, sym, strict, unsigned_sym, want_qdq4=False):
+def _search(states, first, count, quant_mode, bw, sym, strict, unsigned_sym, enc_ptr, qdq4_ptr, percentile):
+    """ab_compute_encodings, or its percentile twin when `percentile` is given (the percentile scheme's statistics are
+    the tf_enhanced ones; only the closing computation differs)."""
+    flags = (int(bool(sym)), int(bool(strict)), int(bool(unsigned_sym)))
+    if percentile is None:
+        _lib.check(_L.ab_compute_encodings(_state_ptr(states, first), int(count), int(quant_mode), int(bw), *flags,
+                                           enc_ptr, qdq4_ptr, _stream(states)))
+    else:
+        _lib.check(_L.ab_compute_encodings_percentile(_state_ptr(states, first), int(count), float(percentile), int(bw),
+                                                      *flags, enc_ptr, qdq4_ptr, _stream(states)))
+    LAUNCHES["search"] += 1
+
+
+def compute_encodings_impl(states, first, count, quant_mode, bw, sym, strict, unsigned_sym, want_qdq4=False,
+                           percentile=None):
     """Returns (enc[count,5] float64 CUDA tensor, qdq4[count,4] float32 CUDA tensor or None)."""
     _require_cuda(states)
     enc = torch.empty((count, 5), dtype=torch.float64, device=states.device)
     qdq4 = torch.empty((count, 4), dtype=torch.float32, device=states.device) if want_qdq4 else None
     with _on_device(states):
-        _lib.check(_L.ab_compute_encodings(_state_ptr(states, first), int(count), int(quant_mode), int(bw),
-                                           int(bool(sym)), int(bool(strict)), int(bool(unsigned_sym)),
-                                           enc.data_ptr(), qdq4.data_ptr() if want_qdq4 else None, _stream(states)))
-    LAUNCHES["search"] += 1
+        _search(states, first, count, quant_mode, bw, sym, strict, unsigned_sym, enc.data_ptr(),
+                qdq4.data_ptr() if want_qdq4 else None, percentile)
     return enc, qdq4
 
 
-def compute_encodings_into(states, first, count, quant_mode, bw, sym, strict, unsigned_sym, out):
+def compute_encodings_into(states, first, count, quant_mode, bw, sym, strict, unsigned_sym, out, percentile=None):
     """Same as compute_encodings_impl, but writes into `out` (float64 CUDA, [count, 5], contiguous): lets a caller
     enqueue many searches and read them back with one copy."""
     _require_cuda(states, out)
     if out.dtype != torch.float64 or out.numel() != 5 * count or not out.is_contiguous():
         raise ValueError("out must be a contiguous float64 CUDA tensor [count, 5]")
     with _on_device(states):
-        _lib.check(_L.ab_compute_encodings(_state_ptr(states, first), int(count), int(quant_mode), int(bw),
-                                           int(bool(sym)), int(bool(strict)), int(bool(unsigned_sym)),
-                                           out.data_ptr(), None, _stream(states)))
-    LAUNCHES["search"] += 1
+        _search(states, first, count, quant_mode, bw, sym, strict, unsigned_sym, out.data_ptr(), None, percentile)
 
 
 def stats_init_range_impl(states, first, count, minmax):

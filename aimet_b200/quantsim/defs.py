@@ -43,8 +43,8 @@ class QuantizationDataType(enum.Enum):
 MAP_QUANT_SCHEME_TO_PYMO = {
     QuantScheme.post_training_tf: libpymo.QuantizationMode.QUANTIZATION_TF,
     QuantScheme.post_training_tf_enhanced: libpymo.QuantizationMode.QUANTIZATION_TF_ENHANCED,
-    # range learning initialises from tf / tf_enhanced statistics (reference defs.py:84-91); the learned-grid
-    # wrappers themselves are outside this hot path
+    QuantScheme.post_training_percentile: libpymo.QuantizationMode.QUANTIZATION_PERCENTILE,
+    # range learning initialises from tf / tf_enhanced statistics (reference defs.py:84-91)
     QuantScheme.training_range_learning_with_tf_init: libpymo.QuantizationMode.QUANTIZATION_TF,
     QuantScheme.training_range_learning_with_tf_enhanced_init: libpymo.QuantizationMode.QUANTIZATION_TF_ENHANCED,
 }

@@ -213,6 +213,11 @@ class StaticGridQuantWrapper(nn.Module):
         for q in self.output_quantizers:
             q.compute_encoding()
 
+    def set_percentile_value(self, percentile_value: float):
+        """reference :827-835: the activation quantizers only"""
+        for q in self.input_quantizers + self.output_quantizers:
+            q.set_percentile_value(percentile_value)
+
     @staticmethod
     def should_perform_quant_dequant(tensor, tensor_quantizer) -> bool:
         """reference :451-473"""

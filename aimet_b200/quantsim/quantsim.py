@@ -23,7 +23,8 @@ from .qc_quantize_op import QcQuantizeOpMode, StaticGridQuantWrapper
 ENCODING_VERSION = "0.6.1"   # reference aimet_common/quantsim.py:55-57
 _RANGE_LEARNING_SCHEMES = (QuantScheme.training_range_learning_with_tf_init,
                            QuantScheme.training_range_learning_with_tf_enhanced_init)
-_SUPPORTED_SCHEMES = (QuantScheme.post_training_tf, QuantScheme.post_training_tf_enhanced) + _RANGE_LEARNING_SCHEMES
+_SUPPORTED_SCHEMES = (QuantScheme.post_training_tf, QuantScheme.post_training_tf_enhanced,
+                      QuantScheme.post_training_percentile) + _RANGE_LEARNING_SCHEMES
 _WRAPPER_TYPES = (StaticGridQuantWrapper, LearnedGridQuantWrapper)
 unquantizable_modules = (nn.Identity,)
 
@@ -123,8 +124,8 @@ class QuantizationSimModel:
         if isinstance(quant_scheme, str):
             quant_scheme = QuantScheme.from_str(quant_scheme)
         if quant_scheme not in _SUPPORTED_SCHEMES:
-            raise NotImplementedError(f"{quant_scheme} is outside the aimet_b200 hot path (tf / tf_enhanced and the "
-                                      "range-learning schemes initialised from them)")
+            raise NotImplementedError(f"{quant_scheme} is outside the aimet_b200 hot path (tf / tf_enhanced / percentile "
+                                      "and the range-learning schemes initialised from tf / tf_enhanced)")
         if default_data_type != QuantizationDataType.int:
             raise NotImplementedError("only integer quantization simulation is on the aimet_b200 hot path")
         self.model = model if in_place else copy.deepcopy(model)
@@ -132,6 +133,7 @@ class QuantizationSimModel:
         self._rounding_mode = rounding_mode
         self._default_output_bw = default_output_bw
         self._default_param_bw = default_param_bw
+        self._percentile_value = 100   # reference :278
         self._config = qconfig.load_config(config_file)
 
         try:
@@ -193,6 +195,15 @@ class QuantizationSimModel:
         for _, layer in sim.quant_wrappers():
             layer.reset_encodings()
             layer.set_mode(QcQuantizeOpMode.ANALYSIS)
+        if sim._quant_scheme == QuantScheme.post_training_percentile:   # pylint: disable=protected-access
+            for _, layer in sim.quant_wrappers():                       # reference :397-400
+                layer.set_percentile_value(sim._percentile_value)       # pylint: disable=protected-access
+
+    def set_percentile_value(self, percentile_value: float):
+        """reference :478-484"""
+        if percentile_value < 90 or percentile_value > 100:
+            raise ValueError("Percentile value must be in range [90, 100]")
+        self._percentile_value = percentile_value
 
     def activation_quantizers(self):
         """Enabled per-tensor activation quantizers in a deterministic (module, input/output, index) order."""
@@ -312,18 +323,19 @@ class QuantizationSimModel:
         for device, items in by_device.items():
             out = torch.empty((len(items), 5), dtype=torch.float64, device=device)
             first_q, first_op = items[0]
-            key = lambda q, op: (op._code, q.bitwidth, q.use_symmetric_encodings, q.use_strict_symmetric,   # noqa: E731
-                                 q.use_unsigned_symmetric)
+            key = lambda q, op: (op._code, op._percentile, q.bitwidth, q.use_symmetric_encodings,   # noqa: E731
+                                 q.use_strict_symmetric, q.use_unsigned_symmetric)
             contiguous = all(op._block is first_op._block and op._index == first_op._index + i and   # pylint: disable=protected-access
                              key(q, op) == key(first_q, first_op) for i, (q, op) in enumerate(items))
             if contiguous:
                 ops.compute_encodings_into(first_op._block.arena, first_op._block.first + first_op._index, len(items),   # pylint: disable=protected-access
                                            first_op._code, first_q.bitwidth, first_q.use_symmetric_encodings,   # pylint: disable=protected-access
-                                           first_q.use_strict_symmetric, first_q.use_unsigned_symmetric, out)
+                                           first_q.use_strict_symmetric, first_q.use_unsigned_symmetric, out,
+                                           percentile=first_op._percentile)   # pylint: disable=protected-access
             for row, (q, op) in enumerate(items if not contiguous else []):
                 ops.compute_encodings_into(op._block.arena, op._block.first + op._index, 1, op._code, q.bitwidth,   # pylint: disable=protected-access
                                            q.use_symmetric_encodings, q.use_strict_symmetric,
-                                           q.use_unsigned_symmetric, out[row:row + 1])
+                                           q.use_unsigned_symmetric, out[row:row + 1], percentile=op._percentile)   # pylint: disable=protected-access
             rows = out.cpu().tolist()
             for (q, _), r in zip(items, rows):
                 q._encoding = [libpymo.TfEncoding._from_values(r[0], r[1], r[2], r[3], int(r[4]))]   # pylint: disable=protected-access

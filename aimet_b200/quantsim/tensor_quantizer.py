@@ -153,7 +153,7 @@ class StaticGridTensorQuantizer:
         per_tensor = self.channel_axis is None
         enc, qdq4 = ops.compute_encodings_impl(arena, first, count, code, self.bitwidth, self.use_symmetric_encodings,
                                                self.use_strict_symmetric, self.use_unsigned_symmetric,
-                                               want_qdq4=per_tensor)
+                                               want_qdq4=per_tensor, percentile=self._cppOp[0]._percentile)   # pylint: disable=protected-access
         self._enc_dev = enc
         self._qdq4_dev = qdq4
         self._params_dev = None if per_tensor else ops.per_channel_params_dev(enc, self.bitwidth)
@@ -347,7 +347,7 @@ class StaticGridPerChannelQuantizer(StaticGridTensorQuantizer):
                 return [(libpymo.TfEncoding(), op._is_encoding_valid) for op in self._cppOp]   # pylint: disable=protected-access
             enc, _ = ops.compute_encodings_impl(self._block.arena, self._block.first, len(self._cppOp), op0._code,   # pylint: disable=protected-access
                                                 self.bitwidth, self.use_symmetric_encodings, self.use_strict_symmetric,
-                                                self.use_unsigned_symmetric)
+                                                self.use_unsigned_symmetric, percentile=op0._percentile)   # pylint: disable=protected-access
             rows = enc.cpu().tolist()
             return [(libpymo.TfEncoding._from_values(r[0], r[1], r[2], r[3], int(r[4])), True) for r in rows]   # pylint: disable=protected-access
         return super()._collect_encodings()

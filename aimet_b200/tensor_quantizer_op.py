@@ -37,6 +37,7 @@ class AimetTensorQuantizer:
     def __init__(self, quantization_scheme):
         self._scheme = libpymo.QuantizationMode(int(quantization_scheme))
         self._code = libpymo.scheme_code(self._scheme)
+        self._percentile = 100.0 if libpymo.is_percentile(self._scheme) else None   # None: not the percentile scheme
         self._is_encoding_valid = False
         self._block = None            # StateBlock with one record, allocated on first use
         self._index = 0
@@ -55,8 +56,10 @@ class AimetTensorQuantizer:
 
     # ---- reference API ---------------------------------------------------------------------------------------
     def resetEncodingStats(self):
-        """AimetTensorQuantizer.cpp:85-92"""
+        """AimetTensorQuantizer.cpp:85-92 (a new analyzer: the percentile value falls back to its default as well)"""
         self._is_encoding_valid = False
+        if self._percentile is not None:
+            self._percentile = 100.0
         self._range_fixed, self._probe = False, None
         if self._block is not None:
             ops.stats_reset_impl(self._block.arena, self._block.first + self._index, 1)
@@ -102,7 +105,7 @@ class AimetTensorQuantizer:
             assert not (use_strict_symmetric and use_unsigned_symmetric)   # TfEncodingAnalyzer.cpp:85-86
         enc, _ = ops.compute_encodings_impl(self._block.arena, self._block.first + self._index, 1, self._code,
                                             bitwidth, use_symmetric_encodings, use_strict_symmetric,
-                                            use_unsigned_symmetric)
+                                            use_unsigned_symmetric, percentile=self._percentile)
         v = enc[0].tolist()
         return libpymo.TfEncoding._from_values(v[0], v[1], v[2], v[3], int(v[4])), True
 
@@ -147,8 +150,9 @@ class AimetTensorQuantizer:
         return self._block.histogram(self._index)
 
     def setPercentileValue(self, percentile):
-        """AimetTensorQuantizer.cpp:200-207: a no-op unless the scheme is percentile (out of scope here)."""
-        return None
+        """AimetTensorQuantizer.cpp:200-207: a no-op unless the scheme is percentile."""
+        if self._percentile is not None:
+            self._percentile = float(percentile)
 
     # ---- helpers ---------------------------------------------------------------------------------------------
     def _per_channel_params(self, encodings, device):

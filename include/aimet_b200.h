@@ -49,11 +49,12 @@ typedef enum
     AB_ROUND_STOCHASTIC = 1
 } ab_round_mode;
 
-/* DlQ/include/DlQuantization/Quantization.hpp:83-107 (only the two schemes on the hot path) */
+/* DlQ/include/DlQuantization/Quantization.hpp:83-107 (the schemes on the hot path, with the reference's values) */
 typedef enum
 {
     AB_QUANTIZATION_TF          = 0,
-    AB_QUANTIZATION_TF_ENHANCED = 1
+    AB_QUANTIZATION_TF_ENHANCED = 1,
+    AB_QUANTIZATION_PERCENTILE  = 3 /* statistics identical to TF_ENHANCED (UpdatePdf); see ab_compute_encodings_percentile */
 } ab_quant_mode;
 
 /* DlQ/include/DlQuantization/Quantization.hpp:113-120 (TfEncoding), same field order */
@@ -213,6 +214,13 @@ int ab_stats_update_segmented(const void* in, int64_t num_segments, int64_t segm
 int ab_compute_encodings(const ab_stats_state* states, int64_t count, int quant_mode, int bw, int use_symmetric,
                          int use_strict_symmetric, int use_unsigned_symmetric, double* enc_out, float* qdq4_out,
                          void* stream);
+
+/* PercentileEncodingAnalyzer<float>::computeEncoding (DlQ/src/PercentileEncodingAnalyzer.cpp:77-196) for `count` consecutive
+ * records whose statistics were collected with AB_QUANTIZATION_PERCENTILE (or TF_ENHANCED: the PDF is the same).
+ * `percentile` is what setPercentileValue received (:203-206; 100 = the observed range). Outputs as ab_compute_encodings. */
+int ab_compute_encodings_percentile(const ab_stats_state* states, int64_t count, float percentile, int bw,
+                                    int use_symmetric, int use_strict_symmetric, int use_unsigned_symmetric,
+                                    double* enc_out, float* qdq4_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Range learning ("learned grid" QAT): fused forward and backward of QuantizeDequantizeFunc

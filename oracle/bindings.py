@@ -90,6 +90,8 @@ class Oracle:
         L.qo_tfe_fold_histogram.argtypes = [C.POINTER(TfeState), _u32p, C.c_size_t]
         L.qo_tfe_compute.restype = Encoding
         L.qo_tfe_compute.argtypes = [C.POINTER(TfeState), C.c_int, C.c_int, C.c_int, C.c_int]
+        L.qo_percentile_compute.restype = Encoding
+        L.qo_percentile_compute.argtypes = [C.POINTER(TfeState), C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]
         L.qo_tfe_cost.restype = C.c_double
         L.qo_tfe_cost.argtypes = [C.POINTER(TfeState), C.c_int, C.c_float, C.c_int]
         L.qo_tfe_candidates.restype = C.c_int
@@ -220,6 +222,21 @@ class OracleTfe:
         return np.array(self.s.x_left[:]), np.array(self.s.pdf[:])
 
 
+class OraclePercentile(OracleTfe):
+    """PercentileEncodingAnalyzer: the tf_enhanced statistics with a percentile-clipped range."""
+
+    def __init__(self, oracle, percentile=100.0):
+        super().__init__(oracle)
+        self.percentile = float(percentile)
+
+    def set_percentile(self, percentile):
+        self.percentile = float(percentile)
+
+    def compute(self, bw, sym=False, strict=False, unsigned=False):
+        return self.o.L.qo_percentile_compute(C.byref(self.s), self.percentile, bw, int(sym), int(strict),
+                                              int(unsigned)).astuple()
+
+
 class Reference:
     """The reference's own C++ (CPU mode), compiled by oracle/Makefile into oracle/_ref/."""
 
@@ -232,6 +249,7 @@ class Reference:
         L.ref_analyzer_free.argtypes = [C.c_void_p]
         L.ref_analyzer_update.argtypes = [C.c_void_p, _fp, C.c_size_t]
         L.ref_analyzer_compute.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _dp]
+        L.ref_analyzer_set_percentile.argtypes = [C.c_void_p, C.c_float]
         L.ref_analyzer_histogram.restype = C.c_int
         L.ref_analyzer_histogram.argtypes = [C.c_void_p, _dp, _dp]
         L.ref_fill_encoding_info.argtypes = [C.c_int, C.c_double, C.c_double, _dp]
@@ -297,6 +315,9 @@ class RefAnalyzer:
     def update(self, x):
         x = np.ascontiguousarray(x, dtype=np.float32)
         self.r.L.ref_analyzer_update(self.h, _f(x), x.size)
+
+    def set_percentile(self, percentile):
+        self.r.L.ref_analyzer_set_percentile(self.h, float(percentile))
 
     def compute(self, bw, sym=False, strict=False, unsigned=False):
         out = np.zeros(5)

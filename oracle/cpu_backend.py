@@ -95,7 +95,8 @@ class ReferenceTensorQuantizer:
         return [] if h is None else list(zip(h[0].tolist(), h[1].tolist()))
 
     def setPercentileValue(self, p):
-        pass
+        if self._mode == int(libpymo.QuantizationMode.QUANTIZATION_PERCENTILE):
+            self._a.set_percentile(p)
 
 
 class PortTensorQuantizer:
@@ -103,11 +104,15 @@ class PortTensorQuantizer:
 
     def __init__(self, quantization_scheme):
         self._tfe = int(quantization_scheme) == int(libpymo.QuantizationMode.QUANTIZATION_TF_ENHANCED)
+        self._pct = int(quantization_scheme) == int(libpymo.QuantizationMode.QUANTIZATION_PERCENTILE)
         self._valid = False
         self._new()
 
     def _new(self):
-        self._a = bindings.OracleTfe(_port()) if self._tfe else bindings.OracleTf(_port())
+        if self._pct:
+            self._a = bindings.OraclePercentile(_port())
+        else:
+            self._a = bindings.OracleTfe(_port()) if self._tfe else bindings.OracleTf(_port())
 
     def resetEncodingStats(self):
         self._valid = False
@@ -139,7 +144,8 @@ class PortTensorQuantizer:
         return [] if h is None else list(zip(h[0].tolist(), h[1].tolist()))
 
     def setPercentileValue(self, p):
-        pass
+        if self._pct:
+            self._a.set_percentile(p)
 
 
 def best_cpu_backend():

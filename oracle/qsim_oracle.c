@@ -593,3 +593,70 @@ qo_encoding qo_tfe_compute(const qo_tfe_state* s, int bw_in, int sym, int strict
     e.max          = best_max;
     return e;
 }
+
+/* ---- percentile calibration: src/PercentileEncodingAnalyzer.cpp:77-196 (DTYPE = float). The statistics are the
+ * tf_enhanced ones (UpdatePdf, :69-75), so a qo_tfe_state carries them. ---- */
+static void percentile_range(const qo_tfe_state* s, float percentile, float* o_min, float* o_max)
+{
+    float min_val, max_val;
+    tfe_range(s, &min_val, &max_val); /* findOriginalRange, math_functions.cpp:404-436: same function */
+    if (percentile == 100.0f)
+    {
+        *o_min = min_val, *o_max = max_val;
+        return;
+    }
+    const float bin_width = (float) (s->x_left[1] - s->x_left[0]);
+    float hist_min        = (float) s->x_left[0];
+    float hist_max        = (float) (s->x_left[QO_PDF_SIZE - 1] + bin_width);
+    float p_min = hist_min, p_max = hist_max;
+    double cdf[QO_PDF_SIZE];
+    memcpy(cdf, s->pdf, sizeof(cdf));
+    for (int i = 1; i < QO_PDF_SIZE; i++)
+        cdf[i] += cdf[i - 1];
+    float left = 1 - percentile / 100;
+    for (int i = 0; i < QO_PDF_SIZE; i++)
+        if (cdf[i] >= left)
+        {
+            p_min = (float) s->x_left[i];
+            break;
+        }
+    float right = percentile / 100;
+    for (int i = QO_PDF_SIZE - 1; i >= 0; i--)
+        if (cdf[i] < right && s->x_left[i] < max_val)
+        {
+            p_max = (float) (s->x_left[i] + bin_width);
+            break;
+        }
+    if (p_min == p_max)
+        p_max += bin_width;
+    *o_min = p_min, *o_max = p_max;
+}
+
+qo_encoding qo_percentile_compute(const qo_tfe_state* s, float percentile, int bw_in, int sym, int strict,
+                                  int unsigned_sym)
+{
+    qo_encoding e   = {0, 0, 0, 0, 0};
+    uint8_t bw      = (uint8_t) bw_in;
+    float num_steps = (float) (pow(2, bw) - 1);
+    if (sym && strict)
+        num_steps -= 1;
+    if (!s->initialized)
+    {
+        if (s->stats_updated)
+        {
+            e.min    = -1;
+            e.max    = 1;
+            e.delta  = (e.max - e.min) / (int) num_steps;
+            e.offset = floor(e.min / e.delta);
+            e.min    = e.offset * e.delta;
+            e.max    = e.min + (int) num_steps * e.delta;
+            e.bw     = bw;
+        }
+        return e;
+    }
+    float a_min, a_max;
+    percentile_range(s, percentile, &a_min, &a_max);
+    a_min = fminx(a_min, 0.0f);
+    a_max = fmaxx(a_max, 0.0f);
+    return qo_tf_encoding(bw, a_min, a_max, sym, strict, unsigned_sym);
+}

@@ -67,6 +67,11 @@ void ref_analyzer_compute(void* h, int bw, int sym, int strict, int unsigned_sym
     put(e, out5);
 }
 
+void ref_analyzer_set_percentile(void* h, float percentile)
+{
+    static_cast<Analyzer*>(h)->impl->setPercentileValue(percentile);
+}
+
 // returns the number of buckets written (512, or 0 if the PDF was never initialised)
 int ref_analyzer_histogram(void* h, double* x_left, double* pdf)
 {

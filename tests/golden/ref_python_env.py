@@ -151,7 +151,8 @@ class AimetTensorQuantizer:
         return list(zip(h[0].tolist(), h[1].tolist()))
 
     def setPercentileValue(self, p):
-        pass
+        if self.scheme == int(QuantizationMode.QUANTIZATION_PERCENTILE):   # AimetTensorQuantizer.cpp:200-207
+            self.a.set_percentile(p)
 
 
 atq = types.ModuleType("aimet_common.AimetTensorQuantizer")

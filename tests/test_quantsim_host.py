@@ -33,10 +33,18 @@ def oracle_backend(oracle):
     tensor_quantizer.set_default_op_factory(prev)
 
 
+PERCENTILE_CASE = ("resnet18_percentile", (torchvision.models.resnet18, "default", "percentile", (4, 3, 64, 64)), 99.9)
+
+
 def build_and_calibrate(name, device="cpu"):
     from aimet_b200.quantsim import QuantizationSimModel
     from aimet_b200.quantsim import config as qconfig
-    ctor, cfg, scheme, shape = CASES[name]
+    percentile = None
+    if name == PERCENTILE_CASE[0]:
+        ctor, cfg, scheme, shape = PERCENTILE_CASE[1]
+        percentile = PERCENTILE_CASE[2]
+    else:
+        ctor, cfg, scheme, shape = CASES[name]
     torch.manual_seed(0)
     model = ctor().eval()
     torch.manual_seed(1)
@@ -45,6 +53,8 @@ def build_and_calibrate(name, device="cpu"):
     model, x, x2 = model.to(device), x.to(device), x2.to(device)
     sim = QuantizationSimModel(model, dummy_input=x, quant_scheme=scheme, default_output_bw=8, default_param_bw=8,
                                config_file=qconfig.DEFAULT_CONFIG_PER_CHANNEL if cfg == "per_channel" else None)
+    if percentile is not None:
+        sim.set_percentile_value(percentile)
     structure = {}
     for mname, w in sim.quant_wrappers():
         structure[mname] = {
@@ -83,6 +93,22 @@ def test_host_layer_reproduces_reference_python(oracle_backend, name):
             assert json.loads(json.dumps(par[k][:3])) == v
     assert hashlib.sha256(canonical.encode()).hexdigest() == golden["sha256"]
     assert hashlib.sha256(out.numpy().tobytes()).hexdigest() == golden["output_sha256"]
+
+
+def test_percentile_scheme_reproduces_reference_python(oracle_backend):
+    """post_training_percentile with set_percentile_value(99.9): activations are clipped at the percentile, parameters
+    keep the analyzer's default of 100 (the reference's wrapper only forwards the value to activation quantizers)."""
+    golden = json.load(open(os.path.join(GOLDEN, "quantsim_resnet18_percentile.json")))
+    sim, _, out = build_and_calibrate(PERCENTILE_CASE[0])
+    act, par = sim.get_activation_param_encodings()
+    canonical = json.dumps({"activation_encodings": act, "param_encodings": par}, sort_keys=True)
+    mine = json.loads(canonical)
+    assert mine["activation_encodings"] == golden["encodings"]["activation_encodings"]
+    assert mine["param_encodings"] == golden["encodings"]["param_encodings"]
+    assert hashlib.sha256(canonical.encode()).hexdigest() == golden["sha256"]
+    assert hashlib.sha256(out.numpy().tobytes()).hexdigest() == golden["output_sha256"]
+    with pytest.raises(ValueError):
+        sim.set_percentile_value(50)
 
 
 def test_export_files(oracle_backend, tmp_path):
