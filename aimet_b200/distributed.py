@@ -83,6 +83,27 @@ def _all_gather(t: torch.Tensor, group) -> torch.Tensor:
     return out.to(t.device)
 
 
+_WARMED = set()
+
+
+def warm_collectives(group, device):
+    """Once per (process group, device): run the gather this module uses at a small, a medium and a large payload, so
+    that NCCL's lazily established protocols / channels (LL, LL128, Simple pick themselves by message size) exist before
+    a job needs them. Without it the first job whose log is larger than anything gathered before pays tens of
+    milliseconds of connection setup inside `_merge`."""
+    key = (id(group) if group is not None else None, str(device))
+    if key in _WARMED or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    _WARMED.add(key)
+    if device.type != "cuda" or dist.get_backend(group) != "nccl":
+        return
+    for words in (8 * 1024, 512 * 1024, 16 * 1024 * 1024):
+        _all_gather(torch.zeros(words, dtype=torch.int32, device=device), group)
+    t = torch.zeros(4, dtype=torch.float64, device=device)
+    _all_reduce(t, dist.ReduceOp.MAX, group)
+    torch.cuda.current_stream(device).synchronize()
+
+
 def _all_reduce(t: torch.Tensor, op, group):
     if t.is_cuda and dist.get_backend(group) != "nccl":
         host = t.detach().cpu()
@@ -113,6 +134,7 @@ class ShardedCalibrator:
         self.quantizers = list(sim._act_block_quantizers)   # pylint: disable=protected-access
         self.block = sim._act_block                         # pylint: disable=protected-access
         self.device = self.block.device
+        warm_collectives(self.group, self.device)
         q_count = len(self.quantizers)
         self.tfe = sim._quant_scheme == QuantScheme.post_training_tf_enhanced   # pylint: disable=protected-access
         self.local_batch = -1

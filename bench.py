@@ -14,6 +14,7 @@ value = images calibrated by all ranks / that time. N > 1 is weak scaling: every
 One JSON line on stdout (rank 0). See README / DESIGN.md for the key meanings.
 """
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -224,6 +225,7 @@ def run_ours(args):
     import aimet_b200  # noqa: F401
     from aimet_b200 import ops
     from aimet_b200.distributed import ShardedCalibrator
+    from aimet_b200.utils import DevicePrefetcher
 
     sim = build_sim(device)
     steps, warmup = args.steps, args.warmup
@@ -236,24 +238,32 @@ def run_ours(args):
     # measures the plain eager path; BENCH_CUDA_GRAPH=1 switches it on.
     use_graph = os.environ.get("BENCH_CUDA_GRAPH", "0") == "1" and not args.eager
 
-    def job(batch_source, n, graph=None):
-        """One complete calibration job over n batches through the public API."""
+    def job(batches_of, n, graph=None):
+        """One complete calibration job over n batches through the public API. `batches_of(n)` returns the iterable of
+        this rank's n batches."""
         graph = use_graph if graph is None else graph
         if not graph:
             def cb(model, _):
-                for i in range(n):
-                    model(batch_source(i))
+                for x in batches_of(n):
+                    model(x)
             if world > 1:
                 ShardedCalibrator(sim).compute_encodings(cb, None)
             else:
                 sim.compute_encodings(cb, None)
         else:
-            batches = (batch_source(i) for i in range(n))
             if world > 1:
-                ShardedCalibrator(sim).compute_encodings_for_batches(batches, cuda_graph=True)
+                ShardedCalibrator(sim).compute_encodings_for_batches(batches_of(n), cuda_graph=True)
             else:
-                sim.compute_encodings_for_batches(batches, cuda_graph=True)
+                sim.compute_encodings_for_batches(batches_of(n), cuda_graph=True)
         return sim.get_activation_param_encodings()
+
+    def resident(n):
+        return (dev_batches[i % steps] for i in range(n))
+
+    def from_host(n):
+        # pinned host batches, copied to the device step by step INSIDE the timed region; the copy of the next batch is
+        # enqueued on a second stream while the current one is being processed (aimet_b200.utils.DevicePrefetcher)
+        return DevicePrefetcher(host_batches[:n], device)
 
     def barrier():
         if world > 1:
@@ -262,10 +272,17 @@ def run_ours(args):
 
     # ---- warm-up: W steps of a complete job (cuDNN autotune, allocator, lazy module loading) ----
     if warmup > 0:
-        job(lambda i: dev_batches[i % steps], warmup)
+        job(resident, warmup)
+        job(from_host, warmup)      # the host-fed path too: copy stream, staging buffers, first async H2D of the process
     barrier()
+    # Everything built so far (model, wrappers, torch internals: ~1e6 Python objects) is long-lived: move it out of the
+    # collector's sight so that a generation-2 pass triggered by the 26 560 encodings a job exports does not walk it in
+    # the middle of a timed job (measured: +77 ms on every other 32-step job without this).
+    gc.collect()
+    gc.freeze()
 
     # ---- timed: value (inputs resident in HBM) ----
+    gc.collect()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -274,7 +291,7 @@ def run_ours(args):
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.nvtx.range_push("timed")          # lets `ncu --nvtx --nvtx-include "timed/"` see only the timed region
     start.record()
-    act, par = job(lambda i: dev_batches[i], steps)
+    act, par = job(resident, steps)
     stop.record()
     torch.cuda.nvtx.range_pop()
     barrier()
@@ -285,6 +302,15 @@ def run_ours(args):
     launched = {k: ops.LAUNCHES[k] - launches0[k] for k in ops.LAUNCHES}
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- timed: e2e (host buffers; H2D of every batch and D2H of the result inside the region) ----
+    gc.collect()
+    barrier()
+    t0 = time.perf_counter()
+    act, par = job(from_host, steps)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+
     # ---- the same job once more with CUDA events around every statistics call (roofline of the dominant kernel) ----
     # The eager step is host-bound, so an event pair around a launch would also time the GPU waiting for the host to
     # enqueue it. This repeat therefore replays the steady-state step from a CUDA graph in which the event pairs are
@@ -293,19 +319,11 @@ def run_ours(args):
     ops.reserve_timing_events(2 * 100 * steps + 64)
     ops.STATS_TIMING = []
     per_step0 = dict(ops.LAUNCHES)
-    job(lambda i: dev_batches[i], steps, graph=steps > 2)
+    job(resident, steps, graph=steps > 2)
     barrier()
     timing, ops.STATS_TIMING = ops.STATS_TIMING, None
     # launches of one captured (replayed) step = launches issued while capturing = total of this job minus the eager ones
     job_launches = {k: ops.LAUNCHES[k] - per_step0[k] for k in ops.LAUNCHES}
-
-    # ---- timed: e2e (host buffers; H2D of every batch and D2H of the result inside the region) ----
-    barrier()
-    t0 = time.perf_counter()
-    act, par = job(lambda i: host_batches[i].to(device, non_blocking=True), steps)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    barrier()
 
     # max over ranks
     t = torch.tensor([ms, e2e_s * 1000.0], device=device, dtype=torch.float64)
@@ -366,7 +384,9 @@ def run_ours(args):
                        "num_activation_encodings": len(act), "num_param_tensors": len(par),
                        "parallelism": f"batch-sharded x{world}"},
             "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": BATCH * 3 * 224 * 224 * 4,
-                    "d2h_bytes_per_step": int(enc_bytes / steps)},
+                    "d2h_bytes_per_step": int(enc_bytes / steps),
+                    "h2d": "every step's batch is copied from pinned host memory inside the timed region, on a copy "
+                           "stream one batch ahead of the compute stream (aimet_b200.utils.DevicePrefetcher)"},
             "gpu_launches": gpu_launches, "launches_by_kernel": launched,
             "cuda_graph": dict(graph_info, enabled=bool(use_graph)),
             "roofline": roofline, "clocks": clocks}

@@ -122,3 +122,21 @@ def test_quantizer_pickle_round_trip():
     assert len(pc2.encoding) == 4 and len(pc2._cppOp) == 4
     assert torch.equal(pc2.quantize_dequantize(w, libpymo.RoundingMode.ROUND_NEAREST),
                        pc.quantize_dequantize(w, libpymo.RoundingMode.ROUND_NEAREST))
+
+
+def test_device_prefetcher_yields_every_batch_in_order():
+    """Double-buffered H2D feeding (aimet_b200.utils.DevicePrefetcher): values and order are those of the host batches,
+    including a trailing batch of a different shape; works with depth 1 and 2."""
+    import torch
+    from aimet_b200.utils import DevicePrefetcher
+    g = torch.Generator().manual_seed(0)
+    host = [torch.randn(8, 3, 16, 16, generator=g).pin_memory() for _ in range(7)] + [torch.randn(3, 3, 16, 16, generator=g)]
+    for depth in (1, 2):
+        seen = []
+        for x in DevicePrefetcher(host, torch.device("cuda", 0), depth=depth):
+            assert x.is_cuda
+            seen.append((x * 2.0).sum(dim=(1, 2, 3)).cpu())      # some work on the consumer's stream
+        assert len(seen) == len(host)
+        for got, h in zip(seen, host):
+            assert torch.allclose(got, (h * 2.0).sum(dim=(1, 2, 3)), rtol=1e-5, atol=1e-4)
+    assert list(DevicePrefetcher([], torch.device("cuda", 0))) == []
