@@ -126,6 +126,13 @@ class StaticGridTensorQuantizer:
             self._encoding = [libpymo.TfEncoding._from_values(r[0], r[1], r[2], r[3], int(r[4])) for r in rows]   # pylint: disable=protected-access
             self._host_epoch = libpymo.encoding_epoch()
 
+    def _device_rows(self):
+        """[[min, max, delta, offset, bw], ...] of a result that lives only on the device (None otherwise): lets the
+        exporter build its dictionaries without materialising TfEncoding objects."""
+        if self._encoding is _LAZY:
+            return self._enc_dev.cpu().tolist()
+        return None
+
     def _device_encoding_valid(self) -> bool:
         """The device-side copy still describes the encodings: nothing has written to a TfEncoding since it was made."""
         if getattr(self, "_enc_dev", None) is None:
