@@ -148,10 +148,19 @@ AB_HD double cost(const PdfView& p, int bw, float delta, int offset)
     // The reference runs three loops (bottom saturation, top saturation, quantisation), each visiting its bins in
     // ascending order into its own accumulator. One ascending pass with three accumulators adds the same terms in
     // the same order to each accumulator, so every sum is bit-identical.
+    // An empty bin contributes pr * (d * d) = +0.0 * finite = +0.0 (with a finite histogram geometry and a finite, non-zero
+    // delta every d is finite and its square cannot overflow a double), and adding +0.0 changes no accumulator, so empty
+    // bins are skipped: the PDF spans three times the first batch's range (InitializePdf), i.e. most of its 512 bins are
+    // empty. With a degenerate geometry (a range fixed from +-inf inputs) nothing is skipped: there 0 * NaN must poison
+    // the sum exactly as it does in the reference.
+    const bool skip_empty = (pdf_start - pdf_start == 0.0f) && (pdf_step - pdf_step == 0.0) && (delta - delta == 0.0f) &&
+                            delta != 0.0f;
     double sat_bottom = 0, sat_top = 0, quant = 0;
     for (int i = 0; i < AB_PDF_SIZE; ++i)
     {
         const double pr  = p.pdf[i];
+        if (skip_empty && pr == 0.0)
+            continue;
         const double mid = pdf_start + i * pdf_step + pdf_step / 2;
         if (i < min_ind)
         {

@@ -19,7 +19,7 @@ import torch
 
 from .. import libpymo, ops
 from ..state import StateArena
-from ..tensor_quantizer_op import AimetTensorQuantizer
+from ..tensor_quantizer_op import AimetTensorQuantizer, ValidityGroup
 from .defs import MAP_QUANT_SCHEME_TO_PYMO, QuantizationDataType, QuantScheme
 
 _DEFAULT_OP_FACTORY = AimetTensorQuantizer
@@ -146,6 +146,10 @@ class StaticGridTensorQuantizer:
         if not _is_native(op0) or op0._block is None:   # pylint: disable=protected-access
             return None
         blk, idx0 = op0._block, op0._index              # pylint: disable=protected-access
+        group = getattr(self, "_group", None)
+        if group is not None and group.detached == 0 and blk is getattr(self, "_block", None) and idx0 == 0:
+            # all channels were bound together by _ensure_block and nobody has touched an op individually since
+            return (blk.arena, blk.first, len(ops_), op0._code) if group.valid else None   # pylint: disable=protected-access
         for i, op in enumerate(ops_):
             if op._block is not blk or op._index != idx0 + i or not op._is_encoding_valid:   # pylint: disable=protected-access
                 return None
@@ -238,6 +242,7 @@ class StaticGridTensorQuantizer:
         state = self.__dict__.copy()
         state["_cppOp"] = len(self._cppOp)
         state.pop("_block", None)
+        state.pop("_group", None)
         state.pop("_op_factory", None)
         for k in ("_enc_dev", "_qdq4_dev", "_params_dev"):
             state[k] = None
@@ -248,6 +253,7 @@ class StaticGridTensorQuantizer:
         self.__dict__.update(state)
         self._op_factory = _DEFAULT_OP_FACTORY
         self._block = None
+        self._group = None
         self._cppOp = [self._op_factory(MAP_QUANT_SCHEME_TO_PYMO[self._quant_scheme]) for _ in range(n)]
 
 
@@ -299,6 +305,7 @@ class StaticGridPerChannelQuantizer(StaticGridTensorQuantizer):
         self._cppOp = [self._op_factory(MAP_QUANT_SCHEME_TO_PYMO[quant_scheme]) for _ in range(num_channels)]
         self._ch_axis = ch_axis
         self._block = None          # one contiguous block of statistics records shared by all channels (native ops)
+        self._group = None          # their shared isEncodingValid flag (tensor_quantizer_op.ValidityGroup)
         self._params_cache = None
 
     @property
@@ -308,14 +315,18 @@ class StaticGridPerChannelQuantizer(StaticGridTensorQuantizer):
     def _ensure_block(self, device):
         if self._block is None or self._block.device != device:
             self._block = StateArena.for_device(device).allocate(len(self._cppOp))
+            self._group = ValidityGroup()
             for i, op in enumerate(self._cppOp):
-                op._bind(self._block, i)   # pylint: disable=protected-access
+                op._bind(self._block, i, self._group)   # pylint: disable=protected-access
 
     def _reset_ops(self):
         if self._block is not None and _is_native(self._cppOp[0]):
             self._block.reset()
-            for op in self._cppOp:
-                op._is_encoding_valid = False   # pylint: disable=protected-access
+            if self._group is not None and self._group.detached == 0:
+                self._group.valid = False
+            else:
+                for op in self._cppOp:
+                    op._is_encoding_valid = False   # pylint: disable=protected-access
         else:
             super()._reset_ops()
 
@@ -340,8 +351,11 @@ class StaticGridPerChannelQuantizer(StaticGridTensorQuantizer):
                 self._ensure_block(tensor.device)
                 ops.stats_update_segmented_impl(moved, self._block.arena, self._block.first, n_ch,
                                                 moved.numel() // n_ch, self._cppOp[0]._code)   # pylint: disable=protected-access
-                for op in self._cppOp:
-                    op._is_encoding_valid = True   # pylint: disable=protected-access
+                if self._group is not None and self._group.detached == 0:
+                    self._group.valid = True
+                else:
+                    for op in self._cppOp:
+                        op._is_encoding_valid = True   # pylint: disable=protected-access
                 return
             for channel_idx, op in enumerate(self._cppOp):
                 tensor_slice = tensor.select(self._ch_axis, channel_idx).contiguous(memory_format=torch.contiguous_format)

@@ -31,10 +31,35 @@ def _to_device_tensor(t: torch.Tensor):
     return t, orig
 
 
+class ValidityGroup:
+    """`isEncodingValid` shared by the ops of one per-channel quantizer: the host layer updates and resets all channels
+    together (one launch), so it flips ONE flag instead of looping over up to thousands of ops. An op that is written
+    individually leaves the group (`detached` counts those), and the host layer falls back to looking at every op."""
+    __slots__ = ("valid", "detached")
+
+    def __init__(self):
+        self.valid = False
+        self.detached = 0
+
+
 class AimetTensorQuantizer:
     """One encoding analyzer + one quantize-dequantize simulator (AimetTensorQuantizer.cpp:75-83)."""
 
+    @property
+    def _is_encoding_valid(self):
+        group = self._group
+        return group.valid if group is not None else self._valid
+
+    @_is_encoding_valid.setter
+    def _is_encoding_valid(self, value):
+        if self._group is not None:
+            self._group.detached += 1
+            self._group = None
+        self._valid = bool(value)
+
     def __init__(self, quantization_scheme):
+        self._group = None
+        self._valid = False
         self._scheme = libpymo.QuantizationMode(int(quantization_scheme))
         self._code = libpymo.scheme_code(self._scheme)
         self._percentile = 100.0 if libpymo.is_percentile(self._scheme) else None   # None: not the percentile scheme
@@ -46,9 +71,11 @@ class AimetTensorQuantizer:
         self._probe = None            # (pinned int32 tensor, event) of an in-flight read-back of `initialized`
 
     # ---- wiring used by the batched host layer (aimet_b200.quantsim): share one contiguous block per weight -------
-    def _bind(self, block, index):
+    def _bind(self, block, index, group=None):
         self._block, self._index = block, index
         self._range_fixed, self._probe = False, None
+        if group is not None:
+            self._group = group
 
     def _ensure_state(self, device):
         if self._block is None or self._block.device != device:
