@@ -824,7 +824,7 @@ bool check_common(const void* in, int64_t count, int dtype, int quant_mode, cons
     }
     if (quant_mode != AB_QUANTIZATION_TF && quant_mode != AB_QUANTIZATION_TF_ENHANCED)
     {
-        set_error("unsupported quantization mode %d (tf, tf_enhanced and percentile are on the hot path)", quant_mode);
+        set_error("unsupported quantization mode %d (tf, tf_enhanced, percentile and mse are on the hot path)", quant_mode);
         return false;
     }
     return true;
@@ -899,10 +899,12 @@ int ab_stats_reset(ab_stats_state* states, int64_t count, void* stream)
     return AB_OK;
 }
 
-// the percentile analyzer keeps exactly the tf_enhanced statistics (PercentileEncodingAnalyzer.cpp:69-75 -> UpdatePdf)
+// the percentile and MSE analyzers keep exactly the tf_enhanced statistics (PercentileEncodingAnalyzer.cpp:69-75,
+// MseEncodingAnalyzer.cpp:70-76 -> UpdatePdf)
 static inline int stats_mode(int quant_mode)
 {
-    return quant_mode == AB_QUANTIZATION_PERCENTILE ? AB_QUANTIZATION_TF_ENHANCED : quant_mode;
+    return (quant_mode == AB_QUANTIZATION_PERCENTILE || quant_mode == AB_QUANTIZATION_MSE) ? AB_QUANTIZATION_TF_ENHANCED
+                                                                                            : quant_mode;
 }
 
 int ab_stats_update(const void* in, int64_t count, int dtype, int quant_mode, ab_stats_state* state,

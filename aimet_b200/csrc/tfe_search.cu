@@ -11,6 +11,7 @@
 // change rounding. The epilogue also emits the fp32 kernel parameters fillEncodingInfo would derive, so a per-tensor
 // QDQ can follow on the same stream without a host round trip.
 #include "common.cuh"
+#include "mse_math.h"
 #include "percentile_math.h"
 #include "tfe_math.h"
 
@@ -51,6 +52,7 @@ __global__ void __launch_bounds__(kSearchThreads)
 {
     __shared__ double s_pdf[AB_PDF_SIZE];
     __shared__ double s_cdf[AB_PDF_SIZE];
+    __shared__ mse::Tables s_mse;
     __shared__ float s_sym_deltas[tfe::kMaxSymDeltas];
     __shared__ tfe::AsymSetup s_asym;
     __shared__ float s_num_steps;
@@ -86,8 +88,8 @@ __global__ void __launch_bounds__(kSearchThreads)
                 if (ok)
                 {
                     // only zeros seen so far (TfEnhancedEncodingAnalyzer.cpp:85-100, PercentileEncodingAnalyzer.cpp:91-105)
-                    if (a.quant_mode == AB_QUANTIZATION_PERCENTILE)
-                        pct::all_zero_encoding(a.bw, a.sym != 0 && a.strict != 0, e);
+                    if (a.quant_mode == AB_QUANTIZATION_PERCENTILE || a.quant_mode == AB_QUANTIZATION_MSE)
+                        pct::all_zero_encoding(a.bw, a.sym != 0 && a.strict != 0, e);   // MseEncodingAnalyzer.cpp:91-105: same
                     else
                         tfe::all_zero_encoding(a.bw, e);
                 }
@@ -123,6 +125,51 @@ __global__ void __launch_bounds__(kSearchThreads)
             {
                 ab_encoding e;
                 pct::encoding(view, s_cdf, a.percentile, a.bw, a.sym != 0, a.strict != 0, a.unsigned_sym != 0, e);
+                write_encoding(enc_out, qdq4_out, s, e, true);
+            }
+            continue;
+        }
+
+        if (a.quant_mode == AB_QUANTIZATION_MSE)
+        {
+            // thread 0 lays out bin edges / centres (float accumulations, inherently sequential), then the (min, max)
+            // candidates -- up to 257 x 257 of them -- are spread over the CTA; (cost, index) arg-min = the reference's
+            // first strict minimum
+            if (tid == 0)
+                mse::build_tables(view, s_mse);
+            __syncthreads();
+            const int n_cand = mse::num_candidates(s_mse);
+            double bc = INFINITY;
+            int bi    = INT_MAX;
+            for (int k = tid; k < n_cand; k += blockDim.x)
+            {
+                float cmin, cmax;
+                mse::candidate(s_mse, k, cmin, cmax);
+                const float c = mse::cost(s_mse, a.bw, cmin, cmax, a.sym != 0, a.strict != 0, a.unsigned_sym != 0);
+                if (c < FLT_MAX && (double) c < bc)   // `mse < mseMin` with mseMin starting at FLT_MAX; ascending k per thread
+                    bc = c, bi = k;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+            {
+                const double oc = __shfl_xor_sync(0xffffffffu, bc, o);
+                const int oi    = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (oc < bc || (oc == bc && oi < bi))
+                    bc = oc, bi = oi;
+            }
+            if ((tid & 31) == 0)
+                s_best_cost[tid >> 5] = bc, s_best_idx[tid >> 5] = bi;
+            __syncthreads();
+            if (tid == 0)
+            {
+                for (int w = 1; w < (int) blockDim.x / 32; ++w)
+                    if (s_best_cost[w] < bc || (s_best_cost[w] == bc && s_best_idx[w] < bi))
+                        bc = s_best_cost[w], bi = s_best_idx[w];
+                float best_min = s_mse.min_val, best_max = s_mse.max_val;
+                if (bi != INT_MAX)
+                    mse::candidate(s_mse, bi, best_min, best_max);
+                ab_encoding e;
+                mse::finish(a.bw, best_min, best_max, a.sym != 0, a.strict != 0, a.unsigned_sym != 0, e);
                 write_encoding(enc_out, qdq4_out, s, e, true);
             }
             continue;
@@ -230,7 +277,7 @@ int launch_search(const ab_stats_state* states, int64_t count, int quant_mode, f
         return AB_ERR_INVALID;
     }
     if (quant_mode != AB_QUANTIZATION_TF && quant_mode != AB_QUANTIZATION_TF_ENHANCED &&
-        quant_mode != AB_QUANTIZATION_PERCENTILE)
+        quant_mode != AB_QUANTIZATION_PERCENTILE && quant_mode != AB_QUANTIZATION_MSE)
     {
         set_error("unsupported quantization mode %d", quant_mode);
         return AB_ERR_INVALID;

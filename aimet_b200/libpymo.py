@@ -119,13 +119,15 @@ def scheme_code(quant_scheme) -> int:
     percentile are on the hot path; percentile keeps the tf_enhanced statistics (PercentileEncodingAnalyzer.cpp:69-75)
     and differs only in how the encoding is closed (see is_percentile). The reference's factory
     (QuantizerFactory.cpp:72-103) falls back to the TF analyzer for anything it does not know, range learning included,
-    and so do we. MSE / entropy are out of scope."""
+    and so do we. The entropy analyzer (a different, rescaling histogram) is out of scope."""
     mode = QuantizationMode(int(quant_scheme))
     if mode in (QuantizationMode.QUANTIZATION_TF_ENHANCED, QuantizationMode.QUANTIZATION_PERCENTILE):
         return ops.QUANTIZATION_TF_ENHANCED
+    if mode == QuantizationMode.QUANTIZATION_MSE:
+        return ops.QUANTIZATION_MSE        # tf_enhanced statistics, MseEncodingAnalyzer's closing search
     if mode in (QuantizationMode.QUANTIZATION_TF, QuantizationMode.QUANTIZATION_RANGE_LEARNING):
         return ops.QUANTIZATION_TF
-    raise NotImplementedError(f"{mode.name} is outside the aimet_b200 hot path (tf / tf_enhanced / percentile only)")
+    raise NotImplementedError(f"{mode.name} is outside the aimet_b200 hot path (tf / tf_enhanced / percentile / mse only)")
 
 
 def is_percentile(quant_scheme) -> bool:
@@ -172,7 +174,7 @@ class _Analyzer:
         return TfEncoding._from_values(v[0], v[1], v[2], v[3], int(v[4]))
 
     def histogram(self):
-        if self._code != ops.QUANTIZATION_TF_ENHANCED:
+        if not ops.keeps_histogram(self._code):
             raise AssertionError("No real histogram data is kept for TF Encoding analyzer")   # TfEncodingAnalyzer.cpp:53-57
         if self._slot is None:
             return []

@@ -14,7 +14,13 @@ import torch
 from . import _lib
 
 ROUND_NEAREST, ROUND_STOCHASTIC = 0, 1
-QUANTIZATION_TF, QUANTIZATION_TF_ENHANCED = 0, 1
+QUANTIZATION_TF, QUANTIZATION_TF_ENHANCED, QUANTIZATION_PERCENTILE, QUANTIZATION_MSE = 0, 1, 3, 4
+
+
+def keeps_histogram(quant_mode) -> bool:
+    """tf_enhanced, percentile and mse all keep the 512-bin running PDF (UpdatePdf); tf keeps a running min/max."""
+    return int(quant_mode) in (QUANTIZATION_TF_ENHANCED, QUANTIZATION_PERCENTILE, QUANTIZATION_MSE)
+
 STATE_BYTES = None          # filled at import from ab_stats_state_bytes()
 LOG_WORDS = _lib.PDF_SIZE + 2
 
@@ -236,7 +242,7 @@ def stats_update_impl(x, states, index, quant_mode, batch_log, log_entry, flags=
             stop.record()
             timing.append((x.numel() * x.element_size(), start, stop, int(quant_mode),
                            torch.cuda.is_current_stream_capturing()))
-    if int(quant_mode) == QUANTIZATION_TF_ENHANCED:
+    if keeps_histogram(quant_mode):
         LAUNCHES["hist"] += 1
         if not flags & STATS_RANGE_FIXED:
             LAUNCHES["minmax"] += 1

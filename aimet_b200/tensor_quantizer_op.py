@@ -98,7 +98,7 @@ class AimetTensorQuantizer:
         self._ensure_state(t.device)
         ops.stats_update_impl(t, self._block.arena, self._block.first + self._index, self._code, None, 0,
                               ops.STATS_RANGE_FIXED if self._range_fixed else 0)
-        if self._code == ops.QUANTIZATION_TF_ENHANCED and not self._range_fixed:
+        if ops.keeps_histogram(self._code) and not self._range_fixed:
             self._poll_range_fixed()
 
     _INITIALIZED_WORD = field_index("initialized", 4)      # ab_stats_state.initialized as an int32 index
@@ -170,7 +170,7 @@ class AimetTensorQuantizer:
 
     def getStatsHistogram(self):
         """AimetTensorQuantizer.cpp:194-198"""
-        if self._code != ops.QUANTIZATION_TF_ENHANCED:
+        if not ops.keeps_histogram(self._code):
             raise AssertionError("No real histogram data is kept for TF Encoding analyzer")
         if self._block is None:
             return []

@@ -54,7 +54,8 @@ typedef enum
 {
     AB_QUANTIZATION_TF          = 0,
     AB_QUANTIZATION_TF_ENHANCED = 1,
-    AB_QUANTIZATION_PERCENTILE  = 3 /* statistics identical to TF_ENHANCED (UpdatePdf); see ab_compute_encodings_percentile */
+    AB_QUANTIZATION_PERCENTILE  = 3, /* statistics identical to TF_ENHANCED (UpdatePdf); see ab_compute_encodings_percentile */
+    AB_QUANTIZATION_MSE         = 4  /* MseEncodingAnalyzer (DlQ/src/MseEncodingAnalyzer.cpp): same statistics again */
 } ab_quant_mode;
 
 /* DlQ/include/DlQuantization/Quantization.hpp:113-120 (TfEncoding), same field order */
@@ -210,7 +211,9 @@ int ab_stats_update_segmented(const void* in, int64_t num_segments, int64_t segm
  * enc_out   : DEVICE array of count * 5 doubles {min, max, delta, offset, bw}; all zero when no stats were seen
  * qdq4_out  : optional DEVICE array of count * 4 floats: the {min, max, delta, offset} fp32 kernel parameters that
  *             fillEncodingInfo(enc.min, enc.max, bw) yields (per-tensor QDQ, for ab_qdq_per_tensor_fwd_dev); may be NULL
- * AB_QUANTIZATION_TF states are also accepted (then the encoding is TfEncodingAnalyzer::computeEncoding). */
+ * AB_QUANTIZATION_TF states are also accepted (then the encoding is TfEncodingAnalyzer::computeEncoding), and so is
+ * AB_QUANTIZATION_MSE (MseEncodingAnalyzer<float>::computeEncoding, DlQ/src/MseEncodingAnalyzer.cpp:77-285, on
+ * tf_enhanced-style statistics). */
 int ab_compute_encodings(const ab_stats_state* states, int64_t count, int quant_mode, int bw, int use_symmetric,
                          int use_strict_symmetric, int use_unsigned_symmetric, double* enc_out, float* qdq4_out,
                          void* stream);

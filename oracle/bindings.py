@@ -90,6 +90,8 @@ class Oracle:
         L.qo_tfe_fold_histogram.argtypes = [C.POINTER(TfeState), _u32p, C.c_size_t]
         L.qo_tfe_compute.restype = Encoding
         L.qo_tfe_compute.argtypes = [C.POINTER(TfeState), C.c_int, C.c_int, C.c_int, C.c_int]
+        L.qo_mse_compute.restype = Encoding
+        L.qo_mse_compute.argtypes = [C.POINTER(TfeState), C.c_int, C.c_int, C.c_int, C.c_int]
         L.qo_percentile_compute.restype = Encoding
         L.qo_percentile_compute.argtypes = [C.POINTER(TfeState), C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]
         L.qo_tfe_cost.restype = C.c_double
@@ -235,6 +237,13 @@ class OraclePercentile(OracleTfe):
     def compute(self, bw, sym=False, strict=False, unsigned=False):
         return self.o.L.qo_percentile_compute(C.byref(self.s), self.percentile, bw, int(sym), int(strict),
                                               int(unsigned)).astuple()
+
+
+class OracleMse(OracleTfe):
+    """MseEncodingAnalyzer: the tf_enhanced statistics, (min, max) chosen by least quantisation MSE on the bin centres."""
+
+    def compute(self, bw, sym=False, strict=False, unsigned=False):
+        return self.o.L.qo_mse_compute(C.byref(self.s), bw, int(sym), int(strict), int(unsigned)).astuple()
 
 
 class Reference:

@@ -660,3 +660,105 @@ qo_encoding qo_percentile_compute(const qo_tfe_state* s, float percentile, int b
     a_max = fmaxx(a_max, 0.0f);
     return qo_tf_encoding(bw, a_min, a_max, sym, strict, unsigned_sym);
 }
+
+/* ---- MSE calibration: src/MseEncodingAnalyzer.cpp:77-285 (DTYPE = float), on tf_enhanced statistics (:70-76) ---- */
+#define QO_MSE_MAX_EDGES 1024
+
+static float mse_cost(int bw, const float* centers, const float* cpdf, int n_centers, float cand_min, float cand_max,
+                      int sym, int strict, int unsigned_sym)
+{
+    qo_encoding enc = qo_tf_encoding(bw, cand_min, cand_max, sym, strict, unsigned_sym);
+    float err       = 0;
+    for (int i = 0; i < n_centers; i++)
+    {
+        float val     = centers[i];
+        float clamped = fmaxx(cand_min, fminx(val, cand_max));
+        int quantized = d2i(round(clamped / enc.delta - enc.offset));
+        float deq     = (float) (enc.delta * (quantized + enc.offset));
+        double diff   = (double) (val - deq);
+        err           = (float) (err + cpdf[i] * (diff * diff)); /* float += float * pow(float, 2) */
+    }
+    return err;
+}
+
+qo_encoding qo_mse_compute(const qo_tfe_state* s, int bw_in, int sym, int strict, int unsigned_sym)
+{
+    qo_encoding e   = {0, 0, 0, 0, 0};
+    uint8_t bw      = (uint8_t) bw_in;
+    float num_steps = (float) (pow(2, bw) - 1);
+    if (sym && strict)
+        num_steps -= 1;
+    if (!s->initialized)
+    {
+        if (s->stats_updated)
+        {
+            e.min    = -1;
+            e.max    = 1;
+            e.delta  = (e.max - e.min) / (int) num_steps;
+            e.offset = floor(e.min / e.delta);
+            e.min    = e.offset * e.delta;
+            e.max    = e.min + (int) num_steps * e.delta;
+            e.bw     = bw;
+        }
+        return e;
+    }
+    /* _minimizeMSE :139-201 */
+    const float width = (float) (s->x_left[1] - s->x_left[0]);
+    float hist_min    = (float) s->x_left[0];
+    float hist_max    = (float) (s->x_left[QO_PDF_SIZE - 1] + width);
+    float min_val, max_val;
+    tfe_range(s, &min_val, &max_val);
+    max_val = max_val + width;
+
+    static __thread float edges[QO_MSE_MAX_EDGES + 2], centers[QO_MSE_MAX_EDGES + 2], cpdf[QO_MSE_MAX_EDGES + 2];
+    static __thread float mins[QO_MSE_MAX_EDGES + 2], maxs[QO_MSE_MAX_EDGES + 2];
+    int n_edges      = 0;
+    edges[n_edges++] = min_val;
+    int guard        = 0;
+    for (float i = hist_min; i <= hist_max && n_edges < QO_MSE_MAX_EDGES && guard < 4 * QO_MSE_MAX_EDGES;
+         i += width, guard++)
+        if (i >= min_val && i <= max_val)
+            edges[n_edges++] = i;
+
+    /* _pickMinMaxCandidatesMSECalib :204-238 */
+    int n_min = 0, n_max = 0;
+    for (int k = 0; k < n_edges; k++)
+    {
+        if (edges[k] < 0)
+            mins[n_min++] = edges[k];
+        else if (edges[k] > 0)
+            maxs[n_max++] = edges[k];
+    }
+    mins[n_min++] = 0;
+    maxs[n_max++] = 0;
+
+    float pdf_start = (float) s->x_left[0];
+    float pdf_step  = (float) (s->x_left[1] - s->x_left[0]);
+    int n_centers   = n_edges - 1;
+    for (int i = 0; i < n_centers; i++)
+    {
+        centers[i] = (i == 0) ? min_val + width / 2 : centers[i - 1] + width;
+        int ind    = f2i(floorf((centers[i] - pdf_start) / pdf_step));
+        ind        = imin(imax(0, ind), QO_PDF_SIZE - 1);
+        cpdf[i]    = (float) s->pdf[ind];
+    }
+
+    float mse_min  = FLT_MAX;
+    float best_min = min_val, best_max = max_val;
+    for (int a = 0; a < n_min; a++)
+        for (int b = 0; b < n_max; b++)
+        {
+            if (a == n_min - 1 && b == n_max - 1)
+                break; /* the trailing {0, 0} was popped */
+            float c = mse_cost(bw, centers, cpdf, n_centers, mins[a], maxs[b], sym, strict, unsigned_sym);
+            if (c < mse_min)
+            {
+                mse_min  = c;
+                best_min = mins[a];
+                best_max = maxs[b];
+            }
+        }
+    best_min = fminx(best_min, 0.0f);
+    best_max = fmaxx(best_max, 0.0f);
+    return qo_tf_encoding(bw, best_min, best_max, sym, strict, unsigned_sym);
+}

@@ -91,6 +91,8 @@ void qo_tfe_fold_histogram(qo_tfe_state* s, const uint32_t* hist, size_t cnt);
 qo_encoding qo_tfe_compute(const qo_tfe_state* s, int bw, int sym, int strict, int unsigned_sym); /* src/TfEnhancedEncodingAnalyzer.cpp:79-113,358-397 */
 /* percentile calibration on the same statistics: src/PercentileEncodingAnalyzer.cpp:77-196 */
 qo_encoding qo_percentile_compute(const qo_tfe_state* s, float percentile, int bw, int sym, int strict, int unsigned_sym);
+/* MSE calibration on the same statistics: src/MseEncodingAnalyzer.cpp:77-285 */
+qo_encoding qo_mse_compute(const qo_tfe_state* s, int bw, int sym, int strict, int unsigned_sym);
 /* cost of one candidate: TfEnhancedEncodingAnalyzer.cpp:294-355 */
 double qo_tfe_cost(const qo_tfe_state* s, int bw, float delta, int offset);
 /* candidate list (delta[], offset[]) in the reference's order; returns count (<= 358): :178-253 */

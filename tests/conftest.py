@@ -58,7 +58,7 @@ def hostmath():
     import ctypes as C
     src = os.path.join(ROOT, "tests", "native", "hostmath_test.cpp")
     so = os.path.join(ROOT, "tests", "native", "libhostmath_test.so")
-    deps = [src] + [os.path.join(ROOT, "aimet_b200", "csrc", h) for h in ("encoding_math.h", "tfe_math.h")]
+    deps = [src] + [os.path.join(ROOT, "aimet_b200", "csrc", h) for h in ("encoding_math.h", "tfe_math.h", "percentile_math.h", "mse_math.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", src, "-o", so],
                        check=True)
@@ -66,6 +66,8 @@ def hostmath():
     dp = C.POINTER(C.c_double)
     fp = C.POINTER(C.c_float)
     lib.ht_tfe_compute.argtypes = [dp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, dp]
+    lib.ht_percentile_compute.argtypes = [dp, C.c_double, C.c_double, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, dp]
+    lib.ht_mse_compute.argtypes = [dp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, dp]
     lib.ht_init_pdf_range.argtypes = [C.c_float, C.c_float, dp, dp, fp, fp]
     lib.ht_x_left.restype = C.c_double
     lib.ht_x_left.argtypes = [C.c_double, C.c_double, C.c_int]

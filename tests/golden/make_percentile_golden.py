@@ -34,6 +34,19 @@ def analyzer_goldens():
         out[name] = np.array(rows, dtype=np.float64)
     np.savez_compressed(os.path.join(HERE, "percentile.npz"), **out)
     print("percentile.npz:", {k: v.shape for k, v in out.items()})
+    # the MSE analyzer (QuantizationMode 4) on the same inputs
+    out = {}
+    for name, spec in ANALYZER_CASES.items():
+        batches = analyzer_batches(name)
+        rows = []
+        for (bw, sym, strict, unsigned) in spec["variants"]:
+            a = bindings.RefAnalyzer(ref, 4)
+            for b in batches:
+                a.update(b)
+            rows.append(list(a.compute(bw, sym, strict, unsigned)))
+        out[name] = np.array(rows, dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "mse.npz"), **out)
+    print("mse.npz:", {k: v.shape for k, v in out.items()})
 
 
 def quantsim_golden():

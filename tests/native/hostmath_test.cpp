@@ -3,6 +3,8 @@
 // This library is never loaded by the aimet_b200 package.
 #include <cstring>
 
+#include "../../aimet_b200/csrc/mse_math.h"
+#include "../../aimet_b200/csrc/percentile_math.h"
 #include "../../aimet_b200/csrc/tfe_math.h"
 
 using namespace ab;
@@ -53,6 +55,27 @@ void ht_tfe_compute(const double* pdf, double x_left0, double bucket_d, int init
         }
         tfe::finish(best_delta, best_offset, steps, bw, e);
     }
+    out5[0] = e.min, out5[1] = e.max, out5[2] = e.delta, out5[3] = e.offset, out5[4] = e.bw;
+}
+
+// the percentile and MSE modes of compute_encodings_kernel on an initialised PDF
+void ht_percentile_compute(const double* pdf, double x_left0, double bucket_d, float percentile, int bw, int sym,
+                           int strict, int unsigned_sym, double* out5)
+{
+    tfe::PdfView view {pdf, x_left0, bucket_d};
+    double cdf[AB_PDF_SIZE];
+    ab_encoding e;
+    pct::encoding(view, cdf, percentile, bw, sym, strict, unsigned_sym, e);
+    out5[0] = e.min, out5[1] = e.max, out5[2] = e.delta, out5[3] = e.offset, out5[4] = e.bw;
+}
+
+void ht_mse_compute(const double* pdf, double x_left0, double bucket_d, int bw, int sym, int strict, int unsigned_sym,
+                    double* out5)
+{
+    tfe::PdfView view {pdf, x_left0, bucket_d};
+    static mse::Tables tables;
+    ab_encoding e;
+    mse::encoding(view, tables, bw, sym, strict, unsigned_sym, e);
     out5[0] = e.min, out5[1] = e.max, out5[2] = e.delta, out5[3] = e.offset, out5[4] = e.bw;
 }
 

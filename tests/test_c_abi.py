@@ -123,7 +123,7 @@ def test_host_per_channel_params_match_oracle(lib, oracle):
 def test_kernel_math_headers_match_oracle_on_host(hostmath, oracle):
     """tfe_math.h / encoding_math.h are what the CUDA kernels execute; compiled for the host they must agree with the
     oracle bit for bit: histogram range, xLeft, and the full grid search."""
-    from oracle.bindings import OracleTfe
+    from oracle.bindings import OracleMse, OraclePercentile, OracleTfe
     rng = np.random.default_rng(13)
     dp = C.POINTER(C.c_double)
     for t in range(120):
@@ -148,6 +148,19 @@ def test_kernel_math_headers_match_oracle_on_host(hostmath, oracle):
                 hostmath.ht_tfe_compute(pdf.ctypes.data_as(dp), x0.value, bd.value, 1, 1, bw, s, st, u,
                                         out.ctypes.data_as(dp))
                 assert tuple(out[:4]) == a.compute(bw, s, st, u)[:4], (t, bw, s, st, u)
+        if t % 4 == 0:
+            # the percentile and MSE closings (percentile_math.h, mse_math.h) on the same statistics
+            pct, mse = OraclePercentile(oracle, 99.0 + (t % 7) * 0.1), OracleMse(oracle)
+            pct.s, mse.s = a.s, a.s
+            for bw in (4, 8):
+                for (s, st, u) in VARIANTS:
+                    out = np.zeros(5)
+                    hostmath.ht_percentile_compute(pdf.ctypes.data_as(dp), x0.value, bd.value, pct.percentile, bw, s, st, u,
+                                                   out.ctypes.data_as(dp))
+                    assert tuple(out[:4]) == pct.compute(bw, s, st, u)[:4], ("percentile", t, bw, s, st, u)
+                    hostmath.ht_mse_compute(pdf.ctypes.data_as(dp), x0.value, bd.value, bw, s, st, u,
+                                            out.ctypes.data_as(dp))
+                    assert tuple(out[:4]) == mse.compute(bw, s, st, u)[:4], ("mse", t, bw, s, st, u)
     out = np.zeros(5)
     z = np.zeros(512)
     hostmath.ht_tfe_compute(z.ctypes.data_as(dp), 0.0, 0.0, 0, 1, 8, 0, 0, 0, out.ctypes.data_as(dp))

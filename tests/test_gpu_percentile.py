@@ -101,3 +101,56 @@ def test_python_api(ops):
         from aimet_b200.state import StateArena
         blk = StateArena.for_device(torch.device("cuda", 0)).allocate(1)
         ops.compute_encodings_impl(blk.arena, blk.first, 1, PERCENTILE, 8, False, False, False)
+
+
+# ---- MSE scheme ------------------------------------------------------------------------------------------------------
+MSE = 4
+
+
+@pytest.mark.parametrize("name", list(ANALYZER_CASES))
+def test_mse_device_matches_reference_goldens(ops, name):
+    from aimet_b200.state import StateArena
+    gold = np.load(os.path.join(GOLDEN, "mse.npz"))[name]
+    batches = analyzer_batches(name)
+    blk = StateArena.for_device(torch.device("cuda", 0)).allocate(1)
+    for b in batches:
+        ops.stats_update_impl(torch.from_numpy(b).cuda(), blk.arena, blk.first, MSE, None, 0)
+    for row, (bw, sym, strict, unsigned) in enumerate(ANALYZER_CASES[name]["variants"]):
+        enc, _ = ops.compute_encodings_impl(blk.arena, blk.first, 1, MSE, bw, sym, strict, unsigned)
+        assert np.array_equal(enc[0].cpu().numpy(), gold[row]), (name, bw, sym, strict, unsigned)
+
+
+def test_mse_batched_records_and_python_api(ops, oracle):
+    from aimet_b200 import AimetTensorQuantizer, libpymo
+    from aimet_b200.state import StateArena
+    rng = np.random.default_rng(5)
+    n_rec = 19
+    blk = StateArena.for_device(torch.device("cuda", 0)).allocate(n_rec)
+    ports = []
+    for i in range(n_rec):
+        a = bindings.OracleMse(oracle)
+        for _ in range(1 + i % 2):
+            x = (rng.standard_normal(2000 + 31 * i) * (0.3 + i % 4) + (i % 3 - 1)).astype(np.float32)
+            if i % 5 == 0:
+                x = np.maximum(x, 0)
+            ops.stats_update_impl(torch.from_numpy(x).cuda(), blk.arena, blk.first + i, MSE, None, 0)
+            a.update(x)
+        ports.append(a)
+    for (bw, sym, strict, unsigned) in ((8, 0, 0, 0), (8, 1, 0, 0), (4, 1, 1, 0), (8, 1, 0, 1)):
+        enc, _ = ops.compute_encodings_impl(blk.arena, blk.first, n_rec, MSE, bw, sym, strict, unsigned)
+        enc = enc.cpu().numpy()
+        for i, a in enumerate(ports):
+            assert tuple(enc[i]) == tuple(float(v) for v in a.compute(bw, sym, strict, unsigned)), (i, bw, sym)
+    # the class-level drop-ins
+    x = torch.randn(30000, device="cuda") * 2 + 0.5
+    q = AimetTensorQuantizer(libpymo.QuantizationMode.QUANTIZATION_MSE)
+    q.updateStats(x, True)
+    enc, ok = q.getEncoding(8, False, False, False)
+    port = bindings.OracleMse(oracle)
+    port.update(x.cpu().numpy())
+    assert ok and (enc.min, enc.max, enc.delta, enc.offset, enc.bw) == port.compute(8)
+    assert len(q.getStatsHistogram()) == 512
+    tq = libpymo.TensorQuantizer(libpymo.QuantizationMode.QUANTIZATION_MSE, libpymo.RoundingMode.ROUND_NEAREST)
+    tq.updateStats(x.cpu().numpy(), False)
+    e = tq.computeEncoding(8, False)
+    assert (e.min, e.max) == (enc.min, enc.max)
