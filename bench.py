@@ -30,7 +30,12 @@ if ROOT not in sys.path:
 
 BATCH = 32
 IMAGE = (3, 224, 224)
-CPU_BATCH = 4          # bounded sample for the CPU arms: images per step
+CPU_BATCH = 4          # bounded sample for the CPU arms: images per step ...
+CPU_IMAGE_BUDGET = 256  # ... shrunk when K steps of it would exceed this many images (~2 minutes of host time)
+
+
+def cpu_batch_for(steps):
+    return max(1, min(CPU_BATCH, CPU_IMAGE_BUDGET // max(steps, 1)))
 METRIC = "resnet50_quantsim_calibration_throughput"
 UNIT = "img/s"
 
@@ -157,9 +162,10 @@ def ncu_traffic_ratio():
 # CPU arms (the reference's own implementation on the host cores)
 # ---------------------------------------------------------------------------------------------------------------------
 def cpu_job(steps, warmup):
-    """A complete calibration job of `steps` batches of CPU_BATCH images on the host: torch CPU forward (all threads) and
-    the reference's C++ statistics / encodings (single-threaded, as the reference is). Returns (img/s, info)."""
+    """A complete calibration job of `steps` batches of cpu_batch_for(steps) images on the host: torch CPU forward (all
+    threads) and the reference's C++ statistics / encodings (single-threaded, as the reference is). Returns (img/s, info)."""
     import torch
+    batch = cpu_batch_for(steps)
 
     from aimet_b200.quantsim import tensor_quantizer
     from oracle import cpu_backend
@@ -167,7 +173,7 @@ def cpu_job(steps, warmup):
     sim = build_sim("cpu", factory)
     prev = tensor_quantizer.set_default_op_factory(factory)
     try:
-        batches = [synthetic_batch(b, CPU_BATCH) for b in range(max(steps, warmup))]
+        batches = [synthetic_batch(b, batch) for b in range(max(steps, 1))]
         if warmup > 0:
             # warm-up: forward passes only touch the allocator / thread pool; one tiny complete job primes everything
             sim.compute_encodings(lambda m, _: [m(batches[i % len(batches)][:1]) for i in range(1)], None)
@@ -178,11 +184,12 @@ def cpu_job(steps, warmup):
     finally:
         tensor_quantizer.set_default_op_factory(prev)
     info = {"kind": factory.KIND, "cores": torch.get_num_threads(),
-            "sample": f"complete calibration job of {steps} steps x {CPU_BATCH} images (ResNet-50 per-channel "
+            "images_per_step": batch,
+            "sample": f"complete calibration job of {steps} steps x {batch} images (ResNet-50 per-channel "
                       f"tf_enhanced; includes the 26 560 weight-channel encodings and the final grid search); "
                       f"torch CPU forward on {torch.get_num_threads()} threads, reference statistics single-threaded",
             "num_activation_encodings": len(act), "num_param_encodings": len(par), "seconds": round(dt, 3)}
-    return steps * CPU_BATCH / dt, info
+    return steps * batch / dt, info
 
 
 def run_reference_arm(args):
@@ -191,10 +198,11 @@ def run_reference_arm(args):
         return
     value, info = cpu_job(args.steps, args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1000.0 * CPU_BATCH / value, 3),
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1000.0 * info["images_per_step"] / value, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "ResNet-50 W8A8 per-channel weights, tf_enhanced calibration (BASELINE configs[1])",
-                       "images_per_step": CPU_BATCH, "note": "host CPU only; bounded sample of the same workload"},
+                       "images_per_step": info["images_per_step"],
+                       "note": "host CPU only; bounded sample of the same workload"},
             "cpu_baseline": dict(info, value=round(value, 3), unit=UNIT),
             "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
