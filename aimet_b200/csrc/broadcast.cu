@@ -1,0 +1,268 @@
+// Quantize-dequantize with an encoding tensor BROADCAST over the input (blockwise / LPBQ weights, any mix of per-channel
+// axes): every element uses the {min, max, delta, offset} at the position its index maps to in the encoding tensor.
+//
+// Reference: quantizeDequantizeBroadcast (DlQ/include/DlQuantization/Quantization.hpp:193-221,
+// DlQ/src/trim_functions.cpp:633-662 = CPU parity target; the reference's own GPU twin is trim_functions.cu:96-122), used
+// by the ONNX custom op (TrainingExtensions/onnx/src/AimetOpUtils.h:269). Per element it decomposes the flat index
+// dimension by dimension (two integer divisions per dimension) and loads four scalars.
+//
+// Here the trailing dimensions along which the encoding is broadcast are folded into one run length `inner`: the encoding
+// index only depends on i / inner. A 128-bit vector that lies inside one run (the common case: a block is >= 4 elements)
+// resolves its encoding once -- 32-bit multiply-high divisions with host-prepared constants -- and runs the straight-line
+// XU-free QDQ of common.cuh; vectors that straddle a run boundary, unaligned tensors and tensors of 2^31 elements or more
+// take the element-wise path. Bytes: 2 s per element (+ the encoding tensor, which lives in L1/L2).
+#include "common.cuh"
+
+namespace ab
+{
+namespace
+{
+
+constexpr int kBcThreads = 256;
+constexpr int kBcUnroll  = 4;
+constexpr int kMaxDims   = 8;
+
+struct Dim
+{
+    int64_t stride;       // elements of the OUTER index space (flat index / inner) per step along this dimension
+    int64_t enc_stride;   // encoding elements per step along this dimension (0 = broadcast)
+    uint32_t mul, shift;  // n / stride == umulhi(n, mul) >> shift for n < 2^31 (stride > 1)
+};
+
+struct BroadcastArgs
+{
+    Dim dims[kMaxDims];   // outer dimensions only, outermost first
+    int num_dims;
+    int64_t inner;                       // run length over which the encoding index is constant
+    uint32_t inner_mul, inner_shift;     // fast division by inner
+    const float *mn, *mx, *delta, *offset;
+};
+
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, int64_t d, uint32_t mul, uint32_t shift)
+{
+    return d == 1 ? n : (__umulhi(n, mul) >> shift);
+}
+
+// encoding index of outer position g (32-bit fast path)
+__device__ __forceinline__ int64_t enc_index32(const BroadcastArgs& a, uint32_t g)
+{
+    int64_t idx = 0;
+#pragma unroll 1
+    for (int d = 0; d < a.num_dims; ++d)
+    {
+        const uint32_t q = fast_div(g, a.dims[d].stride, a.dims[d].mul, a.dims[d].shift);
+        g -= q * (uint32_t) a.dims[d].stride;
+        idx += a.dims[d].enc_stride * (int64_t) q;
+    }
+    return idx;
+}
+__device__ __forceinline__ int64_t enc_index64(const BroadcastArgs& a, int64_t g)
+{
+    int64_t idx = 0;
+    for (int d = 0; d < a.num_dims; ++d)
+    {
+        const int64_t q = g / a.dims[d].stride;
+        g -= q * a.dims[d].stride;
+        idx += a.dims[d].enc_stride * q;
+    }
+    return idx;
+}
+
+__device__ __forceinline__ Enc4 load_enc(const BroadcastArgs& a, int64_t idx)
+{
+    return Enc4 {__ldg(a.mn + idx), __ldg(a.mx + idx), __ldg(a.delta + idx), __ldg(a.offset + idx)};
+}
+
+__device__ __forceinline__ float qdq_exact(float x, const Enc4& e)
+{
+    return dequantize_value(quantize_value<false>(x, e, 0, 0), e);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBcThreads)
+    broadcast_fast_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t count, BroadcastArgs a)
+{
+    constexpr int kV        = Elem<T>::kPerVec;
+    const int64_t num_vec   = count / kV;
+    const int64_t num_tiles = (num_vec + kBcThreads * kBcUnroll - 1) / (kBcThreads * kBcUnroll);
+    const uint32_t inner    = (uint32_t) a.inner;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+    {
+        const int64_t v0 = tile * (kBcThreads * kBcUnroll) + threadIdx.x;
+        uint4 raw[kBcUnroll];
+#pragma unroll
+        for (int u = 0; u < kBcUnroll; ++u)
+        {
+            const int64_t v = v0 + (int64_t) u * kBcThreads;
+            if (v < num_vec)
+                raw[u] = ldg_stream(reinterpret_cast<const uint4*>(in) + v);
+        }
+#pragma unroll
+        for (int u = 0; u < kBcUnroll; ++u)
+        {
+            const int64_t v = v0 + (int64_t) u * kBcThreads;
+            if (v >= num_vec)
+                continue;
+            float f[kV];
+            Elem<T>::unpack(raw[u], f);
+            const uint32_t i0 = (uint32_t) (v * kV);
+            uint32_t g        = fast_div(i0, a.inner, a.inner_mul, a.inner_shift);
+            uint32_t rem      = i0 - g * inner;
+            Enc4 e            = load_enc(a, enc_index32(a, g));
+            if (rem + kV <= inner)
+            {
+                const Divisor dv = make_divisor(e.delta);
+                if (qdq_fast_ok(e, dv))
+                {
+#pragma unroll
+                    for (int k = 0; k < kV; ++k)
+                        f[k] = qdq_fast(f[k], e, dv);
+                }
+                else
+                {
+#pragma unroll
+                    for (int k = 0; k < kV; ++k)
+                        f[k] = qdq_exact(f[k], e);
+                }
+            }
+            else
+            {
+#pragma unroll
+                for (int k = 0; k < kV; ++k)
+                {
+                    f[k] = qdq_exact(f[k], e);
+                    if (++rem == inner && k + 1 < kV)
+                    {
+                        rem = 0;
+                        e   = load_enc(a, enc_index32(a, ++g));
+                    }
+                }
+            }
+            stg_stream(reinterpret_cast<uint4*>(out) + v, Elem<T>::pack(f));
+        }
+    }
+    if (blockIdx.x == 0)
+    {
+        const int64_t i = num_vec * kV + threadIdx.x;
+        if (i < count)
+            Elem<T>::store(out + i, qdq_exact(Elem<T>::load(in + i), load_enc(a, enc_index64(a, i / a.inner))));
+    }
+}
+
+// any alignment, any size
+template <typename T>
+__global__ void __launch_bounds__(kBcThreads)
+    broadcast_scalar_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t count, BroadcastArgs a)
+{
+    const int64_t stride = (int64_t) gridDim.x * kBcThreads;
+    for (int64_t i = (int64_t) blockIdx.x * kBcThreads + threadIdx.x; i < count; i += stride)
+        Elem<T>::store(out + i, qdq_exact(Elem<T>::load(in + i), load_enc(a, enc_index64(a, i / a.inner))));
+}
+
+void magic(int64_t d, uint32_t& mul, uint32_t& shift)
+{
+    mul = 0, shift = 0;
+    if (d > 1 && d < (int64_t) 0x7fff0000)
+    {
+        uint32_t lg = 0;
+        while ((1ull << lg) < (uint64_t) d)
+            ++lg;
+        const uint32_t p = 31 + lg;
+        mul              = (uint32_t) (((1ull << p) + (uint64_t) d - 1) / (uint64_t) d);
+        shift            = p - 32;
+    }
+}
+
+int grid_size(const void* kernel, int64_t tiles)
+{
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBcThreads, 0) != cudaSuccess || per_sm <= 0)
+        per_sm = 1;
+    int64_t grid = (int64_t) per_sm * num_sms();
+    if (tiles < grid)
+        grid = tiles;
+    return (int) (grid < 1 ? 1 : grid);
+}
+
+template <typename T>
+int launch(const void* in, void* out, int64_t count, const BroadcastArgs& a, bool fast, cudaStream_t st)
+{
+    const T* x = reinterpret_cast<const T*>(in);
+    T* y       = reinterpret_cast<T*>(out);
+    if (fast)
+    {
+        constexpr int kV    = Elem<T>::kPerVec;
+        const int64_t tiles = (count / kV + kBcThreads * kBcUnroll - 1) / (kBcThreads * kBcUnroll);
+        broadcast_fast_kernel<T><<<grid_size((const void*) broadcast_fast_kernel<T>, tiles), kBcThreads, 0, st>>>(x, y, count, a);
+    }
+    else
+    {
+        const int64_t tiles = (count + kBcThreads - 1) / kBcThreads;
+        broadcast_scalar_kernel<T><<<grid_size((const void*) broadcast_scalar_kernel<T>, tiles), kBcThreads, 0, st>>>(x, y, count,
+                                                                                                                 a);
+    }
+    AB_CUDA_CHECK(cudaGetLastError());
+    return AB_OK;
+}
+
+}   // namespace
+}   // namespace ab
+
+using namespace ab;
+
+extern "C" int ab_qdq_broadcast_fwd(const void* in, void* out, int64_t num_element, int num_dims,
+                                    const int64_t* input_strides, const int64_t* encoding_strides, const float* enc_min,
+                                    const float* enc_max, const float* enc_delta, const float* enc_offset, int dtype,
+                                    void* stream)
+{
+    if (num_element < 0 || num_dims < 1 || num_dims > kMaxDims || !input_strides || !encoding_strides)
+    {
+        set_error("bad geometry: %d dimensions (1..%d supported), %lld elements", num_dims, kMaxDims, (long long) num_element);
+        return AB_ERR_INVALID;
+    }
+    if (dtype != AB_F32 && dtype != AB_BF16)
+    {
+        set_error("unsupported dtype %d", dtype);
+        return AB_ERR_INVALID;
+    }
+    if (!enc_min || !enc_max || !enc_delta || !enc_offset || (num_element > 0 && (!in || !out)))
+    {
+        set_error("null pointer");
+        return AB_ERR_INVALID;
+    }
+    for (int d = 0; d < num_dims; ++d)
+        if (input_strides[d] < 1 || encoding_strides[d] < 0 || (d > 0 && input_strides[d - 1] % input_strides[d] != 0))
+        {
+            set_error("input strides must be those of a contiguous tensor, encoding strides non-negative");
+            return AB_ERR_INVALID;
+        }
+    if (num_element == 0)
+        return AB_OK;
+
+    // fold the trailing broadcast dimensions into one run length
+    BroadcastArgs a {};
+    a.mn = enc_min, a.mx = enc_max, a.delta = enc_delta, a.offset = enc_offset;
+    int last = -1;
+    for (int d = 0; d < num_dims; ++d)
+        if (encoding_strides[d] != 0)
+            last = d;
+    a.inner = (last < 0) ? (num_element > 0 ? num_element : 1) : input_strides[last];
+    if (a.inner < 1)
+        a.inner = 1;
+    a.num_dims = 0;
+    for (int d = 0; d <= last; ++d)
+    {
+        Dim& dim       = a.dims[a.num_dims++];
+        dim.stride     = input_strides[d] / a.inner;
+        dim.enc_stride = encoding_strides[d];
+        magic(dim.stride, dim.mul, dim.shift);
+    }
+    magic(a.inner, a.inner_mul, a.inner_shift);
+
+    const bool fast = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0 &&
+                      num_element < (int64_t) 0x7fff0000;
+    cudaStream_t st = (cudaStream_t) stream;
+    if (dtype == AB_F32)
+        return launch<float>(in, out, num_element, a, fast, st);
+    return launch<__nv_bfloat16>(in, out, num_element, a, fast, st);
+}

@@ -29,7 +29,7 @@ STATE_BYTES = int(_L.ab_stats_state_bytes())
 
 # kernel launches issued through this module, by kernel family (bench.py reports their sum as gpu_launches)
 LAUNCHES = {"qdq": 0, "quantize": 0, "qdq_per_channel": 0, "ste_bwd": 0, "minmax": 0, "hist": 0, "segmented": 0,
-            "search": 0, "reset": 0, "init_range": 0, "fold": 0, "lg_fwd": 0, "lg_bwd": 0}
+            "search": 0, "reset": 0, "init_range": 0, "fold": 0, "lg_fwd": 0, "lg_bwd": 0, "qdq_broadcast": 0}
 # when a list, stats_update_impl brackets its launches with CUDA events and appends (bytes, start, stop, quant_mode)
 STATS_TIMING = None
 _EVENT_POOL = []
@@ -150,6 +150,41 @@ def qdq_per_channel_impl(x, params, num_channel, num_element_per_channel, round_
                                              int(num_element_per_channel), _dtype_code(x), params.data_ptr(),
                                              int(round_mode), int(seed) & (2**64 - 1), _stream(x)))
     LAUNCHES["qdq_per_channel"] += 1
+    return out
+
+
+def qdq_broadcast_impl(x, enc_min, enc_max, enc_delta, enc_offset):
+    """QDQ of `x` with an encoding tensor that broadcasts against it (torch broadcasting rules: the four encoding tensors
+    share one shape, which is x's shape with some dimensions of size 1, possibly with fewer leading dimensions). The
+    encodings are used as they are -- the reference's quantizeDequantizeBroadcast does no gating -- rounding to nearest."""
+    _require_cuda(x, enc_min, enc_max, enc_delta, enc_offset)
+    shape = tuple(enc_min.shape)
+    for e in (enc_min, enc_max, enc_delta, enc_offset):
+        if e.dtype != torch.float32 or tuple(e.shape) != shape or not e.is_contiguous():
+            raise ValueError("the four encoding tensors must be contiguous float32 tensors of one shape")
+    if len(shape) > x.dim():
+        raise ValueError("the encoding tensor has more dimensions than the input")
+    x = x.contiguous()
+    nd = max(x.dim(), 1)
+    xs = tuple(x.shape) if x.dim() else (1,)
+    padded = (1,) * (nd - len(shape)) + shape
+    for a, b in zip(padded, xs):
+        if a not in (1, b):
+            raise ValueError(f"encoding shape {shape} does not broadcast to input shape {tuple(x.shape)}")
+    in_strides, enc_strides = [0] * nd, [0] * nd
+    acc_in = acc_enc = 1
+    for d in range(nd - 1, -1, -1):
+        in_strides[d] = acc_in
+        enc_strides[d] = acc_enc if padded[d] != 1 else 0
+        acc_in *= xs[d]
+        acc_enc *= padded[d]
+    out = torch.empty_like(x)
+    arr = C.c_int64 * nd
+    with _on_device(x):
+        _lib.check(_L.ab_qdq_broadcast_fwd(x.data_ptr(), out.data_ptr(), x.numel(), nd, arr(*in_strides), arr(*enc_strides),
+                                           enc_min.data_ptr(), enc_max.data_ptr(), enc_delta.data_ptr(),
+                                           enc_offset.data_ptr(), _dtype_code(x), _stream(x)))
+    LAUNCHES["qdq_broadcast"] += 1
     return out
 
 

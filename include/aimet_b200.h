@@ -165,6 +165,17 @@ int ab_qdq_per_channel_fwd(const void* in, void* out, int64_t num_channel, int64
  * encodings feed ab_qdq_per_channel_fwd without a host round trip (same arithmetic: ATQ:236-299). */
 int ab_per_channel_params_dev(const double* enc5, int64_t num_channel, int bw, float* params, void* stream);
 
+/* quantizeDequantizeBroadcast (DlQ/include/DlQuantization/Quantization.hpp:193-221 -> DlQ/src/trim_functions.cpp:633-662; GPU
+ * twin trim_functions.cu:96-122; caller: the ONNX custom op, TrainingExtensions/onnx/src/AimetOpUtils.h:269): QDQ with an
+ * encoding tensor broadcast over the input (blockwise / LPBQ, several per-channel axes ...). The input is a contiguous
+ * tensor of `num_dims` (<= 8) dimensions whose element strides are `input_strides`; `encoding_strides` are the element
+ * strides of the encoding tensor padded to the same rank, 0 along broadcast dimensions. Both stride arrays are HOST arrays
+ * here (they travel as kernel arguments; the reference wants them in device memory). enc_min / enc_max / enc_delta /
+ * enc_offset: DEVICE float arrays holding the encoding tensor, used as they are (no gating), rounding to nearest. */
+int ab_qdq_broadcast_fwd(const void* in, void* out, int64_t num_element, int num_dims, const int64_t* input_strides,
+                         const int64_t* encoding_strides, const float* enc_min, const float* enc_max,
+                         const float* enc_delta, const float* enc_offset, int dtype, void* stream);
+
 /* compute_dloss_by_dx (TrainingExtensions/torch/src/python/aimet_torch/v1/quantsim_straight_through_grad.py:91-118):
  * grad_in = grad * [enc_min <= x <= enc_max]. x, grad, grad_in share `dtype`. */
 int ab_qdq_ste_bwd(const void* x, const void* grad, void* grad_in, int64_t count, int dtype, float enc_min,

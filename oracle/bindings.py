@@ -68,6 +68,8 @@ class Oracle:
         L.qo_quantize_tensor.argtypes = [_fp, C.c_size_t, _fp, C.c_double, C.c_double, C.c_int, C.c_int]
         L.qo_per_channel_prepare.argtypes = [_dp, _dp, C.c_int, C.c_int, _fp, _fp, _fp, _fp]
         L.qo_qdq_per_channel.argtypes = [_fp, C.c_size_t, C.c_size_t, C.c_size_t, _fp, _fp, _fp, _fp, _fp]
+        L.qo_qdq_broadcast.argtypes = [_fp, _fp, C.c_int64, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _fp, _fp,
+                                       _fp, _fp]
         L.qo_ste_bwd.argtypes = [_fp, _fp, C.c_size_t, C.c_float, C.c_float, _fp]
         L.qo_ste_bwd_per_channel.argtypes = [_fp, _fp, C.c_size_t, C.c_size_t, C.c_size_t, _fp, _fp, _fp]
         L.qo_bf16_to_f32.restype = C.c_float
@@ -156,6 +158,17 @@ class Oracle:
                                       _f(out))
         return out
 
+    def qdq_broadcast(self, x, enc_min, enc_max, enc_delta, enc_offset):
+        """x: any-rank fp32 array; the four encoding arrays share a shape that broadcasts to x's."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        encs = [np.ascontiguousarray(e, dtype=np.float32) for e in (enc_min, enc_max, enc_delta, enc_offset)]
+        in_strides, enc_strides = broadcast_strides(x.shape, encs[0].shape)
+        out = np.empty_like(x)
+        i64 = C.c_int64 * len(in_strides)
+        self.L.qo_qdq_broadcast(_f(x), _f(out), x.size, len(in_strides), i64(*in_strides), i64(*enc_strides),
+                                *[_f(e) for e in encs])
+        return out
+
     # -- statistics -----------------------------------------------------------------------------
     def get_min_max(self, x):
         x = np.ascontiguousarray(x, dtype=np.float32)
@@ -166,6 +179,21 @@ class Oracle:
         h = np.zeros(PDF_SIZE, np.uint32)
         self.L.qo_histogram(_f(x), x.size, h.ctypes.data_as(_u32p), bucket_size, pdf_offset)
         return h
+
+
+def broadcast_strides(x_shape, enc_shape):
+    """Element strides of a contiguous input and of the encoding tensor padded to the same rank (0 where it broadcasts)."""
+    nd = max(len(x_shape), 1)
+    xs = tuple(x_shape) if len(x_shape) else (1,)
+    padded = (1,) * (nd - len(enc_shape)) + tuple(enc_shape)
+    in_strides, enc_strides = [0] * nd, [0] * nd
+    acc_in = acc_enc = 1
+    for d in range(nd - 1, -1, -1):
+        in_strides[d] = acc_in
+        enc_strides[d] = acc_enc if padded[d] != 1 else 0
+        acc_in *= xs[d]
+        acc_enc *= padded[d]
+    return in_strides, enc_strides
 
 
 class OracleTf:
@@ -265,6 +293,8 @@ class Reference:
         L.ref_qdq.argtypes = [_fp, C.c_size_t, _fp, C.c_double, C.c_double, C.c_int, C.c_int]
         L.ref_quantize.argtypes = [_fp, C.c_size_t, _fp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int]
         L.ref_qdq_per_channel.argtypes = [_fp, C.c_size_t, C.c_size_t, C.c_size_t, _fp, _fp, _fp, _fp, _fp, C.c_int]
+        L.ref_qdq_broadcast.argtypes = [_fp, _fp, C.c_int64, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _fp, _fp,
+                                        _fp, _fp]
         L.ref_tq_new.restype = C.c_void_p
         L.ref_tq_new.argtypes = [C.c_int, C.c_int]
         L.ref_tq_free.argtypes = [C.c_void_p]
@@ -301,6 +331,16 @@ class Reference:
         out = np.empty_like(x)
         self.L.ref_qdq_per_channel(_f(x), num_channel, x.size, num_per_channel, _f(out), _f(emin), _f(emax),
                                    _f(edelta), _f(eoffset), ROUND_NEAREST)
+        return out
+
+    def qdq_broadcast(self, x, enc_min, enc_max, enc_delta, enc_offset):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        encs = [np.ascontiguousarray(e, dtype=np.float32) for e in (enc_min, enc_max, enc_delta, enc_offset)]
+        in_strides, enc_strides = broadcast_strides(x.shape, encs[0].shape)
+        out = np.empty_like(x)
+        i64 = C.c_int64 * len(in_strides)
+        self.L.ref_qdq_broadcast(_f(x), _f(out), x.size, len(in_strides), i64(*in_strides), i64(*enc_strides),
+                                 *[_f(e) for e in encs])
         return out
 
     def partial_encoding(self, bw, enc, sym, unsigned, strict):

@@ -762,3 +762,23 @@ qo_encoding qo_mse_compute(const qo_tfe_state* s, int bw_in, int sym, int strict
     best_max = fmaxx(best_max, 0.0f);
     return qo_tf_encoding(bw, best_min, best_max, sym, strict, unsigned_sym);
 }
+
+/* ---- broadcast QDQ: src/trim_functions.cpp:633-662 ---- */
+void qo_qdq_broadcast(const float* in, float* out, int64_t num_element, int64_t num_dims, const int64_t* input_strides,
+                      const int64_t* encoding_strides, const float* enc_min, const float* enc_max, const float* enc_delta,
+                      const float* enc_offset)
+{
+    for (size_t i = 0; i < (size_t) num_element; i++)
+    {
+        int enc_idx   = 0;
+        int remainder = (int) i;
+        for (int64_t dim = 0; dim < num_dims; dim++)
+        {
+            int dim_idx = (int) (remainder / input_strides[dim]);
+            remainder   = (int) (remainder - dim_idx * input_strides[dim]);
+            enc_idx += (int) (encoding_strides[dim] * dim_idx);
+        }
+        qo_encoding e = {enc_min[enc_idx], enc_max[enc_idx], enc_delta[enc_idx], enc_offset[enc_idx], 0};
+        qo_qdq(in + i, 1, out + i, &e);
+    }
+}

@@ -63,6 +63,10 @@ void qo_per_channel_prepare(const double* enc_min, const double* enc_max, int nu
 void qo_qdq_per_channel(const float* in, size_t num_channel, size_t num_element, size_t num_element_per_channel,
                         float* out, const float* enc_min, const float* enc_max, const float* enc_delta,
                         const float* enc_offset);                                   /* src/trim_functions.cpp:697-709 */
+/* src/trim_functions.cpp:633-662 (quantizeDequantizeBroadcastCpu) */
+void qo_qdq_broadcast(const float* in, float* out, int64_t num_element, int64_t num_dims, const int64_t* input_strides,
+                      const int64_t* encoding_strides, const float* enc_min, const float* enc_max, const float* enc_delta,
+                      const float* enc_offset);
 /* TrainingExtensions/torch/src/python/aimet_torch/v1/quantsim_straight_through_grad.py:91-118 */
 void qo_ste_bwd(const float* x, const float* grad, size_t n, float enc_min, float enc_max, float* grad_in);
 void qo_ste_bwd_per_channel(const float* x, const float* grad, size_t num_channel, size_t num_element,

@@ -109,6 +109,14 @@ void ref_quantize(const float* in, size_t n, float* out, double enc_min, double 
                         shift_to_signed != 0);
 }
 
+void ref_qdq_broadcast(const float* in, float* out, int64_t num_element, int64_t num_dims, const int64_t* input_strides,
+                       const int64_t* encoding_strides, const float* enc_min, const float* enc_max,
+                       const float* enc_delta, const float* enc_offset)
+{
+    quantizeDequantizeBroadcast<float>(in, out, num_element, num_dims, input_strides, encoding_strides, enc_min, enc_max,
+                                       enc_delta, enc_offset, COMP_MODE_CPU, nullptr);
+}
+
 void ref_qdq_per_channel(const float* in, size_t num_channel, size_t num_element, size_t num_element_per_channel,
                          float* out, float* enc_min, float* enc_max, float* enc_delta, float* enc_offset,
                          int round_mode)
