@@ -97,6 +97,18 @@ __global__ void __launch_bounds__(kBcThreads)
             if (v < num_vec)
                 raw[u] = ldg_stream(reinterpret_cast<const uint4*>(in) + v);
         }
+        // the encodings only depend on the vector's position: resolve and request them while the data is in flight
+        uint32_t g[kBcUnroll], rem[kBcUnroll];
+        Enc4 enc[kBcUnroll];
+#pragma unroll
+        for (int u = 0; u < kBcUnroll; ++u)
+        {
+            const int64_t v   = v0 + (int64_t) u * kBcThreads;
+            const uint32_t i0 = (uint32_t) ((v < num_vec ? v : 0) * kV);
+            g[u]              = fast_div(i0, a.inner, a.inner_mul, a.inner_shift);
+            rem[u]            = i0 - g[u] * inner;
+            enc[u]            = load_enc(a, enc_index32(a, g[u]));
+        }
 #pragma unroll
         for (int u = 0; u < kBcUnroll; ++u)
         {
@@ -105,11 +117,8 @@ __global__ void __launch_bounds__(kBcThreads)
                 continue;
             float f[kV];
             Elem<T>::unpack(raw[u], f);
-            const uint32_t i0 = (uint32_t) (v * kV);
-            uint32_t g        = fast_div(i0, a.inner, a.inner_mul, a.inner_shift);
-            uint32_t rem      = i0 - g * inner;
-            Enc4 e            = load_enc(a, enc_index32(a, g));
-            if (rem + kV <= inner)
+            Enc4 e = enc[u];
+            if (rem[u] + kV <= inner)
             {
                 const Divisor dv = make_divisor(e.delta);
                 if (qdq_fast_ok(e, dv))
@@ -127,14 +136,15 @@ __global__ void __launch_bounds__(kBcThreads)
             }
             else
             {
+                uint32_t r = rem[u], gg = g[u];
 #pragma unroll
                 for (int k = 0; k < kV; ++k)
                 {
                     f[k] = qdq_exact(f[k], e);
-                    if (++rem == inner && k + 1 < kV)
+                    if (++r == inner && k + 1 < kV)
                     {
-                        rem = 0;
-                        e   = load_enc(a, enc_index32(a, ++g));
+                        r = 0;
+                        e = load_enc(a, enc_index32(a, ++gg));
                     }
                 }
             }
