@@ -274,3 +274,54 @@ def test_sim_training_step_kernels_vs_torch_ops_on_gpu(name):
     for n, v in ref["weight_grad_norms"].items():
         assert mine["weight_grad_norms"][n] == pytest.approx(v, rel=1e-5, abs=1e-9), n
     assert mine["output2_head"] == pytest.approx(ref["output2_head"], rel=1e-3, abs=1e-3)
+
+
+def test_more_than_2_31_elements():
+    """The range-learning kernels take int64 element counts: per-tensor and per-channel forward / backward on a tensor just
+    above 2^31 bf16 elements (bitwidth 16 -> fp32 arithmetic). Checked by self-consistency across the 2^31 boundary (the
+    same kernels on sub-ranges that start before and after it) and against the oracle on samples; the per-channel sums are
+    checked for one channel on either side of the boundary."""
+    from aimet_b200 import ops
+    c = 2050
+    per = (2**31 + 2**20) // c + 3
+    n = c * per
+    assert n > 2**31
+    g = torch.Generator(device="cuda").manual_seed(21)
+    x = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+    grad = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+    chunk = 2**28
+    for s in range(0, n, chunk):
+        m = min(chunk, n - s)
+        x[s:s + m] = torch.randn(m, device="cuda", generator=g).to(torch.bfloat16)
+        grad[s:s + m] = torch.randn(m, device="cuda", generator=g).to(torch.bfloat16)
+    bw, mode = 16, rl.ASYMMETRIC
+    # ---- per tensor
+    mn, mx = torch.tensor([-2.0], device="cuda", dtype=torch.bfloat16), torch.tensor([2.5], device="cuda", dtype=torch.bfloat16)
+    y = ops.lg_qdq_fwd_impl(x, mn, mx, bw, mode)
+    gx, gmin, gmax = ops.lg_qdq_bwd_impl(x, grad, mn, mx, bw, mode)
+    lo = 2**31 - 4096
+    for start in (0, lo, n - 8192):
+        sl = slice(start, start + 8192)
+        y_ref, saved = rl.forward(x[sl].cpu(), mn.cpu(), mx.cpu(), bw, mode)
+        gx_ref, _, _ = rl.backward(grad[sl].cpu(), saved)
+        assert bits_equal(y[sl], y_ref) and bits_equal(gx[sl], gx_ref.to(torch.bfloat16)), start
+    # the sums over the whole tensor == the sums over its two halves (double accumulation, so to ~1e-6)
+    half = (n // 2) // 8 * 8
+    _, a_min, a_max = ops.lg_qdq_bwd_impl(x[:half], grad[:half], mn, mx, bw, mode, need_grad_x=False)
+    _, b_min, b_max = ops.lg_qdq_bwd_impl(x[half:], grad[half:], mn, mx, bw, mode, need_grad_x=False)
+    # grad_min / grad_max are affine in the two sums, so they add up across a split of the tensor (up to bf16 rounding)
+    assert torch.allclose(gmin.float(), a_min.float() + b_min.float(), rtol=2e-2, atol=1.0)
+    assert torch.allclose(gmax.float(), a_max.float() + b_max.float(), rtol=2e-2, atol=1.0)
+    del y, gx
+    # ---- per channel (axis 0 of a [c, per] view): channels 1024 / 1025 straddle element 2^31
+    scale = (0.5 + torch.rand(c, device="cuda", generator=g)).to(torch.bfloat16)
+    mnc, mxc = (-2.0 * scale).contiguous(), (2.5 * scale).contiguous()
+    xc, gc = x.view(c, per), grad.view(c, per)
+    yc = ops.lg_qdq_fwd_impl(xc, mnc.clone(), mxc.clone(), bw, mode)
+    gxc, gminc, gmaxc = ops.lg_qdq_bwd_impl(xc, gc, mnc, mxc, bw, mode)
+    for ch in (0, 1023, 1024, 1025, c - 1):
+        y_ref, saved = rl.forward(xc[ch].cpu(), mnc[ch:ch + 1].cpu(), mxc[ch:ch + 1].cpu(), bw, mode)
+        gx_ref, gmin_ref, gmax_ref = rl.backward(gc[ch].cpu(), saved)
+        assert bits_equal(yc[ch], y_ref) and bits_equal(gxc[ch], gx_ref.to(torch.bfloat16)), ch
+        assert torch.allclose(gminc[ch].float().cpu(), gmin_ref.float().reshape(()), rtol=2e-2, atol=2e-2), ch
+        assert torch.allclose(gmaxc[ch].float().cpu(), gmax_ref.float().reshape(()), rtol=2e-2, atol=2e-2), ch
