@@ -12,10 +12,10 @@ import sys
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from aimet_b200 import ops  # noqa: E402
-from oracle import range_learning as rl  # noqa: E402  (baseline leg only)
+from oracle import range_learning as rl  # noqa: E402  (baseline leg only; this script lives under tests/ because it uses the oracle)
 
 L2_BYTES = 126 * 2**20
 
