@@ -11,6 +11,7 @@ import sys
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.environ.get("GOLDEN_OUT", HERE)   # tests regenerate the sim golden into a scratch directory (see conftest.py)
 sys.path.insert(0, HERE)
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
@@ -60,6 +61,8 @@ def quantsim_golden():
     torch.manual_seed(1)
     x = torch.randn(4, 3, 64, 64)
     x2 = torch.randn(4, 3, 64, 64) * 1.5
+    with torch.no_grad():   # torch's CPU convolutions differ in the last bit between hosts: record which host this is
+        fingerprint = hashlib.sha256(model(x).numpy().tobytes()).hexdigest()
     sim = QuantizationSimModel(model, dummy_input=x, quant_scheme=QuantScheme.post_training_percentile,
                                default_output_bw=8, default_param_bw=8)
     sim.set_percentile_value(99.9)
@@ -73,13 +76,14 @@ def quantsim_golden():
     with torch.no_grad():
         out = sim.model(x)
     enc = json.loads(json.dumps({"activation_encodings": act, "param_encodings": par}, sort_keys=True))
-    gold = {"encodings": enc, "sha256": hashlib.sha256(json.dumps(enc, sort_keys=True).encode()).hexdigest(),
+    gold = {"forward_fingerprint": fingerprint, "encodings": enc, "sha256": hashlib.sha256(json.dumps(enc, sort_keys=True).encode()).hexdigest(),
             "output_sha256": hashlib.sha256(out.numpy().tobytes()).hexdigest(), "percentile": 99.9}
-    with open(os.path.join(HERE, "quantsim_resnet18_percentile.json"), "w") as f:
+    with open(os.path.join(OUT, "quantsim_resnet18_percentile.json"), "w") as f:
         json.dump(gold, f, sort_keys=True, indent=1)
     print("quantsim_resnet18_percentile:", gold["sha256"][:12], len(act), len(par))
 
 
 if __name__ == "__main__":
-    analyzer_goldens()
+    if "--sim-only" not in sys.argv:
+        analyzer_goldens()
     quantsim_golden()

@@ -10,6 +10,7 @@ import os
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.environ.get("GOLDEN_OUT", HERE)   # tests regenerate into a scratch directory on a host with other CPU numerics
 sys.path.insert(0, HERE)
 import ref_python_env  # noqa: E402,F401
 import torch  # noqa: E402
@@ -46,6 +47,8 @@ def main():
         torch.manual_seed(1)
         x = torch.randn(*shape)
         x2 = torch.randn(*shape) * 1.5
+        with torch.no_grad():   # torch's CPU convolutions differ in the last bit between hosts: record which host this is
+            fingerprint = hashlib.sha256(model(x).numpy().tobytes()).hexdigest()
         sim = QuantizationSimModel(model, dummy_input=x, quant_scheme=scheme, default_output_bw=8, default_param_bw=8,
                                    config_file=cfg)
         structure = {}
@@ -68,7 +71,7 @@ def main():
         with torch.no_grad():
             out = sim.model(x)
         enc = {"activation_encodings": act, "param_encodings": par}
-        golden = {"structure": structure, "sha256": hashlib.sha256(canonical(enc).encode()).hexdigest(),
+        golden = {"forward_fingerprint": fingerprint, "structure": structure, "sha256": hashlib.sha256(canonical(enc).encode()).hexdigest(),
                   "output_sha256": hashlib.sha256(out.numpy().tobytes()).hexdigest(),
                   "num_activation": sum(len(v.get("input", {})) + len(v.get("output", {})) for v in act.values()),
                   "num_param": len(par)}
@@ -78,7 +81,7 @@ def main():
             golden["activation_encodings"] = json.loads(canonical(act))
             first = {k: par[k][:3] for k in list(par)[:4]}
             golden["param_encodings_sample"] = json.loads(canonical(first))
-        with open(os.path.join(HERE, f"quantsim_{name}.json"), "w") as f:
+        with open(os.path.join(OUT, f"quantsim_{name}.json"), "w") as f:
             json.dump(golden, f, sort_keys=True, indent=1)
         print(name, golden["num_activation"], golden["num_param"], golden["sha256"][:12])
 

@@ -13,6 +13,7 @@ import os
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.environ.get("GOLDEN_OUT", HERE)   # tests regenerate into a scratch directory on a host with other CPU numerics
 sys.path.insert(0, HERE)
 import ref_python_env  # noqa: E402,F401
 import torch  # noqa: E402
@@ -41,6 +42,8 @@ def main():
     for name, (arch, cfg, scheme, shape) in SIM_CASES.items():
         model = sim_model(arch)
         x, x2, target = sim_inputs(shape)
+        with torch.no_grad():   # torch's CPU convolutions differ in the last bit between hosts: record which host this is
+            fingerprint = hashlib.sha256(model(x).numpy().tobytes()).hexdigest()
         sim = QuantizationSimModel(model, dummy_input=x, quant_scheme=SCHEMES[scheme], default_output_bw=8,
                                    default_param_bw=8, config_file=(CFG + cfg) if cfg else None)
 
@@ -49,7 +52,7 @@ def main():
             m(x2)
 
         sim.compute_encodings(calib, None)
-        gold = {"wrapper_types": sorted({type(m).__name__ for m in sim.model.modules()
+        gold = {"forward_fingerprint": fingerprint, "wrapper_types": sorted({type(m).__name__ for m in sim.model.modules()
                                          if type(m).__name__.endswith("QuantWrapper")})}
         gold["initial_params"] = {n: p.detach().tolist() for n, p in encoding_params(sim.model).items()}
         act, par = sim.get_activation_param_encodings()
@@ -75,7 +78,7 @@ def main():
         gold["output2_head"] = out2.reshape(-1)[:8].tolist()
         act, par = sim.get_activation_param_encodings()
         gold["encodings_after_step"] = compact(act, par)
-        with open(os.path.join(HERE, f"range_learning_sim_{name}.json"), "w") as f:
+        with open(os.path.join(OUT, f"range_learning_sim_{name}.json"), "w") as f:
             json.dump(gold, f, sort_keys=True, indent=1)
         print(name, gold["wrapper_types"], "loss", gold["loss"], "params", len(gold["initial_params"]))
 

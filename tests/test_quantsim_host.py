@@ -13,7 +13,7 @@ import pytest
 import torch
 import torchvision
 
-from tests.conftest import GOLDEN
+from tests.conftest import forward_fingerprint, sim_golden
 
 CASES = {
     "resnet18_default_tfe": (torchvision.models.resnet18, "default", "tf_enhanced", (4, 3, 64, 64)),
@@ -50,6 +50,7 @@ def build_and_calibrate(name, device="cpu"):
     torch.manual_seed(1)
     x = torch.randn(*shape)
     x2 = torch.randn(*shape) * 1.5
+    fingerprint = forward_fingerprint(model, x)
     model, x, x2 = model.to(device), x.to(device), x2.to(device)
     sim = QuantizationSimModel(model, dummy_input=x, quant_scheme=scheme, default_output_bw=8, default_param_bw=8,
                                config_file=qconfig.DEFAULT_CONFIG_PER_CHANNEL if cfg == "per_channel" else None)
@@ -72,13 +73,14 @@ def build_and_calibrate(name, device="cpu"):
     sim.compute_encodings(calib, None)
     with torch.no_grad():
         out = sim.model(x)
+    sim.forward_fingerprint = fingerprint
     return sim, structure, out
 
 
 @pytest.mark.parametrize("name", list(CASES))
 def test_host_layer_reproduces_reference_python(oracle_backend, name):
-    golden = json.load(open(os.path.join(GOLDEN, f"quantsim_{name}.json")))
     sim, structure, out = build_and_calibrate(name)
+    golden = sim_golden(f"quantsim_{name}.json", "make_quantsim_golden.py", [name], sim.forward_fingerprint)
     assert structure == golden["structure"]
     act, par = sim.get_activation_param_encodings()
     enc = {"activation_encodings": act, "param_encodings": par}
@@ -98,8 +100,9 @@ def test_host_layer_reproduces_reference_python(oracle_backend, name):
 def test_percentile_scheme_reproduces_reference_python(oracle_backend):
     """post_training_percentile with set_percentile_value(99.9): activations are clipped at the percentile, parameters
     keep the analyzer's default of 100 (the reference's wrapper only forwards the value to activation quantizers)."""
-    golden = json.load(open(os.path.join(GOLDEN, "quantsim_resnet18_percentile.json")))
     sim, _, out = build_and_calibrate(PERCENTILE_CASE[0])
+    golden = sim_golden("quantsim_resnet18_percentile.json", "make_percentile_golden.py", ["--sim-only"],
+                        sim.forward_fingerprint)
     act, par = sim.get_activation_param_encodings()
     canonical = json.dumps({"activation_encodings": act, "param_encodings": par}, sort_keys=True)
     mine = json.loads(canonical)

@@ -13,7 +13,7 @@ import os
 import pytest
 import torch
 
-from tests.conftest import GOLDEN
+from tests.conftest import forward_fingerprint, sim_golden
 from tests.golden.make_range_learning_cases import SIM_CASES, sim_inputs, sim_model
 
 
@@ -63,7 +63,9 @@ def run_flow(name, device="cpu"):
     from aimet_b200.quantsim import config as qconfig
     arch, cfg, scheme, shape = SIM_CASES[name]
     model = sim_model(arch).to(device)
-    x, x2, target = (t.to(device) for t in sim_inputs(shape))
+    x, x2, target = sim_inputs(shape)
+    fingerprint = forward_fingerprint(model.cpu(), x) if device == "cpu" else None
+    x, x2, target = (t.to(device) for t in (x, x2, target))
     schemes = {"tf": QuantScheme.training_range_learning_with_tf_init,
                "tf_enhanced": QuantScheme.training_range_learning_with_tf_enhanced_init}
     sim = QuantizationSimModel(model, dummy_input=x, quant_scheme=schemes[scheme], default_output_bw=8,
@@ -95,6 +97,7 @@ def run_flow(name, device="cpu"):
         out2 = sim.model(x)
     res["output2_head"] = out2.reshape(-1)[:8].cpu().tolist()
     res["encodings_after_step"] = compact(*sim.get_activation_param_encodings())
+    sim.forward_fingerprint = fingerprint
     return sim, res
 
 
@@ -122,8 +125,8 @@ def check_against_golden(res, gold, rel):
 
 @pytest.mark.parametrize("name", list(SIM_CASES))
 def test_range_learning_sim_reproduces_reference_python(oracle_backends, name):
-    gold = json.load(open(os.path.join(GOLDEN, f"range_learning_sim_{name}.json")))
-    _, res = run_flow(name)
+    sim, res = run_flow(name)
+    gold = sim_golden(f"range_learning_sim_{name}.json", "make_range_learning_sim_golden.py", [], sim.forward_fingerprint)
     check_against_golden(res, gold, rel=1e-5)
 
 
