@@ -12,12 +12,18 @@ Layout
 
 Importing this package loads the CUDA library; if it has not been built the import fails (there is no fallback).
 """
+import sys as _sys
+
 from . import _lib
 
-_lib.load()
+# `python -m aimet_b200._build` is how the library gets built in the first place: only then the package may be imported
+# without it (nothing but the build script runs).
+_BUILDING = "aimet_b200._build" in getattr(_sys, "orig_argv", [])[1:3]
+if not _BUILDING:
+    _lib.load()
 
-from . import ops  # noqa: E402,F401  (registers torch.ops.aimet_b200.*)
-from . import libpymo  # noqa: E402,F401
-from .tensor_quantizer_op import AimetTensorQuantizer  # noqa: E402,F401
+    from . import ops  # noqa: E402,F401  (registers torch.ops.aimet_b200.*)
+    from . import libpymo  # noqa: E402,F401
+    from .tensor_quantizer_op import AimetTensorQuantizer  # noqa: E402,F401
 
 __version__ = "0.1.0"

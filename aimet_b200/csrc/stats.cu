@@ -143,7 +143,10 @@ __global__ void reset_kernel(ab_stats_state* states, int64_t count)
         st->stats_updated  = 0;
         st->iterations     = 0;
         st->ticket         = 0;
-        st->pad_[0] = st->pad_[1] = st->pad_[2] = st->pad_[3] = 0;
+        st->bf16_scale     = 0.0f;
+        st->bf16_shift     = 0.0f;
+        st->bf16_formula   = 0;
+        st->bf16_fail_mask = 0;
     }
 }
 
@@ -387,6 +390,100 @@ __device__ __forceinline__ void consume_tile(const uint4* __restrict__ src, int 
     }
 }
 
+// ---- bf16 only: the bin index in one FFMA, certified against the reference sequence over the whole bf16 domain -------
+// A bf16 sample has 2^16 bit patterns, so "is floor(fma(x, c, b)) the reference's round(x / bucket - offset) for every
+// input?" can be answered by trying them all. The first statistics call on a large bf16 tensor after the range is known
+// does that (each CTA's keeper warp takes a slice of the patterns while the consumers stream) for nine (c, b) candidates
+// around (1 / bucket, 0.5 - offset); the last CTA records the first candidate that reproduced every pattern -- counted
+// bins, samples below and above the range, NaN, +-inf, denormals, the round(-0.5) = -1 corner. Later calls bin with
+//   t = RD(fma(x, c, b) + M);  u = min(bits(t) - bits(M), 512)
+// 6 instructions per sample with the unpack and the atomic, against 14 for the exact sequence, which made the bf16
+// histogram issue-bound at 0.66 of the HBM roofline. If no candidate is exact the record keeps the exact sequence.
+// The comparison uses bf16_formula_bin itself, so the claim is about the very instructions the hot loop executes.
+constexpr int kBf16Candidates          = 9;
+constexpr int64_t kBf16FormulaMinCount = 1 << 20;   // below this the call is latency-bound either way: no certification
+
+__device__ __forceinline__ uint32_t bf16_formula_bin(float x, float c, float b)
+{
+    constexpr float kMagic = 12582912.0f;   // 1.5 * 2^23: RD(v + M) = M + floor(v), and the ulp of the sum is 1
+    const float t          = __fadd_rd(__fmaf_rn(x, c, b), kMagic);
+    return min(__float_as_uint(t) - __float_as_uint(kMagic), (uint32_t) kDumpBin);
+}
+// candidate j: (1 / bucket, 0.5 - offset) moved by -1 / 0 / +1 units in the last place each; j = 0 is the unmoved pair
+__device__ __forceinline__ void bf16_candidate(float bucket, float offset, int j, float& c, float& b)
+{
+    const int i = (j + 4) % kBf16Candidates;
+    c           = __int_as_float(__float_as_int(__frcp_rn(bucket)) + (i % 3 - 1));
+    b           = __int_as_float(__float_as_int(__fsub_rn(0.5f, offset)) + (i / 3 - 1));
+}
+// One warp checks the patterns [first, last) against the reference sequence; returns the candidates that failed (bit j).
+__device__ __forceinline__ uint32_t bf16_certify_slice(uint32_t first, uint32_t last, int lane, float bucket, float offset)
+{
+    float c[kBf16Candidates], b[kBf16Candidates];
+#pragma unroll
+    for (int j = 0; j < kBf16Candidates; ++j)
+        bf16_candidate(bucket, offset, j, c[j], b[j]);
+    uint32_t failed = 0;
+    for (uint32_t p = first + lane; p < last; p += 32)
+    {
+        const float x      = __uint_as_float(p << 16);
+        const int ref      = bin_index(x, bucket, offset);
+        const uint32_t exp = ref >= 0 ? (uint32_t) ref : (uint32_t) kDumpBin;
+#pragma unroll
+        for (int j = 0; j < kBf16Candidates; ++j)
+            failed |= (bf16_formula_bin(x, c[j], b[j]) != exp ? 1u : 0u) << j;
+    }
+    return __reduce_or_sync(0xffffffffu, failed);
+}
+
+// Last CTA, one thread, after every CTA has taken its ticket (each published its failures before that): keep the first
+// candidate nobody saw fail.
+__device__ __forceinline__ void record_bf16_formula(ab_stats_state* st, float bucket, float offset)
+{
+    __threadfence();
+    const uint32_t failed = atomicExch(&st->bf16_fail_mask, 0u);
+    const uint32_t good   = ~failed & ((1u << kBf16Candidates) - 1u);
+    if (good)
+    {
+        float c, b;
+        bf16_candidate(bucket, offset, __ffs((int) good) - 1, c, b);
+        st->bf16_scale   = c;
+        st->bf16_shift   = b;
+        st->bf16_formula = 1;
+    }
+    else
+        st->bf16_formula = -1;
+}
+
+// consumer loop of the certified form: tile words hold two samples each
+__device__ __forceinline__ void consume_tile_bf16_formula(const uint4* __restrict__ src, int nb, int ctid,
+                                                          uint32_t* s_hist_lane, float c, float b)
+{
+    uint4 raw[kVecPerThread];
+#pragma unroll
+    for (int u = 0; u < kVecPerThread; ++u)
+    {
+        const int v = ctid + u * (kConsumerWarps * 32);
+        if (v * 16 < nb)
+            raw[u] = src[v];
+    }
+#pragma unroll
+    for (int u = 0; u < kVecPerThread; ++u)
+    {
+        const int v = ctid + u * (kConsumerWarps * 32);
+        if (v * 16 < nb)
+        {
+            const uint32_t w[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+            {
+                atomicAdd(s_hist_lane + bf16_formula_bin(__uint_as_float(w[e] << 16), c, b) * kLaneCopies, 1u);
+                atomicAdd(s_hist_lane + bf16_formula_bin(__uint_as_float(w[e] & 0xffff0000u), c, b) * kLaneCopies, 1u);
+            }
+        }
+    }
+}
+
 template <typename T, bool kPdl>
 __global__ void __launch_bounds__(kHistThreads, 1)
     hist_kernel(const T* __restrict__ in, int64_t count, ab_stats_state* st, uint32_t* batch_log)
@@ -452,6 +549,12 @@ __global__ void __launch_bounds__(kHistThreads, 1)
     // With a batch log (multi-GPU exact merge) the batch is folded and logged at the end of this launch; otherwise its
     // counts stay parked in hist[parity] and the NEXT call on this record folds them while it streams its own data.
     const bool lazy = batch_log == nullptr;
+    // bf16: the certified one-FFMA bin index (see bf16_formula_bin). `formula` and the pair are stable for the launch.
+    constexpr bool kIsBf16 = sizeof(T) == 2;
+    const int formula      = kIsBf16 ? st->bf16_formula : 0;
+    const float formula_c  = kIsBf16 ? st->bf16_scale : 0.0f;
+    const float formula_b  = kIsBf16 ? st->bf16_shift : 0.0f;
+    const bool certify     = kIsBf16 && rg.valid && formula == 0 && count >= kBf16FormulaMinCount;
 
     if (rg.valid)
     {
@@ -491,8 +594,17 @@ __global__ void __launch_bounds__(kHistThreads, 1)
                     fold_bin(&st->pdf[b], st->hist[pp][b], cnt, iterations0);
                     st->hist[pp][b] = 0;
                 }
-                __threadfence();   // ordered before this CTA's ticket, hence before the last CTA's bookkeeping
             }
+            if (certify)
+            {
+                const uint32_t per    = (65536u + gridDim.x - 1) / gridDim.x;
+                const uint32_t first  = min(65536u, blockIdx.x * per);
+                const uint32_t failed = bf16_certify_slice(first, min(65536u, first + per), lane, rg.bucket, rg.offset);
+                if (lane == 0 && failed)
+                    atomicOr(&st->bf16_fail_mask, failed);
+            }
+            if (had_pending || certify)
+                __threadfence();   // ordered before this CTA's ticket, hence before the last CTA's bookkeeping
         }
         else
         {
@@ -504,7 +616,9 @@ __global__ void __launch_bounds__(kHistThreads, 1)
                 const int nb      = (int) min((int64_t) kTileBytes, bytes - off);
                 mbar_wait(s_full + s, (uint32_t) ((k / kStages) & 1));
                 const uint4* src = reinterpret_cast<const uint4*>(s_tiles + (size_t) s * kTileBytes);
-                if (binner.fast)
+                if (kIsBf16 && formula == 1)
+                    consume_tile_bf16_formula(src, nb, tid, s_hist_lane, formula_c, formula_b);
+                else if (binner.fast)
                     consume_tile<T, true>(src, nb, tid, s_hist_lane, binner);
                 else
                     consume_tile<T, false>(src, nb, tid, s_hist_lane, binner);
@@ -574,6 +688,8 @@ __global__ void __launch_bounds__(kHistThreads, 1)
                 st->pending_count = (double) count;
                 st->pending       = 1;
                 st->write_parity  = parity ^ 1;
+                if (certify)
+                    record_bf16_formula(st, rg.bucket, rg.offset);
             }
             st->stats_updated  = 1;
             st->batch_min_bits = kPosInfBits;
@@ -617,6 +733,8 @@ __global__ void __launch_bounds__(kHistThreads, 1)
             }
             st->iterations = iterations + 1;
             st->pending    = 0;
+            if (certify)
+                record_bf16_formula(st, rg.bucket, rg.offset);
         }
         st->stats_updated  = 1;
         st->batch_min_bits = kPosInfBits;

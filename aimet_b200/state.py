@@ -19,7 +19,7 @@ STATE_DTYPE = np.dtype([
     ("pdf", "<f8", PDF_SIZE), ("hist", "<u4", (2, PDF_SIZE)), ("x_left0", "<f8"), ("bucket_size_d", "<f8"),
     ("run_min", "<f8"), ("run_max", "<f8"), ("pending_count", "<f8"), ("bucket_size", "<f4"), ("pdf_offset", "<f4"),
     ("batch_min_bits", "<i4"), ("batch_max_bits", "<i4"), ("initialized", "<i4"), ("stats_updated", "<i4"),
-    ("iterations", "<i4"), ("ticket", "<u4"), ("pending", "<i4"), ("write_parity", "<i4"), ("pad", "<u4", 4)])
+    ("iterations", "<i4"), ("ticket", "<u4"), ("pending", "<i4"), ("write_parity", "<i4"), ("bf16_scale", "<f4"), ("bf16_shift", "<f4"), ("bf16_formula", "<i4"), ("bf16_fail_mask", "<u4")])
 assert STATE_DTYPE.itemsize == ops.STATE_BYTES, (STATE_DTYPE.itemsize, ops.STATE_BYTES)
 
 

@@ -97,7 +97,15 @@ typedef struct
                                       next call on this record, where it overlaps the streaming of batch k+1 instead of
                                       sitting on the kernel's tail; every reader folds it on the fly. */
     int32_t write_parity;          /* which hist[] buffer the next batch's counts go to */
-    uint32_t pad_[4];              /* keeps sizeof a multiple of 16 */
+    /* bf16 tensors only: a certified one-FMA form of the bin index. Once the range is frozen, a statistics call on a
+     * large bf16 tensor compares  floor(fma(x, scale, shift))  with the reference's  round(x / bucket - offset)  for
+     * ALL 65536 bf16 bit patterns (a few per warp, off the critical path), for nine (scale, shift) candidates around
+     * (1 / bucket, 0.5 - offset); later calls use the first candidate that reproduced every pattern (6 instructions
+     * per sample instead of 14). If none did, the exact sequence stays. */
+    float bf16_scale;
+    float bf16_shift;
+    int32_t bf16_formula;          /* 0: not examined yet, 1: (bf16_scale, bf16_shift) certified, -1: no candidate is exact */
+    uint32_t bf16_fail_mask;       /* scratch while certifying: bit j = candidate j misplaced some pattern; zero between calls */
 } ab_stats_state;
 
 const char* ab_last_error(void);
