@@ -33,6 +33,7 @@ struct BroadcastArgs
 {
     Dim dims[kMaxDims];   // outer dimensions only, outermost first
     int num_dims;
+    int linear;                          // the encoding tensor is laid out like the outer index space: index == i / inner
     int64_t inner;                       // run length over which the encoding index is constant
     uint32_t inner_mul, inner_shift;     // fast division by inner
     const float *mn, *mx, *delta, *offset;
@@ -46,6 +47,8 @@ __device__ __forceinline__ uint32_t fast_div(uint32_t n, int64_t d, uint32_t mul
 // encoding index of outer position g (32-bit fast path)
 __device__ __forceinline__ int64_t enc_index32(const BroadcastArgs& a, uint32_t g)
 {
+    if (a.linear)   // blockwise / per-channel encodings stored contiguously: the common case, no decomposition at all
+        return (int64_t) g;
     int64_t idx = 0;
 #pragma unroll 1
     for (int d = 0; d < a.num_dims; ++d)
@@ -58,6 +61,8 @@ __device__ __forceinline__ int64_t enc_index32(const BroadcastArgs& a, uint32_t 
 }
 __device__ __forceinline__ int64_t enc_index64(const BroadcastArgs& a, int64_t g)
 {
+    if (a.linear)
+        return g;
     int64_t idx = 0;
     for (int d = 0; d < a.num_dims; ++d)
     {
@@ -78,7 +83,10 @@ __device__ __forceinline__ float qdq_exact(float x, const Enc4& e)
     return dequantize_value(quantize_value<false>(x, e, 0, 0), e);
 }
 
-template <typename T>
+// kSimple: the encoding index is the run index itself (a.linear) and a run is a whole number of 128-bit vectors, so no
+// vector straddles a run boundary -- blockwise and per-channel encodings with block sizes that are multiples of 4 (fp32) /
+// 8 (bf16) elements. The per-vector work is then one multiply-high, four loads and the divisor set-up.
+template <typename T, bool kSimple>
 __global__ void __launch_bounds__(kBcThreads)
     broadcast_fast_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t count, BroadcastArgs a)
 {
@@ -106,8 +114,8 @@ __global__ void __launch_bounds__(kBcThreads)
             const int64_t v   = v0 + (int64_t) u * kBcThreads;
             const uint32_t i0 = (uint32_t) ((v < num_vec ? v : 0) * kV);
             g[u]              = fast_div(i0, a.inner, a.inner_mul, a.inner_shift);
-            rem[u]            = i0 - g[u] * inner;
-            enc[u]            = load_enc(a, enc_index32(a, g[u]));
+            rem[u]            = kSimple ? 0u : i0 - g[u] * inner;
+            enc[u]            = load_enc(a, kSimple ? (int64_t) g[u] : enc_index32(a, g[u]));
         }
 #pragma unroll
         for (int u = 0; u < kBcUnroll; ++u)
@@ -118,7 +126,7 @@ __global__ void __launch_bounds__(kBcThreads)
             float f[kV];
             Elem<T>::unpack(raw[u], f);
             Enc4 e = enc[u];
-            if (rem[u] + kV <= inner)
+            if (kSimple || rem[u] + kV <= inner)
             {
                 const Divisor dv = make_divisor(e.delta);
                 if (qdq_fast_ok(e, dv))
@@ -203,7 +211,12 @@ int launch(const void* in, void* out, int64_t count, const BroadcastArgs& a, boo
     {
         constexpr int kV    = Elem<T>::kPerVec;
         const int64_t tiles = (count / kV + kBcThreads * kBcUnroll - 1) / (kBcThreads * kBcUnroll);
-        broadcast_fast_kernel<T><<<grid_size((const void*) broadcast_fast_kernel<T>, tiles), kBcThreads, 0, st>>>(x, y, count, a);
+        if (a.linear && a.inner % kV == 0)
+            broadcast_fast_kernel<T, true><<<grid_size((const void*) broadcast_fast_kernel<T, true>, tiles), kBcThreads, 0, st>>>(
+                x, y, count, a);
+        else
+            broadcast_fast_kernel<T, false><<<grid_size((const void*) broadcast_fast_kernel<T, false>, tiles), kBcThreads, 0, st>>>(
+                x, y, count, a);
     }
     else
     {
@@ -268,6 +281,16 @@ extern "C" int ab_qdq_broadcast_fwd(const void* in, void* out, int64_t num_eleme
         magic(dim.stride, dim.mul, dim.shift);
     }
     magic(a.inner, a.inner_mul, a.inner_shift);
+    // outer position g = sum_d q_d * stride_d and encoding index = sum_d q_d * enc_stride_d: identical when the strides are
+    a.linear = 1;
+    for (int d = 0; d < a.num_dims; ++d)
+        if (a.dims[d].enc_stride != a.dims[d].stride)
+        {
+            // a dimension of extent 1 never contributes (q_d == 0), whatever its strides say
+            const int64_t extent = (d == 0 ? num_element : input_strides[d - 1]) / input_strides[d];
+            if (extent != 1)
+                a.linear = 0;
+        }
 
     const bool fast = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0 &&
                       num_element < (int64_t) 0x7fff0000;

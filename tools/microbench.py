@@ -39,6 +39,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--sizes-mb", type=float, nargs="*", default=[1, 16, 64, 256, 1024, 4096])
     ap.add_argument("--out", default=None)
+    ap.add_argument("--only", nargs="*", default=None, help="substrings of kernel names to run")
     args = ap.parse_args()
     peak, which = peak_gbs()
     dev = torch.device("cuda", 0)
@@ -58,7 +59,15 @@ def main():
             c, per = 2048, n // 2048
             params = ops.per_channel_params([-4.0] * c, [8.0] * c, 8).cuda()
             npc = c * per
+            # blockwise (LPBQ-style) encodings: one {min, max, delta, offset} per run of 64 / 16 elements
+            nb64, nb16 = n // 64, n // 16
+            enc64 = [torch.full((nb64, 1), v, device=dev) for v in (-4.0, 8.0, 12.0 / 255, -85.0)]
+            enc16 = [torch.full((nb16, 1), v, device=dev) for v in (-4.0, 8.0, 12.0 / 255, -85.0)]
             cases = {
+                "qdq_broadcast_block64": (lambda x: ops.qdq_broadcast_impl(x[:nb64 * 64].view(nb64, 64), *enc64),
+                                          2 * es * nb64 * 64),
+                "qdq_broadcast_block16": (lambda x: ops.qdq_broadcast_impl(x[:nb16 * 16].view(nb16, 16), *enc16),
+                                          2 * es * nb16 * 16),
                 "qdq_per_tensor_bw8": (lambda x: ops.qdq_per_tensor_impl(x, -4.0, 8.0, 8, 0, 0), 2 * es * n),
                 "qdq_per_tensor_bw4": (lambda x: ops.qdq_per_tensor_impl(x, -4.0, 8.0, 4, 0, 0), 2 * es * n),
                 "qdq_per_tensor_bw16": (lambda x: ops.qdq_per_tensor_impl(x, -4.0, 8.0, 16, 0, 0), 2 * es * n),
@@ -73,6 +82,8 @@ def main():
                                           es * n),
             }
             for kname, (fn, alg_bytes) in cases.items():
+                if args.only and not any(o in kname for o in args.only):
+                    continue
                 ms = time_ms(fn, pool)
                 gbs = alg_bytes / ms / 1e6
                 row = dict(kernel=kname, dtype=name, mb=mb, ms=round(ms, 4), gbs=round(gbs, 1),
