@@ -229,6 +229,21 @@ int launch(const void* in, void* out, int64_t count, const BroadcastArgs& a, boo
 }
 
 }   // namespace
+
+int launch_run_qdq(const void* in, void* out, int64_t count, int64_t run, const float* mn, const float* mx,
+                   const float* delta, const float* offset, int dtype, cudaStream_t stream)
+{
+    BroadcastArgs a {};
+    a.mn = mn, a.mx = mx, a.delta = delta, a.offset = offset;
+    a.inner    = run;
+    a.linear   = 1;
+    a.num_dims = 0;
+    magic(a.inner, a.inner_mul, a.inner_shift);
+    if (dtype == AB_F32)
+        return launch<float>(in, out, count, a, true, stream);
+    return launch<__nv_bfloat16>(in, out, count, a, true, stream);
+}
+
 }   // namespace ab
 
 using namespace ab;

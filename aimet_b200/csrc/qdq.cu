@@ -668,6 +668,12 @@ int ab_qdq_per_channel_fwd(const void* in, void* out, int64_t num_channel, int64
     const bool stochastic = round_mode == AB_ROUND_STOCHASTIC;
     const bool fast       = !stochastic && num_element_per_channel < (int64_t) 0x7fff0000 &&
                       num_channel < (int64_t) 0x7fffffff;
+    // bf16 is issue-bound, and there the straight-line run kernel of broadcast.cu (no staging, no barriers: every vector
+    // fetches its channel's four parameters through L1) is the faster one: 0.85 against 0.78 of the HBM roofline.
+    if (fast && dtype == AB_BF16 && num_element_per_channel % 8 == 0 && num_element < (int64_t) 0x7fff0000 &&
+        num_element <= num_channel * num_element_per_channel)
+        return launch_run_qdq(in, out, num_element, num_element_per_channel, params, params + num_channel,
+                              params + 2 * num_channel, params + 3 * num_channel, dtype, st);
     if (fast)
     {
         // CUTLASS-style fast divmod constants, exact for dividends below 2^31
