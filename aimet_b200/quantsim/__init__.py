@@ -7,3 +7,4 @@ from .tensor_quantizer import (Quantize, QuantizeDequantize, StaticGridPerChanne
                                StaticGridPerTensorQuantizer, StaticGridTensorQuantizer, compute_dloss_by_dx)
 from .learned_grid import (LearnedGridQuantWrapper, LearnedGridTensorQuantizer,  # noqa: F401
                            set_encoding_min_max_gating_threshold)
+from .quant_analyzer import CallbackFunc, QuantAnalyzer  # noqa: F401,E402

@@ -185,6 +185,24 @@ class QuantizationSimModel:
 
     _get_qc_quantized_layers = lambda self, model=None: list(self.quant_wrappers())   # noqa: E731
 
+    def exclude_layers_from_quantization(self, layers_to_exclude):
+        """Take the wrappers inside the given layers (modules of `self.model`) out again (reference :731-751)."""
+        doomed = {m for layer in layers_to_exclude for m in layer.modules() if isinstance(m, _WRAPPER_TYPES)}
+        if not doomed:
+            return
+
+        def strip(parent):
+            for name, child in list(parent.named_children()):
+                if child in doomed:
+                    setattr(parent, name, child.get_original_module())
+                else:
+                    strip(child)
+
+        strip(self.model)
+        self._wrappers = {orig: w for orig, w in self._wrappers.items() if w not in doomed}
+        self.__dict__.pop("_act_block", None)               # the activation statistics block is rebuilt on the next bind
+        self.__dict__.pop("_act_block_quantizers", None)
+
     # ---- calibration -------------------------------------------------------------------------------------------
     @staticmethod
     def prepare_sim_for_compute_encodings(sim: "QuantizationSimModel"):
