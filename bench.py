@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="do not replay the steady state from a CUDA graph")
     ap.add_argument("--cpu-baseline-steps", type=int, default=2)
+    ap.add_argument("--images-per-step", type=int, default=BATCH,
+                    help="calibration batch (SURVEY section 8d fixes 32 for the headline; larger batches mean larger "
+                         "tensors per statistics launch -- a sensitivity knob, not the headline config)")
     return ap.parse_args()
 
 
@@ -420,8 +423,9 @@ def emit(line: dict):
 
 
 def main():
-    global _REAL_STDOUT
+    global _REAL_STDOUT, BATCH
     args = parse_args()
+    BATCH = args.images_per_step
     # C libraries print to fd 1 too (e.g. "NCCL version ..." on the first collective): keep stdout clean for the JSON line
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)
