@@ -50,6 +50,7 @@ PROTOTYPES = {
                                     _int, _vp]),
     "ab_qdq_ste_bwd": (_int, [_vp, _vp, _vp, _i64, _int, _flt, _flt, _vp]),
     "ab_qdq_ste_bwd_per_channel": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _int, _vp, _vp, _vp]),
+    "ab_qdq_ste_bwd_enc5": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _int, _vp, _int, _vp]),
     "ab_stats_reset": (_int, [_vp, _i64, _vp]),
     "ab_stats_update": (_int, [_vp, _i64, _int, _int, _vp, _vp, _int, _vp]),
     "ab_stats_update_segmented": (_int, [_vp, _i64, _i64, _int, _int, _vp, _vp]),

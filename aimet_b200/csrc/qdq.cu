@@ -44,6 +44,7 @@ struct TensorArgs
     const float* enc_dev;   // optional device-resident {min,max,delta,offset}
     float shift;         // quantize-only: subtracted from the grid value
     uint64_t seed;
+    int reverse;         // walk the tiles from the end of the tensor backwards (see per_tensor_body)
 };
 
 template <Op kOp, bool kStochastic>
@@ -60,14 +61,20 @@ __device__ __forceinline__ float apply(float x, const Enc4& e, float shift, uint
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T, Op kOp, bool kStochastic, bool kFast>
 __device__ __forceinline__ void per_tensor_body(const T* __restrict__ in, T* __restrict__ out, int64_t count,
-                                                const Enc4& e, const Divisor& dv, float shift, uint64_t seed)
+                                                const Enc4& e, const Divisor& dv, float shift, uint64_t seed,
+                                                int reverse)
 {
     constexpr int kV        = Elem<T>::kPerVec;
     const int64_t num_vec   = count / kV;
     const int64_t num_tiles = (num_vec + kThreads * kUnroll - 1) / (kThreads * kUnroll);
 
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+    // Tile order. The input was usually written by the kernel just before this one and the output is usually read from
+    // its start by the kernel just after it. What the L2 holds of a tensor larger than itself is the part written last.
+    // Walking backwards therefore reads the producer's tail from L2 before it is evicted, and leaves the HEAD of the
+    // output as the most recent lines for the consumer; walking forwards does neither. Element-wise: order is free.
+    for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x)
     {
+        const int64_t tile = reverse ? num_tiles - 1 - t : t;
         const int64_t v0 = tile * (kThreads * kUnroll) + threadIdx.x;
         uint4 raw[kUnroll];
 #pragma unroll
@@ -116,9 +123,9 @@ __global__ void __launch_bounds__(kThreads) per_tensor_kernel(const T* __restric
     const Divisor dv = make_divisor(e.delta);
     // Nearest rounding with an ordinary grid takes the XU-free path; the choice is uniform over the launch.
     if (!kStochastic && qdq_fast_ok(e, dv))
-        per_tensor_body<T, kOp, kStochastic, true>(in, out, count, e, dv, args.shift, args.seed);
+        per_tensor_body<T, kOp, kStochastic, true>(in, out, count, e, dv, args.shift, args.seed, args.reverse);
     else
-        per_tensor_body<T, kOp, kStochastic, false>(in, out, count, e, dv, args.shift, args.seed);
+        per_tensor_body<T, kOp, kStochastic, false>(in, out, count, e, dv, args.shift, args.seed, args.reverse);
 }
 
 // element-wise variant for tensors that are not 16-byte aligned
@@ -398,11 +405,36 @@ __global__ void __launch_bounds__(kThreads) ste_bwd_kernel(const T* __restrict__
     }
 }
 
+// Where the per-channel range comes from: two float arrays, or the rows {min, max, delta, offset, bw} (doubles) the grid
+// search left on the device -- narrowed here exactly as `tensor.to(torch.float32)` narrows them (round to nearest even),
+// and, for the reference's 0-dim comparison in a bf16 tensor's dtype, rounded once more to bf16.
+struct RangeSrc
+{
+    const float* mins;
+    const float* maxs;
+    const double* enc5;   // non-null: use this instead of mins / maxs
+    int bf16_round;
+    __device__ __forceinline__ void load(int64_t c, float& mn, float& mx) const
+    {
+        if (enc5 == nullptr)
+        {
+            mn = __ldg(mins + c), mx = __ldg(maxs + c);
+            return;
+        }
+        mn = __double2float_rn(__ldg(enc5 + 5 * c));
+        mx = __double2float_rn(__ldg(enc5 + 5 * c + 1));
+        if (bf16_round)
+        {
+            mn = __bfloat162float(__float2bfloat16_rn(mn));
+            mx = __bfloat162float(__float2bfloat16_rn(mx));
+        }
+    }
+};
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
     ste_bwd_per_channel_kernel(const T* __restrict__ x, const T* __restrict__ grad, T* __restrict__ grad_in,
-                               int64_t count, int64_t C, int64_t L, const float* __restrict__ mins,
-                               const float* __restrict__ maxs)
+                               int64_t count, int64_t C, int64_t L, RangeSrc src)
 {
     constexpr int kV        = Elem<T>::kPerVec;
     const int64_t num_vec   = count / kV;
@@ -418,7 +450,8 @@ __global__ void __launch_bounds__(kThreads)
         int64_t g        = i0 / L;
         int64_t rem      = i0 - g * L;
         int64_t c        = g % C;
-        float mn = __ldg(mins + c), mx = __ldg(maxs + c);
+        float mn, mx;
+        src.load(c, mn, mx);
 #pragma unroll
         for (int k = 0; k < kV; ++k)
         {
@@ -427,7 +460,7 @@ __global__ void __launch_bounds__(kThreads)
             {
                 rem = 0;
                 c   = (c + 1 == C) ? 0 : c + 1;
-                mn = __ldg(mins + c), mx = __ldg(maxs + c);
+                src.load(c, mn, mx);
             }
         }
         stg_stream(reinterpret_cast<uint4*>(grad_in) + v, Elem<T>::pack(fg));
@@ -439,8 +472,9 @@ __global__ void __launch_bounds__(kThreads)
         {
             const int64_t c = (i / L) % C;
             const float xv  = Elem<T>::load(x + i);
-            Elem<T>::store(grad_in + i, __fmul_rn(Elem<T>::load(grad + i),
-                                                  (__ldg(mins + c) <= xv && xv <= __ldg(maxs + c)) ? 1.0f : 0.0f));
+            float mn, mx;
+            src.load(c, mn, mx);
+            Elem<T>::store(grad_in + i, __fmul_rn(Elem<T>::load(grad + i), (mn <= xv && xv <= mx) ? 1.0f : 0.0f));
         }
     }
 }
@@ -544,6 +578,11 @@ static int launch_per_tensor(const void* in, void* out, int64_t count, int dtype
         set_error("null tensor pointer or negative count");
         return AB_ERR_INVALID;
     }
+    static const int reverse = [] {
+        const char* e = getenv("AB_QDQ_REVERSE");
+        return (e == nullptr || e[0] != '0') ? 1 : 0;
+    }();
+    a.reverse = reverse;
     if (dtype != AB_F32 && dtype != AB_BF16)
     {
         set_error("unsupported dtype %d", dtype);
@@ -789,12 +828,39 @@ int ab_qdq_ste_bwd(const void* x, const void* grad, void* grad_in, int64_t count
     return AB_OK;
 }
 
+static int launch_ste_per_channel(const void* x, const void* grad, void* grad_in, int64_t num_channel, int64_t num_element,
+                                  int64_t num_element_per_channel, int dtype, RangeSrc src, void* stream);
+
 int ab_qdq_ste_bwd_per_channel(const void* x, const void* grad, void* grad_in, int64_t num_channel,
                                int64_t num_element, int64_t num_element_per_channel, int dtype,
                                const float* enc_min, const float* enc_max, void* stream)
 {
-    if (num_element < 0 || num_channel <= 0 || num_element_per_channel <= 0 || enc_min == nullptr ||
-        enc_max == nullptr || (num_element > 0 && (x == nullptr || grad == nullptr || grad_in == nullptr)))
+    if (enc_min == nullptr || enc_max == nullptr)
+    {
+        set_error("invalid per-channel arguments");
+        return AB_ERR_INVALID;
+    }
+    return launch_ste_per_channel(x, grad, grad_in, num_channel, num_element, num_element_per_channel, dtype,
+                                  RangeSrc {enc_min, enc_max, nullptr, 0}, stream);
+}
+
+int ab_qdq_ste_bwd_enc5(const void* x, const void* grad, void* grad_in, int64_t num_channel, int64_t num_element,
+                        int64_t num_element_per_channel, int dtype, const double* enc5, int range_in_bf16, void* stream)
+{
+    if (enc5 == nullptr)
+    {
+        set_error("invalid per-channel arguments");
+        return AB_ERR_INVALID;
+    }
+    return launch_ste_per_channel(x, grad, grad_in, num_channel, num_element, num_element_per_channel, dtype,
+                                  RangeSrc {nullptr, nullptr, enc5, range_in_bf16 ? 1 : 0}, stream);
+}
+
+static int launch_ste_per_channel(const void* x, const void* grad, void* grad_in, int64_t num_channel, int64_t num_element,
+                                  int64_t num_element_per_channel, int dtype, RangeSrc src, void* stream)
+{
+    if (num_element < 0 || num_channel <= 0 || num_element_per_channel <= 0 ||
+        (num_element > 0 && (x == nullptr || grad == nullptr || grad_in == nullptr)))
     {
         set_error("invalid per-channel arguments");
         return AB_ERR_INVALID;
@@ -817,8 +883,7 @@ int ab_qdq_ste_bwd_per_channel(const void* x, const void* grad, void* grad_in, i
         auto k              = ste_bwd_per_channel_kernel<float>;
         const int64_t tiles = (num_element / 4 + kThreads - 1) / kThreads;
         k<<<grid_for(k, tiles, kThreads), kThreads, 0, st>>>((const float*) x, (const float*) grad, (float*) grad_in,
-                                                             num_element, num_channel, num_element_per_channel,
-                                                             enc_min, enc_max);
+                                                             num_element, num_channel, num_element_per_channel, src);
     }
     else
     {
@@ -826,7 +891,7 @@ int ab_qdq_ste_bwd_per_channel(const void* x, const void* grad, void* grad_in, i
         const int64_t tiles = (num_element / 8 + kThreads - 1) / kThreads;
         k<<<grid_for(k, tiles, kThreads), kThreads, 0, st>>>((const __nv_bfloat16*) x, (const __nv_bfloat16*) grad,
                                                              (__nv_bfloat16*) grad_in, num_element, num_channel,
-                                                             num_element_per_channel, enc_min, enc_max);
+                                                             num_element_per_channel, src);
     }
     AB_CUDA_CHECK(cudaGetLastError());
     return AB_OK;

@@ -486,7 +486,7 @@ __device__ __forceinline__ void consume_tile_bf16_formula(const uint4* __restric
 
 template <typename T, bool kPdl>
 __global__ void __launch_bounds__(kHistThreads, 1)
-    hist_kernel(const T* __restrict__ in, int64_t count, ab_stats_state* st, uint32_t* batch_log)
+    hist_kernel(const T* __restrict__ in, int64_t count, ab_stats_state* st, uint32_t* batch_log, int reverse)
 {
     constexpr int kV = Elem<T>::kPerVec;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -510,9 +510,16 @@ __global__ void __launch_bounds__(kHistThreads, 1)
     const int64_t num_tiles = (bytes + kTileBytes - 1) / kTileBytes;
     // tiles owned by this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
     const int64_t my_tiles = (num_tiles > blockIdx.x) ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    // Tile order: a statistics call usually follows the kernel that PRODUCED the tensor, whose most recently written part
+    // (its end) is what the L2 still holds. Walking the tiles from the end backwards consumes that part from L2 before it
+    // is evicted; walking forwards would evict it to make room for the start. Bin counts do not depend on the order.
+    auto tile_offset = [&](int64_t k) {
+        const int64_t t = blockIdx.x + k * gridDim.x;
+        return (reverse ? num_tiles - 1 - t : t) * (int64_t) kTileBytes;
+    };
     auto issue_tile = [&](int64_t k) {
         const int s       = (int) (k % kStages);
-        const int64_t off = (blockIdx.x + k * gridDim.x) * (int64_t) kTileBytes;
+        const int64_t off = tile_offset(k);
         const uint32_t nb = (uint32_t) min((int64_t) kTileBytes, bytes - off);
         mbar_expect_tx(s_full + s, nb);
         tma_load_1d(s_tiles + (size_t) s * kTileBytes, reinterpret_cast<const uint8_t*>(in) + off, nb, s_full + s);
@@ -612,7 +619,7 @@ __global__ void __launch_bounds__(kHistThreads, 1)
             for (int64_t k = 0; k < my_tiles; ++k)
             {
                 const int s       = (int) (k % kStages);
-                const int64_t off = (blockIdx.x + k * gridDim.x) * (int64_t) kTileBytes;
+                const int64_t off = tile_offset(k);
                 const int nb      = (int) min((int64_t) kTileBytes, bytes - off);
                 mbar_wait(s_full + s, (uint32_t) ((k / kStages) & 1));
                 const uint4* src = reinterpret_cast<const uint4*>(s_tiles + (size_t) s * kTileBytes);
@@ -986,6 +993,10 @@ int launch_update(const T* in, int64_t count, int quant_mode, ab_stats_state* st
             const char* e = getenv("AB_PDL");
             return e == nullptr || e[0] != '0';
         }();
+        static const int reverse = [] {
+            const char* e = getenv("AB_HIST_REVERSE");
+            return (e == nullptr || e[0] != '0') ? 1 : 0;
+        }();
         static thread_local bool configured[2] = {false, false};
         const int which                        = sizeof(T) == 4 ? 0 : 1;
         if (!configured[which])
@@ -1012,11 +1023,11 @@ int launch_update(const T* in, int64_t count, int quant_mode, ab_stats_state* st
             attr[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs                                          = attr;
             cfg.numAttrs                                       = 1;
-            AB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, hist_kernel<T, true>, in, count, st, batch_log));
+            AB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, hist_kernel<T, true>, in, count, st, batch_log, reverse));
         }
         else
         {
-            hist_kernel<T, false><<<grid, kHistThreads, kHistSmem, stream>>>(in, count, st, batch_log);
+            hist_kernel<T, false><<<grid, kHistThreads, kHistSmem, stream>>>(in, count, st, batch_log, reverse);
             AB_CUDA_CHECK(cudaGetLastError());
         }
     }

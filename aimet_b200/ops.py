@@ -67,8 +67,14 @@ def _require_cuda(*tensors):
                                "(reference analogue: 'Not compiled for GPU mode.' in the other direction)")
 
 
+_raw_stream = torch._C._cuda_getCurrentRawStream   # pylint: disable=protected-access
+_current_device = torch._C._cuda_getDevice         # pylint: disable=protected-access
+
+
 def _stream(t: torch.Tensor) -> int:
-    return torch.cuda.current_stream(t.device).cuda_stream
+    """The raw cudaStream_t torch currently uses on `t`'s device. torch.cuda.current_stream() builds a Python Stream object on
+    every call (8.6 us measured): the QAT step makes 444 such calls (tools/host_profile_qat.py)."""
+    return _raw_stream(t.device.index)
 
 
 class _on_device:
@@ -79,7 +85,7 @@ class _on_device:
         self.prev = None
 
     def __enter__(self):
-        cur = torch.cuda.current_device()
+        cur = _current_device()
         if cur != self.idx:
             self.prev = cur
             torch.cuda.set_device(self.idx)
@@ -218,6 +224,24 @@ def ste_bwd_impl(x, grad, enc_min, enc_max):
     with _on_device(x):
         _lib.check(_L.ab_qdq_ste_bwd(x.data_ptr(), grad.data_ptr(), out.data_ptr(), x.numel(), _dtype_code(x),
                                      float(enc_min), float(enc_max), _stream(x)))
+    LAUNCHES["ste_bwd"] += 1
+    return out
+
+
+def ste_bwd_enc5_impl(x, grad, enc5, num_channel, num_element_per_channel, range_in_bf16=False):
+    """STE backward with the range read from device-resident encoding rows ([num_channel, 5] float64, as
+    compute_encodings_impl returns them): no slicing / casting kernels on the host side."""
+    _require_cuda(x, grad, enc5)
+    if x.dtype != grad.dtype or x.shape != grad.shape:
+        raise ValueError("x and grad must share dtype and shape")
+    if enc5.dtype != torch.float64 or enc5.numel() != 5 * num_channel or not enc5.is_contiguous():
+        raise ValueError("enc5 must be a contiguous float64 CUDA tensor [num_channel, 5]")
+    x, grad = _contig16(x), _contig16(grad)
+    out = torch.empty_like(grad, memory_format=torch.contiguous_format)
+    with _on_device(x):
+        _lib.check(_L.ab_qdq_ste_bwd_enc5(x.data_ptr(), grad.data_ptr(), out.data_ptr(), int(num_channel), x.numel(),
+                                          int(num_element_per_channel), _dtype_code(x), enc5.data_ptr(),
+                                          1 if range_in_bf16 else 0, _stream(x)))
     LAUNCHES["ste_bwd"] += 1
     return out
 
@@ -368,7 +392,7 @@ def lg_symmetry_mode(use_symmetric_encodings: bool, is_unsigned_symmetric: bool)
 
 def _lg_workspace(device, num_channel):
     """Zero-filled scratch, one per (device, stream): the kernels leave it zeroed, so it is reused launch after launch."""
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    key = (device.index, _raw_stream(device.index))
     need = int(_L.ab_lg_workspace_bytes(int(num_channel)))
     ws = _LG_WORKSPACES.get(key)
     if ws is None or ws.numel() < need:

@@ -64,16 +64,15 @@ def ste_for_quantizer(x, grad, q):
     torch.tensor(python floats) yields in the reference -- and no host synchronisation happens."""
     from .. import ops
     if q._device_encoding_valid() and x.is_cuda and x.dtype in (torch.float32, torch.bfloat16):   # pylint: disable=protected-access
-        rng = q._enc_dev[:, :2].to(torch.float32)                                                   # pylint: disable=protected-access
-        mins, maxs = rng[:, 0].contiguous(), rng[:, 1].contiguous()
-        n_ch = mins.numel()
+        enc5 = q._enc_dev                                                                           # pylint: disable=protected-access
+        n_ch = enc5.shape[0]
         axis = q.channel_axis if q.channel_axis is not None else 0
         per_channel = 1
         for d in (x.shape[axis + 1:] if n_ch > 1 else x.shape):
             per_channel *= d
-        if x.dtype == torch.bfloat16 and q.channel_axis is None:
-            mins, maxs = mins.to(torch.bfloat16).float(), maxs.to(torch.bfloat16).float()   # 0-dim compare in x's dtype
-        return ops.ste_bwd_per_channel_impl(x, grad, mins, maxs, n_ch, per_channel)
+        # a per-tensor bound is a 0-dim tensor in the reference: compared in x's dtype
+        return ops.ste_bwd_enc5_impl(x, grad, enc5, n_ch, per_channel,
+                                     range_in_bf16=x.dtype == torch.bfloat16 and q.channel_axis is None)
     enc = q.encoding
     if isinstance(enc, list):
         return compute_dloss_by_dx(x, grad, [e.min for e in enc], [e.max for e in enc], q.channel_axis)

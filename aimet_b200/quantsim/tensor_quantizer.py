@@ -416,7 +416,7 @@ class QuantizeDequantize(torch.autograd.Function):
             out = ops.qdq_per_tensor_dev_impl(tensor, q._qdq4_dev[0], int(round_mode), 0)   # pylint: disable=protected-access
         else:
             out = q._cppOp[0].quantizeDequantize(tensor, q.encoding, round_mode, tensor.is_cuda)   # pylint: disable=protected-access
-        return out.to(dtype)
+        return out if out.dtype == dtype else out.to(dtype)
 
     @staticmethod
     def _per_channel(tensor, tensor_quantizer, round_mode):
@@ -434,7 +434,7 @@ class QuantizeDequantize(torch.autograd.Function):
         else:
             out = q._cppOp[0].quantizeDequantizePerChannel(tensor, q.encoding, num_channel, num_element,   # pylint: disable=protected-access
                                                            num_element_per_channel, round_mode, tensor.is_cuda)
-        return out.to(dtype)
+        return out if out.dtype == dtype else out.to(dtype)
 
     @staticmethod
     def run(tensor, tensor_quantizer, round_mode):

@@ -193,6 +193,13 @@ int ab_qdq_ste_bwd_per_channel(const void* x, const void* grad, void* grad_in, i
                                int64_t num_element, int64_t num_element_per_channel, int dtype,
                                const float* enc_min, const float* enc_max, void* stream);
 
+/* same, with the range taken from the rows {min, max, delta, offset, bw} (num_channel x 5 doubles, DEVICE) that
+ * ab_compute_encodings leaves behind: float32(min) <= x <= float32(max), the narrowing `torch.tensor(python float)` does
+ * in the reference; range_in_bf16 != 0 rounds the two bounds once more to bf16 (the reference compares a bf16 tensor with a
+ * 0-dim bound in the tensor's dtype). Saves the host the slicing / casting kernels in front of every backward. */
+int ab_qdq_ste_bwd_enc5(const void* x, const void* grad, void* grad_in, int64_t num_channel, int64_t num_element,
+                        int64_t num_element_per_channel, int dtype, const double* enc5, int range_in_bf16, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Job 2: statistics -- min/max and the 512-bin histogram, accumulated into device-resident state.
  * ---------------------------------------------------------------------------------------------------------- */
