@@ -79,6 +79,23 @@ def ste_for_quantizer(x, grad, q):
     return compute_dloss_by_dx(x, grad, enc.min, enc.max)
 
 
+_NEVER_IN_PLACE = (nn.modules.conv._ConvNd, nn.Linear, nn.modules.batchnorm._BatchNorm, nn.LayerNorm, nn.GroupNorm,   # pylint: disable=protected-access
+                   nn.Embedding, nn.modules.pooling._AvgPoolNd, nn.modules.pooling._MaxPoolNd,                        # pylint: disable=protected-access
+                   nn.modules.pooling._AdaptiveAvgPoolNd, nn.modules.pooling._AdaptiveMaxPoolNd, nn.Flatten, nn.Identity)  # pylint: disable=protected-access
+
+
+ALWAYS_GATE_AND_CLONE = False   # test hook: the reference's unconditional gating + clone in every wrapper
+
+
+def _leaves_its_input_alone(module: nn.Module) -> bool:
+    """True for torch.nn modules whose forward never writes to its input tensor."""
+    if type(module).__module__.startswith("torch.nn."):
+        if isinstance(module, _NEVER_IN_PLACE):
+            return True
+        return getattr(module, "inplace", None) is False
+    return False
+
+
 class SteGatingFuncForParameters(torch.autograd.Function):
     """Gates the parameter gradients with the straight-through estimator after the wrapped module's backward
     (reference :1314-1366)."""
@@ -179,10 +196,17 @@ class StaticGridQuantWrapper(nn.Module):
         """reference :705-745"""
         quantized_inputs = self._quantize_activation(self.input_quantizers, list(inputs))
         shadow_params = self._quantize_dequantize_params()
-        if torch.is_grad_enabled():
+        # The reference routes the inputs through the gating function and clones them in every wrapper whenever grad mode
+        # is on (:716-726). The gating function only touches the gradients of parameters whose quantizer is enabled, so a
+        # wrapper without any (activations, batch norms, pooling ...) skips it: nothing would happen in its backward. The
+        # clone protects the gating function's outputs -- aliases of the wrapper's inputs -- from a wrapped module that
+        # works in place; a module known not to write to its input gets the alias itself (same values, same gradients, one
+        # copy of the activation less per layer and step).
+        if (shadow_params or ALWAYS_GATE_AND_CLONE) and torch.is_grad_enabled():
             quantized_inputs = SteGatingFuncForParameters.apply(self, *quantized_inputs)
-            quantized_inputs = [inp.clone() if isinstance(inp, torch.Tensor) and inp.requires_grad else inp
-                                for inp in quantized_inputs]
+            if ALWAYS_GATE_AND_CLONE or not _leaves_its_input_alone(self._module_to_wrap):
+                quantized_inputs = [inp.clone() if isinstance(inp, torch.Tensor) and inp.requires_grad else inp
+                                    for inp in quantized_inputs]
         wrapped_output = self._module_to_wrap(*quantized_inputs, **kwargs)
         self._restore_shadow_params(shadow_params)
         is_seq = isinstance(wrapped_output, (list, tuple))

@@ -108,3 +108,38 @@ def test_cuda_graph_calibration_equals_eager(name):
         act, par = sim.get_activation_param_encodings()
         results.append(json.dumps({"a": act, "p": par}, sort_keys=True))
     assert results[0] == results[1]
+
+
+def test_gating_and_clone_elision_changes_nothing():
+    """The wrapper skips the parameter-gradient gating where no parameter quantizer is enabled and the input clone where the
+    wrapped module cannot write to its input; the reference does both in every wrapper. Outputs and every gradient must be
+    the same bits either way (MobileNet-v2 block shapes: in-place ReLU6, residual add, batch norm, dropout)."""
+    import torchvision
+    from aimet_b200.quantsim import QuantizationSimModel, qc_quantize_op
+
+    def step(legacy):
+        qc_quantize_op.ALWAYS_GATE_AND_CLONE = legacy
+        try:
+            torch.backends.cudnn.deterministic = True
+            torch.backends.cudnn.benchmark = False
+            torch.manual_seed(0)
+            model = torchvision.models.mobilenet_v2(width_mult=0.35, num_classes=10).cuda()
+            x = torch.randn(4, 3, 64, 64, device="cuda")
+            sim = QuantizationSimModel(model, dummy_input=x, quant_scheme="tf_enhanced")
+            with torch.no_grad():
+                sim.compute_encodings(lambda m, _: m(x), None)
+            sim.model.train()
+            xin = x.clone().requires_grad_(True)
+            out = sim.model(xin)
+            out.square().mean().backward()
+            grads = {n: p.grad.clone() for n, p in sim.model.named_parameters() if p.grad is not None}
+            return out.detach(), xin.grad.clone(), grads
+        finally:
+            qc_quantize_op.ALWAYS_GATE_AND_CLONE = False
+
+    out_a, gx_a, grads_a = step(False)
+    out_b, gx_b, grads_b = step(True)
+    assert torch.equal(out_a, out_b) and torch.equal(gx_a, gx_b)
+    assert grads_a.keys() == grads_b.keys() and len(grads_a) > 50
+    for n in grads_a:
+        assert torch.equal(grads_a[n], grads_b[n]), n
