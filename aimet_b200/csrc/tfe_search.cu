@@ -331,3 +331,30 @@ extern "C" int ab_compute_encodings_percentile(const ab_stats_state* states, int
     return launch_search(states, count, AB_QUANTIZATION_PERCENTILE, percentile, bw, use_symmetric, use_strict_symmetric,
                          use_unsigned_symmetric, enc_out, qdq4_out, stream);
 }
+
+// reset -> updateStats -> computeEncoding (-> per-channel parameter block) for one tensor, enqueued by ONE host call.
+// A parameter quantizer in training mode does exactly this sequence before every forward (TEt/.../v1/qc_quantize_op.py:
+// 753-798); issuing it as four separate calls from Python costs more host time than the kernels take on the device.
+extern "C" int ab_stats_refresh_encodings(const void* in, int64_t num_segments, int64_t segment_len, int dtype,
+                                          int quant_mode, ab_stats_state* states, int bw, int use_symmetric,
+                                          int use_strict_symmetric, int use_unsigned_symmetric, double* enc_out,
+                                          float* qdq4_out, float* params_out, void* stream)
+{
+    if (num_segments < 1 || segment_len < 0 || enc_out == nullptr)
+    {
+        ab::set_error("invalid refresh arguments");
+        return AB_ERR_INVALID;
+    }
+    int rc = ab_stats_reset(states, num_segments, stream);
+    if (rc != AB_OK)
+        return rc;
+    rc = num_segments == 1 ? ab_stats_update(in, segment_len, dtype, quant_mode, states, nullptr, 0, stream)
+                           : ab_stats_update_segmented(in, num_segments, segment_len, dtype, quant_mode, states, stream);
+    if (rc != AB_OK)
+        return rc;
+    rc = ab_compute_encodings(states, num_segments, quant_mode, bw, use_symmetric, use_strict_symmetric,
+                              use_unsigned_symmetric, enc_out, qdq4_out, stream);
+    if (rc != AB_OK || params_out == nullptr)
+        return rc;
+    return ab_per_channel_params_dev(enc_out, num_segments, bw, params_out, stream);
+}

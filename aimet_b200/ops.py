@@ -345,6 +345,33 @@ def compute_encodings_impl(states, first, count, quant_mode, bw, sym, strict, un
     return enc, qdq4
 
 
+def stats_refresh_encodings_impl(x, states, first, num_segments, segment_len, quant_mode, bw, sym, strict, unsigned_sym):
+    """reset + updateStats + computeEncoding for one tensor in one native call (see ab_stats_refresh_encodings).
+    Returns (enc [n, 5] float64, qdq4 [1, 4] float32 or None, params [4 * n] float32 or None)."""
+    _require_cuda(x, states)
+    if x.numel() != num_segments * segment_len:
+        raise ValueError("tensor size does not match num_segments * segment_len")
+    per_tensor = num_segments == 1
+    enc = torch.empty((num_segments, 5), dtype=torch.float64, device=states.device)
+    qdq4 = torch.empty((1, 4), dtype=torch.float32, device=states.device) if per_tensor else None
+    params = None if per_tensor else torch.empty(4 * num_segments, dtype=torch.float32, device=states.device)
+    with _on_device(x):
+        _lib.check(_L.ab_stats_refresh_encodings(x.data_ptr(), int(num_segments), int(segment_len), _dtype_code(x),
+                                                 int(quant_mode), _state_ptr(states, first), int(bw), int(bool(sym)),
+                                                 int(bool(strict)), int(bool(unsigned_sym)), enc.data_ptr(),
+                                                 qdq4.data_ptr() if per_tensor else None,
+                                                 None if per_tensor else params.data_ptr(), _stream(x)))
+    LAUNCHES["reset"] += 1
+    LAUNCHES["search"] += 1
+    if per_tensor:
+        LAUNCHES["minmax"] += 1
+        if keeps_histogram(quant_mode):
+            LAUNCHES["hist"] += 1
+    else:
+        LAUNCHES["segmented"] += 1
+    return enc, qdq4, params
+
+
 def compute_encodings_into(states, first, count, quant_mode, bw, sym, strict, unsigned_sym, out, percentile=None):
     """Same as compute_encodings_impl, but writes into `out` (float64 CUDA, [count, 5], contiguous): lets a caller
     enqueue many searches and read them back with one copy."""

@@ -227,9 +227,10 @@ class StaticGridQuantWrapper(nn.Module):
             if q.enabled and q.bitwidth != 32:
                 shadow_params[name] = param.data
                 if self._module_to_wrap.training or not q._has_encoding():   # pylint: disable=protected-access
-                    q.reset_encoding_stats()
-                    q.update_encoding_stats(param.data)
-                    q.compute_encoding()
+                    if not q.refresh_encoding_from(param.data):                # one native call where possible
+                        q.reset_encoding_stats()
+                        q.update_encoding_stats(param.data)
+                        q.compute_encoding()
                 round_mode = q.round_mode if self.training else libpymo.RoundingMode.ROUND_NEAREST
                 param.data = q.quantize_dequantize(param.data, round_mode)
         return shadow_params

@@ -13,6 +13,7 @@ A different op class (anything with AimetTensorQuantizer's nine methods) can be 
 uses that to drive this layer with the CPU oracle.
 """
 import functools
+import os
 from typing import List, Optional, Tuple, Union
 
 import torch
@@ -28,6 +29,9 @@ _DEFAULT_OP_FACTORY = AimetTensorQuantizer
 # one device->host copy -- the first time anybody asks for `.encoding`. For per-channel ResNet-50 this takes 53 host
 # synchronisations and 26 560 Python objects out of every calibration job.
 _LAZY = object()
+
+
+FUSED_REFRESH = os.environ.get("AB_FUSED_REFRESH", "1") != "0"   # A/B switch for refresh_encoding_from
 
 
 def set_default_op_factory(factory):
@@ -200,6 +204,57 @@ class StaticGridTensorQuantizer:
                 all(enc.min >= 0 and enc.max >= 0 for enc in self._encoding)
             if not self.enabled and self._encoding:
                 raise AssertionError("At least one encoding for a multi-encoding quantizer is invalid.")
+
+    def refresh_encoding_from(self, tensor: torch.Tensor) -> bool:
+        """reset_encoding_stats(); update_encoding_stats(tensor); compute_encoding() -- what the wrapper does with every
+        parameter before a training-mode forward (reference qc_quantize_op.py:753-798) -- as ONE native call that enqueues
+        the same kernels (ab_stats_refresh_encodings). Returns False when this quantizer cannot take that route (not on the
+        device-resident path, frozen, fixed min/max, a calibration hook, the percentile scheme, ...): the caller then
+        makes the three calls."""
+        if not (FUSED_REFRESH and self.enabled and self._lazy_ok and not self._is_encoding_frozen and self.bitwidth != 32):
+            return False
+        if getattr(self, "_calib_hook", None) is not None or self.encoding_min_max_fixed_vals is not None:
+            return False
+        if self.use_symmetric_encodings and self.use_unsigned_symmetric:
+            return False        # is_unsigned_symmetric needs the values on the host
+        op0 = self._cppOp[0]
+        if not _is_native(op0) or op0._percentile is not None or not tensor.is_cuda or \
+                tensor.dtype not in (torch.float32, torch.bfloat16):   # pylint: disable=protected-access
+            return False
+        n = len(self._cppOp)
+        if n == 1:
+            if self.channel_axis is not None:
+                return False
+            op0._ensure_state(tensor.device)                                       # pylint: disable=protected-access
+            arena, first = op0._block.arena, op0._block.first + op0._index          # pylint: disable=protected-access
+            data = tensor if (tensor.is_contiguous() or tensor.is_contiguous(memory_format=torch.channels_last)) \
+                else tensor.contiguous()
+            seg_len = data.numel()
+        else:
+            self._ensure_block(tensor.device)
+            if self._group is None or self._group.detached != 0:
+                return False
+            arena, first = self._block.arena, self._block.first
+            data = tensor if self._ch_axis == 0 else tensor.movedim(self._ch_axis, 0)
+            data = data.contiguous(memory_format=torch.contiguous_format)
+            seg_len = data.numel() // n
+        enc, qdq4, params = ops.stats_refresh_encodings_impl(data, arena, first, n, seg_len, op0._code, self.bitwidth,   # pylint: disable=protected-access
+                                                             self.use_symmetric_encodings, self.use_strict_symmetric,
+                                                             self.use_unsigned_symmetric)
+        # the bookkeeping of resetEncodingStats + updateStats on the native ops ...
+        if n == 1:
+            op0._is_encoding_valid = True                                          # pylint: disable=protected-access
+            op0._range_fixed, op0._probe, op0._updates = False, None, 1            # pylint: disable=protected-access
+        else:
+            self._group.valid = True
+            for op in self._cppOp:
+                op._range_fixed, op._probe, op._updates = False, None, 1           # pylint: disable=protected-access
+        # ... and of reset_encoding_stats + update_encoding_stats + compute_encoding on this quantizer
+        self._enc_dev, self._qdq4_dev, self._params_dev = enc, qdq4, params
+        self._encoding = _LAZY
+        self.is_unsigned_symmetric = False
+        self._stats_dirty = False
+        return True
 
     def quantize_dequantize(self, tensor: torch.Tensor, round_mode) -> torch.Tensor:
         if not (torch.is_grad_enabled() and tensor.requires_grad):

@@ -244,6 +244,16 @@ int ab_compute_encodings(const ab_stats_state* states, int64_t count, int quant_
                          int use_strict_symmetric, int use_unsigned_symmetric, double* enc_out, float* qdq4_out,
                          void* stream);
 
+/* One tensor's resetEncodingStats + updateStats + computeEncoding enqueued by a single call: what a parameter quantizer does
+ * before every forward in training mode (TrainingExtensions/torch/src/python/aimet_torch/v1/qc_quantize_op.py:753-798).
+ * num_segments == 1: the tensor is one quantizer's input of segment_len elements (ab_stats_update); otherwise segment s
+ * updates states[s] (ab_stats_update_segmented). enc_out / qdq4_out as in ab_compute_encodings; params_out (optional):
+ * the float[4][num_segments] block of ab_per_channel_params_dev. Same kernels, same results as the separate calls. */
+int ab_stats_refresh_encodings(const void* in, int64_t num_segments, int64_t segment_len, int dtype, int quant_mode,
+                               ab_stats_state* states, int bw, int use_symmetric, int use_strict_symmetric,
+                               int use_unsigned_symmetric, double* enc_out, float* qdq4_out, float* params_out,
+                               void* stream);
+
 /* PercentileEncodingAnalyzer<float>::computeEncoding (DlQ/src/PercentileEncodingAnalyzer.cpp:77-196) for `count` consecutive
  * records whose statistics were collected with AB_QUANTIZATION_PERCENTILE (or TF_ENHANCED: the PDF is the same).
  * `percentile` is what setPercentileValue received (:203-206; 100 = the observed range). Outputs as ab_compute_encodings. */
