@@ -143,3 +143,82 @@ def test_gating_and_clone_elision_changes_nothing():
     assert grads_a.keys() == grads_b.keys() and len(grads_a) > 50
     for n in grads_a:
         assert torch.equal(grads_a[n], grads_b[n]), n
+
+
+@pytest.mark.parametrize("per_channel", [False, True])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fused_parameter_refresh_equals_the_three_calls(per_channel, dtype):
+    """refresh_encoding_from (one native call) against reset_encoding_stats + update_encoding_stats + compute_encoding:
+    same device-resident encodings, same kernel parameters, same quantize-dequantized weight, call after call."""
+    from aimet_b200 import libpymo
+    from aimet_b200.quantsim import tensor_quantizer as tq
+    from aimet_b200.quantsim.defs import QuantScheme
+
+    def make():
+        if per_channel:
+            q = tq.StaticGridPerChannelQuantizer(8, libpymo.RoundingMode.ROUND_NEAREST, QuantScheme.post_training_tf_enhanced,
+                                                 True, 24, True, ch_axis=0)
+        else:
+            q = tq.StaticGridPerTensorQuantizer(8, libpymo.RoundingMode.ROUND_NEAREST, QuantScheme.post_training_tf_enhanced,
+                                                True, True)
+        q._lazy_ok = True   # pylint: disable=protected-access
+        return q
+
+    fused, plain = make(), make()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for step in range(3):
+        w = (torch.randn(24, 16, 3, 3, device="cuda", generator=g) * (0.05 + 0.02 * step)).to(dtype)
+        assert fused.refresh_encoding_from(w)
+        plain.reset_encoding_stats()
+        plain.update_encoding_stats(w)
+        plain.compute_encoding()
+        assert torch.equal(fused._enc_dev, plain._enc_dev)   # pylint: disable=protected-access
+        if per_channel:
+            assert torch.equal(fused._params_dev, plain._params_dev)   # pylint: disable=protected-access
+        else:
+            assert torch.equal(fused._qdq4_dev, plain._qdq4_dev)       # pylint: disable=protected-access
+        a = fused.quantize_dequantize(w, libpymo.RoundingMode.ROUND_NEAREST)
+        b = plain.quantize_dequantize(w, libpymo.RoundingMode.ROUND_NEAREST)
+        assert torch.equal(a, b) and not torch.equal(a, w)
+        ea, eb = fused.encoding, plain.encoding
+        ea, eb = (ea, eb) if isinstance(ea, list) else ([ea], [eb])
+        assert [(e.min, e.max, e.delta, e.offset, e.bw) for e in ea] == [(e.min, e.max, e.delta, e.offset, e.bw) for e in eb]
+    # quantizers that cannot take the fused route say so
+    frozen = make()
+    frozen.refresh_encoding_from(w)
+    frozen.freeze_encoding()
+    assert not frozen.refresh_encoding_from(w)
+    unsigned = make()
+    unsigned.use_unsigned_symmetric = True
+    assert not unsigned.refresh_encoding_from(w)
+
+
+def test_quantized_forward_is_cuda_graph_capturable():
+    """Eval forward of a calibrated sim captured with torch.cuda.graph: replay == eager, bit for bit (the layers launch on
+    the capturing stream, allocate through torch, and never synchronise once the encodings are on the device)."""
+    import torchvision
+    from aimet_b200.quantsim import QuantizationSimModel
+    from aimet_b200.quantsim import config as qconfig
+    torch.manual_seed(0)
+    model = torchvision.models.resnet18().cuda().eval()
+    x = torch.randn(4, 3, 64, 64, device="cuda")
+    sim = QuantizationSimModel(model, dummy_input=x, quant_scheme="tf_enhanced", config_file=qconfig.DEFAULT_CONFIG_PER_CHANNEL)
+    sim.compute_encodings(lambda m, _: m(x), None)
+    with torch.no_grad():
+        eager = sim.model(x)
+        static_x = x.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                sim.model(static_x)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_y = sim.model(static_x)
+        for scale in (1.0, 0.5):
+            static_x.copy_(x * scale)
+            graph.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(static_y, sim.model(x * scale))
+    assert torch.equal(eager, sim.model(x))

@@ -44,6 +44,29 @@ def main():
             b.record()
             torch.cuda.synchronize()
             res[name + "_ms"] = round(a.elapsed_time(b) / args.iters, 3)
+        # the same forward replayed from a CUDA graph: the quantsim layers launch through the C ABI on the capturing stream
+        # and keep their encodings on the device, so torch.cuda.graph captures them like any other op
+        static_x = x.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                sim.model(static_x)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_y = sim.model(static_x)
+        eager_y = sim.model(x)
+        graph.replay()
+        torch.cuda.synchronize()
+        res["graph_equals_eager"] = bool(torch.equal(static_y, eager_y))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.iters):
+            graph.replay()
+        b.record()
+        torch.cuda.synchronize()
+        res["quantsim_graph_ms"] = round(a.elapsed_time(b) / args.iters, 3)
     res.update(batch=args.batch, dtype=args.dtype, qdq_overhead_ms=round(res["quantsim_ms"] - res["plain_ms"], 3),
                reverse=os.environ.get("AB_QDQ_REVERSE", "1"))
     print(json.dumps(res))
