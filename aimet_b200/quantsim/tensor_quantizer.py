@@ -13,7 +13,9 @@ A different op class (anything with AimetTensorQuantizer's nine methods) can be 
 uses that to drive this layer with the CPU oracle.
 """
 import functools
+import math
 import os
+import struct
 from typing import List, Optional, Tuple, Union
 
 import torch
@@ -432,6 +434,29 @@ class StaticGridPerChannelQuantizer(StaticGridTensorQuantizer):
 # ---------------------------------------------------------------------------------------------------------------------
 # autograd functions
 # ---------------------------------------------------------------------------------------------------------------------
+def scalar_in_dtype(value, dtype) -> float:
+    """float(torch.tensor(float(value), dtype=torch.float32).to(dtype)) without building tensors: the value narrowed to
+    float32 (round to nearest even, overflow to infinity), then to bfloat16 / float16 the same way. The backward of every
+    activation quantizer needs two of these per step."""
+    value = float(value)
+    try:
+        f32 = struct.unpack("<f", struct.pack("<f", value))[0]
+    except OverflowError:
+        f32 = math.copysign(math.inf, value)
+    if dtype == torch.float32 or f32 != f32 or math.isinf(f32):
+        return f32
+    if dtype == torch.bfloat16:
+        bits = struct.unpack("<I", struct.pack("<f", f32))[0]
+        bits = (bits + 0x7fff + ((bits >> 16) & 1)) & 0xffff0000
+        return struct.unpack("<f", struct.pack("<I", bits))[0]
+    if dtype == torch.float16:
+        try:
+            return struct.unpack("<e", struct.pack("<e", f32))[0]
+        except OverflowError:
+            return math.copysign(math.inf, f32)
+    raise TypeError(dtype)
+
+
 def compute_dloss_by_dx(x, grad, encoding_min, encoding_max, ch_axis=0):
     """Straight-through estimator, reference quantsim_straight_through_grad.py:91-118: grad * [min <= x <= max].
     On CUDA tensors this is one fused kernel (3 tensors of traffic) instead of three element-wise torch kernels."""
@@ -451,8 +476,7 @@ def compute_dloss_by_dx(x, grad, encoding_min, encoding_max, ch_axis=0):
     # torch.tensor(python float) is a 0-dim float32 tensor; compared with a lower-precision tensor it does not promote,
     # i.e. the reference compares in x's dtype with the range rounded to that dtype
     cmp_dtype = x.dtype if x.dtype in (torch.bfloat16, torch.float16) else torch.float32
-    lo = float(torch.tensor(float(encoding_min), dtype=torch.float32).to(cmp_dtype))
-    hi = float(torch.tensor(float(encoding_max), dtype=torch.float32).to(cmp_dtype))
+    lo, hi = scalar_in_dtype(encoding_min, cmp_dtype), scalar_in_dtype(encoding_max, cmp_dtype)
     if x.dtype == torch.float16:
         return ops.ste_bwd_impl(x.float(), grad.float(), lo, hi).to(torch.float16)
     return ops.ste_bwd_impl(x, grad, lo, hi)

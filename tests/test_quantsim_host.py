@@ -159,3 +159,24 @@ def test_load_encodings_and_checkpoint_round_trip(oracle_backend, tmp_path):
     restored = load_checkpoint(str(tmp_path / "sim.ckpt"))
     with torch.no_grad():
         assert torch.equal(restored.model(x), out)
+
+
+def test_scalar_in_dtype_rounds_like_torch():
+    """The tensor-free narrowing of an encoding bound (float64 -> float32 -> bf16 / fp16, ties to even, overflow to inf)."""
+    import struct
+
+    import numpy as np
+    from aimet_b200.quantsim.tensor_quantizer import scalar_in_dtype
+    rng = np.random.default_rng(0)
+    values = [0.0, -0.0, 1e39, -1e39, 3.4028235e38, 3.4028236e38, 65504.0, 65519.99, 65520.0, 5.96e-8, 2.98e-8, 1e-45,
+              7e-46, float("inf"), float("-inf")]
+    # float32 bit patterns that are exact bf16 ties (low half 0x8000) and their neighbours, even and odd upper halves
+    for hi in (0x3f80, 0x3f81, 0x4000, 0x7f7f, 0x0001, 0xbf80, 0xbf81):
+        for lo in (0x7fff, 0x8000, 0x8001):
+            values.append(struct.unpack("<f", struct.pack("<I", (hi << 16) | lo))[0])
+    values += list(rng.standard_normal(2000) * 10.0 ** rng.uniform(-10, 10, 2000))
+    for v in values:
+        for dt in (torch.float32, torch.bfloat16, torch.float16):
+            ref = float(torch.tensor(float(v), dtype=torch.float32).to(dt))
+            got = scalar_in_dtype(v, dt)
+            assert struct.pack("<d", ref) == struct.pack("<d", got), (v, dt, ref, got)
