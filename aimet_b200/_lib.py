@@ -56,6 +56,7 @@ PROTOTYPES = {
     "ab_stats_update_segmented": (_int, [_vp, _i64, _i64, _int, _int, _vp, _vp]),
     "ab_compute_encodings": (_int, [_vp, _i64, _int, _int, _int, _int, _int, _vp, _vp, _vp]),
     "ab_compute_encodings_percentile": (_int, [_vp, _i64, _flt, _int, _int, _int, _int, _vp, _vp, _vp]),
+    "ab_debug_hist_timer": (_i64, [_vp, _i64]),
     "ab_stats_refresh_encodings": (_int, [_vp, _i64, _i64, _int, _int, _vp, _int, _int, _int, _int, _vp, _vp, _vp, _vp]),
     "ab_stats_init_range": (_int, [_vp, _i64, _vp, _vp]),
     "ab_stats_fold_batches": (_int, [_vp, _i64, _vp, _vp, _i64, _vp]),

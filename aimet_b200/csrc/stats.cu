@@ -484,10 +484,35 @@ __device__ __forceinline__ void consume_tile_bf16_formula(const uint4* __restric
     }
 }
 
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 template <typename T, bool kPdl>
 __global__ void __launch_bounds__(kHistThreads, 1)
-    hist_kernel(const T* __restrict__ in, int64_t count, ab_stats_state* st, uint32_t* batch_log, int reverse)
+    hist_kernel(const T* __restrict__ in, int64_t count, ab_stats_state* st, uint32_t* batch_log, int reverse,
+                unsigned long long* timer_slot)
 {
+    // measurement hook (ab_debug_hist_timer): earliest start / latest end of any CTA of this launch on the GPU's global
+    // timer, i.e. the launch's execution time without launch latency or event overhead. nullptr in normal operation.
+    if (timer_slot != nullptr && threadIdx.x == 0)
+    {
+        atomicMin(timer_slot, global_timer_ns());
+        if (blockIdx.x == 0)
+            timer_slot[2] = (unsigned long long) count * sizeof(T);
+    }
+    struct TimerEnd
+    {
+        unsigned long long* slot;
+        __device__ ~TimerEnd()
+        {
+            if (slot != nullptr && threadIdx.x == 0)
+                atomicMax(slot + 1, global_timer_ns());
+        }
+    } timer_end {timer_slot};
     constexpr int kV = Elem<T>::kPerVec;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_tiles  = smem;
@@ -967,6 +992,10 @@ bool check_common(const void* in, int64_t count, int dtype, int quant_mode, cons
     return true;
 }
 
+// ab_debug_hist_timer: slots handed to the histogram launches that follow, one {start, end} pair each
+unsigned long long* g_timer_slots = nullptr;
+int64_t g_timer_capacity = 0, g_timer_used = 0;
+
 template <typename T>
 int launch_update(const T* in, int64_t count, int quant_mode, ab_stats_state* st, uint32_t* batch_log, int flags,
                   cudaStream_t stream)
@@ -997,6 +1026,9 @@ int launch_update(const T* in, int64_t count, int quant_mode, ab_stats_state* st
             const char* e = getenv("AB_HIST_REVERSE");
             return (e == nullptr || e[0] != '0') ? 1 : 0;
         }();
+        unsigned long long* timer_slot = nullptr;
+        if (g_timer_slots != nullptr && g_timer_used < g_timer_capacity)
+            timer_slot = g_timer_slots + 3 * g_timer_used++;
         static thread_local bool configured[2] = {false, false};
         const int which                        = sizeof(T) == 4 ? 0 : 1;
         if (!configured[which])
@@ -1023,11 +1055,13 @@ int launch_update(const T* in, int64_t count, int quant_mode, ab_stats_state* st
             attr[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs                                          = attr;
             cfg.numAttrs                                       = 1;
-            AB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, hist_kernel<T, true>, in, count, st, batch_log, reverse));
+            AB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, hist_kernel<T, true>, in, count, st, batch_log, reverse,
+                                             timer_slot));
         }
         else
         {
-            hist_kernel<T, false><<<grid, kHistThreads, kHistSmem, stream>>>(in, count, st, batch_log, reverse);
+            hist_kernel<T, false><<<grid, kHistThreads, kHistSmem, stream>>>(in, count, st, batch_log, reverse,
+                                                                             timer_slot);
             AB_CUDA_CHECK(cudaGetLastError());
         }
     }
@@ -1044,6 +1078,15 @@ extern "C"
 size_t ab_stats_state_bytes(void)
 {
     return sizeof(ab_stats_state);
+}
+
+int64_t ab_debug_hist_timer(unsigned long long* slots, int64_t capacity)
+{
+    const int64_t used = g_timer_used;
+    g_timer_slots      = slots;
+    g_timer_capacity   = slots != nullptr ? capacity : 0;
+    g_timer_used       = 0;
+    return used;
 }
 
 int ab_stats_reset(ab_stats_state* states, int64_t count, void* stream)

@@ -336,6 +336,34 @@ def run_ours(args):
     # launches of one captured (replayed) step = launches issued while capturing = total of this job minus the eager ones
     job_launches = {k: ops.LAUNCHES[k] - per_step0[k] for k in ops.LAUNCHES}
 
+    # ---- and a short eager pass with the kernel's own clock (ab_debug_hist_timer): first CTA start to last CTA end of every
+    # histogram launch on the GPU's global timer. No launch latency, no event records between the kernels: what the
+    # histogram itself takes in its real surroundings (input just written by the producing layer, L2 in whatever state).
+    from aimet_b200 import _lib as ab_lib
+    dev_timer = None
+    if True:   # every rank runs it (the sharded job has collectives); only rank 0's numbers are printed
+        probe_steps = min(steps, 4)
+        cap = 128 * probe_steps + 64
+        slots = torch.zeros((cap, 3), dtype=torch.int64, device=device)
+        slots[:, 0] = torch.iinfo(torch.int64).max
+        ab_lib.load().ab_debug_hist_timer(slots.data_ptr(), cap)
+        job(resident, probe_steps)
+        torch.cuda.synchronize()
+        used = int(ab_lib.load().ab_debug_hist_timer(None, 0))
+        if 0 < used <= cap:
+            rows = slots[:used].cpu().tolist()
+            # the activation statistics of the LAST step: the trailing launches, as many as one steady-state step makes
+            per_step = n_act_hist = sum(1 for r in rows if r[2] >= 64 * 1024) // probe_steps
+            last = [r for r in rows if r[2] >= 64 * 1024][-per_step:] if per_step else []
+            if last:
+                b, t_ns = sum(r[2] for r in last), sum(r[1] - r[0] for r in last)
+                big = [r for r in last if r[2] >= 32 * 2**20]
+                dev_timer = {"launches": len(last), "avg_launch_us": round(t_ns / 1000.0 / len(last), 2),
+                             "achieved": round(b / t_ns, 1), "algorithmic_bytes_per_launch": round(b / len(last), 1),
+                             "achieved_large_tensors":
+                                 round(sum(r[2] for r in big) / sum(r[1] - r[0] for r in big), 1) if big else None}
+    barrier()
+
     # max over ranks
     t = torch.tensor([ms, e2e_s * 1000.0], device=device, dtype=torch.float64)
     if world > 1:
@@ -366,6 +394,10 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": round(tot_bytes / max(n_l, 1), 1), "launches": n_l,
                 "avg_launch_us": round(1000.0 * tot_ms / max(n_l, 1), 2), "peak_source": peak_src,
                 "achieved_large_tensors": round(big_bytes / big_ms / 1e6, 1) if big_ms > 0 else None,
+                "device_timer": (dict(dev_timer, frac=round(dev_timer["achieved"] / peak, 4), unit="GB/s",
+                                      how="first CTA start to last CTA end on %globaltimer, last step of a short "
+                                          "eager repeat (no launch latency, no event records between kernels)")
+                                 if dev_timer else None),
                 "note": "4 B/element x elements of every activation tensor handed to updateStats, divided by the "
                         "CUDA-event time of those launches (events on the launching stream; in CUDA-graph mode: "
                         "external event nodes inside the replayed step, read for the last step of an instrumented "

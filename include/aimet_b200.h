@@ -113,6 +113,12 @@ const char* ab_last_error(void);
 int ab_version(void);
 int ab_device_count(void);
 size_t ab_stats_state_bytes(void); /* == sizeof(ab_stats_state) */
+/* Measurement hook, not used in normal operation. slots: DEVICE array of capacity x 3 uint64, each triple initialised to
+ * {INT64_MAX, 0, 0}. Every histogram launch (tf_enhanced ab_stats_update) issued afterwards takes the next triple and
+ * records the earliest start / latest end of its CTAs on the GPU's global nanosecond timer and the bytes of its input:
+ * the launch's execution time on the device, free of launch latency and of the event records a host-side bracket needs.
+ * slots == NULL switches it off. Returns the number of triples handed out since the previous call. Not thread-safe. */
+int64_t ab_debug_hist_timer(unsigned long long* slots, int64_t capacity);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Host helpers: encoding math in double, bit-identical to the reference's host code.
