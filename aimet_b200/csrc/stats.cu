@@ -62,7 +62,8 @@ struct Range
 };
 
 // Range for this call: the frozen one, or (first non-zero batch) the one InitializePdf derives from the batch min/max.
-__device__ __forceinline__ Range resolve_range(const ab_stats_state* st, double* x_left0, double* bucket_d)
+template <typename S>
+__device__ __forceinline__ Range resolve_range(const S* st, double* x_left0, double* bucket_d)
 {
     Range r;
     if (st->initialized)
@@ -484,6 +485,17 @@ __device__ __forceinline__ void consume_tile_bf16_formula(const uint4* __restric
     }
 }
 
+// What a histogram launch needs to know about its record, read from global memory by ONE thread and handed to the rest of
+// the CTA through shared memory: after the barrier that publishes it, no thread of this CTA has a load of these fields in
+// flight any more, which is what lets the CTA announce "I have read the record" with a single atomic (see fast_tail).
+struct StateSnap
+{
+    float bucket_size, pdf_offset;
+    int32_t batch_min_bits, batch_max_bits, initialized, iterations, pending, write_parity, bf16_formula;
+    float bf16_scale, bf16_shift;
+    double pending_count;
+};
+
 __device__ __forceinline__ unsigned long long global_timer_ns()
 {
     unsigned long long t;
@@ -498,12 +510,16 @@ __global__ void __launch_bounds__(kHistThreads, 1)
 {
     // measurement hook (ab_debug_hist_timer): earliest start / latest end of any CTA of this launch on the GPU's global
     // timer, i.e. the launch's execution time without launch latency or event overhead. nullptr in normal operation.
-    if (timer_slot != nullptr && threadIdx.x == 0)
-    {
-        atomicMin(timer_slot, global_timer_ns());
-        if (blockIdx.x == 0)
-            timer_slot[2] = (unsigned long long) count * sizeof(T);
-    }
+    auto stamp_start = [&]() {
+        if (timer_slot != nullptr && threadIdx.x == 0)
+        {
+            atomicMin(timer_slot, global_timer_ns());
+            if (blockIdx.x == 0)
+                timer_slot[2] = (unsigned long long) count * sizeof(T);
+        }
+    };
+    if (!kPdl)
+        stamp_start();   // with PDL the CTA may be resident while the previous kernel still runs: stamped after the wait
     struct TimerEnd
     {
         unsigned long long* slot;
@@ -567,34 +583,62 @@ __global__ void __launch_bounds__(kHistThreads, 1)
         for (int i = tid; i < kHistWords / 4; i += kHistThreads)
             reinterpret_cast<uint4*>(s_hist)[i] = make_uint4(0, 0, 0, 0);
         asm volatile("griddepcontrol.wait;" ::: "memory");
+        stamp_start();
     }
     if (warp == kProducerWarp && lane == 0)
         for (int64_t k = 0; k < my_tiles && k < kStages; ++k)
             issue_tile(k);
 
+    __shared__ StateSnap s_snap;
+    if (tid == 0)
+    {
+        s_snap.bucket_size    = st->bucket_size;
+        s_snap.pdf_offset     = st->pdf_offset;
+        s_snap.batch_min_bits = st->batch_min_bits;
+        s_snap.batch_max_bits = st->batch_max_bits;
+        s_snap.initialized    = st->initialized;
+        s_snap.iterations     = st->iterations;
+        s_snap.pending        = st->pending;
+        s_snap.write_parity   = st->write_parity;
+        s_snap.pending_count  = st->pending_count;
+        s_snap.bf16_formula   = st->bf16_formula;
+        s_snap.bf16_scale     = st->bf16_scale;
+        s_snap.bf16_shift     = st->bf16_shift;
+    }
+    if (!kPdl)
+        for (int i = tid; i < kHistWords / 4; i += kHistThreads)
+            reinterpret_cast<uint4*>(s_hist)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();   // record snapshot published, barriers initialised, bins zeroed
+    const StateSnap sn = s_snap;
     double x_left0 = 0, bucket_d = 0;
-    const Range rg   = resolve_range(st, &x_left0, &bucket_d);   // every thread derives the same range
-    // stable for the whole launch: only the last CTA, after every CTA has taken its ticket, changes them
-    const int parity      = st->write_parity;
-    const bool had_pending = st->pending != 0;
-    const int iterations0 = st->iterations;
+    const Range rg   = resolve_range(&sn, &x_left0, &bucket_d);   // every thread derives the same range
+    // stable for the whole launch: whoever changes them does so after every CTA has taken its snapshot
+    const int parity       = sn.write_parity;
+    const bool had_pending = sn.pending != 0;
+    const int iterations0  = sn.iterations;
     // With a batch log (multi-GPU exact merge) the batch is folded and logged at the end of this launch; otherwise its
     // counts stay parked in hist[parity] and the NEXT call on this record folds them while it streams its own data.
     const bool lazy = batch_log == nullptr;
     // bf16: the certified one-FFMA bin index (see bf16_formula_bin). `formula` and the pair are stable for the launch.
     constexpr bool kIsBf16 = sizeof(T) == 2;
-    const int formula      = kIsBf16 ? st->bf16_formula : 0;
-    const float formula_c  = kIsBf16 ? st->bf16_scale : 0.0f;
-    const float formula_b  = kIsBf16 ? st->bf16_shift : 0.0f;
+    const int formula      = kIsBf16 ? sn.bf16_formula : 0;
+    const float formula_c  = kIsBf16 ? sn.bf16_scale : 0.0f;
+    const float formula_b  = kIsBf16 ? sn.bf16_shift : 0.0f;
     const bool certify     = kIsBf16 && rg.valid && formula == 0 && count >= kBf16FormulaMinCount;
+    // Tail of the launch. Somebody has to update the record's bookkeeping (pending / parity / iterations ...) once no CTA
+    // needs the old values any more. Logging and certifying launches need the LAST CTA TO FINISH (it reads what the others
+    // flushed): a ticket taken at the very end, whose round trip to L2 sits on every CTA's critical path. All other
+    // launches only need "every CTA has read the record", which is known much earlier: the ticket is taken right here --
+    // this CTA's only reads of those fields went into the snapshot above -- and its result is looked at when the CTA is
+    // done, by which time it has long arrived. The CTA that drew the last ticket writes the bookkeeping; nobody waits, the
+    // consumer warps synchronise among themselves only, and the keeper warp's fold is off the critical path.
+    const bool fast_tail = lazy && !certify;
+    uint32_t my_ticket   = 0xffffffffu;
+    if (fast_tail && tid == 0)
+        my_ticket = atomicAdd(&st->ticket, 1u);
 
     if (rg.valid)
     {
-        if (!kPdl)
-            for (int i = tid; i < kHistWords / 4; i += kHistThreads)
-                reinterpret_cast<uint4*>(s_hist)[i] = make_uint4(0, 0, 0, 0);
-        __syncthreads();   // barriers initialised, bins zeroed
-
         Binner binner;
         binner.dv     = make_divisor(rg.bucket);
         binner.offset = rg.offset;
@@ -620,7 +664,7 @@ __global__ void __launch_bounds__(kHistThreads, 1)
             if (had_pending)
             {
                 const int pp     = parity ^ 1;
-                const double cnt = st->pending_count;
+                const double cnt = sn.pending_count;
                 for (int b = blockIdx.x * 32 + lane; b < kBins; b += gridDim.x * 32)
                 {
                     fold_bin(&st->pdf[b], st->hist[pp][b], cnt, iterations0);
@@ -635,8 +679,8 @@ __global__ void __launch_bounds__(kHistThreads, 1)
                 if (lane == 0 && failed)
                     atomicOr(&st->bf16_fail_mask, failed);
             }
-            if (had_pending || certify)
-                __threadfence();   // ordered before this CTA's ticket, hence before the last CTA's bookkeeping
+            if (!fast_tail && (had_pending || certify))
+                __threadfence();   // ordered before this CTA's end ticket, hence before what the last CTA reads
         }
         else
         {
@@ -664,7 +708,10 @@ __global__ void __launch_bounds__(kHistThreads, 1)
                  i += (int64_t) gridDim.x * (kConsumerWarps * 32))
                 binner.count(s_hist_lane, Elem<T>::load(in + i));
         }
-        __syncthreads();
+        if (!fast_tail)
+            __syncthreads();
+        else if (warp < kConsumerWarps)
+            asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory");   // the consumers among themselves
 
         // reduce the 32 lane copies of bin `tid` (rotated start: conflict-free) and flush
         if (tid < kBins)
@@ -685,7 +732,36 @@ __global__ void __launch_bounds__(kHistThreads, 1)
             mbar_wait(s_full + k, 0);
     }
 
-    // ---- election of the last CTA ------------------------------------------------------------------------------------
+    if (fast_tail)
+    {
+        // ---- the CTA that drew the last "I have read the record" ticket does the bookkeeping; everybody leaves ----------
+        if (tid == 0 && my_ticket == gridDim.x - 1)
+        {
+            if (rg.valid)
+            {
+                if (!sn.initialized)
+                {
+                    st->x_left0       = x_left0;
+                    st->bucket_size_d = bucket_d;
+                    st->bucket_size   = rg.bucket;
+                    st->pdf_offset    = rg.offset;
+                    st->initialized   = 1;
+                }
+                if (had_pending)
+                    st->iterations = iterations0 + 1;   // the keepers fold the previous batch during this launch
+                st->pending_count = (double) count;
+                st->pending       = 1;
+                st->write_parity  = parity ^ 1;
+            }
+            st->stats_updated  = 1;
+            st->batch_min_bits = kPosInfBits;
+            st->batch_max_bits = kNegInfBits;
+            st->ticket         = 0;
+        }
+        return;
+    }
+
+    // ---- election of the last CTA to finish (logging / certifying launches) ---------------------------------------------
     if (!lazy)
         __threadfence();   // the last CTA will READ the flushed counts in this very launch
     __syncthreads();
@@ -693,7 +769,7 @@ __global__ void __launch_bounds__(kHistThreads, 1)
     {
         const uint32_t t = atomicAdd(&st->ticket, 1u);
         s_is_last        = (t == gridDim.x - 1);
-        if (s_is_last && rg.valid && !st->initialized)
+        if (s_is_last && rg.valid && !sn.initialized)
             s_x_left0 = x_left0, s_bucket_d = bucket_d;
     }
     __syncthreads();
