@@ -222,3 +222,21 @@ def test_quantized_forward_is_cuda_graph_capturable():
             torch.cuda.synchronize()
             assert torch.equal(static_y, sim.model(x * scale))
     assert torch.equal(eager, sim.model(x))
+
+
+def test_capture_forward_helper():
+    import torchvision
+    from aimet_b200.quantsim import QuantizationSimModel
+    torch.manual_seed(0)
+    model = torchvision.models.resnet18().cuda().eval()
+    x = torch.randn(2, 3, 64, 64, device="cuda")
+    sim = QuantizationSimModel(model, dummy_input=x, quant_scheme="tf")
+    sim.compute_encodings(lambda m, _: m(x), None)
+    fwd = sim.capture_forward(x)
+    with torch.no_grad():
+        for scale in (1.0, -0.7, 2.5):
+            assert torch.equal(fwd(x * scale), sim.model(x * scale))
+    with pytest.raises(ValueError):
+        fwd(x[:1])
+    with pytest.raises(ValueError):
+        sim.capture_forward(x.cpu())
