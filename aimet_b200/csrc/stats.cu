@@ -274,8 +274,14 @@ __global__ void __launch_bounds__(kMmThreads)
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kConsumerWarps = 16;
 constexpr int kHistThreads   = (kConsumerWarps + 2) * 32;   // + a producer warp (drives the TMA engine) + a housekeeping warp
-constexpr int kTileBytes     = 32768;
-constexpr int kStages        = 4;
+#ifndef AB_HIST_TILE_BYTES
+#define AB_HIST_TILE_BYTES 32768
+#endif
+#ifndef AB_HIST_STAGES
+#define AB_HIST_STAGES 4
+#endif
+constexpr int kTileBytes     = AB_HIST_TILE_BYTES;   // tuning hooks: -DAB_HIST_TILE_BYTES=... -DAB_HIST_STAGES=... (AB_NVCC_EXTRA)
+constexpr int kStages        = AB_HIST_STAGES;
 constexpr int kLaneCopies    = 32;
 constexpr int kVecPerThread  = kTileBytes / 16 / (kConsumerWarps * 32);
 constexpr int kHistWords     = (kBins + 1) * kLaneCopies;   // + the dump row for dropped samples
