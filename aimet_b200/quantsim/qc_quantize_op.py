@@ -36,13 +36,13 @@ def export_quantizer_encoding(quantizer) -> Optional[List[Dict]]:
         return None
     if quantizer.data_type == QuantizationDataType.int and quantizer.bitwidth == 32:
         return None
-    rows = quantizer._device_rows() if hasattr(quantizer, "_device_rows") else None   # pylint: disable=protected-access
-    if rows is not None:
-        # encodings that still live only on the device: one copy, dictionaries built straight from the rows (no
-        # intermediate TfEncoding objects -- 26 560 of them for per-channel ResNet-50)
+    cols = quantizer._device_columns() if hasattr(quantizer, "_device_columns") else None   # pylint: disable=protected-access
+    if cols is not None:
+        # encodings that still live only on the device: one copy, dictionaries built straight from the columns (no
+        # intermediate TfEncoding objects or per-row lists -- 26 560 of them for per-channel ResNet-50)
         sym = str(quantizer.use_symmetric_encodings)
-        return [{"min": r[0], "max": r[1], "scale": r[2], "offset": int(r[3]), "bitwidth": int(r[4]),
-                 "is_symmetric": sym, "dtype": "int"} for r in rows]
+        return [{"min": mn, "max": mx, "scale": sc, "offset": off, "bitwidth": bw, "is_symmetric": sym, "dtype": "int"}
+                for mn, mx, sc, off, bw in zip(*cols)]
     # a learned-grid quantizer exports its effective encoding (reference get_encoding_by_quantizer :1514-1526)
     encoding = quantizer.get_effective_encoding() if hasattr(quantizer, "get_effective_encoding") else quantizer.encoding
 

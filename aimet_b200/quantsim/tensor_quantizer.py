@@ -132,11 +132,13 @@ class StaticGridTensorQuantizer:
             self._encoding = [libpymo.TfEncoding._from_values(r[0], r[1], r[2], r[3], int(r[4])) for r in rows]   # pylint: disable=protected-access
             self._host_epoch = libpymo.encoding_epoch()
 
-    def _device_rows(self):
-        """[[min, max, delta, offset, bw], ...] of a result that lives only on the device (None otherwise): lets the
-        exporter build its dictionaries without materialising TfEncoding objects."""
+    def _device_columns(self):
+        """(mins, maxs, deltas, offsets, bitwidths) as Python lists for a result that lives only on the device (None
+        otherwise): one copy, five vectorised conversions -- the exporter builds 26 560 dictionaries per ResNet-50 job."""
         if self._encoding is _LAZY:
-            return self._enc_dev.cpu().tolist()
+            a = self._enc_dev.cpu().numpy()
+            return (a[:, 0].tolist(), a[:, 1].tolist(), a[:, 2].tolist(), a[:, 3].astype("int64").tolist(),
+                    a[:, 4].astype("int64").tolist())
         return None
 
     def _device_encoding_valid(self) -> bool:
