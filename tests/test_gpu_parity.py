@@ -492,3 +492,28 @@ def test_per_channel_more_than_2_31_elements(ops, oracle):
             exp[m] = oracle.qdq_per_channel(xs[m], 1, int(m.sum()), *[np.ascontiguousarray(a[cc:cc + 1]) for a in p])
         got = out[start:stop].float().cpu().numpy()
         assert np.array_equal(got, torch.from_numpy(exp).to(torch.bfloat16).float().numpy()), start
+
+
+def test_tfe_stats_many_batches_of_mixed_sizes(ops, oracle):
+    """40 updates of one record back to back, sizes from a handful of samples (16 CTAs) to several million (148 CTAs), fp32
+    and bf16 alternating, with a read of the parked batch in the middle: every launch hands its bookkeeping over to the
+    next one through the record (early ticket, parked fold), and the final PDF must be the reference's bit for bit."""
+    from oracle.bindings import OracleTfe
+    rng = np.random.default_rng(2024)
+    blk = new_state()
+    o = OracleTfe(oracle)
+    sizes = [3, 700_001, 17, 4_000_003, 1, 65_536, 2_097_152, 33, 1_000_000, 5] * 4
+    for b, n in enumerate(sizes):
+        x = make(rng, n, "shifted" if b % 3 else "normal") * np.float32(rng.uniform(0.3, 1.2))
+        if b % 2:
+            xd = dev(x, torch.bfloat16)
+            x = host(xd)
+        else:
+            xd = dev(x)
+        ops.stats_update_impl(xd, blk.arena, blk.first, ops.QUANTIZATION_TF_ENHANCED, None, 0)
+        o.update(x)
+        if b == 17:
+            assert np.array_equal(blk.read()[0]["pdf"], o.histogram()[1])
+    rec = blk.read()[0]
+    assert rec["ticket"] == 0 and rec["iterations"] == o.s.iterations
+    assert np.array_equal(rec["pdf"], o.histogram()[1])
