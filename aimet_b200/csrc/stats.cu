@@ -622,8 +622,9 @@ __global__ void __launch_bounds__(kHistThreads, 1)
     const int parity       = sn.write_parity;
     const bool had_pending = sn.pending != 0;
     const int iterations0  = sn.iterations;
-    // With a batch log (multi-GPU exact merge) the batch is folded and logged at the end of this launch; otherwise its
-    // counts stay parked in hist[parity] and the NEXT call on this record folds them while it streams its own data.
+    // The batch's counts stay parked in hist[parity]; the NEXT call on this record folds them while it streams its own
+    // data. With a batch log (multi-GPU exact merge) every CTA also ADDS its counts to the log entry, which the caller has
+    // zeroed. Only a certifying launch with a log still folds and logs at its end (`lazy` false: the old path).
     const bool lazy = batch_log == nullptr;
     // bf16: the certified one-FFMA bin index (see bf16_formula_bin). `formula` and the pair are stable for the launch.
     constexpr bool kIsBf16 = sizeof(T) == 2;
@@ -638,7 +639,7 @@ __global__ void __launch_bounds__(kHistThreads, 1)
     // this CTA's only reads of those fields went into the snapshot above -- and its result is looked at when the CTA is
     // done, by which time it has long arrived. The CTA that drew the last ticket writes the bookkeeping; nobody waits, the
     // consumer warps synchronise among themselves only, and the keeper warp's fold is off the critical path.
-    const bool fast_tail = lazy && !certify;
+    const bool fast_tail = !certify;
     uint32_t my_ticket   = 0xffffffffu;
     if (fast_tail && tid == 0)
         my_ticket = atomicAdd(&st->ticket, 1u);
@@ -727,7 +728,11 @@ __global__ void __launch_bounds__(kHistThreads, 1)
             for (int l = 0; l < kLaneCopies; ++l)
                 sum += s_hist[tid * kLaneCopies + ((l + tid) & (kLaneCopies - 1))];
             if (sum)
+            {
                 atomicAdd(&st->hist[parity][tid], sum);
+                if (fast_tail && batch_log != nullptr)
+                    atomicAdd(&batch_log[tid], sum);
+            }
         }
     }
     else if (warp == kProducerWarp && lane == 0)
@@ -763,6 +768,13 @@ __global__ void __launch_bounds__(kHistThreads, 1)
             st->batch_min_bits = kPosInfBits;
             st->batch_max_bits = kNegInfBits;
             st->ticket         = 0;
+            if (batch_log != nullptr)
+            {
+                // element count (0 when the batch was skipped, as the reference skips all-zero batches before init)
+                const uint64_t c     = rg.valid ? (uint64_t) count : 0;
+                batch_log[kBins]     = (uint32_t) c;
+                batch_log[kBins + 1] = (uint32_t) (c >> 32);
+            }
         }
         return;
     }

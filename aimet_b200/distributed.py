@@ -170,6 +170,8 @@ class ShardedCalibrator:
             self._fix_ranges()
         self.local_batch += 1
         self.calls = [0] * len(self.quantizers)
+        if self.tfe and self.ranges_fixed:
+            self.stage.zero_()     # the statistics launches ADD their counts to their log entry (one memset per batch)
 
     def _end_batch(self):
         """File the staged log of the batch that just ran under its slot."""
@@ -294,6 +296,8 @@ class ShardedCalibrator:
             def start_batch():
                 self.local_batch += 1
                 self.calls = [0] * len(self.quantizers)
+                if self.tfe and self.ranges_fixed:
+                    self.stage.zero_()          # before the forward, eager or replayed: the launches add to their entries
 
             def after_each(n):
                 if n == 0:

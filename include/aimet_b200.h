@@ -220,9 +220,9 @@ int ab_stats_reset(ab_stats_state* states, int64_t count, void* stream);
  *                                pass fixes the histogram range (InitializePdf :207-241), then GetHistogram (:367-384)
  *                                bins the batch and the counts are folded into the running PDF -- all on the device,
  *                                with no host synchronisation (two launches; one once the range is fixed).
- * `batch_log_entry`, if not NULL, is a DEVICE array of AB_PDF_SIZE + 2 uint32 that also receives this batch's raw
- * counts followed by the element count (low word, high word; 0 when the batch was skipped because the PDF was still
- * uninitialised and the batch was all zeros). Used by the multi-GPU exact merge (ab_stats_fold_batches).
+ * `batch_log_entry`, if not NULL, is a DEVICE array of AB_PDF_SIZE + 2 uint32, ZEROED BY THE CALLER, to which this batch's
+ * raw counts are added, followed by the element count (low word, high word; 0 when the batch was skipped because the PDF
+ * was still uninitialised and the batch was all zeros). Used by the multi-GPU exact merge (ab_stats_fold_batches).
  * `flags`: AB_STATS_RANGE_FIXED -- the caller KNOWS (from an earlier read-back of `initialized`) that this record's
  * histogram range is fixed, so the min/max kernel, which would exit immediately, is not even launched. */
 #define AB_STATS_RANGE_FIXED 1
