@@ -399,8 +399,11 @@ class QuantizationSimModel:
         if isinstance(encodings, (str, os.PathLike)):
             with open(encodings) as f:
                 encodings = json.load(f)
-        param_encodings = encodings.get("param_encodings", {})
-        activation_encodings = encodings.get("activation_encodings", {})
+        if "param_encodings" not in encodings:     # the older AdaRound export: parameter encodings only (reference :1726-1732)
+            param_encodings, activation_encodings = encodings, {}
+        else:
+            param_encodings = encodings.get("param_encodings", {})
+            activation_encodings = encodings.get("activation_encodings", {})
         if not param_encodings and not activation_encodings:
             raise RuntimeError("no encodings to load")
         wrappers = dict(self.quant_wrappers())
@@ -418,6 +421,32 @@ class QuantizationSimModel:
             wrapper.import_input_encodings(act.get("input", {}), strict, partial, requires_grad, allow_overwrite)
             wrapper.import_output_encodings(act.get("output", {}), strict, partial, requires_grad, allow_overwrite)
             wrapper.set_mode(QcQuantizeOpMode.ACTIVE)
+
+    def load_and_freeze_encodings(self, encoding_path: str, ignore_when_quantizer_disabled: bool = False):
+        """Set activation and parameter encodings from a `<prefix>_torch.encodings` / save_encodings_to_json file and
+        freeze them: later compute_encodings / load_encodings calls leave them alone (reference :1759-1775)."""
+        self.load_encodings(encoding_path, strict=not ignore_when_quantizer_disabled, partial=True, requires_grad=False,
+                            allow_overwrite=False)
+
+    def set_and_freeze_param_encodings(self, encoding_path: str):
+        """Parameter encodings only, frozen (reference :1838-1855; deprecated there in favour of load_encodings)."""
+        with open(encoding_path) as f:
+            encodings = json.load(f)
+        encodings.pop("activation_encodings", None)
+        self.load_encodings(encodings, strict=True, partial=True, requires_grad=False, allow_overwrite=False)
+
+    def exclude_param_from_quantization(self, param_name_to_exclude: str):
+        """Disable the quantizer of every parameter with this name, e.g. "bias" (reference :753-762)."""
+        for _, wrapper in self.quant_wrappers():
+            if param_name_to_exclude in wrapper.param_quantizers:
+                wrapper.param_quantizers[param_name_to_exclude].enabled = False
+
+    def named_qmodules(self):
+        """(name, quantized module) pairs (reference :1857-1862)."""
+        yield from self.quant_wrappers()
+
+    def qmodules(self):
+        yield from (m for _, m in self.named_qmodules())
 
     def export(self, path: str, filename_prefix: str, dummy_input=None, **_unused):
         """Writes `<prefix>_torch.encodings` (torch-module-name keyed, reference :1000-1042 layout) and the original

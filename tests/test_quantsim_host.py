@@ -180,3 +180,42 @@ def test_scalar_in_dtype_rounds_like_torch():
             ref = float(torch.tensor(float(v), dtype=torch.float32).to(dt))
             got = scalar_in_dtype(v, dt)
             assert struct.pack("<d", ref) == struct.pack("<d", got), (v, dt, ref, got)
+
+
+def test_load_and_freeze_encodings(oracle_backend, tmp_path):
+    """reference v1/quantsim.py:1759-1855: encodings loaded with allow_overwrite=False survive a later compute_encodings;
+    set_and_freeze_param_encodings touches parameters only; exclude_param_from_quantization disables by parameter name."""
+    from aimet_b200.quantsim import QuantizationSimModel
+    sim_a, _, _ = build_and_calibrate("resnet18_default_tfe")
+    sim_a.save_encodings_to_json(str(tmp_path), "enc")
+    act_a, par_a = sim_a.get_activation_param_encodings()
+
+    torch.manual_seed(0)
+    model = torchvision.models.resnet18().eval()
+    x = torch.randn(4, 3, 64, 64) * 3.0          # different calibration data: would give different encodings
+    sim_b = QuantizationSimModel(model, dummy_input=x, quant_scheme="tf_enhanced")
+    sim_b.load_and_freeze_encodings(str(tmp_path / "enc.json"))
+    assert all(q.is_encoding_frozen for _, w in sim_b.named_qmodules() for q in w.param_quantizers.values() if q.enabled)
+    sim_b.compute_encodings(lambda m, _: m(x), None)
+    act_b, par_b = sim_b.get_activation_param_encodings()
+    assert json.dumps(act_a, sort_keys=True) == json.dumps(act_b, sort_keys=True)
+    assert json.dumps(par_a, sort_keys=True) == json.dumps(par_b, sort_keys=True)
+    with torch.no_grad():
+        torch.manual_seed(1)
+        probe = torch.randn(4, 3, 64, 64)
+        assert torch.equal(sim_a.model(probe), sim_b.model(probe))
+
+    sim_c = QuantizationSimModel(model, dummy_input=x, quant_scheme="tf_enhanced")
+    sim_c.set_and_freeze_param_encodings(str(tmp_path / "enc.json"))
+    sim_c.compute_encodings(lambda m, _: m(x), None)
+    act_c, par_c = sim_c.get_activation_param_encodings()
+    assert json.dumps(par_a, sort_keys=True) == json.dumps(par_c, sort_keys=True)       # parameters: loaded and kept
+    assert json.dumps(act_a, sort_keys=True) != json.dumps(act_c, sort_keys=True)       # activations: recalibrated on x
+    # the older parameter-only file layout (reference :1726-1732)
+    sim_d = QuantizationSimModel(model, dummy_input=x, quant_scheme="tf_enhanced")
+    sim_d.load_encodings(par_a)
+    assert json.dumps(sim_d.get_activation_param_encodings()[1], sort_keys=True) == json.dumps(par_a, sort_keys=True)
+
+    assert any(w.param_quantizers["weight"].enabled for w in sim_c.qmodules() if "weight" in w.param_quantizers)
+    sim_c.exclude_param_from_quantization("weight")
+    assert not any(w.param_quantizers["weight"].enabled for w in sim_c.qmodules() if "weight" in w.param_quantizers)
