@@ -517,3 +517,28 @@ def test_tfe_stats_many_batches_of_mixed_sizes(ops, oracle):
     rec = blk.read()[0]
     assert rec["ticket"] == 0 and rec["iterations"] == o.s.iterations
     assert np.array_equal(rec["pdf"], o.histogram()[1])
+
+
+def test_hist_timer_hook(ops):
+    """ab_debug_hist_timer: every histogram launch records {first CTA start, last CTA end, input bytes}; switched off again
+    it leaves later launches alone."""
+    from aimet_b200 import _lib
+    L = _lib.load()
+    blk = new_state()
+    x = torch.randn(3_000_000, device="cuda")
+    ops.stats_update_impl(x, blk.arena, blk.first, ops.QUANTIZATION_TF_ENHANCED, None, 0)      # fixes the range
+    slots = torch.zeros((8, 3), dtype=torch.int64, device="cuda")
+    slots[:, 0] = torch.iinfo(torch.int64).max
+    L.ab_debug_hist_timer(slots.data_ptr(), 8)
+    for n in (3_000_000, 1_000_000):
+        ops.stats_update_impl(x[:n], blk.arena, blk.first, ops.QUANTIZATION_TF_ENHANCED, None, 0)
+        ops.stats_update_impl(x[:n].bfloat16(), blk.arena, blk.first, ops.QUANTIZATION_TF_ENHANCED, None, 0)
+    torch.cuda.synchronize()
+    assert L.ab_debug_hist_timer(None, 0) == 4
+    ops.stats_update_impl(x, blk.arena, blk.first, ops.QUANTIZATION_TF_ENHANCED, None, 0)
+    torch.cuda.synchronize()
+    rows = slots.cpu().tolist()
+    assert [r[2] for r in rows[:4]] == [12_000_000, 6_000_000, 4_000_000, 2_000_000]
+    for start, end, _ in rows[:4]:
+        assert 0 < end - start < 5_000_000          # nanoseconds
+    assert rows[4] == [torch.iinfo(torch.int64).max, 0, 0]
