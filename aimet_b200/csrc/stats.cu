@@ -11,13 +11,18 @@
 //                     atomicMin/atomicMax per CTA on an order-preserving integer image of the float; the last CTA
 //                     (ticket) folds the batch result into the state. For tf_enhanced it exits immediately once the
 //                     histogram range is fixed, so the steady state is ONE pass over the data.
-//   hist_kernel     : persistent, one CTA per SM. Tiles of 16 KB are staged into a 6-deep shared-memory ring by the
-//                     TMA engine (cp.async.bulk + mbarrier complete_tx), so no registers or LSU issue slots are
-//                     spent on global loads. Bins are counted in a shared-memory histogram privatised PER LANE
+//   hist_kernel     : persistent, one CTA per SM. Tiles of 32 KB are staged into a 4-deep shared-memory ring by the
+//                     TMA engine (cp.async.bulk + mbarrier complete_tx), walking the tensor from its end backwards (what
+//                     the producing kernel wrote last is what the L2 still holds), so no registers or LSU issue slots
+//                     are spent on global loads. Bins are counted in a shared-memory histogram privatised PER LANE
 //                     (bin b of lane l lives at word b*32+l: bank == lane, so a warp's 32 atomics never conflict,
 //                     whatever the data distribution -- ReLU outputs put half the samples in one bin). The CTA then
-//                     reduces its 32 copies and flushes with at most 512 global atomics; the last CTA folds the
-//                     batch into the running PDF in double precision, exactly as UpdatePdf does.
+//                     reduces its 32 copies and flushes with at most 512 global atomics. The batch's counts stay parked
+//                     in the record; the NEXT launch's keeper warps fold them into the running PDF in double precision,
+//                     exactly as UpdatePdf does, while that launch streams. Nobody waits at the end of a launch: the
+//                     record is read once per CTA into a shared-memory snapshot, announced with an early ticket, and the
+//                     CTA that drew the last ticket writes the bookkeeping (see `fast_tail`). bf16 tensors bin with a
+//                     one-FFMA index certified against the reference sequence over all 65536 bit patterns.
 //   segmented kernel: one CTA per segment (= per output channel of a weight): min/max, range, histogram and PDF fold
 //                     for thousands of quantizers in ONE launch, replacing a Python loop of per-channel calls.
 #include "common.cuh"
@@ -667,7 +672,7 @@ __global__ void __launch_bounds__(kHistThreads, 1)
         {
             // ---- housekeeping warps: fold the previous batch of this record while the consumers stream. Every CTA's
             // keeper takes a 32-bin slice (one independent load / divide / store per lane), so the whole fold is one
-            // memory round trip off the critical path; `iterations` / `pending` are updated by the last CTA. ----
+            // memory round trip off the critical path; `iterations` / `pending` are updated by the elected CTA. ----
             if (had_pending)
             {
                 const int pp     = parity ^ 1;
