@@ -542,3 +542,29 @@ def test_hist_timer_hook(ops):
     for start, end, _ in rows[:4]:
         assert 0 < end - start < 5_000_000          # nanoseconds
     assert rows[4] == [torch.iinfo(torch.int64).max, 0, 0]
+
+
+def test_histogram_more_than_2_31_elements(ops):
+    """One statistics call on 2^31 + 2^20 bf16 samples (the reference's `int` counts stop at 2^31 - 1): the logged counts are
+    the sum of the counts of four pieces binned separately (linearity under a frozen range), nothing is lost, and the
+    element count comes back in two 32-bit words."""
+    n = 2**31 + 2**20
+    g = torch.Generator(device="cuda").manual_seed(23)
+    x = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+    chunk = 2**28
+    for s in range(0, n, chunk):
+        x[s:s + chunk] = (torch.randn(min(chunk, n - s), device="cuda", generator=g) * 1.5 + 0.25).to(torch.bfloat16)
+    blk = new_state()
+    ops.stats_init_range_impl(blk.arena, blk.first, 1, torch.tensor([[-8.0, 8.0]], dtype=torch.float32, device="cuda"))
+    log = torch.zeros((6, ops.LOG_WORDS), dtype=torch.int32, device="cuda")
+    # pieces first: the first of them certifies the bf16 bin formula, the rest and the whole tensor use it
+    bounds = [0, 2**29 + 8, 2**30 + 2**29, 2**31 - 16, n]
+    for k in range(4):
+        ops.stats_update_impl(x[bounds[k]:bounds[k + 1]], blk.arena, blk.first, ops.QUANTIZATION_TF_ENHANCED, log, k)
+    ops.stats_update_impl(x, blk.arena, blk.first, ops.QUANTIZATION_TF_ENHANCED, log, 4)
+    assert blk.read_raw()[0]["bf16_formula"] == 1
+    got = log.cpu().numpy().view(np.uint32).astype(np.int64)
+    assert np.array_equal(got[4, :512], got[:4, :512].sum(axis=0))
+    assert int(got[4, :512].sum()) == n                                   # range (-24, 24): every sample is counted
+    assert int(got[4, 512]) + (int(got[4, 513]) << 32) == n
+    assert int(got[4, :512].max()) < 2**31
