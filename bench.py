@@ -88,7 +88,7 @@ def synthetic_batch(global_index, batch, device="cpu", pin=False):
 
 class ClockSampler:
     """nvidia-smi in the background during the timed region (B200_PROFILING.md clocks line)."""
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -96,6 +96,16 @@ class ClockSampler:
         self.gpu_index = gpu_index
         self.proc = None
         self.path = None
+        self.window = None      # (t0, t1) wall-clock bounds of the timed region: only samples inside it count
+
+    @staticmethod
+    def _stamp(text):
+        """'2026/10/18 21:04:05.123' -> seconds since the epoch (local time, like time.time())"""
+        import datetime
+        try:
+            return datetime.datetime.strptime(text, "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None          # unknown format: the sample is kept (see stop)
 
     def start(self):
         try:
@@ -118,15 +128,20 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         try:
+            rows = []
             for line in open(self.path):
                 parts = [p.strip() for p in line.split(",")]
                 if len(parts) < 9:
                     continue
                 try:
-                    sm.append(float(parts[1]))
-                    mx.append(float(parts[2]))
+                    rows.append((self._stamp(parts[0]), float(parts[1]), float(parts[2]), parts))
                 except ValueError:
                     continue
+            inside = [r for r in rows if r[0] is None or
+                      (self.window and self.window[0] - 0.05 <= r[0] <= self.window[1] + 0.05)]
+            for _, a, b, parts in (inside or rows):       # a region shorter than the sampling period: all samples
+                sm.append(a)
+                mx.append(b)
                 for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
                                      parts[5:9]):
                     if val.lower().startswith("active"):
@@ -296,9 +311,13 @@ def run_ours(args):
     gc.collect()
     sampler = ClockSampler(local_rank)
     if rank == 0:
+        # nvidia-smi takes a while to start and takes driver locks while it does (measured: +8 ms on an 8-step job when it
+        # starts together with the timed region): start it first, let it settle, and count the samples inside the region
         sampler.start()
+        time.sleep(0.5)
     launches0 = dict(ops.LAUNCHES)
     barrier()
+    t_region0 = time.time()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.nvtx.range_push("timed")          # lets `ncu --nvtx --nvtx-include "timed/"` see only the timed region
     start.record()
@@ -311,6 +330,7 @@ def run_ours(args):
     graph_info = dict(_qs.LAST_GRAPH_INFO)
     eager_batches = min(steps, 2) if use_graph else steps
     launched = {k: ops.LAUNCHES[k] - launches0[k] for k in ops.LAUNCHES}
+    sampler.window = (t_region0, t_region0 + ms / 1000.0 + 0.01)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- timed: e2e (host buffers; H2D of every batch and D2H of the result inside the region) ----
