@@ -36,6 +36,14 @@ def export_quantizer_encoding(quantizer) -> Optional[List[Dict]]:
         return None
     if quantizer.data_type == QuantizationDataType.int and quantizer.bitwidth == 32:
         return None
+    # dictionaries built while the calibration forwards were running (quantsim._ParamExportPrefetch): served once, and only
+    # if the encodings still are the device table they were made from
+    cache = quantizer.__dict__.pop("_export_cache", None)
+    if cache is not None and hasattr(quantizer, "_device_columns"):
+        from .tensor_quantizer import _LAZY
+        table, sym, dicts = cache
+        if quantizer._encoding is _LAZY and table is quantizer._enc_dev and sym == str(quantizer.use_symmetric_encodings):   # pylint: disable=protected-access
+            return dicts
     cols = quantizer._device_columns() if hasattr(quantizer, "_device_columns") else None   # pylint: disable=protected-access
     if cols is not None:
         # encodings that still live only on the device: one copy, dictionaries built straight from the columns (no

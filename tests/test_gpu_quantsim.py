@@ -240,3 +240,40 @@ def test_capture_forward_helper():
         fwd(x[:1])
     with pytest.raises(ValueError):
         sim.capture_forward(x.cpu())
+
+
+def test_parameter_export_prefetch_serves_the_same_dictionaries():
+    """During the calibration forwards the per-channel parameter encodings are copied out and turned into dictionaries
+    (quantsim._ParamExportPrefetch); the export must hand out exactly what it would have built itself, serve the parked
+    dictionaries once only, and never serve them for encodings that were recomputed afterwards."""
+    import torchvision
+    from aimet_b200.quantsim import QuantizationSimModel
+    from aimet_b200.quantsim import config as qconfig
+    torch.manual_seed(0)
+    model = torchvision.models.resnet18().cuda().eval()
+    xs = [torch.randn(4, 3, 64, 64, device="cuda") for _ in range(6)]
+    sim = QuantizationSimModel(model, dummy_input=xs[0], quant_scheme="tf_enhanced", config_file=qconfig.DEFAULT_CONFIG_PER_CHANNEL)
+
+    def calibrate(m, _):
+        for x in xs:
+            m(x)
+            torch.cuda.synchronize()          # lets the stream-ordered copy land between two forwards
+
+    sim.compute_encodings(calibrate, None)
+    parked = [q for _, w in sim.quant_wrappers() for q in w.param_quantizers.values() if "_export_cache" in q.__dict__]
+    assert len(parked) >= 20
+    first = json.dumps(sim.get_activation_param_encodings(), sort_keys=True)
+    assert not any("_export_cache" in q.__dict__ for q in parked)              # served once
+    again = json.dumps(sim.get_activation_param_encodings(), sort_keys=True)   # rebuilt from the device tables
+    assert first == again
+    # a cache left over from an earlier calibration is not served for recomputed encodings
+    sim.compute_encodings(calibrate, None)
+    stale = {q: q.__dict__["_export_cache"] for q in parked}
+    with torch.no_grad():
+        for p in sim.model.parameters():
+            p.mul_(1.5)
+    sim.compute_encodings(lambda m, _: m(xs[0]), None)                         # one forward: no prefetch this time
+    for q, c in stale.items():
+        q.__dict__["_export_cache"] = c
+    fresh = json.dumps(sim.get_activation_param_encodings(), sort_keys=True)
+    assert fresh != first and fresh == json.dumps(sim.get_activation_param_encodings(), sort_keys=True)
