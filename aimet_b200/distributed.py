@@ -317,16 +317,18 @@ class ShardedCalibrator:
         QuantizationSimModel.compute_layer_encodings_for_sim(sim)
 
     def compute_encodings(self, forward_pass_callback, forward_pass_callback_args):
-        from .quantsim.quantsim import QuantizationSimModel, in_eval_mode
+        from .quantsim.quantsim import QuantizationSimModel, _ParamExportPrefetch, in_eval_mode
         sim = self.sim
         QuantizationSimModel.prepare_sim_for_compute_encodings(sim)
         if not getattr(sim, "_act_block_quantizers", None):
             raise RuntimeError("sharded calibration needs the model on a CUDA device")
         self._install()
+        prefetch = _ParamExportPrefetch(sim)     # parameter encodings are rank-local and final after the first forward
         try:
             with in_eval_mode(sim.model), torch.no_grad():
                 forward_pass_callback(sim.model, forward_pass_callback_args)
             self._merge()
         finally:
+            prefetch.close()
             self._uninstall()
         QuantizationSimModel.compute_layer_encodings_for_sim(sim)
