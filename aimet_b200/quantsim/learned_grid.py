@@ -21,6 +21,7 @@ from torch import nn
 
 from .. import libpymo, ops
 from .defs import MAP_ROUND_MODE_TO_PYMO, QuantizationDataType, QuantScheme
+from .qc_quantize_op import EncodingImportMixin
 
 _IGNORED_DTYPES = (torch.int, torch.int8, torch.int16, torch.int32, torch.int64, torch.bool, torch.uint8)
 
@@ -298,7 +299,7 @@ class _PatchedParams:
         self.undo = []
 
 
-class LearnedGridQuantWrapper(nn.Module):
+class LearnedGridQuantWrapper(EncodingImportMixin, nn.Module):
     """Learns min and max of every enabled quantizer of one wrapped layer (reference qc_quantize_op.py:947-1158)."""
 
     def __init__(self, module_to_wrap: nn.Module, weight_bw: int, activation_bw: int, round_mode, quant_scheme,

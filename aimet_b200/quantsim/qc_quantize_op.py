@@ -125,7 +125,83 @@ class SteGatingFuncForParameters(torch.autograd.Function):
         return (None, *output_grad)
 
 
-class StaticGridQuantWrapper(nn.Module):
+class EncodingImportMixin:
+    """import_param_encodings / import_input_encodings / import_output_encodings of the reference's QcQuantizeWrapper
+    (:499-677), which both StaticGridQuantWrapper and LearnedGridQuantWrapper inherit there."""
+
+    @staticmethod
+    def _encoding_from_dict(quantizer, enc_dict):
+        """utils.create_encoding_from_dict + compute_partial_encoding (reference :1548-1570): fill whatever half of
+        (min, max) / (scale, offset) the dictionary leaves out through the native computePartialEncoding."""
+        enc = libpymo.TfEncoding()
+        enc.bw = int(enc_dict["bitwidth"])
+        enc.min = float(enc_dict.get("min", 0.0))
+        enc.max = float(enc_dict.get("max", 0.0))
+        enc.delta = float(enc_dict.get("scale", 0.0))
+        enc.offset = float(enc_dict.get("offset", 0.0))
+        if (enc.min == 0 and enc.max == 0) or enc.delta == 0:
+            tq = libpymo.TensorQuantizer(libpymo.QuantizationMode.QUANTIZATION_TF, libpymo.RoundingMode.ROUND_NEAREST)
+            tq.computePartialEncoding(enc.bw, enc, quantizer.use_symmetric_encodings,
+                                      quantizer.use_unsigned_symmetric, quantizer.use_strict_symmetric)
+        return enc
+
+    def _import_quantizer(self, quantizer, enc_dicts, strict, partial, requires_grad, allow_overwrite):
+        if quantizer.is_encoding_frozen:
+            return
+        if not enc_dicts:
+            if not partial:
+                quantizer.enabled = False       # dangling quantizers are removed when the encodings are not partial
+            return
+        if not quantizer.enabled:
+            if strict:
+                raise RuntimeError("The quantsim passed for loading encodings does not have the same "
+                                   "configuration as the quantsim which was used to export the encodings")
+            return
+        if isinstance(enc_dicts, dict):
+            enc_dicts = [enc_dicts]
+        if enc_dicts[0].get("dtype", "int") != "int":
+            raise NotImplementedError("float encodings are outside the aimet_b200 hot path")
+        is_symmetric = enc_dicts[0]["is_symmetric"] == "True"
+        quantizer.use_symmetric_encodings = is_symmetric
+        if not is_symmetric:
+            quantizer.use_unsigned_symmetric = False
+            quantizer.use_strict_symmetric = False
+        encodings = [self._encoding_from_dict(quantizer, d) for d in enc_dicts]
+        quantizer.bitwidth = encodings[0].bw
+        learned = getattr(quantizer, "wrapper_ref", None) is not None      # LearnedGridTensorQuantizer
+        if learned:
+            # the setter re-creates the <name>_encoding_min / _max parameters of the wrapper (reference :851-883)
+            quantizer.encoding = encodings if len(encodings) > 1 else encodings[0]
+            if requires_grad is not None:
+                for suffix in ("_encoding_min", "_encoding_max"):
+                    getattr(quantizer.wrapper_ref, quantizer.name + suffix).requires_grad_(requires_grad)
+        elif hasattr(quantizer, "_ch_axis"):
+            if len(encodings) != len(quantizer._cppOp):   # pylint: disable=protected-access
+                raise RuntimeError("number of per-channel encodings does not match the number of channels")
+            quantizer.encoding = encodings
+        else:
+            quantizer.encoding = encodings[0]
+        if hasattr(quantizer, "_stats_dirty"):
+            quantizer._stats_dirty = False                 # pylint: disable=protected-access
+        if allow_overwrite is False and quantizer.encoding is not None:
+            quantizer.freeze_encoding()
+
+    def import_input_encodings(self, encodings, strict, partial, requires_grad, allow_overwrite):
+        for i, q in enumerate(self.input_quantizers):
+            self._import_quantizer(q, encodings.get(str(i), encodings.get(i)), strict, partial, requires_grad,
+                                   allow_overwrite)
+
+    def import_output_encodings(self, encodings, strict, partial, requires_grad, allow_overwrite):
+        for i, q in enumerate(self.output_quantizers):
+            self._import_quantizer(q, encodings.get(str(i), encodings.get(i)), strict, partial, requires_grad,
+                                   allow_overwrite)
+
+    def import_param_encodings(self, encodings, strict, partial, requires_grad, allow_overwrite):
+        for name, q in self.param_quantizers.items():
+            self._import_quantizer(q, encodings.get(name), strict, partial, requires_grad, allow_overwrite)
+
+
+class StaticGridQuantWrapper(EncodingImportMixin, nn.Module):
     """Wraps one leaf module: quantizes its inputs, parameters and outputs around the wrapped forward."""
 
     def __init__(self, module_to_wrap: nn.Module, weight_bw: int, activation_bw: int, round_mode, quant_scheme,
@@ -293,69 +369,6 @@ class StaticGridQuantWrapper(nn.Module):
             assert len(tensor_quantizers) > index, f"Not enough tensor quantizers ({len(tensor_quantizers)}) allocated"
             outputs.append(inner(t, index))
         return outputs
-
-    # ---- import (reference :499-677) -----------------------------------------------------------------------------
-    @staticmethod
-    def _encoding_from_dict(quantizer, enc_dict):
-        """utils.create_encoding_from_dict + compute_partial_encoding (reference :1548-1570): fill whatever half of
-        (min, max) / (scale, offset) the dictionary leaves out through the native computePartialEncoding."""
-        enc = libpymo.TfEncoding()
-        enc.bw = int(enc_dict["bitwidth"])
-        enc.min = float(enc_dict.get("min", 0.0))
-        enc.max = float(enc_dict.get("max", 0.0))
-        enc.delta = float(enc_dict.get("scale", 0.0))
-        enc.offset = float(enc_dict.get("offset", 0.0))
-        if (enc.min == 0 and enc.max == 0) or enc.delta == 0:
-            tq = libpymo.TensorQuantizer(libpymo.QuantizationMode.QUANTIZATION_TF, libpymo.RoundingMode.ROUND_NEAREST)
-            tq.computePartialEncoding(enc.bw, enc, quantizer.use_symmetric_encodings,
-                                      quantizer.use_unsigned_symmetric, quantizer.use_strict_symmetric)
-        return enc
-
-    def _import_quantizer(self, quantizer, enc_dicts, strict, partial, allow_overwrite):
-        if quantizer.is_encoding_frozen:
-            return
-        if not enc_dicts:
-            if not partial:
-                quantizer.enabled = False       # dangling quantizers are removed when the encodings are not partial
-            return
-        if not quantizer.enabled:
-            if strict:
-                raise RuntimeError("The quantsim passed for loading encodings does not have the same "
-                                   "configuration as the quantsim which was used to export the encodings")
-            return
-        if isinstance(enc_dicts, dict):
-            enc_dicts = [enc_dicts]
-        if enc_dicts[0].get("dtype", "int") != "int":
-            raise NotImplementedError("float encodings are outside the aimet_b200 hot path")
-        is_symmetric = enc_dicts[0]["is_symmetric"] == "True"
-        quantizer.use_symmetric_encodings = is_symmetric
-        if not is_symmetric:
-            quantizer.use_unsigned_symmetric = False
-            quantizer.use_strict_symmetric = False
-        encodings = [self._encoding_from_dict(quantizer, d) for d in enc_dicts]
-        quantizer.bitwidth = encodings[0].bw
-        expects_list = hasattr(quantizer, "_ch_axis")
-        if expects_list:
-            if len(encodings) != len(quantizer._cppOp):   # pylint: disable=protected-access
-                raise RuntimeError("number of per-channel encodings does not match the number of channels")
-            quantizer.encoding = encodings
-        else:
-            quantizer.encoding = encodings[0]
-        quantizer._stats_dirty = False                     # pylint: disable=protected-access
-        if allow_overwrite is False:
-            quantizer.freeze_encoding()
-
-    def import_input_encodings(self, encodings, strict, partial, requires_grad, allow_overwrite):
-        for i, q in enumerate(self.input_quantizers):
-            self._import_quantizer(q, encodings.get(str(i), encodings.get(i)), strict, partial, allow_overwrite)
-
-    def import_output_encodings(self, encodings, strict, partial, requires_grad, allow_overwrite):
-        for i, q in enumerate(self.output_quantizers):
-            self._import_quantizer(q, encodings.get(str(i), encodings.get(i)), strict, partial, allow_overwrite)
-
-    def import_param_encodings(self, encodings, strict, partial, requires_grad, allow_overwrite):
-        for name, q in self.param_quantizers.items():
-            self._import_quantizer(q, encodings.get(name), strict, partial, allow_overwrite)
 
     # ---- export --------------------------------------------------------------------------------------------------
     def export_param_encodings(self):

@@ -453,26 +453,41 @@ class QuantizationSimModel:
         yield from (m for _, m in self.named_qmodules())
 
     def export(self, path: str, filename_prefix: str, dummy_input=None, **_unused):
-        """Writes `<prefix>_torch.encodings` (torch-module-name keyed, reference :1000-1042 layout) and the original
-        model's state_dict with quantize-dequantized weights. The ONNX-tensor-name keyed `<prefix>.encodings` needs an
-        ONNX export and is not produced here."""
+        """Writes `<prefix>_torch.encodings` (torch-module-name keyed, reference :1000-1042 layout) and `<prefix>.pth`, the
+        pickled original model as the reference saves it. The ONNX-tensor-name keyed `<prefix>.encodings` needs an ONNX
+        export and is not produced here."""
         os.makedirs(path, exist_ok=True)
         activation_encodings, param_encodings = self.get_activation_param_encodings()
         torch_encodings = {"version": ENCODING_VERSION,
                            "activation_encodings": activation_encodings,
                            "param_encodings": param_encodings,
                            "excluded_layers": [],
-                           "quantizer_args": {"activation_bitwidth": self._default_output_bw,
-                                              "param_bitwidth": self._default_param_bw,
-                                              "dtype": "int",
-                                              "is_symmetric": True,
-                                              "quant_scheme": self._quant_scheme.name,
-                                              "per_channel_quantization": qconfig._truthy(   # pylint: disable=protected-access
-                                                  self._config["defaults"].get("per_channel_quantization", "False"))}}
+                           "quantizer_args": self._quantizer_args()}
         with open(os.path.join(path, filename_prefix + "_torch.encodings"), "w") as f:
             json.dump(torch_encodings, f, sort_keys=True, indent=4)
+        # `<prefix>.pth` is the pickled ORIGINAL model (wrappers removed, weights untouched), as the reference writes it
+        # (v1/quantsim.py:529-531 torch.save(model_to_export, ...)); the quantize-dequantized weights additionally go to
+        # `<prefix>_qdq_state_dict.pth` (not a reference artefact; a plain state_dict).
+        torch.save(self.get_original_model(self.model), os.path.join(path, filename_prefix + ".pth"))
         torch.save(self.get_original_model(self.model, qdq_weights=True).state_dict(),
-                   os.path.join(path, filename_prefix + ".pth"))
+                   os.path.join(path, filename_prefix + "_qdq_state_dict.pth"))
+
+    def _quantizer_args(self) -> Dict:
+        """reference aimet_common/quantsim.py:280-311 (extract_global_quantizer_args): range-learning schemes are reported
+        as the post-training scheme they were initialised from; is_symmetric is the parameter default of the config,
+        falling back to the per-channel flag."""
+        defaults = self._config.get("defaults", {})
+        per_channel = qconfig._truthy(defaults.get("per_channel_quantization", False))   # pylint: disable=protected-access
+        params = defaults.get("params", {})
+        scheme = {QuantScheme.training_range_learning_with_tf_init: QuantScheme.post_training_tf,
+                  QuantScheme.training_range_learning_with_tf_enhanced_init: QuantScheme.post_training_tf_enhanced
+                  }.get(self._quant_scheme, self._quant_scheme)
+        return {"quant_scheme": scheme.name,
+                "param_bitwidth": self._default_param_bw,
+                "activation_bitwidth": self._default_output_bw,
+                "dtype": "int",
+                "is_symmetric": qconfig._truthy(params["is_symmetric"]) if "is_symmetric" in params else per_channel,   # pylint: disable=protected-access
+                "per_channel_quantization": per_channel}
 
     def capture_forward(self, *sample_inputs, warmup: int = 3) -> "GraphedForward":
         """The calibrated model's inference forward as a CUDA graph (no counterpart in the reference; B200 idiom for a

@@ -9,8 +9,9 @@ Same attribute and method names, same state machine. What changes is underneath 
     launch and `compute_encoding` one batched grid search + one device->host copy, instead of the reference's Python loop
     of num_channels native calls each (:567-570, :296-299);
   * bfloat16 tensors go to the kernels as they are (the reference only knows how to upcast float16).
-A different op class (anything with AimetTensorQuantizer's nine methods) can be injected with `op_factory`; the test suite
-uses that to drive this layer with the CPU oracle.
+The product has ONE native op class (AimetTensorQuantizer over the sm_100a library); `_set_op_class_for_testing` is a
+private hook with which tests/ and bench.py's CPU-baseline leg drive this same host layer with the CPU oracle -- it is
+not a backend-dispatch mechanism and nothing in aimet_b200/ calls it.
 """
 import functools
 import math
@@ -36,8 +37,9 @@ _LAZY = object()
 FUSED_REFRESH = os.environ.get("AB_FUSED_REFRESH", "1") != "0"   # A/B switch for refresh_encoding_from
 
 
-def set_default_op_factory(factory):
-    """Replace the class used for `_cppOp` objects (test hook). Returns the previous one."""
+def _set_op_class_for_testing(factory):
+    """PRIVATE, test infrastructure only: replace the class used for `_cppOp` objects (tests/ and bench.py's CPU-baseline
+    leg put the CPU oracle underneath this host layer to check it). Returns the previous one."""
     global _DEFAULT_OP_FACTORY
     prev, _DEFAULT_OP_FACTORY = _DEFAULT_OP_FACTORY, factory
     return prev
@@ -480,6 +482,9 @@ def compute_dloss_by_dx(x, grad, encoding_min, encoding_max, ch_axis=0):
             per_channel = 1
             for d in x.shape[ch_axis + 1:]:
                 per_channel *= d
+            if x.dtype == torch.float16:      # same route as the per-tensor branch and both forwards: upcast, cast back
+                return ops.ste_bwd_per_channel_impl(x.float(), grad.float(), mins, maxs, n_ch,
+                                                    per_channel).to(torch.float16)
             return ops.ste_bwd_per_channel_impl(x, grad, mins, maxs, n_ch, per_channel)
         encoding_min, encoding_max = float(mins), float(maxs)
     # torch.tensor(python float) is a 0-dim float32 tensor; compared with a lower-precision tensor it does not promote,

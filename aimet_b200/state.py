@@ -5,6 +5,7 @@ The reference keeps one encoding-analyzer object per quantizer -- and one per *c
 in HBM, packed in large uint8 tensors, so that statistics kernels update them in place with no host round trip and a
 per-channel quantizer owns one contiguous block that a single segmented launch can update.
 """
+import collections
 import threading
 
 import numpy as np
@@ -94,13 +95,16 @@ class StateArena:
     """Per-device pool of statistics records."""
     CHUNK_STATES = 1024
     _arenas = {}
-    _lock = threading.Lock()
+    # Re-entrant: the cyclic garbage collector may run inside a locked region and finalise StateBlocks on this very thread.
+    # (StateBlock.__del__ does not take the lock at all -- see `_released` -- this is the second line of defence.)
+    _lock = threading.RLock()
 
     def __init__(self, device):
         self.device = torch.device(device)
         self._chunk = None
         self._used = 0
         self._free = {}        # count -> [(chunk, first)]
+        self._released = collections.deque()   # blocks given back by finalisers: appended lock-free, drained by allocate()
 
     @classmethod
     def for_device(cls, device) -> "StateArena":
@@ -115,26 +119,44 @@ class StateArena:
                 arena = cls._arenas[device] = StateArena(device)
             return arena
 
+    def _carve(self, count: int):
+        """(chunk, first) from the free lists or the current chunk, or None when a new chunk is needed. Lock held."""
+        while self._released:
+            try:
+                n, arena, first = self._released.popleft()
+            except IndexError:
+                break
+            self._free.setdefault(n, []).append((arena, first))
+        free = self._free.get(count)
+        if free:
+            return free.pop()
+        cap = 0 if self._chunk is None else self._chunk.numel() // ops.STATE_BYTES
+        if self._chunk is not None and self._used + count <= cap:
+            first = self._used
+            self._used += count
+            return self._chunk, first
+        return None
+
     def allocate(self, count: int) -> StateBlock:
         with self._lock:
-            free = self._free.get(count)
-            if free:
-                chunk, first = free.pop()
-            else:
-                cap = 0 if self._chunk is None else self._chunk.numel() // ops.STATE_BYTES
-                if self._chunk is None or self._used + count > cap:
-                    n = max(count, self.CHUNK_STATES)
-                    self._chunk = torch.empty(n * ops.STATE_BYTES, dtype=torch.uint8, device=self.device)
-                    self._used = 0
-                chunk, first = self._chunk, self._used
-                self._used += count
+            got = self._carve(count)
+        if got is None:
+            # the device allocation runs OUTSIDE the lock (it can trigger the garbage collector, synchronise, or raise)
+            fresh = torch.empty(max(count, self.CHUNK_STATES) * ops.STATE_BYTES, dtype=torch.uint8, device=self.device)
+            with self._lock:
+                got = self._carve(count)           # somebody else may have installed a chunk meanwhile
+                if got is None:
+                    self._chunk, self._used = fresh, count
+                    got = (fresh, 0)
+        chunk, first = got
         block = StateBlock(self, chunk, first, count)
         block.reset()
         return block
 
     def _release(self, block):
+        # called from StateBlock.__del__, possibly by the garbage collector in the middle of allocate(): no lock here.
+        # deque.append is atomic; allocate() files the entry under the lock.
         try:
-            with self._lock:
-                self._free.setdefault(block.count, []).append((block.arena, block.first))
+            self._released.append((block.count, block.arena, block.first))
         except Exception:   # interpreter shutdown
             pass

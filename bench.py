@@ -64,7 +64,7 @@ def build_sim(device, op_factory=None):
 
     from aimet_b200.quantsim import QuantizationSimModel, tensor_quantizer
     from aimet_b200.quantsim import config as qconfig
-    prev = tensor_quantizer.set_default_op_factory(op_factory) if op_factory is not None else None
+    prev = tensor_quantizer._set_op_class_for_testing(op_factory) if op_factory is not None else None
     try:
         torch.manual_seed(0)
         model = torchvision.models.resnet50().eval().to(device)
@@ -73,7 +73,7 @@ def build_sim(device, op_factory=None):
                                    default_param_bw=8, config_file=qconfig.DEFAULT_CONFIG_PER_CHANNEL, in_place=True)
     finally:
         if prev is not None:
-            tensor_quantizer.set_default_op_factory(prev)
+            tensor_quantizer._set_op_class_for_testing(prev)
     return sim
 
 
@@ -189,7 +189,7 @@ def cpu_job(steps, warmup):
     from oracle import cpu_backend
     factory = cpu_backend.best_cpu_backend()
     sim = build_sim("cpu", factory)
-    prev = tensor_quantizer.set_default_op_factory(factory)
+    prev = tensor_quantizer._set_op_class_for_testing(factory)
     try:
         batches = [synthetic_batch(b, batch) for b in range(max(steps, 1))]
         if warmup > 0:
@@ -200,7 +200,7 @@ def cpu_job(steps, warmup):
         act, par = sim.get_activation_param_encodings()
         dt = time.perf_counter() - t0
     finally:
-        tensor_quantizer.set_default_op_factory(prev)
+        tensor_quantizer._set_op_class_for_testing(prev)
     info = {"kind": factory.KIND, "cores": torch.get_num_threads(),
             "images_per_step": batch,
             "sample": f"complete calibration job of {steps} steps x {batch} images (ResNet-50 per-channel "

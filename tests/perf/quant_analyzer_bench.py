@@ -20,7 +20,7 @@ sys.path.insert(0, ROOT)
 
 def run(device, batch, eval_batches, factory=None):
     from aimet_b200.quantsim import CallbackFunc, QuantAnalyzer, tensor_quantizer
-    prev = tensor_quantizer.set_default_op_factory(factory) if factory is not None else None
+    prev = tensor_quantizer._set_op_class_for_testing(factory) if factory is not None else None
     try:
         torch.manual_seed(0)
         model = torchvision.models.resnet18().eval().to(device)
@@ -59,7 +59,7 @@ def run(device, batch, eval_batches, factory=None):
                 "evaluated_images_per_s": round(images / (t2 - t1), 1)}
     finally:
         if factory is not None:
-            tensor_quantizer.set_default_op_factory(prev)
+            tensor_quantizer._set_op_class_for_testing(prev)
 
 
 def main():

@@ -24,7 +24,7 @@ def test_mobilenet_v2_bf16_qat_step(oracle):
     from tests.oracle_backend import OracleTensorQuantizer
 
     def step(factory):
-        prev = tensor_quantizer.set_default_op_factory(factory)
+        prev = tensor_quantizer._set_op_class_for_testing(factory)
         try:
             deterministic()
             torch.manual_seed(0)
@@ -41,7 +41,7 @@ def test_mobilenet_v2_bf16_qat_step(oracle):
             act, par = sim.get_activation_param_encodings()
             return out.detach(), grads, (act, par)
         finally:
-            tensor_quantizer.set_default_op_factory(prev)
+            tensor_quantizer._set_op_class_for_testing(prev)
 
     out_n, grads_n, enc_n = step(AimetTensorQuantizer)
     out_o, grads_o, enc_o = step(OracleTensorQuantizer)

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 
 def run(name, factory):
     from aimet_b200.quantsim import tensor_quantizer
-    prev = tensor_quantizer.set_default_op_factory(factory)
+    prev = tensor_quantizer._set_op_class_for_testing(factory)
     try:
         torch.backends.cudnn.deterministic = True
         torch.backends.cudnn.benchmark = False
@@ -26,7 +26,7 @@ def run(name, factory):
         act, par = sim.get_activation_param_encodings()
         return json.dumps({"activation_encodings": act, "param_encodings": par}, sort_keys=True), structure, out
     finally:
-        tensor_quantizer.set_default_op_factory(prev)
+        tensor_quantizer._set_op_class_for_testing(prev)
 
 
 @pytest.mark.parametrize("name", ["resnet18_default_tfe", "resnet18_perchannel_tfe", "resnet18_default_tf",
@@ -54,7 +54,7 @@ def test_qat_step_forward_backward(oracle):
     from tests.oracle_backend import OracleTensorQuantizer
 
     def step(factory):
-        prev = tensor_quantizer.set_default_op_factory(factory)
+        prev = tensor_quantizer._set_op_class_for_testing(factory)
         try:
             torch.backends.cudnn.deterministic = True
             torch.manual_seed(0)
@@ -70,7 +70,7 @@ def test_qat_step_forward_backward(oracle):
             grads = [p.grad.clone() for p in sim.model.parameters() if p.grad is not None]
             return out.detach(), grads
         finally:
-            tensor_quantizer.set_default_op_factory(prev)
+            tensor_quantizer._set_op_class_for_testing(prev)
 
     out_n, grads_n = step(AimetTensorQuantizer)
     out_o, grads_o = step(OracleTensorQuantizer)

@@ -48,9 +48,9 @@ def analyze(name, results_dir, device="cpu"):
 def oracle_backend(oracle):
     from aimet_b200.quantsim import tensor_quantizer
     from tests.oracle_backend import OracleTensorQuantizer
-    prev = tensor_quantizer.set_default_op_factory(OracleTensorQuantizer)
+    prev = tensor_quantizer._set_op_class_for_testing(OracleTensorQuantizer)
     yield
-    tensor_quantizer.set_default_op_factory(prev)
+    tensor_quantizer._set_op_class_for_testing(prev)
 
 
 @pytest.mark.parametrize("name", list(CASES))
@@ -113,10 +113,10 @@ def test_cuda_ops_and_oracle_give_identical_tables(oracle, tmp_path, name):
     torch.backends.cudnn.allow_tf32 = False
     results = []
     for sub, factory in (("native", AimetTensorQuantizer), ("oracle", OracleTensorQuantizer)):
-        prev = tensor_quantizer.set_default_op_factory(factory)
+        prev = tensor_quantizer._set_op_class_for_testing(factory)
         try:
             results.append(analyze(name, str(tmp_path / sub), device="cuda")[0])
         finally:
-            tensor_quantizer.set_default_op_factory(prev)
+            tensor_quantizer._set_op_class_for_testing(prev)
     native, oracle_res = results
     assert native == oracle_res

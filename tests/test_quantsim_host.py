@@ -28,9 +28,9 @@ CASES = {
 def oracle_backend(oracle):
     from aimet_b200.quantsim import tensor_quantizer
     from tests.oracle_backend import OracleTensorQuantizer
-    prev = tensor_quantizer.set_default_op_factory(OracleTensorQuantizer)
+    prev = tensor_quantizer._set_op_class_for_testing(OracleTensorQuantizer)
     yield
-    tensor_quantizer.set_default_op_factory(prev)
+    tensor_quantizer._set_op_class_for_testing(prev)
 
 
 PERCENTILE_CASE = ("resnet18_percentile", (torchvision.models.resnet18, "default", "percentile", (4, 3, 64, 64)), 99.9)
@@ -129,6 +129,13 @@ def test_export_files(oracle_backend, tmp_path):
     assert exported["version"] == "0.6.1"
     assert exported["param_encodings"] == saved["param_encodings"]
     assert os.path.exists(tmp_path / "model.pth")
+    # quantizer_args as extract_global_quantizer_args writes them (aimet_common/quantsim.py:280-311)
+    assert exported["quantizer_args"] == {"quant_scheme": "post_training_tf_enhanced", "param_bitwidth": 8,
+                                          "activation_bitwidth": 8, "dtype": "int", "is_symmetric": True,
+                                          "per_channel_quantization": False}
+    # <prefix>.pth is the pickled original model (reference v1/quantsim.py:548), wrappers removed
+    restored = torch.load(tmp_path / "model.pth", weights_only=False)
+    assert isinstance(restored, torchvision.models.ResNet) and isinstance(restored.conv1, torch.nn.Conv2d)
     # text form is json.dump(sort_keys=True, indent=4), as the reference writes it
     assert open(tmp_path / "enc.json").read() == json.dumps(saved, sort_keys=True, indent=4)
 

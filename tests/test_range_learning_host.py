@@ -21,10 +21,10 @@ from tests.golden.make_range_learning_cases import SIM_CASES, sim_inputs, sim_mo
 def oracle_backends(oracle):
     from aimet_b200.quantsim import learned_grid, tensor_quantizer
     from tests.oracle_backend import OracleTensorQuantizer, oracle_learned_grid_qdq
-    prev_op = tensor_quantizer.set_default_op_factory(OracleTensorQuantizer)
+    prev_op = tensor_quantizer._set_op_class_for_testing(OracleTensorQuantizer)
     prev_fn = learned_grid.set_qdq_function(oracle_learned_grid_qdq)
     yield
-    tensor_quantizer.set_default_op_factory(prev_op)
+    tensor_quantizer._set_op_class_for_testing(prev_op)
     learned_grid.set_qdq_function(prev_fn)
 
 
@@ -154,3 +154,47 @@ def test_learned_grid_quantizer_interface(oracle_backends):
             out_q.encoding = bad
     with pytest.raises(RuntimeError):
         sim.compute_encodings(lambda m, _: None, None)             # the encodings are parameters now
+
+
+def test_load_encodings_into_range_learning_sim(oracle_backends, tmp_path):
+    """reference qc_quantize_op.py:499-677: LearnedGridQuantWrapper inherits import_*_encodings, so load_encodings /
+    load_and_freeze_encodings work on a sim whose wrappers have already been replaced (v1/quantsim.py:1696-1775)."""
+    sim, _ = run_flow("resnet18_default_tf")
+    act, par = sim.get_activation_param_encodings()
+    params_before = {n: p.detach().clone() for n, p in encoding_params(sim.model).items()}
+    # shift every encoding; the exported (effective) encoding of a symmetric weight has one extra bin below (min - delta)
+    doc = json.loads(json.dumps({"activation_encodings": act, "param_encodings": par}))
+    for sec in doc["activation_encodings"].values():
+        for io in sec.values():
+            for e in io.values():
+                e["min"], e["max"] = e["min"] * 0.5, e["max"] * 0.5
+                e["scale"] = (e["max"] - e["min"]) / 255
+                e["offset"] = round(e["min"] / e["scale"])
+    sim.load_encodings(doc, strict=True, partial=True, requires_grad=False, allow_overwrite=True)
+    after = encoding_params(sim.model)
+    changed = [n for n in params_before if n.startswith("relu") or ".relu" in n or "output0" in n]
+    assert changed
+    moved = 0
+    for n, p in after.items():
+        if "output" in n or "input" in n:
+            if p is not None and n in params_before and not torch.equal(p.detach(), params_before[n]):
+                moved += 1
+                assert p.detach().abs().max() <= params_before[n].abs().max() * 0.5 + 1e-6
+        assert p is None or not p.requires_grad               # requires_grad=False reached the wrapper parameters
+    assert moved > 0
+    # allow_overwrite=False freezes: a second load leaves the parameters alone
+    sim.load_encodings(doc, strict=True, partial=True, requires_grad=None, allow_overwrite=False)
+    frozen = {n: p.detach().clone() for n, p in encoding_params(sim.model).items() if p is not None}
+    assert all(q.is_encoding_frozen for _, w in sim.quant_wrappers() for q in w.output_quantizers if q.enabled)
+    sim.load_encodings({"activation_encodings": act, "param_encodings": par})
+    for n, p in encoding_params(sim.model).items():
+        if p is not None:
+            assert torch.equal(p.detach(), frozen[n]), n
+    # the file route, and a forward still runs
+    with open(tmp_path / "e.json", "w") as f:
+        json.dump(doc, f)
+    sim2, _ = run_flow("resnet18_default_tf")
+    sim2.load_and_freeze_encodings(str(tmp_path / "e.json"))
+    x, _, _ = sim_inputs(SIM_CASES["resnet18_default_tf"][3])
+    with torch.no_grad():
+        assert torch.isfinite(sim2.model(x)).all()
