@@ -9,10 +9,17 @@ Workload (BASELINE.json configs[1]): torchvision ResNet-50, random init (seed 0)
 images through the quantsim model (fp32 forward with every wrapper collecting statistics). The timed region is a
 COMPLETE calibration job of K steps: reset -> K batches (the first one also derives the 26 560 per-channel weight
 encodings) -> (N > 1: NCCL merge of the per-rank statistics) -> grid search for every quantizer -> encodings on the host.
-value = images calibrated by all ranks / that time. N > 1 is weak scaling: every rank runs K batches.
+value = images calibrated by all ranks / that time. N > 1 is weak scaling: every rank runs K batches; the same line also
+carries `strong_scaling` (BASELINE's 2048 images in total, 2048 / (32 N) steps per rank), and `--global-images G` makes
+that the headline (`"scaling": "strong"`).
+
+Also on the line: `encodings_sha256` + `parity` (ranks agree; the sharded result equals a single-process run over the same
+global batches), `kernels` (driver-run QDQ / STE / min-max / histogram GB/s sweep with the reference C++ single-core times),
+`roofline` (dominant kernel, CUDA events in the workload), `cpu_baseline`, `clocks`.
 
 One JSON line on stdout (rank 0). See README / DESIGN.md for the key meanings.
 """
+import hashlib
 import argparse
 import gc
 import json
@@ -30,12 +37,7 @@ if ROOT not in sys.path:
 
 BATCH = 32
 IMAGE = (3, 224, 224)
-CPU_BATCH = 4          # bounded sample for the CPU arms: images per step ...
-CPU_IMAGE_BUDGET = 256  # ... shrunk when K steps of it would exceed this many images (~2 minutes of host time)
-
-
-def cpu_batch_for(steps):
-    return max(1, min(CPU_BATCH, CPU_IMAGE_BUDGET // max(steps, 1)))
+STRONG_IMAGES = 2048   # BASELINE configs[1]: "calibration over 2048 synthetic images on 1/2/4/8 x B200"
 METRIC = "resnet50_quantsim_calibration_throughput"
 UNIT = "img/s"
 
@@ -49,6 +51,12 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="do not replay the steady state from a CUDA graph")
     ap.add_argument("--cpu-baseline-steps", type=int, default=2)
+    ap.add_argument("--global-images", type=int, default=0,
+                    help="strong scaling: this many images IN TOTAL, i.e. G / (images_per_step * N) steps per rank "
+                         "(overrides --steps); BASELINE configs[1] is 2048")
+    ap.add_argument("--no-kernels", action="store_true", help="skip the kernel sweep (`kernels` block)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity passes (`parity` block)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the extra 2048-image strong-scaling job")
     ap.add_argument("--images-per-step", type=int, default=BATCH,
                     help="calibration batch (SURVEY section 8d fixes 32 for the headline; larger batches mean larger "
                          "tensors per statistics launch -- a sensitivity knob, not the headline config)")
@@ -176,14 +184,44 @@ def ncu_traffic_ratio():
     return None
 
 
+def workload_config(world, steps, n_act, n_par):
+    """The `config` object of the JSON line -- one function for both arms, so that they describe the same workload."""
+    return {"workload": "ResNet-50 W8A8 per-channel weights, tf_enhanced calibration (BASELINE configs[1])",
+            "images_per_step": BATCH, "image": list(IMAGE), "global_images": BATCH * steps * world,
+            "timed_region": "complete job: reset, K batches (incl. per-channel weight encodings), merge (N>1), "
+                            "grid search, encodings on host",
+            "l2": "activation working set per step (2.2 GB) exceeds the 126 MB L2; no flush needed",
+            "num_activation_encodings": n_act, "num_param_tensors": n_par,
+            "parallelism": f"batch-sharded x{world}"}
+
+
+def encodings_sha256(act, par) -> str:
+    """sha256 of the canonical encodings JSON (what save_encodings_to_json writes, sort_keys, no indentation)."""
+    doc = json.dumps({"activation_encodings": act, "param_encodings": par}, sort_keys=True)
+    return hashlib.sha256(doc.encode()).hexdigest()
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # CPU arms (the reference's own implementation on the host cores)
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_job(steps, warmup):
-    """A complete calibration job of `steps` batches of cpu_batch_for(steps) images on the host: torch CPU forward (all
-    threads) and the reference's C++ statistics / encodings (single-threaded, as the reference is). Returns (img/s, info)."""
+def host_threads():
+    """All the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 to its workers: undo that here)."""
     import torch
-    batch = cpu_batch_for(steps)
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
+def cpu_job(steps, warmup, batch=None):
+    """A complete calibration job of `steps` batches of `batch` images on the host: torch CPU forward (all threads) and
+    the reference's C++ statistics / encodings (single-threaded, as the reference is). Same model, same quantsim
+    configuration, same seeded batches, same images per step as the GPU arm. Returns (img/s, info)."""
+    import torch
+    batch = BATCH if batch is None else batch
+    threads = host_threads()
 
     from aimet_b200.quantsim import tensor_quantizer
     from oracle import cpu_backend
@@ -191,40 +229,210 @@ def cpu_job(steps, warmup):
     sim = build_sim("cpu", factory)
     prev = tensor_quantizer._set_op_class_for_testing(factory)
     try:
-        batches = [synthetic_batch(b, batch) for b in range(max(steps, 1))]
         if warmup > 0:
-            # warm-up: forward passes only touch the allocator / thread pool; one tiny complete job primes everything
-            sim.compute_encodings(lambda m, _: [m(batches[i % len(batches)][:1]) for i in range(1)], None)
+            # one tiny complete job primes the allocator, the thread pool and oneDNN's primitive cache
+            tiny = synthetic_batch(0, 1)
+            sim.compute_encodings(lambda m, _: m(tiny), None)
         t0 = time.perf_counter()
-        sim.compute_encodings(lambda m, _: [m(batches[i]) for i in range(steps)], None)
+        # batches are generated inside the loop on purpose -- the GPU arm's e2e leg copies them in, this arm creates them;
+        # randn of 32 x 3 x 224 x 224 is ~1 % of a CPU step
+        sim.compute_encodings(lambda m, _: [m(synthetic_batch(i, batch)) for i in range(steps)], None)
         act, par = sim.get_activation_param_encodings()
         dt = time.perf_counter() - t0
     finally:
         tensor_quantizer._set_op_class_for_testing(prev)
-    info = {"kind": factory.KIND, "cores": torch.get_num_threads(),
-            "images_per_step": batch,
+    info = {"kind": factory.KIND, "cores": threads, "images_per_step": batch,
             "sample": f"complete calibration job of {steps} steps x {batch} images (ResNet-50 per-channel "
                       f"tf_enhanced; includes the 26 560 weight-channel encodings and the final grid search); "
-                      f"torch CPU forward on {torch.get_num_threads()} threads, reference statistics single-threaded",
-            "num_activation_encodings": len(act), "num_param_encodings": len(par), "seconds": round(dt, 3)}
+                      f"torch CPU forward on {threads} threads, reference statistics single-threaded (as the "
+                      f"reference's loops are)",
+            "num_activation_encodings": len(act), "num_param_encodings": len(par), "seconds": round(dt, 3),
+            "encodings_sha256": encodings_sha256(act, par)}
     return steps * batch / dt, info
+
+
+def cpu_kernel_baseline(sizes_mb=(1, 64, 1024)):
+    """the reference's own C++ loops (oracle/_ref, else the C port), ONE host core, on fp32 tensors
+    of 1 / 64 / 1024 MB: per-tensor and per-channel quantize-dequantize, tf_enhanced updateStats (first call = min/max +
+    histogram, later calls = histogram only), tf updateStats, and the tf_enhanced grid search latency."""
+    import numpy as np
+    from oracle import bindings, cpu_backend
+    have_ref = cpu_backend.have_reference()
+    lib = bindings.Reference() if have_ref else bindings.Oracle()
+    rng = np.random.default_rng(0)
+    rows = []
+    for mb in sizes_mb:
+        n = int(mb * 2**20) // 4
+        x = (rng.standard_normal(n, dtype=np.float32) * 2 + 2)
+
+        def timed(fn, reps=1):
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            return (time.perf_counter() - t0) / reps
+
+        reps = 3 if mb <= 64 else 1
+        t_qdq = timed(lambda: lib.qdq(x, -4.0, 8.0, 8), reps)
+        c = 2048
+        per = n // c
+        if have_ref:
+            prm = [np.full(c, v, dtype=np.float32) for v in (-4.0, 8.0, 12.0 / 255, -85.0)]
+        else:
+            prm = lib.per_channel_prepare(np.full(c, -4.0), np.full(c, 8.0), 8)
+        t_pc = timed(lambda: lib.qdq_per_channel(x[:c * per], c, per, *prm), reps)
+        if have_ref:
+            tfe = bindings.RefAnalyzer(lib, 1)
+            tf = bindings.RefAnalyzer(lib, 0)
+        else:
+            tfe, tf = bindings.OracleTfe(lib), bindings.OracleTf(lib)
+        t_first = timed(lambda: tfe.update(x))
+        t_later = timed(lambda: tfe.update(x), reps)
+        t_tf = timed(lambda: tf.update(x), reps)
+        t_search = timed(lambda: tfe.compute(8, False, False, False), 20)
+        for kernel, sec, bytes_ in (("qdq_per_tensor_bw8", t_qdq, 8 * n), ("qdq_per_channel_c2048_bw8", t_pc, 8 * c * per),
+                                    ("stats_tfe_first_call", t_first, 8 * n), ("stats_tfe_hist_steady", t_later, 4 * n),
+                                    ("stats_tf_minmax", t_tf, 4 * n)):
+            rows.append({"kernel": kernel, "dtype": "f32", "mb": mb, "ms": round(sec * 1e3, 3),
+                         "gbs": round(bytes_ / sec / 1e9, 3)})
+        rows.append({"kernel": "tfe_grid_search_asym_bw8", "us_per_quantizer": round(t_search * 1e6, 1)})
+    return {"kind": "reference" if have_ref else "port", "cores": 1, "rows": rows,
+            "note": "the reference's QDQ and statistics loops are single-threaded (trim_functions.cpp:174-182, "
+                    "math_functions.cpp:367-384); gbs = algorithmic bytes / time"}
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    value, info = cpu_job(args.steps, args.warmup)
+    steps = args.steps
+    if args.global_images:
+        steps = max(1, args.global_images // BATCH)        # the whole job runs on this one host
+    value, info = cpu_job(steps, args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1000.0 * info["images_per_step"] / value, 3),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "ResNet-50 W8A8 per-channel weights, tf_enhanced calibration (BASELINE configs[1])",
-                       "images_per_step": info["images_per_step"],
-                       "note": "host CPU only; bounded sample of the same workload"},
+            "steps": steps, "warmup": args.warmup, "ms_per_step": round(1000.0 * info["images_per_step"] / value, 3),
+            "higher_is_better": True, "scaling": "strong" if args.global_images else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            # one host, whatever --gpus says: rank 0's share of the job (same model, configuration, seeded batches, images
+            # per step and steps as the GPU arm's rank 0)
+            "config": workload_config(1, steps, info["num_activation_encodings"], info["num_param_encodings"]),
             "cpu_baseline": dict(info, value=round(value, 3), unit=UNIT),
             "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "encodings_sha256": info["encodings_sha256"],
             "gpu_launches": 0}
     emit(line)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# kernel sweep (BASELINE configs[4]; the "QDQ HBM GB/s vs peak" half of BASELINE.json's metric)
+# ---------------------------------------------------------------------------------------------------------------------
+def kernel_sweep(device, peak, sizes_mb=(1, 16, 64, 256, 1024), iters=12):
+    """Every hot-path kernel alone on synthetic tensors: algorithmic bytes / CUDA-event time of ONE launch (median of
+    `iters`), the L2 flushed before every launch (a 256 MB buffer is overwritten), events on the launching stream.
+    Distribution N(2, 2) (the reference's own test distribution), encodings [-4, 8]."""
+    import torch
+    from aimet_b200 import ops
+    from aimet_b200.state import StateArena
+    flush = torch.empty(256 * 2**20, dtype=torch.uint8, device=device)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    arena = StateArena.for_device(device)
+    rows = []
+
+    def measure(name, dtype_name, mb, fn, alg_bytes, extra=None):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        for a, b in ev:
+            flush.zero_()
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize()
+        us = statistics.median(a.elapsed_time(b) for a, b in ev) * 1e3
+        gbs = alg_bytes / us / 1e3
+        row = {"kernel": name, "dtype": dtype_name, "mb": mb, "us": round(us, 2), "gbs": round(gbs, 1),
+               "frac": round(gbs / peak, 3)}
+        if extra:
+            row.update(extra)
+        rows.append(row)
+
+    for dtype, es, dname in ((torch.float32, 4, "f32"), (torch.bfloat16, 2, "bf16")):
+        for mb in sizes_mb:
+            n = int(mb * 2**20) // es
+            g = torch.Generator(device=device).manual_seed(int(mb) * 7 + es)
+            x = (torch.randn(n, device=device, generator=g) * 2 + 2).to(dtype)
+            grad = torch.randn(n, device=device, generator=g).to(dtype)
+            blk = arena.allocate(2)
+            ops.stats_update_impl(x, blk.arena, blk.first, ops.QUANTIZATION_TF_ENHANCED, None, 0)     # fixes the range
+            if dtype == torch.bfloat16:
+                # second call: certifies the one-FFMA bin index on large tensors (see stats.cu); steady state from then on
+                ops.stats_update_impl(x, blk.arena, blk.first, ops.QUANTIZATION_TF_ENHANCED, None, 0)
+            bws = (4, 8, 16) if mb in (64, 1024) else (8,)
+            for bw in bws:
+                measure(f"qdq_per_tensor_bw{bw}", dname, mb, lambda bw=bw: ops.qdq_per_tensor_impl(x, -4.0, 8.0, bw, 0, 0),
+                        2 * es * n)
+            measure("quantize_to_grid_bw8", dname, mb, lambda: ops.quantize_to_grid_impl(x, -4.0, 8.0, 8, 0, True, 0),
+                    2 * es * n)
+            chans = (64, 2048, 11008) if mb in (64, 1024) else (2048,)
+            for c in chans:
+                per = n // c
+                if per < 8:
+                    continue
+                for sym, (lo, hi) in (("asym", (-4.0, 8.0)), ("sym", (-8.0, 8.0))):
+                    if sym == "sym" and c != 2048:
+                        continue
+                    params = ops.per_channel_params([lo] * c, [hi] * c, 8).to(device)
+                    xc = x[:c * per]
+                    measure(f"qdq_per_channel_c{c}_{sym}_bw8", dname, mb,
+                            lambda xc=xc, params=params, c=c, per=per: ops.qdq_per_channel_impl(xc, params, c, per, 0, 0),
+                            2 * es * c * per, {"channel_len": per})
+            if mb in (64, 1024):
+                # the reference's conv-weight / linear-weight channel lengths (SURVEY section 8d)
+                for per in (576, 4096):
+                    c = n // per
+                    params = ops.per_channel_params([-4.0] * c, [8.0] * c, 8).to(device)
+                    xc = x[:c * per]
+                    measure(f"qdq_per_channel_len{per}_bw8", dname, mb,
+                            lambda xc=xc, params=params, c=c, per=per: ops.qdq_per_channel_impl(xc, params, c, per, 0, 0),
+                            2 * es * c * per, {"channels": c})
+            measure("ste_bwd", dname, mb, lambda: ops.ste_bwd_impl(x, grad, -4.0, 8.0), 3 * es * n)
+            measure("stats_tf_minmax", dname, mb,
+                    lambda: ops.stats_update_impl(x, blk.arena, blk.first + 1, ops.QUANTIZATION_TF, None, 0), es * n)
+            measure("stats_tfe_hist_steady", dname, mb,
+                    lambda: ops.stats_update_impl(x, blk.arena, blk.first, ops.QUANTIZATION_TF_ENHANCED, None, 0,
+                                                  ops.STATS_RANGE_FIXED), es * n)
+            if mb == 64 and dtype == torch.float32:
+                # the other distribution of SURVEY section 8d: N(0, 1)
+                x0 = torch.randn(n, device=device, generator=g)
+                blk0 = arena.allocate(1)
+                ops.stats_update_impl(x0, blk0.arena, blk0.first, ops.QUANTIZATION_TF_ENHANCED, None, 0)
+                measure("stats_tfe_hist_steady_n01", dname, mb,
+                        lambda: ops.stats_update_impl(x0, blk0.arena, blk0.first, ops.QUANTIZATION_TF_ENHANCED, None, 0,
+                                                      ops.STATS_RANGE_FIXED), es * n)
+                measure("qdq_per_tensor_bw8_n01", dname, mb, lambda: ops.qdq_per_tensor_impl(x0, -4.0, 4.0, 8, 0, 0),
+                        2 * es * n)
+                del x0
+            del x, grad
+            torch.cuda.empty_cache()
+    # grid search: microseconds per quantizer, 26 560 per-channel records (ResNet-50's weight channels) in one launch
+    c, per = 26560, 576
+    w = torch.randn(c, per, device=device) * 0.05
+    blk = arena.allocate(c)
+    ops.stats_update_segmented_impl(w, blk.arena, blk.first, c, per, ops.QUANTIZATION_TF_ENHANCED)
+    out = torch.empty((c, 5), dtype=torch.float64, device=device)
+    for sym in (True, False):
+        fn = lambda sym=sym: ops.compute_encodings_into(blk.arena, blk.first, c, ops.QUANTIZATION_TF_ENHANCED, 8, sym,   # noqa: E731
+                                                        False, False, out)
+        fn()
+        torch.cuda.synchronize()
+        a, b = ev[0]
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        rows.append({"kernel": "tfe_grid_search_" + ("sym" if sym else "asym"), "quantizers": c, "ms": round(ms, 3),
+                     "us_per_quantizer": round(ms * 1e3 / c, 4), "quantizers_per_s": round(c / ms * 1e3)})
+    return rows
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -244,7 +452,18 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
-    torch.backends.cudnn.benchmark = os.environ.get("BENCH_CUDNN_BENCHMARK", "1") == "1"
+
+    def fast_forward():
+        torch.backends.cudnn.benchmark = os.environ.get("BENCH_CUDNN_BENCHMARK", "1") == "1"
+        torch.backends.cudnn.deterministic = False
+
+    def deterministic_forward():
+        # one algorithm per shape, whatever rank or process asks: the sharded run and the single-process run must see
+        # bit-identical activations for their encodings to be comparable
+        torch.backends.cudnn.benchmark = False
+        torch.backends.cudnn.deterministic = True
+
+    fast_forward()
     torch.backends.cudnn.allow_tf32 = False          # the reference's forward is plain fp32
     torch.backends.cuda.matmul.allow_tf32 = False
 
@@ -254,7 +473,9 @@ def run_ours(args):
     from aimet_b200.utils import DevicePrefetcher
 
     sim = build_sim(device)
-    steps, warmup = args.steps, args.warmup
+    warmup = args.warmup
+    strong_main = args.global_images > 0
+    steps = max(1, args.global_images // (BATCH * world)) if strong_main else args.steps
     # global batch index of this rank's i-th step: i * world + rank
     dev_batches = [synthetic_batch(i * world + rank, BATCH, device) for i in range(steps)]
     host_batches = [synthetic_batch(i * world + rank, BATCH, "cpu", pin=True) for i in range(steps)]
@@ -264,20 +485,21 @@ def run_ours(args):
     # measures the plain eager path; BENCH_CUDA_GRAPH=1 switches it on.
     use_graph = os.environ.get("BENCH_CUDA_GRAPH", "0") == "1" and not args.eager
 
-    def job(batches_of, n, graph=None):
+    def job(batches_of, n, graph=None, sharded=None):
         """One complete calibration job over n batches through the public API. `batches_of(n)` returns the iterable of
         this rank's n batches."""
         graph = use_graph if graph is None else graph
+        sharded = (world > 1) if sharded is None else sharded
         if not graph:
             def cb(model, _):
                 for x in batches_of(n):
                     model(x)
-            if world > 1:
+            if sharded:
                 ShardedCalibrator(sim).compute_encodings(cb, None)
             else:
                 sim.compute_encodings(cb, None)
         else:
-            if world > 1:
+            if sharded:
                 ShardedCalibrator(sim).compute_encodings_for_batches(batches_of(n), cuda_graph=True)
             else:
                 sim.compute_encodings_for_batches(batches_of(n), cuda_graph=True)
@@ -295,6 +517,23 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(*values):
+        t = torch.tensor(values, device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist()
+
+    def timed_job(batches_of, n):
+        """(milliseconds by CUDA events on this rank, encodings): barrier + synchronize on both sides."""
+        gc.collect()
+        barrier()
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        enc = job(batches_of, n)
+        stop.record()
+        barrier()
+        return start.elapsed_time(stop), enc
 
     # ---- warm-up: W steps of a complete job (cuDNN autotune, allocator, lazy module loading) ----
     if warmup > 0:
@@ -328,10 +567,10 @@ def run_ours(args):
     ms = start.elapsed_time(stop)
     from aimet_b200.quantsim import quantsim as _qs
     graph_info = dict(_qs.LAST_GRAPH_INFO)
-    eager_batches = min(steps, 2) if use_graph else steps
     launched = {k: ops.LAUNCHES[k] - launches0[k] for k in ops.LAUNCHES}
     sampler.window = (t_region0, t_region0 + ms / 1000.0 + 0.01)
     clocks = sampler.stop() if rank == 0 else None
+    sha_timed = encodings_sha256(act, par)
 
     # ---- timed: e2e (host buffers; H2D of every batch and D2H of the result inside the region) ----
     gc.collect()
@@ -341,56 +580,157 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
+    ms, e2e_ms = max_over_ranks(ms, e2e_s * 1000.0)
+
+    # ---- strong scaling: BASELINE's 2048 images IN TOTAL, 2048 / (32 N) steps per rank ----
+    strong = None
+    if not strong_main and not args.no_strong and STRONG_IMAGES % (BATCH * world) == 0:
+        s_steps = STRONG_IMAGES // (BATCH * world)
+        job(resident, min(s_steps, 4))               # the log / staging buffers of this job size exist before it is timed
+        s_ms, _ = timed_job(resident, s_steps)
+        (s_ms,) = max_over_ranks(s_ms)
+        strong = {"global_images": STRONG_IMAGES, "steps_per_rank": s_steps, "value": round(STRONG_IMAGES / (s_ms / 1e3), 2),
+                  "unit": UNIT, "ms": round(s_ms, 3), "scaling": "strong",
+                  "note": "complete job (as the headline), inputs resident, batches cycle through this rank's "
+                          f"{steps} resident ones"}
+
+    # ---- parity of the N-GPU result (reference test it matches: test_quantizer.py:1087-1138, multi-GPU == single-GPU) ----
+    parity = {"encodings_sha256_timed_job": sha_timed}
+    if world > 1:
+        shas = [None] * world
+        dist.all_gather_object(shas, sha_timed)
+        parity["ranks_agree"] = len(set(shas)) == 1
+        assert parity["ranks_agree"], f"ranks disagree on the merged encodings: {shas}"
+    if not args.no_parity:
+        deterministic_forward()
+        p_steps = min(steps, 8)
+        act_d, par_d = job(resident, p_steps)                     # sharded over the ranks when N > 1
+        sha_d = encodings_sha256(act_d, par_d)
+        if world > 1:
+            shas = [None] * world
+            dist.all_gather_object(shas, sha_d)
+            assert len(set(shas)) == 1, f"ranks disagree (deterministic pass): {shas}"
+            sha_single = None
+            if rank == 0:
+                # the same N x steps global batches, in order, in ONE process through the plain (unsharded) API
+                act_s, par_s = job(lambda n: (synthetic_batch(b, BATCH, device) for b in range(n)), p_steps * world,
+                                   graph=False, sharded=False)
+                sha_single = encodings_sha256(act_s, par_s)
+            box = [sha_single]
+            dist.broadcast_object_list(box, src=0)
+            parity.update(sharded_sha256=sha_d, single_process_sha256=box[0], global_batches=p_steps * world,
+                          equals_single_process=box[0] == sha_d)
+            assert parity["equals_single_process"], "sharded calibration differs from the single-process run"
+        else:
+            # N = 1: the first two global batches under the deterministic forward -- the very job
+            # tests/test_gpu_bench_shape.py checks against the CPU oracle on the same device tensors; its hash is committed
+            act_2, par_2 = job(resident, min(steps, 2))
+            sha_2 = encodings_sha256(act_2, par_2)
+            golden = None
+            gpath = os.path.join(ROOT, "tests", "golden", "bench_shape_sha256.json")
+            if os.path.exists(gpath):
+                golden = json.load(open(gpath)).get("resnet50_perchannel_tfe_2x32")
+            parity.update(two_batch_sha256=sha_2, oracle_checked_golden=golden,
+                          equals_oracle_checked_golden=(sha_2 == golden) if (golden and steps >= 2) else None)
+        fast_forward()
+        parity["parity_checked"] = bool(parity.get("equals_single_process") or parity.get("equals_oracle_checked_golden"))
+        barrier()
 
     # ---- the same job once more with CUDA events around every statistics call (roofline of the dominant kernel) ----
-    # The eager step is host-bound, so an event pair around a launch would also time the GPU waiting for the host to
-    # enqueue it. This repeat therefore replays the steady-state step from a CUDA graph in which the event pairs are
+    roofline = measure_roofline(sim, job, resident, steps, barrier, device, rank)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # kernels of ours that ran in the timed region: launches issued from Python (a captured launch counts once, for the
+    # replay that follows the capture) + the captured step's launches for every further replay of the graph
+    gpu_launches = sum(launched.values()) + graph_info["captured_launches"] * max(graph_info["replays"] - 1, 0)
+    images = BATCH * steps * world
+    value = images / (ms / 1000.0)
+    e2e = images / (e2e_ms / 1000.0)
+    enc_bytes = (sum(len(v.get("input", {})) + len(v.get("output", {})) for v in act.values()) +
+                 sum(len(v) for v in par.values())) * 5 * 8
+    line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": round(ms / steps, 3), "higher_is_better": True, "scaling": "strong" if strong_main else "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(world, steps, len(act), len(par)),
+            "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": BATCH * 3 * 224 * 224 * 4,
+                    "d2h_bytes_per_step": int(enc_bytes / steps),
+                    "h2d": "every step's batch is copied from pinned host memory inside the timed region, on a copy "
+                           "stream one batch ahead of the compute stream (aimet_b200.utils.DevicePrefetcher)"},
+            "gpu_launches": gpu_launches, "launches_by_kernel": launched,
+            "cuda_graph": dict(graph_info, enabled=bool(use_graph)),
+            "encodings_sha256": sha_timed, "parity": parity, "parity_checked": parity.get("parity_checked"),
+            "strong_scaling": strong,
+            "roofline": roofline, "clocks": clocks}
+
+    if world == 1 and not args.no_kernels:
+        try:
+            line["kernels"] = {"rows": kernel_sweep(device, roofline["peak"]), "peak": roofline["peak"], "unit": "GB/s",
+                               "how": "one launch per measurement, CUDA events on the launching stream, L2 flushed (256 MB "
+                                      "overwrite) before every launch, median of 12; gbs = algorithmic bytes / time "
+                                      "(QDQ 2s, STE 3s, statistics 1s bytes per element)"}
+        except Exception as exc:   # pylint: disable=broad-except
+            line["kernels"] = {"error": str(exc)[:300]}
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            v, info = cpu_job(args.cpu_baseline_steps, 1)
+            line["cpu_baseline"] = dict(info, value=round(v, 3), unit=UNIT)
+        except Exception as exc:   # pylint: disable=broad-except
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "error": str(exc)[:200]}
+        if not args.no_kernels and isinstance(line.get("kernels"), dict) and "rows" in line["kernels"]:
+            try:
+                line["kernels"]["cpu_reference"] = cpu_kernel_baseline()
+            except Exception as exc:   # pylint: disable=broad-except
+                line["kernels"]["cpu_reference"] = {"error": str(exc)[:200]}
+    emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure_roofline(sim, job, resident, steps, barrier, device, rank):
+    """Roofline of the dominant kernel inside the workload. See DESIGN.md section 6."""
+    import torch
+    from aimet_b200 import ops
+    # The eager step is host-bound at times, so an event pair around a launch could also time the GPU waiting for the host
+    # to enqueue it. This repeat therefore replays the steady-state step from a CUDA graph in which the event pairs are
     # external event-record nodes: what is read afterwards are DEVICE-side durations of the statistics launches of the
     # last replayed step -- same kernels, same tensors, same order as the timed job.
     ops.reserve_timing_events(2 * 100 * steps + 64)
     ops.STATS_TIMING = []
-    per_step0 = dict(ops.LAUNCHES)
     job(resident, steps, graph=steps > 2)
     barrier()
     timing, ops.STATS_TIMING = ops.STATS_TIMING, None
-    # launches of one captured (replayed) step = launches issued while capturing = total of this job minus the eager ones
-    job_launches = {k: ops.LAUNCHES[k] - per_step0[k] for k in ops.LAUNCHES}
 
     # ---- and a short eager pass with the kernel's own clock (ab_debug_hist_timer): first CTA start to last CTA end of every
     # histogram launch on the GPU's global timer. No launch latency, no event records between the kernels: what the
     # histogram itself takes in its real surroundings (input just written by the producing layer, L2 in whatever state).
     from aimet_b200 import _lib as ab_lib
     dev_timer = None
-    if True:   # every rank runs it (the sharded job has collectives); only rank 0's numbers are printed
-        probe_steps = min(steps, 4)
-        cap = 128 * probe_steps + 64
-        slots = torch.zeros((cap, 3), dtype=torch.int64, device=device)
-        slots[:, 0] = torch.iinfo(torch.int64).max
-        ab_lib.load().ab_debug_hist_timer(slots.data_ptr(), cap)
-        job(resident, probe_steps)
-        torch.cuda.synchronize()
-        used = int(ab_lib.load().ab_debug_hist_timer(None, 0))
-        if 0 < used <= cap:
-            rows = slots[:used].cpu().tolist()
-            # the activation statistics of the LAST step: the trailing launches, as many as one steady-state step makes
-            per_step = n_act_hist = sum(1 for r in rows if r[2] >= 64 * 1024) // probe_steps
-            last = [r for r in rows if r[2] >= 64 * 1024][-per_step:] if per_step else []
-            if last:
-                b, t_ns = sum(r[2] for r in last), sum(r[1] - r[0] for r in last)
-                big = [r for r in last if r[2] >= 32 * 2**20]
-                dev_timer = {"launches": len(last), "avg_launch_us": round(t_ns / 1000.0 / len(last), 2),
-                             "achieved": round(b / t_ns, 1), "algorithmic_bytes_per_launch": round(b / len(last), 1),
-                             "achieved_large_tensors":
-                                 round(sum(r[2] for r in big) / sum(r[1] - r[0] for r in big), 1) if big else None}
+    probe_steps = min(steps, 4)
+    cap = 128 * probe_steps + 64
+    slots = torch.zeros((cap, 3), dtype=torch.int64, device=device)
+    slots[:, 0] = torch.iinfo(torch.int64).max
+    ab_lib.load().ab_debug_hist_timer(slots.data_ptr(), cap)
+    job(resident, probe_steps)              # every rank runs it (the sharded job has collectives)
+    torch.cuda.synchronize()
+    used = int(ab_lib.load().ab_debug_hist_timer(None, 0))
+    if 0 < used <= cap:
+        rows = slots[:used].cpu().tolist()
+        # the activation statistics of the LAST step: the trailing launches, as many as one steady-state step makes
+        per_step = sum(1 for r in rows if r[2] >= 64 * 1024) // probe_steps
+        last = [r for r in rows if r[2] >= 64 * 1024][-per_step:] if per_step else []
+        if last:
+            b, t_ns = sum(r[2] for r in last), sum(r[1] - r[0] for r in last)
+            big = [r for r in last if r[2] >= 32 * 2**20]
+            dev_timer = {"launches": len(last), "avg_launch_us": round(t_ns / 1000.0 / len(last), 2),
+                         "achieved": round(b / t_ns, 1), "algorithmic_bytes_per_launch": round(b / len(last), 1),
+                         "achieved_large_tensors":
+                             round(sum(r[2] for r in big) / sum(r[1] - r[0] for r in big), 1) if big else None}
     barrier()
 
-    # max over ranks
-    t = torch.tensor([ms, e2e_s * 1000.0], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = t.tolist()
-
-    # ---- roofline of the dominant kernel: tf_enhanced statistics (histogram) launches of the timed region ----
     tot_bytes = tot_ms = 0.0
     big_bytes = big_ms = 0.0
     n_l = 0
@@ -408,61 +748,20 @@ def run_ours(args):
     peak, peak_src = peak_hbm()
     achieved = tot_bytes / tot_ms / 1e6 if tot_ms > 0 else 0.0
     ratio = ncu_traffic_ratio()
-    roofline = {"bound": "hbm", "kernel": "hist_kernel<float>",
-                "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": round(ratio * tot_bytes / max(n_l, 1), 1) if ratio else None,
-                "algorithmic_bytes_per_launch": round(tot_bytes / max(n_l, 1), 1), "launches": n_l,
-                "avg_launch_us": round(1000.0 * tot_ms / max(n_l, 1), 2), "peak_source": peak_src,
-                "achieved_large_tensors": round(big_bytes / big_ms / 1e6, 1) if big_ms > 0 else None,
-                "device_timer": (dict(dev_timer, frac=round(dev_timer["achieved"] / peak, 4), unit="GB/s",
-                                      how="first CTA start to last CTA end on %globaltimer, last step of a short "
-                                          "eager repeat (no launch latency, no event records between kernels)")
-                                 if dev_timer else None),
-                "note": "4 B/element x elements of every activation tensor handed to updateStats, divided by the "
-                        "CUDA-event time of those launches (events on the launching stream; in CUDA-graph mode: "
-                        "external event nodes inside the replayed step, read for the last step of an instrumented "
-                        "repeat of the timed job); achieved_large_tensors restricts to tensors >= 32 MB"}
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    # kernels of ours that ran in the timed region: launches issued from Python (a captured launch counts once, for the
-    # replay that follows the capture) + the captured step's launches for every further replay of the graph
-    gpu_launches = sum(launched.values()) + graph_info["captured_launches"] * max(graph_info["replays"] - 1, 0)
-    images = BATCH * steps * world
-    value = images / (ms / 1000.0)
-    e2e = images / (e2e_ms / 1000.0)
-    enc_bytes = (sum(len(v.get("input", {})) + len(v.get("output", {})) for v in act.values()) +
-                 sum(len(v) for v in par.values())) * 5 * 8
-    line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
-            "ms_per_step": round(ms / steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "ResNet-50 W8A8 per-channel weights, tf_enhanced calibration (BASELINE configs[1])",
-                       "images_per_step": BATCH, "image": list(IMAGE), "global_images": images,
-                       "timed_region": "complete job: reset, K batches (incl. per-channel weight encodings), "
-                                       "merge (N>1), grid search, encodings on host",
-                       "l2": "activation working set per step (2.2 GB) exceeds the 126 MB L2; no flush needed",
-                       "num_activation_encodings": len(act), "num_param_tensors": len(par),
-                       "parallelism": f"batch-sharded x{world}"},
-            "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": BATCH * 3 * 224 * 224 * 4,
-                    "d2h_bytes_per_step": int(enc_bytes / steps),
-                    "h2d": "every step's batch is copied from pinned host memory inside the timed region, on a copy "
-                           "stream one batch ahead of the compute stream (aimet_b200.utils.DevicePrefetcher)"},
-            "gpu_launches": gpu_launches, "launches_by_kernel": launched,
-            "cuda_graph": dict(graph_info, enabled=bool(use_graph)),
-            "roofline": roofline, "clocks": clocks}
-
-    if world == 1 and not args.no_cpu_baseline:
-        try:
-            v, info = cpu_job(args.cpu_baseline_steps, 1)
-            line["cpu_baseline"] = dict(info, value=round(v, 3), unit=UNIT)
-        except Exception as exc:   # pylint: disable=broad-except
-            line["cpu_baseline"] = {"value": None, "unit": UNIT, "error": str(exc)[:200]}
-    emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    return {"bound": "hbm", "kernel": "hist_kernel<float>",
+            "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+            "traffic": round(ratio * tot_bytes / max(n_l, 1), 1) if ratio else None,
+            "algorithmic_bytes_per_launch": round(tot_bytes / max(n_l, 1), 1), "launches": n_l,
+            "avg_launch_us": round(1000.0 * tot_ms / max(n_l, 1), 2), "peak_source": peak_src,
+            "achieved_large_tensors": round(big_bytes / big_ms / 1e6, 1) if big_ms > 0 else None,
+            "device_timer": (dict(dev_timer, frac=round(dev_timer["achieved"] / peak, 4), unit="GB/s",
+                                  how="first CTA start to last CTA end on %globaltimer, last step of a short "
+                                      "eager repeat (no launch latency, no event records between kernels)")
+                             if dev_timer else None),
+            "note": "4 B/element x elements of every activation tensor handed to updateStats, divided by the "
+                    "CUDA-event time of those launches (events on the launching stream; in CUDA-graph mode: "
+                    "external event nodes inside the replayed step, read for the last step of an instrumented "
+                    "repeat of the timed job); achieved_large_tensors restricts to tensors >= 32 MB"}
 
 
 _REAL_STDOUT = None
