@@ -22,7 +22,14 @@ class Encoding(C.Structure):
                 ("bw", C.c_int)]
 
 
+class StatsSegment(C.Structure):
+    """ab_stats_segment: one (tensor, record) pair of a multi-tensor statistics call."""
+    _fields_ = [("data", C.c_void_p), ("count", C.c_int64), ("state_index", C.c_int32), ("reserved", C.c_int32)]
+
+
 PDF_SIZE = 512
+STATS_MULTI_MAX_SEGMENTS = 128
+STATS_MULTI_LOG_ONLY = 1
 AB_OK, AB_ERR_INVALID, AB_ERR_CUDA, AB_ERR_UNSUPPORTED = 0, -1, -2, -3
 AB_F32, AB_BF16 = 0, 1
 
@@ -54,6 +61,7 @@ PROTOTYPES = {
     "ab_stats_reset": (_int, [_vp, _i64, _vp]),
     "ab_stats_update": (_int, [_vp, _i64, _int, _int, _vp, _vp, _int, _vp]),
     "ab_stats_update_segmented": (_int, [_vp, _i64, _i64, _int, _int, _vp, _vp]),
+    "ab_stats_update_multi": (_int, [C.POINTER(StatsSegment), _int, _int, _vp, _vp, _int, _vp]),
     "ab_compute_encodings": (_int, [_vp, _i64, _int, _int, _int, _int, _int, _vp, _vp, _vp]),
     "ab_compute_encodings_percentile": (_int, [_vp, _i64, _flt, _int, _int, _int, _int, _vp, _vp, _vp]),
     "ab_debug_hist_timer": (_i64, [_vp, _i64]),

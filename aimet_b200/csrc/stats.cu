@@ -1062,6 +1062,246 @@ __global__ void __launch_bounds__(kBins)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// multi-tensor histogram: many (tensor, record) pairs in ONE persistent launch
+// ---------------------------------------------------------------------------------------------------------------
+// A calibration forward hands ~70 activation tensors of 0.4 ... 100 MB to updateStats. One launch per tensor costs a
+// pipeline ramp-up and drain (~2 us inside the kernel) plus a launch gap each, against 4.5 us of streaming for the
+// average 30 MB tensor. Where the host layer can prove that a tensor is not written between the call and the end of the
+// forward (aimet_b200/quantsim/stats_batcher.py), it defers the call, and the whole batch of deferred calls becomes ONE
+// launch here: the 32 KB tiles of all tensors form one global tile list, every persistent CTA takes a contiguous chunk of
+// it (so it changes tensor -- flushes and re-arms its privatised bins, re-reads a range -- once or twice per launch),
+// and the TMA ring never drains between tensors. The raw counts go to one row per call (`seg_counts`); a second, tiny
+// launch folds the rows into the running PDFs in call order, exactly as UpdatePdf would have (math_functions.cpp:279-287)
+// -- or leaves them as log entries for the multi-GPU exact merge.
+constexpr int kMaxSeg   = AB_STATS_MULTI_MAX_SEGMENTS;
+constexpr int kLogWords = kBins + 2;
+struct MultiParams
+{
+    const void* data[kMaxSeg];
+    int64_t count[kMaxSeg];
+    int32_t state_index[kMaxSeg];
+    int32_t first_tile[kMaxSeg + 1];   // prefix sum of the tensors' tile counts; [num_segments] is the total
+    int32_t num_segments;
+};
+static_assert(sizeof(MultiParams) <= 3200, "must travel as a kernel parameter (4 KB limit with the other arguments)");
+
+template <typename T>
+__global__ void __launch_bounds__(kHistThreads, 1)
+    hist_multi_kernel(const __grid_constant__ MultiParams p, const ab_stats_state* __restrict__ states,
+                      uint32_t* __restrict__ seg_counts, unsigned long long* timer_slot)
+{
+    constexpr int kV = Elem<T>::kPerVec;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* s_tiles  = smem;
+    uint32_t* s_hist  = reinterpret_cast<uint32_t*>(smem + (size_t) kStages * kTileBytes);
+    uint64_t* s_full  = reinterpret_cast<uint64_t*>(smem + (size_t) kStages * kTileBytes + (size_t) kHistWords * 4);
+    uint64_t* s_empty = s_full + kStages;
+
+    const int tid  = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    constexpr int kProducerWarp = kConsumerWarps;
+
+    const int total    = p.first_tile[p.num_segments];
+    const int t0       = (int) ((int64_t) blockIdx.x * total / gridDim.x);
+    const int t1       = (int) ((int64_t) (blockIdx.x + 1) * total / gridDim.x);
+    const int my_tiles = t1 - t0;
+    auto seg_of = [&](int tile, int hint) {
+        while (tile >= p.first_tile[hint + 1])
+            ++hint;
+        return hint;
+    };
+    auto tile_bytes = [&](int seg, int tile, int64_t& off) {
+        const int64_t body = (p.count[seg] / kV) * 16;
+        off                = (int64_t) (tile - p.first_tile[seg]) * kTileBytes;
+        return (uint32_t) min((int64_t) kTileBytes, body - off);
+    };
+
+    if (warp == kProducerWarp && lane == 0)
+    {
+        for (int s = 0; s < kStages; ++s)
+        {
+            mbar_init(s_full + s, 1);
+            mbar_init(s_empty + s, kConsumerWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < kHistWords / 4; i += kHistThreads)
+        reinterpret_cast<uint4*>(s_hist)[i] = make_uint4(0, 0, 0, 0);
+    // programmatic stream serialization: everything above touched shared memory only (a no-op in a plain launch)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (timer_slot != nullptr && tid == 0)
+    {
+        atomicMin(timer_slot, global_timer_ns());
+        if (blockIdx.x == 0)
+        {
+            unsigned long long bytes = 0;
+            for (int s = 0; s < p.num_segments; ++s)
+                bytes += (unsigned long long) p.count[s] * sizeof(T);
+            timer_slot[2] = bytes;
+        }
+    }
+    __syncthreads();   // barriers initialised, bins zeroed
+
+    if (warp == kProducerWarp)
+    {
+        if (lane == 0 && my_tiles > 0)
+        {
+            int seg = seg_of(t0, 0);
+            for (int k = 0; k < my_tiles; ++k)
+            {
+                const int tile = t0 + k;
+                seg            = seg_of(tile, seg);
+                const int s    = k % kStages;
+                if (k >= kStages)
+                    mbar_wait(s_empty + s, (uint32_t) (((k / kStages) - 1) & 1));   // consumers released the slot
+                int64_t off;
+                const uint32_t nb = tile_bytes(seg, tile, off);
+                mbar_expect_tx(s_full + s, nb);
+                tma_load_1d(s_tiles + (size_t) s * kTileBytes, reinterpret_cast<const uint8_t*>(p.data[seg]) + off, nb,
+                            s_full + s);
+            }
+        }
+    }
+    else if (warp < kConsumerWarps)
+    {
+        uint32_t* s_hist_lane = s_hist + lane;
+        // reduce the 32 lane copies of bin `tid`, re-arm them, add the sum to the call's row
+        auto flush_bins = [&](int seg) {
+            asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory");   // everybody has counted
+            uint32_t sum = 0;
+#pragma unroll
+            for (int l = 0; l < kLaneCopies; ++l)
+            {
+                uint32_t* w = s_hist + tid * kLaneCopies + ((l + tid) & (kLaneCopies - 1));
+                sum += *w;
+                *w = 0;
+            }
+            if (sum)
+                atomicAdd(seg_counts + (size_t) seg * kLogWords + tid, sum);
+            asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory");   // bins are clean again
+        };
+        int seg = -1;
+        Binner binner;
+        binner.fast      = false;
+        bool valid       = false;
+        int formula      = 0;
+        float formula_c  = 0.0f, formula_b = 0.0f;
+        constexpr bool kIsBf16 = sizeof(T) == 2;
+        for (int k = 0; k < my_tiles; ++k)
+        {
+            const int tile = t0 + k;
+            const int nseg = seg_of(tile, seg < 0 ? 0 : seg);
+            if (nseg != seg)
+            {
+                if (seg >= 0)
+                    flush_bins(seg);
+                seg                      = nseg;
+                const ab_stats_state* st = states + p.state_index[seg];
+                valid                    = st->initialized != 0;   // the host layer only defers calls on fixed ranges
+                binner.dv                = make_divisor(st->bucket_size);
+                binner.offset            = st->pdf_offset;
+                binner.fast              = binner.dv.fast;
+                if (kIsBf16)
+                    formula = st->bf16_formula, formula_c = st->bf16_scale, formula_b = st->bf16_shift;
+            }
+            const int s = k % kStages;
+            int64_t off;
+            const int nb = (int) tile_bytes(seg, tile, off);
+            mbar_wait(s_full + s, (uint32_t) ((k / kStages) & 1));
+            if (valid)
+            {
+                const uint4* src = reinterpret_cast<const uint4*>(s_tiles + (size_t) s * kTileBytes);
+                if (kIsBf16 && formula == 1)
+                    consume_tile_bf16_formula(src, nb, tid, s_hist_lane, formula_c, formula_b);
+                else if (binner.fast)
+                    consume_tile<T, true>(src, nb, tid, s_hist_lane, binner);
+                else
+                    consume_tile<T, false>(src, nb, tid, s_hist_lane, binner);
+            }
+            __syncwarp();
+            if (lane == 0)
+                mbar_arrive(s_empty + s);
+            if (valid && tile == p.first_tile[seg + 1] - 1)
+            {
+                // the sub-vector tail of this tensor (count % kV elements) belongs to whoever owns its last tile
+                const T* in        = reinterpret_cast<const T*>(p.data[seg]);
+                const int64_t body = (p.count[seg] / kV) * kV;
+                if (body + tid < p.count[seg])
+                    binner.count(s_hist_lane, Elem<T>::load(in + body + tid));
+            }
+        }
+        if (seg >= 0)
+            flush_bins(seg);
+    }
+    if (timer_slot != nullptr && tid == 0)
+        atomicMax(timer_slot + 1, global_timer_ns());
+}
+
+// Second launch of a multi-tensor update: CTA s handles the record of call s if s is that record's FIRST call in the table,
+// and then folds all of the record's calls in table order -- a reused module (a ReLU called three times per residual
+// block) updates its quantizer several times per forward, and the running mean is order dependent. One thread per bin.
+__global__ void __launch_bounds__(kBins)
+    fold_segments_kernel(const __grid_constant__ MultiParams p, ab_stats_state* states, uint32_t* seg_counts, int log_only)
+{
+    const int s = blockIdx.x;
+    if (s >= p.num_segments)
+        return;
+    const int idx = p.state_index[s];
+    for (int j = 0; j < s; ++j)
+        if (p.state_index[j] == idx)
+            return;
+    ab_stats_state* st = states + idx;
+    const int b        = threadIdx.x;
+    const bool valid   = st->initialized != 0;
+    if (log_only)
+    {
+        // leave the raw counts where they are and complete the entries with their element counts (0: call not counted)
+        if (b == 0)
+        {
+            for (int j = s; j < p.num_segments; ++j)
+                if (p.state_index[j] == idx)
+                {
+                    const uint64_t c                           = valid ? (uint64_t) p.count[j] : 0;
+                    seg_counts[(size_t) j * kLogWords + kBins]     = (uint32_t) c;
+                    seg_counts[(size_t) j * kLogWords + kBins + 1] = (uint32_t) (c >> 32);
+                }
+            st->stats_updated = 1;
+        }
+        return;
+    }
+    double pdf           = st->pdf[b];
+    int k                = st->iterations;
+    const int pending    = st->pending;
+    if (pending)   // a batch parked by the single-tensor kernel comes first
+    {
+        const int pp = st->write_parity ^ 1;
+        pdf          = __ddiv_rn(__dadd_rn(__dmul_rn(pdf, (double) k), (double) st->hist[pp][b] / st->pending_count),
+                                 (double) (k + 1));
+        st->hist[pp][b] = 0;
+        ++k;
+    }
+    if (valid)
+        for (int j = s; j < p.num_segments; ++j)
+            if (p.state_index[j] == idx)
+            {
+                uint32_t* e      = seg_counts + (size_t) j * kLogWords + b;
+                const double prob = (double) *e / (double) p.count[j];
+                pdf               = __ddiv_rn(__dadd_rn(__dmul_rn(pdf, (double) k), prob), (double) (k + 1));
+                ++k;
+                *e = 0;   // the scratch rows are handed back zeroed
+            }
+    st->pdf[b] = pdf;
+    __syncthreads();   // every thread has read iterations / pending before they change
+    if (b == 0)
+    {
+        st->iterations    = k;
+        st->pending       = 0;
+        st->stats_updated = 1;
+    }
+}
+
 template <typename K>
 int resident_grid(K kernel, int threads, size_t smem)
 {
@@ -1167,6 +1407,64 @@ int launch_update(const T* in, int64_t count, int quant_mode, ab_stats_state* st
     return AB_OK;
 }
 
+template <typename T>
+int launch_multi(const ab_stats_segment* segs, int n, ab_stats_state* states, uint32_t* seg_counts, int flags,
+                 cudaStream_t stream)
+{
+    constexpr int kV = Elem<T>::kPerVec;
+    MultiParams p;
+    memset(&p, 0, sizeof(p));
+    p.num_segments = n;
+    int64_t total  = 0;
+    for (int s = 0; s < n; ++s)
+    {
+        p.data[s]        = segs[s].data;
+        p.count[s]       = segs[s].count;
+        p.state_index[s] = segs[s].state_index;
+        p.first_tile[s]  = (int32_t) total;
+        total += ((segs[s].count / kV) * 16 + kTileBytes - 1) / kTileBytes;
+        if (total > 0x7fffffff)
+        {
+            set_error("too many tiles in one multi-tensor call");
+            return AB_ERR_INVALID;
+        }
+    }
+    p.first_tile[n] = (int32_t) total;
+    static thread_local bool configured[2] = {false, false};
+    const int which                        = sizeof(T) == 4 ? 0 : 1;
+    if (!configured[which])
+    {
+        AB_CUDA_CHECK(cudaFuncSetAttribute(hist_multi_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int) kHistSmem));
+        configured[which] = true;
+    }
+    unsigned long long* timer_slot = nullptr;
+    if (g_timer_slots != nullptr && g_timer_used < g_timer_capacity && !(flags & AB_STATS_MULTI_FOLD_ONLY))
+        timer_slot = g_timer_slots + 3 * g_timer_used++;
+    int grid = num_sms();
+    if (total < grid)
+        grid = (int) total;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim            = dim3((unsigned) grid);
+    cfg.blockDim           = dim3(kHistThreads);
+    cfg.dynamicSmemBytes   = kHistSmem;
+    cfg.stream             = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs                                          = attr;
+    cfg.numAttrs                                       = 1;
+    if (!(flags & AB_STATS_MULTI_FOLD_ONLY))
+        AB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, hist_multi_kernel<T>, p, (const ab_stats_state*) states, seg_counts,
+                                         timer_slot));
+    if (!(flags & AB_STATS_MULTI_HIST_ONLY))
+    {
+        fold_segments_kernel<<<n, kBins, 0, stream>>>(p, states, seg_counts, (flags & AB_STATS_MULTI_LOG_ONLY) ? 1 : 0);
+        AB_CUDA_CHECK(cudaGetLastError());
+    }
+    return AB_OK;
+}
+
 }   // namespace
 }   // namespace ab
 
@@ -1260,6 +1558,37 @@ int ab_stats_update_segmented(const void* in, int64_t num_segments, int64_t segm
     }
     AB_CUDA_CHECK(cudaGetLastError());
     return AB_OK;
+}
+
+int ab_stats_update_multi(const ab_stats_segment* segments, int num_segments, int dtype, ab_stats_state* states,
+                          uint32_t* seg_counts, int flags, void* stream)
+{
+    if (num_segments < 0 || num_segments > AB_STATS_MULTI_MAX_SEGMENTS ||
+        (num_segments > 0 && (segments == nullptr || states == nullptr || seg_counts == nullptr)))
+    {
+        set_error("null pointer, or more than %d segments", AB_STATS_MULTI_MAX_SEGMENTS);
+        return AB_ERR_INVALID;
+    }
+    if (dtype != AB_F32 && dtype != AB_BF16)
+    {
+        set_error("unsupported dtype %d", dtype);
+        return AB_ERR_INVALID;
+    }
+    const int64_t per_vec = dtype == AB_F32 ? 4 : 8;
+    for (int s = 0; s < num_segments; ++s)
+        if (segments[s].data == nullptr || segments[s].count < per_vec || segments[s].state_index < 0 ||
+            (reinterpret_cast<uintptr_t>(segments[s].data) & 15u) != 0)
+        {
+            set_error("segment %d: needs a 16-byte aligned device pointer, at least one 128-bit vector of data and a "
+                      "non-negative record index",
+                      s);
+            return AB_ERR_INVALID;
+        }
+    if (num_segments == 0)
+        return AB_OK;
+    if (dtype == AB_F32)
+        return launch_multi<float>(segments, num_segments, states, seg_counts, flags, (cudaStream_t) stream);
+    return launch_multi<__nv_bfloat16>(segments, num_segments, states, seg_counts, flags, (cudaStream_t) stream);
 }
 
 int ab_stats_init_range(ab_stats_state* states, int64_t count, const float* minmax, void* stream)

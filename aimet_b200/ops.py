@@ -29,7 +29,8 @@ STATE_BYTES = int(_L.ab_stats_state_bytes())
 
 # kernel launches issued through this module, by kernel family (bench.py reports their sum as gpu_launches)
 LAUNCHES = {"qdq": 0, "quantize": 0, "qdq_per_channel": 0, "ste_bwd": 0, "minmax": 0, "hist": 0, "segmented": 0,
-            "search": 0, "reset": 0, "init_range": 0, "fold": 0, "lg_fwd": 0, "lg_bwd": 0, "qdq_broadcast": 0}
+            "search": 0, "reset": 0, "init_range": 0, "fold": 0, "lg_fwd": 0, "lg_bwd": 0, "qdq_broadcast": 0,
+            "hist_multi": 0, "fold_segments": 0}
 # when a list, stats_update_impl brackets its launches with CUDA events and appends (bytes, start, stop, quant_mode)
 STATS_TIMING = None
 _EVENT_POOL = []
@@ -318,6 +319,53 @@ def stats_update_segmented_impl(x, states, first, num_segments, segment_len, qua
         _lib.check(_L.ab_stats_update_segmented(x.data_ptr(), int(num_segments), int(segment_len), _dtype_code(x),
                                                 int(quant_mode), _state_ptr(states, first), _stream(x)))
     LAUNCHES["segmented"] += 1
+
+
+MULTI_MAX_SEGMENTS = _lib.STATS_MULTI_MAX_SEGMENTS
+# when a list, stats_update_multi_impl brackets its histogram + fold launches with CUDA events and appends
+# (bytes, start, stop, num_segments, captured)
+MULTI_TIMING = None
+
+
+def stats_update_multi_impl(tensors, state_indices, states, first, seg_counts, log_only=False):
+    """tf_enhanced updateStats for up to MULTI_MAX_SEGMENTS (tensor, record) pairs in one histogram launch + one fold launch
+    (ab_stats_update_multi). `tensors`: dense CUDA tensors of ONE dtype (float32 or bfloat16), 16-byte aligned; tensor k
+    updates record `first + state_indices[k]` of the arena `states`; `seg_counts`: zeroed int32 CUDA tensor with at least
+    len(tensors) rows of LOG_WORDS words (scratch, or -- `log_only` -- the log entries of the calls)."""
+    n = len(tensors)
+    if n == 0:
+        return
+    if n > MULTI_MAX_SEGMENTS:
+        raise ValueError(f"at most {MULTI_MAX_SEGMENTS} tensors per multi-tensor statistics call")
+    _require_cuda(states, seg_counts, *tensors)
+    if seg_counts.dtype not in (torch.int32, torch.uint32) or seg_counts.numel() < n * LOG_WORDS or \
+            not seg_counts.is_contiguous():
+        raise ValueError("seg_counts must be a contiguous 32-bit integer CUDA tensor of len(tensors) x LOG_WORDS words")
+    code = _dtype_code(tensors[0])
+    segs = (_lib.StatsSegment * n)()
+    nbytes = 0
+    for k, (t, idx) in enumerate(zip(tensors, state_indices)):
+        if t.dtype != tensors[0].dtype:
+            raise TypeError("all tensors of one multi-tensor statistics call must share a dtype")
+        seg = segs[k]
+        seg.data, seg.count, seg.state_index = t.data_ptr(), t.numel(), idx
+        nbytes += t.numel() * t.element_size()
+    timing = MULTI_TIMING
+    flags = _lib.STATS_MULTI_LOG_ONLY if log_only else 0
+    args = (segs, n, code, _state_ptr(states, first), seg_counts.data_ptr())
+    with _on_device(states):
+        if timing is None:
+            _lib.check(_L.ab_stats_update_multi(*args, flags, _stream(states)))
+        else:
+            # the two launches enqueued separately, with a CUDA-event pair around the histogram launch alone
+            start, stop = _timing_event(), _timing_event()
+            start.record()
+            _lib.check(_L.ab_stats_update_multi(*args, flags | 2, _stream(states)))
+            stop.record()
+            _lib.check(_L.ab_stats_update_multi(*args, flags | 4, _stream(states)))
+            timing.append((nbytes, start, stop, n, torch.cuda.is_current_stream_capturing()))
+    LAUNCHES["hist_multi"] += 1
+    LAUNCHES["fold_segments"] += 1
 
 
 def _search(states, first, count, quant_mode, bw, sym, strict, unsigned_sym, enc_ptr, qdq4_ptr, percentile):

@@ -325,53 +325,76 @@ def run_reference_arm(args):
 # ---------------------------------------------------------------------------------------------------------------------
 # kernel sweep (BASELINE configs[4]; the "QDQ HBM GB/s vs peak" half of BASELINE.json's metric)
 # ---------------------------------------------------------------------------------------------------------------------
-def kernel_sweep(device, peak, sizes_mb=(1, 16, 64, 256, 1024), iters=12):
-    """Every hot-path kernel alone on synthetic tensors: algorithmic bytes / CUDA-event time of ONE launch (median of
-    `iters`), the L2 flushed before every launch (a 256 MB buffer is overwritten), events on the launching stream.
-    Distribution N(2, 2) (the reference's own test distribution), encodings [-4, 8]."""
+def kernel_sweep(device, peak, sizes_mb=(1, 16, 64, 256, 1024), window_mb=512):
+    """Every hot-path kernel alone on synthetic tensors. Per (kernel, size): L launches are captured in one CUDA graph, each
+    on its OWN slice of a 512 MB input window (>= 4 x the 126 MB L2, so every launch reads HBM; outputs are distinct
+    allocations held for the whole graph, so every launch writes HBM), the graph is replayed, and the replay is timed with
+    one CUDA-event pair on the launching stream: us = replay time / L, gbs = algorithmic bytes / us. No host in the loop,
+    no per-launch event records. Distribution N(2, 2) (the reference's own test distribution), encodings [-4, 8]."""
     import torch
     from aimet_b200 import ops
     from aimet_b200.state import StateArena
-    flush = torch.empty(256 * 2**20, dtype=torch.uint8, device=device)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    a_ev, b_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     arena = StateArena.for_device(device)
     rows = []
+    window_bytes = window_mb * 2**20
 
-    def measure(name, dtype_name, mb, fn, alg_bytes, extra=None):
-        for _ in range(3):
-            fn()
+    def measure(name, dtype_name, mb, fn, alg_bytes, slices, extra=None):
+        """fn(i) launches on slice i and returns its output tensor (or None)."""
+        launches = max(4, len(slices))          # one pass over the whole window: nothing a launch reads is still in L2
+        for i in range(min(3, launches)):
+            fn(i)
         torch.cuda.synchronize()
-        for a, b in ev:
-            flush.zero_()
-            a.record()
-            fn()
-            b.record()
-        torch.cuda.synchronize()
-        us = statistics.median(a.elapsed_time(b) for a, b in ev) * 1e3
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            keep = [fn(i % len(slices)) for i in range(launches)]
+        reps = []
+        for _ in range(4):
+            a_ev.record()
+            graph.replay()
+            b_ev.record()
+            torch.cuda.synchronize()
+            reps.append(a_ev.elapsed_time(b_ev))
+        del keep, graph
+        us = statistics.median(reps[1:]) * 1e3 / launches
         gbs = alg_bytes / us / 1e3
         row = {"kernel": name, "dtype": dtype_name, "mb": mb, "us": round(us, 2), "gbs": round(gbs, 1),
-               "frac": round(gbs / peak, 3)}
+               "frac": round(gbs / peak, 3), "launches": launches}
         if extra:
             row.update(extra)
         rows.append(row)
 
     for dtype, es, dname in ((torch.float32, 4, "f32"), (torch.bfloat16, 2, "bf16")):
+        g = torch.Generator(device=device).manual_seed(11 + es)
+        total = window_bytes // es
+        window = torch.empty(total, dtype=dtype, device=device)
+        gwindow = torch.empty(total, dtype=dtype, device=device)
+        chunk = 64 * 2**20
+        for o in range(0, total, chunk):                      # filled piecewise: no 2 GB fp32 temporaries
+            m = min(chunk, total - o)
+            window[o:o + m] = (torch.randn(m, device=device, generator=g) * 2 + 2).to(dtype)
+            gwindow[o:o + m] = torch.randn(m, device=device, generator=g).to(dtype)
         for mb in sizes_mb:
             n = int(mb * 2**20) // es
-            g = torch.Generator(device=device).manual_seed(int(mb) * 7 + es)
-            x = (torch.randn(n, device=device, generator=g) * 2 + 2).to(dtype)
-            grad = torch.randn(n, device=device, generator=g).to(dtype)
+            if n > total:
+                # one tensor larger than the window: two of them, alternating (each far larger than L2)
+                big = [(torch.randn(n, device=device, generator=g) * 2 + 2).to(dtype) for _ in range(2)]
+                xs, gs = big, [gwindow.new_empty(n).normal_(generator=g) for _ in range(1)] * 2
+            else:
+                k = total // n
+                xs = [window[i * n:(i + 1) * n] for i in range(k)]
+                gs = [gwindow[i * n:(i + 1) * n] for i in range(k)]
             blk = arena.allocate(2)
-            ops.stats_update_impl(x, blk.arena, blk.first, ops.QUANTIZATION_TF_ENHANCED, None, 0)     # fixes the range
+            ops.stats_update_impl(xs[0], blk.arena, blk.first, ops.QUANTIZATION_TF_ENHANCED, None, 0)     # fixes the range
             if dtype == torch.bfloat16:
                 # second call: certifies the one-FFMA bin index on large tensors (see stats.cu); steady state from then on
-                ops.stats_update_impl(x, blk.arena, blk.first, ops.QUANTIZATION_TF_ENHANCED, None, 0)
+                ops.stats_update_impl(xs[0], blk.arena, blk.first, ops.QUANTIZATION_TF_ENHANCED, None, 0)
             bws = (4, 8, 16) if mb in (64, 1024) else (8,)
             for bw in bws:
-                measure(f"qdq_per_tensor_bw{bw}", dname, mb, lambda bw=bw: ops.qdq_per_tensor_impl(x, -4.0, 8.0, bw, 0, 0),
-                        2 * es * n)
-            measure("quantize_to_grid_bw8", dname, mb, lambda: ops.quantize_to_grid_impl(x, -4.0, 8.0, 8, 0, True, 0),
-                    2 * es * n)
+                measure(f"qdq_per_tensor_bw{bw}", dname, mb,
+                        lambda i, bw=bw: ops.qdq_per_tensor_impl(xs[i], -4.0, 8.0, bw, 0, 0), 2 * es * n, xs)
+            measure("quantize_to_grid_bw8", dname, mb,
+                    lambda i: ops.quantize_to_grid_impl(xs[i], -4.0, 8.0, 8, 0, True, 0), 2 * es * n, xs)
             chans = (64, 2048, 11008) if mb in (64, 1024) else (2048,)
             for c in chans:
                 per = n // c
@@ -381,38 +404,32 @@ def kernel_sweep(device, peak, sizes_mb=(1, 16, 64, 256, 1024), iters=12):
                     if sym == "sym" and c != 2048:
                         continue
                     params = ops.per_channel_params([lo] * c, [hi] * c, 8).to(device)
-                    xc = x[:c * per]
                     measure(f"qdq_per_channel_c{c}_{sym}_bw8", dname, mb,
-                            lambda xc=xc, params=params, c=c, per=per: ops.qdq_per_channel_impl(xc, params, c, per, 0, 0),
-                            2 * es * c * per, {"channel_len": per})
+                            lambda i, params=params, c=c, per=per: ops.qdq_per_channel_impl(xs[i][:c * per], params, c, per,
+                                                                                            0, 0),
+                            2 * es * c * per, xs, {"channel_len": per})
             if mb in (64, 1024):
                 # the reference's conv-weight / linear-weight channel lengths
                 for per in (576, 4096):
                     c = n // per
                     params = ops.per_channel_params([-4.0] * c, [8.0] * c, 8).to(device)
-                    xc = x[:c * per]
                     measure(f"qdq_per_channel_len{per}_bw8", dname, mb,
-                            lambda xc=xc, params=params, c=c, per=per: ops.qdq_per_channel_impl(xc, params, c, per, 0, 0),
-                            2 * es * c * per, {"channels": c})
-            measure("ste_bwd", dname, mb, lambda: ops.ste_bwd_impl(x, grad, -4.0, 8.0), 3 * es * n)
+                            lambda i, params=params, c=c, per=per: ops.qdq_per_channel_impl(xs[i][:c * per], params, c, per,
+                                                                                            0, 0),
+                            2 * es * c * per, xs, {"channels": c})
+            measure("ste_bwd", dname, mb, lambda i: ops.ste_bwd_impl(xs[i], gs[i % len(gs)], -4.0, 8.0), 3 * es * n, xs)
             measure("stats_tf_minmax", dname, mb,
-                    lambda: ops.stats_update_impl(x, blk.arena, blk.first + 1, ops.QUANTIZATION_TF, None, 0), es * n)
+                    lambda i: ops.stats_update_impl(xs[i], blk.arena, blk.first + 1, ops.QUANTIZATION_TF, None, 0),
+                    es * n, xs)
             measure("stats_tfe_hist_steady", dname, mb,
-                    lambda: ops.stats_update_impl(x, blk.arena, blk.first, ops.QUANTIZATION_TF_ENHANCED, None, 0,
-                                                  ops.STATS_RANGE_FIXED), es * n)
-            if mb == 64 and dtype == torch.float32:
-                # the other distribution of SURVEY section 8d: N(0, 1)
-                x0 = torch.randn(n, device=device, generator=g)
-                blk0 = arena.allocate(1)
-                ops.stats_update_impl(x0, blk0.arena, blk0.first, ops.QUANTIZATION_TF_ENHANCED, None, 0)
-                measure("stats_tfe_hist_steady_n01", dname, mb,
-                        lambda: ops.stats_update_impl(x0, blk0.arena, blk0.first, ops.QUANTIZATION_TF_ENHANCED, None, 0,
-                                                      ops.STATS_RANGE_FIXED), es * n)
-                measure("qdq_per_tensor_bw8_n01", dname, mb, lambda: ops.qdq_per_tensor_impl(x0, -4.0, 4.0, 8, 0, 0),
-                        2 * es * n)
-                del x0
-            del x, grad
+                    lambda i: ops.stats_update_impl(xs[i], blk.arena, blk.first, ops.QUANTIZATION_TF_ENHANCED, None, 0,
+                                                    ops.STATS_RANGE_FIXED), es * n, xs)
+            if n > total:
+                del big
+            del xs, gs
             torch.cuda.empty_cache()
+        del window, gwindow
+        torch.cuda.empty_cache()
     # grid search: microseconds per quantizer, 26 560 per-channel records (ResNet-50's weight channels) in one launch
     c, per = 26560, 576
     w = torch.randn(c, per, device=device) * 0.05
@@ -424,12 +441,11 @@ def kernel_sweep(device, peak, sizes_mb=(1, 16, 64, 256, 1024), iters=12):
                                                         False, False, out)
         fn()
         torch.cuda.synchronize()
-        a, b = ev[0]
-        a.record()
+        a_ev.record()
         fn()
-        b.record()
+        b_ev.record()
         torch.cuda.synchronize()
-        ms = a.elapsed_time(b)
+        ms = a_ev.elapsed_time(b_ev)
         rows.append({"kernel": "tfe_grid_search_" + ("sym" if sym else "asym"), "quantizers": c, "ms": round(ms, 3),
                      "us_per_quantizer": round(ms * 1e3 / c, 4), "quantizers_per_s": round(c / ms * 1e3)})
     return rows
@@ -669,9 +685,10 @@ def run_ours(args):
     if world == 1 and not args.no_kernels:
         try:
             line["kernels"] = {"rows": kernel_sweep(device, roofline["peak"]), "peak": roofline["peak"], "unit": "GB/s",
-                               "how": "one launch per measurement, CUDA events on the launching stream, L2 flushed (256 MB "
-                                      "overwrite) before every launch, median of 12; gbs = algorithmic bytes / time "
-                                      "(QDQ 2s, STE 3s, statistics 1s bytes per element)"}
+                               "how": "per row: `launches` launches captured in one CUDA graph, each on its own slice of a "
+                                      "512 MB input window (>= 4 x L2) with distinct output allocations, replay timed by "
+                                      "one CUDA-event pair on the launching stream, median of 3 replays; gbs = "
+                                      "algorithmic bytes / time (QDQ 2s, STE 3s, statistics 1s bytes per element)"}
         except Exception as exc:   # pylint: disable=broad-except
             line["kernels"] = {"error": str(exc)[:300]}
     if world == 1 and not args.no_cpu_baseline:

@@ -234,6 +234,32 @@ int ab_stats_update(const void* in, int64_t count, int dtype, int quant_mode, ab
 int ab_stats_update_segmented(const void* in, int64_t num_segments, int64_t segment_len, int dtype, int quant_mode,
                               ab_stats_state* states, void* stream);
 
+/* Many tf_enhanced updateStats calls -- each on its own tensor and its own record -- as ONE histogram launch plus one tiny
+ * fold launch (net-new: the reference makes one native call, i.e. several kernels and a blocking copy, per tensor:
+ * ATQ:94-126 -> DlQ/src/math_functions.cu:125-211). Every record addressed must have its histogram range fixed
+ * (`initialized`, i.e. a call on a record without a range is not counted); the host layer sends first batches through
+ * ab_stats_update. Records may repeat (a module called several times per forward): their calls are folded in table order.
+ *   segments   : HOST array (the table travels as a kernel argument, so the call is capturable in a CUDA graph)
+ *   dtype      : element type of ALL segments of this call
+ *   states     : DEVICE base of the records; segment s updates states[segments[s].state_index]
+ *   seg_counts : DEVICE uint32 [num_segments][AB_PDF_SIZE + 2], ZEROED by the caller. Without flags the rows are scratch:
+ *                the fold consumes them and hands them back zeroed. With AB_STATS_MULTI_LOG_ONLY nothing is folded: row s
+ *                keeps the raw counts of call s followed by its element count (low, high word) -- the log entry format of
+ *                ab_stats_update / ab_stats_fold_batches for the multi-GPU exact merge. */
+typedef struct
+{
+    const void* data;    /* DEVICE, contiguous, 16-byte aligned */
+    int64_t count;       /* elements (at least one 128-bit vector) */
+    int32_t state_index; /* record index relative to `states` */
+    int32_t reserved;
+} ab_stats_segment;
+#define AB_STATS_MULTI_MAX_SEGMENTS 128
+#define AB_STATS_MULTI_LOG_ONLY 1
+#define AB_STATS_MULTI_HIST_ONLY 2 /* measurement: enqueue only the histogram launch ... */
+#define AB_STATS_MULTI_FOLD_ONLY 4 /* ... and only the fold launch (same table), so that a caller can bracket either */
+int ab_stats_update_multi(const ab_stats_segment* segments, int num_segments, int dtype, ab_stats_state* states,
+                          uint32_t* seg_counts, int flags, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Job 3: tf_enhanced grid search on the device.
  * ---------------------------------------------------------------------------------------------------------- */
