@@ -288,13 +288,19 @@ class QuantizationSimModel:
 
     def compute_encodings(self, forward_pass_callback: Callable, forward_pass_callback_args):
         """Runs the user's calibration callback with every wrapper collecting statistics, then computes the encodings."""
+        from .stats_batcher import StatsBatcher
         QuantizationSimModel.prepare_sim_for_compute_encodings(self)
         prefetch = _ParamExportPrefetch(self)
+        batcher = StatsBatcher.attach(self)     # activation statistics: deferred, one launch per forward (or None)
         try:
             with in_eval_mode(self.model), torch.no_grad():
                 _ = forward_pass_callback(self.model, forward_pass_callback_args)
+            if batcher is not None:
+                batcher.flush()
         finally:
             prefetch.close()
+            if batcher is not None:
+                batcher.detach()
         QuantizationSimModel.compute_layer_encodings_for_sim(self)
 
     def compute_encodings_for_batches(self, batches, cuda_graph: bool = True):
@@ -306,9 +312,19 @@ class QuantizationSimModel:
         host cost of ~130 Python wrappers and ~250 launches per step disappears. Statistics are device-resident and all
         their control flow is on the device, which is what makes the step capturable. Results are identical to
         compute_encodings(). `batches`: iterable of CUDA tensors, or pinned host tensors (copied per step)."""
+        from .stats_batcher import StatsBatcher
         QuantizationSimModel.prepare_sim_for_compute_encodings(self)
-        with in_eval_mode(self.model), torch.no_grad():
-            run_batches(self.model, batches, cuda_graph, after_first=self._learn_fixed_ranges)
+        batcher = StatsBatcher.attach(self)
+        try:
+            with in_eval_mode(self.model), torch.no_grad():
+                # the batcher learns the fixed ranges itself at the end of the first forward
+                run_batches(self.model, batches, cuda_graph,
+                            after_first=None if batcher is not None else self._learn_fixed_ranges)
+            if batcher is not None:
+                batcher.flush()
+        finally:
+            if batcher is not None:
+                batcher.detach()
         QuantizationSimModel.compute_layer_encodings_for_sim(self)
 
     def _learn_fixed_ranges(self):

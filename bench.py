@@ -708,22 +708,25 @@ def run_ours(args):
 
 
 def measure_roofline(sim, job, resident, steps, barrier, device, rank):
-    """Roofline of the dominant kernel inside the workload. See DESIGN.md section 6."""
+    """Roofline of the dominant kernel inside the workload. See DESIGN.md section 6.
+
+    The activation statistics of a calibration step are one multi-tensor histogram launch (`hist_multi_kernel`, every call
+    the host layer could defer to the end of the forward) plus one `hist_kernel` launch for each tensor that is written in
+    place right after its call (ResNet's `out += identity`). Both are timed with CUDA-event pairs around the launches, on
+    the launching stream, in an instrumented repeat of the timed job whose steady-state step is replayed from a CUDA graph
+    (the event pairs are external event-record nodes of that graph): what is read afterwards are device-side durations of
+    the LAST replayed step -- same kernels, same tensors, same order as the timed job, no host in the loop."""
     import torch
     from aimet_b200 import ops
-    # The eager step is host-bound at times, so an event pair around a launch could also time the GPU waiting for the host
-    # to enqueue it. This repeat therefore replays the steady-state step from a CUDA graph in which the event pairs are
-    # external event-record nodes: what is read afterwards are DEVICE-side durations of the statistics launches of the
-    # last replayed step -- same kernels, same tensors, same order as the timed job.
     ops.reserve_timing_events(2 * 100 * steps + 64)
-    ops.STATS_TIMING = []
+    ops.STATS_TIMING, ops.MULTI_TIMING = [], []
     job(resident, steps, graph=steps > 2)
     barrier()
-    timing, ops.STATS_TIMING = ops.STATS_TIMING, None
+    single, ops.STATS_TIMING = ops.STATS_TIMING, None
+    multi, ops.MULTI_TIMING = ops.MULTI_TIMING, None
 
-    # ---- and a short eager pass with the kernel's own clock (ab_debug_hist_timer): first CTA start to last CTA end of every
-    # histogram launch on the GPU's global timer. No launch latency, no event records between the kernels: what the
-    # histogram itself takes in its real surroundings (input just written by the producing layer, L2 in whatever state).
+    # ---- and a short eager pass with the kernels' own clock (ab_debug_hist_timer): first CTA start to last CTA end of every
+    # histogram launch on the GPU's global timer. No launch latency, no event records between the kernels.
     from aimet_b200 import _lib as ab_lib
     dev_timer = None
     probe_steps = min(steps, 4)
@@ -735,50 +738,63 @@ def measure_roofline(sim, job, resident, steps, barrier, device, rank):
     torch.cuda.synchronize()
     used = int(ab_lib.load().ab_debug_hist_timer(None, 0))
     if 0 < used <= cap:
-        rows = slots[:used].cpu().tolist()
-        # the activation statistics of the LAST step: the trailing launches, as many as one steady-state step makes
-        per_step = sum(1 for r in rows if r[2] >= 64 * 1024) // probe_steps
-        last = [r for r in rows if r[2] >= 64 * 1024][-per_step:] if per_step else []
-        if last:
-            b, t_ns = sum(r[2] for r in last), sum(r[1] - r[0] for r in last)
-            big = [r for r in last if r[2] >= 32 * 2**20]
-            dev_timer = {"launches": len(last), "avg_launch_us": round(t_ns / 1000.0 / len(last), 2),
-                         "achieved": round(b / t_ns, 1), "algorithmic_bytes_per_launch": round(b / len(last), 1),
-                         "achieved_large_tensors":
-                             round(sum(r[2] for r in big) / sum(r[1] - r[0] for r in big), 1) if big else None}
+        rows = [r for r in slots[:used].cpu().tolist() if r[2] >= 64 * 1024]
+        # the launches of the LAST step: walk back from the end until one step's activation bytes are covered (every step
+        # hands the same tensors to the statistics, in more launches during the first step than later)
+        if len(rows) and probe_steps >= 3:
+            per_step_bytes = sum(r[2] for r in rows) / probe_steps
+            last, acc = [], 0
+            for r in reversed(rows):
+                if acc >= per_step_bytes - 1:
+                    break
+                last.append(r)
+                acc += r[2]
+            if last:
+                b, t_ns = sum(r[2] for r in last), sum(r[1] - r[0] for r in last)
+                biggest = max(last, key=lambda r: r[2])
+                dev_timer = {"launches": len(last), "achieved": round(b / t_ns, 1), "bytes": int(b),
+                             "us": round(t_ns / 1e3, 1),
+                             "largest_launch": {"bytes": int(biggest[2]), "us": round((biggest[1] - biggest[0]) / 1e3, 2),
+                                                "achieved": round(biggest[2] / (biggest[1] - biggest[0]), 1)}}
     barrier()
 
-    tot_bytes = tot_ms = 0.0
-    big_bytes = big_ms = 0.0
-    n_l = 0
-    steady = [t for t in timing if t[4]] if any(t[4] for t in timing) else timing
-    for nbytes, e0, e1, mode, _captured in steady:
-        if mode != ops.QUANTIZATION_TF_ENHANCED:
-            continue
-        d = e0.elapsed_time(e1)
-        tot_bytes += nbytes
-        tot_ms += d
-        n_l += 1
-        if nbytes >= 32 * 2**20:
-            big_bytes += nbytes
-            big_ms += d
+    def last_step(entries):
+        steady = [t for t in entries if t[4]] if any(t[4] for t in entries) else entries
+        return steady
+
     peak, peak_src = peak_hbm()
-    achieved = tot_bytes / tot_ms / 1e6 if tot_ms > 0 else 0.0
+    m = last_step(multi)
+    m_bytes = sum(t[0] for t in m)
+    m_ms = sum(t[1].elapsed_time(t[2]) for t in m)
+    sgl = [t for t in last_step(single) if t[3] == ops.QUANTIZATION_TF_ENHANCED]
+    s_bytes = sum(t[0] for t in sgl)
+    s_ms = sum(t[1].elapsed_time(t[2]) for t in sgl)
+    dominant_multi = m_bytes >= s_bytes and m_ms > 0
+    d_bytes, d_ms, d_n = (m_bytes, m_ms, len(m)) if dominant_multi else (s_bytes, s_ms, len(sgl))
+    achieved = d_bytes / d_ms / 1e6 if d_ms > 0 else 0.0
+    all_ms = m_ms + s_ms
     ratio = ncu_traffic_ratio()
-    return {"bound": "hbm", "kernel": "hist_kernel<float>",
-            "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-            "traffic": round(ratio * tot_bytes / max(n_l, 1), 1) if ratio else None,
-            "algorithmic_bytes_per_launch": round(tot_bytes / max(n_l, 1), 1), "launches": n_l,
-            "avg_launch_us": round(1000.0 * tot_ms / max(n_l, 1), 2), "peak_source": peak_src,
-            "achieved_large_tensors": round(big_bytes / big_ms / 1e6, 1) if big_ms > 0 else None,
-            "device_timer": (dict(dev_timer, frac=round(dev_timer["achieved"] / peak, 4), unit="GB/s",
-                                  how="first CTA start to last CTA end on %globaltimer, last step of a short "
-                                      "eager repeat (no launch latency, no event records between kernels)")
-                             if dev_timer else None),
-            "note": "4 B/element x elements of every activation tensor handed to updateStats, divided by the "
-                    "CUDA-event time of those launches (events on the launching stream; in CUDA-graph mode: "
-                    "external event nodes inside the replayed step, read for the last step of an instrumented "
-                    "repeat of the timed job); achieved_large_tensors restricts to tensors >= 32 MB"}
+    out = {"bound": "hbm", "kernel": "hist_multi_kernel<float>" if dominant_multi else "hist_kernel<float>",
+           "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+           "traffic": round(ratio * d_bytes / max(d_n, 1), 1) if ratio else None,
+           "algorithmic_bytes_per_launch": round(d_bytes / max(d_n, 1), 1), "launches": d_n,
+           "avg_launch_us": round(1000.0 * d_ms / max(d_n, 1), 2), "peak_source": peak_src,
+           "all_statistics_launches": {
+               "bytes_per_step": int(m_bytes + s_bytes), "us_per_step": round(all_ms * 1e3, 1),
+               "achieved": round((m_bytes + s_bytes) / all_ms / 1e6, 1) if all_ms > 0 else None,
+               "frac": round((m_bytes + s_bytes) / all_ms / 1e6 / peak, 4) if all_ms > 0 else None,
+               "multi_tensor": {"launches": len(m), "bytes": int(m_bytes), "us": round(m_ms * 1e3, 1)},
+               "single_tensor": {"launches": len(sgl), "bytes": int(s_bytes), "us": round(s_ms * 1e3, 1),
+                                 "achieved": round(s_bytes / s_ms / 1e6, 1) if s_ms > 0 else None}},
+           "device_timer": (dict(dev_timer, frac=round(dev_timer["achieved"] / peak, 4), unit="GB/s",
+                                 how="first CTA start to last CTA end on %globaltimer, all histogram launches of the "
+                                     "last step of a short eager repeat") if dev_timer else None),
+           "note": "4 B/element x elements of every activation tensor handed to updateStats, divided by the CUDA-event "
+                   "time of the launches that bin them (events on the launching stream, external event nodes inside the "
+                   "replayed CUDA graph of the steady-state step, read for the last step of an instrumented repeat of "
+                   "the timed job). `kernel` is the launch that carries most of the bytes; all_statistics_launches adds "
+                   "the single-tensor launches of the tensors that cannot be deferred"}
+    return out
 
 
 _REAL_STDOUT = None
