@@ -68,6 +68,7 @@ PROTOTYPES = {
     "ab_stats_refresh_encodings": (_int, [_vp, _i64, _i64, _int, _int, _vp, _int, _int, _int, _int, _vp, _vp, _vp, _vp]),
     "ab_stats_init_range": (_int, [_vp, _i64, _vp, _vp]),
     "ab_stats_fold_batches": (_int, [_vp, _i64, _vp, _vp, _i64, _vp]),
+    "ab_stats_fold_log": (_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
     "ab_lg_workspace_bytes": (_i64, [_i64]),
     "ab_lg_qdq_fwd": (_int, [_vp, _vp, _i64, _i64, _i64, _int, _vp, _vp, _int, _int, _int, _int, _vp, _vp]),
     "ab_lg_qdq_bwd": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _int, _vp, _vp, _int, _int, _int, _vp, _vp, _vp, _vp]),

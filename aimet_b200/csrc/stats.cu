@@ -1302,6 +1302,43 @@ __global__ void __launch_bounds__(kBins)
     }
 }
 
+// One CTA per record, one thread per bin: replay the record's log entries (rows of kLogWords words anywhere in `log`) in
+// the given order. record_begin is a CSR index into entry_rows. Entries whose element count is 0 are skipped.
+__global__ void __launch_bounds__(kBins)
+    fold_log_kernel(ab_stats_state* states, int64_t count, const uint32_t* __restrict__ log,
+                    const int64_t* __restrict__ entry_rows, const int64_t* __restrict__ record_begin)
+{
+    const int64_t s = blockIdx.x;
+    if (s >= count)
+        return;
+    ab_stats_state* st = states + s;
+    const int b        = threadIdx.x;
+    double pdf         = 0.0;
+    int iterations     = 0;
+    bool seen          = false;
+    for (int64_t e = record_begin[s]; e < record_begin[s + 1]; ++e)
+    {
+        const uint32_t* entry = log + entry_rows[e] * kLogWords;
+        const uint64_t cnt    = (uint64_t) entry[kBins] | ((uint64_t) entry[kBins + 1] << 32);
+        if (cnt == 0)
+            continue;
+        seen              = true;
+        const double prob = (double) entry[b] / (double) cnt;
+        pdf               = __ddiv_rn(__dadd_rn(__dmul_rn(pdf, (double) iterations), prob), (double) (iterations + 1));
+        ++iterations;
+    }
+    st->pdf[b]     = pdf;
+    st->hist[0][b] = 0;
+    st->hist[1][b] = 0;
+    if (b == 0)
+    {
+        st->pending    = 0;
+        st->iterations = iterations;
+        if (seen)
+            st->stats_updated = 1;
+    }
+}
+
 template <typename K>
 int resident_grid(K kernel, int threads, size_t smem)
 {
@@ -1556,6 +1593,21 @@ int ab_stats_update_segmented(const void* in, int64_t num_segments, int64_t segm
             grid = (int) num_segments;
         k<<<grid, kSegThreads, 0, st>>>((const __nv_bfloat16*) in, num_segments, segment_len, quant_mode, states);
     }
+    AB_CUDA_CHECK(cudaGetLastError());
+    return AB_OK;
+}
+
+int ab_stats_fold_log(ab_stats_state* states, int64_t count, const uint32_t* log, const int64_t* entry_rows,
+                      const int64_t* record_begin, void* stream)
+{
+    if (count < 0 || (count > 0 && (states == nullptr || log == nullptr || entry_rows == nullptr || record_begin == nullptr)))
+    {
+        set_error("null pointer or negative count");
+        return AB_ERR_INVALID;
+    }
+    if (count == 0)
+        return AB_OK;
+    fold_log_kernel<<<(unsigned) count, kBins, 0, (cudaStream_t) stream>>>(states, count, log, entry_rows, record_begin);
     AB_CUDA_CHECK(cudaGetLastError());
     return AB_OK;
 }

@@ -2,22 +2,27 @@
 
 Net-new relative to the reference (it has no collective anywhere: SURVEY.md sections 2.3, 8e). One process per GPU;
 rank r of W runs global batches r, r+W, r+2W, ...; parameter encodings are computed redundantly (identical weights on
-every rank); activation statistics are merged with two collectives on `torch.distributed` (NCCL over NVLink on a B200
-box, gloo in the CPU tests):
+every rank); activation statistics are merged with collectives on `torch.distributed` (NCCL over NVLink on a B200 box,
+gloo in the CPU tests):
 
   tf           the running (min, max) of every quantizer: all_reduce(MIN) / all_reduce(MAX) -- exact.
   tf_enhanced  the reference's result depends on (i) the histogram range fixed by the first non-zero batch in GLOBAL
                order and (ii) a sequential running mean over batches (DlQuantization/src/math_functions.cpp:248-287).
-               (1) during its first local batch a rank only records each activation's (min, max) and keeps a copy of the
-                   tensor; one all_gather of the [Q, calls, 2] table lets every rank pick, per quantizer, the range the
-                   globally first non-zero call defines, fix it on the device (ab_stats_init_range) and only then bin
-                   the kept tensors -- nobody waits for rank 0's batch to finish;
-               (2) every batch's raw integer counts are logged on the device ([slot, Q, 514] uint32);
-               (3) one all_gather of the logs, then ONE kernel replays pdf = (pdf*k + hist/cnt)/(k+1) in global batch
-                   order for all quantizers (ab_stats_fold_batches). Integer counts make the merge exact.
+               (1) during its first local batch a rank only records each call's (min, max) and keeps a copy of the tensor;
+                   one all_gather of the [Q, calls, 2] table lets every rank pick, per quantizer, the range the globally
+                   first non-zero call defines, fix it on the device (ab_stats_init_range) and only then bin the kept
+                   tensors -- nobody waits for rank 0's batch to finish. (Quantizers that have seen only zeros so far
+                   repeat this round at the end of the next forward; ranks that have run out of batches join the rounds
+                   from their merge, so every rank issues the same sequence of collectives.)
+               (2) from then on the calls go through the deferred multi-tensor statistics of quantsim.stats_batcher in
+                   LOG mode: the raw integer counts of every call that happens land in one row of a device log -- one
+                   histogram launch per forward, no per-batch staging copies, no padding for calls that do not happen;
+               (3) one all_reduce(MAX) of the row count, ONE all_gather of the logs (their (batch, quantizer) tags ride in
+                   the same buffer), then ONE kernel replays pdf = (pdf*k + hist/cnt)/(k+1) in global batch order for
+                   all quantizers (ab_stats_fold_log). Integer counts make the merge exact.
 
-The pure-tensor helpers (`choose_first_ranges`, `global_replay_offsets`) run on any device and are what the gloo tests
-exercise; the device work goes through aimet_b200.ops.
+The pure-tensor helpers (`choose_first_ranges`, `replay_plan`, ...) run on any device and are what the gloo tests exercise;
+the device work goes through aimet_b200.ops.
 """
 from typing import List, Optional
 
@@ -67,6 +72,28 @@ def global_replay_offsets(world: int, local_batches: int, calls: int, num_quanti
     c = torch.arange(calls).view(1, 1, -1)
     slot = r * (local_batches * calls) + i * calls + c
     return (slot.reshape(-1) * (num_quantizers * LOG_WORDS)).to(torch.int64)
+
+
+def replay_plan(meta: torch.Tensor, num_records: int):
+    """meta: int [W, R, 2] -- (local batch, record) of row r of rank w's log, record -1 for padding rows. Returns
+    (entry_rows int64 [E], record_begin int64 [num_records + 1]): for every record the rows (w * R + r) of the gathered log
+    it replays, in the order a single process would have made the calls: global batch = local batch * W + w, then call
+    order inside the batch (= row order)."""
+    w, r, _ = meta.shape
+    meta = meta.to(torch.int64).cpu()
+    rank = torch.arange(w).view(w, 1).expand(w, r)
+    row = torch.arange(r).view(1, r).expand(w, r)
+    record = meta[..., 1]
+    keep = record >= 0
+    global_batch = meta[..., 0] * w + rank
+    # lexicographic (record, global batch, row): rows of one rank and batch are already in call order
+    key = (record[keep] * (int(global_batch.max()) + 2 if keep.any() else 1) + global_batch[keep]) * r + row[keep]
+    order = torch.argsort(key)
+    entry_rows = (rank[keep] * r + row[keep])[order].contiguous()
+    counts = torch.bincount(record[keep], minlength=num_records)
+    record_begin = torch.zeros(num_records + 1, dtype=torch.int64)
+    record_begin[1:] = torch.cumsum(counts, 0)
+    return entry_rows, record_begin
 
 
 def _all_gather(t: torch.Tensor, group) -> torch.Tensor:
@@ -128,158 +155,170 @@ class ShardedCalibrator:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
 
-    # -- hooks ---------------------------------------------------------------------------------------------------
-    def _install(self):
+    # -- set-up ----------------------------------------------------------------------------------------------------
+    def _attach(self, staging: bool):
+        from .quantsim.stats_batcher import LogSink, StatsBatcher
         sim = self.sim
         self.quantizers = list(sim._act_block_quantizers)   # pylint: disable=protected-access
         self.block = sim._act_block                         # pylint: disable=protected-access
         self.device = self.block.device
         warm_collectives(self.group, self.device)
         q_count = len(self.quantizers)
-        self.tfe = sim._quant_scheme == QuantScheme.post_training_tf_enhanced   # pylint: disable=protected-access
-        self.local_batch = -1
+        self.tfe = sim._quant_scheme != QuantScheme.post_training_tf   # pylint: disable=protected-access
+        self.batcher = None
+        if not self.tfe:
+            return            # tf: the ordinary per-call min/max path, merged with two all_reduces
+        self.sink = LogSink(self.device, capacity=max(4096, 64 * q_count),
+                            staging_rows=2 * q_count * self.max_calls if staging else 0)
+        self.batcher = StatsBatcher.attach(sim, sink=self.sink)
+        if self.batcher is None:
+            raise RuntimeError("sharded tf_enhanced calibration needs the activation statistics on a CUDA device")
+        self.batcher.collect = self._collect
+        self.batcher.range_exchange = self._forward_end
+        self.range_block = StateArena.for_device(self.device).allocate(q_count * self.max_calls)
         self.calls = [0] * q_count
-        self.deferred: List[List[torch.Tensor]] = [[] for _ in range(q_count)]
-        self.first_block = StateArena.for_device(self.device).allocate(q_count * self.max_calls) if self.tfe else None
-        self.log = None
-        self.log_slots = 0
-        # every call of the current batch logs into a fixed staging area (constant addresses, so the step can live in a
-        # CUDA graph); `_end_batch` files it under the batch's slot
-        self.stage = torch.zeros((self.max_calls, q_count, LOG_WORDS), dtype=torch.int32, device=self.device) \
-            if self.tfe else None
-        self.staged_batch = -1
-        self.fixed = [False] * q_count
-        self.manual_batches = False
-        self.ranges_fixed = not self.tfe
-        self._pre = sim.model.register_forward_pre_hook(lambda m, a: self._begin_batch())
-        for i, q in enumerate(self.quantizers):
-            q._calib_hook = (lambda t, i=i: self._on_update(i, t))   # pylint: disable=protected-access
+        self.held = []                      # (record, call, private copy) of this forward's calls on records without a range
+        self.called_anywhere = [False] * q_count
+        self.need_round = True              # round 0 always happens; later ones while called records have no range yet
+        self.rounds = 0
+        self.local_fallback = False
 
-    def _uninstall(self):
-        self._pre.remove()
-        for q in self.quantizers:
-            q._calib_hook = None   # pylint: disable=protected-access
-        self.deferred = []
-        self.first_block = None
+    def _detach(self):
+        if self.batcher is not None:
+            self.batcher.detach()
+            self.batcher = None
+        self.held = []
+        self.range_block = None
 
-    def _begin_batch(self):
-        if self.manual_batches:
+    # -- exchange 1: ranges ----------------------------------------------------------------------------------------
+    def _collect(self, i: int, tensor: torch.Tensor):
+        """A call on a record whose range is not known yet: note its (min, max), keep a private copy for binning later."""
+        if not self.need_round:
+            # first call ever on this record, after the range rounds are over (the forward's control flow differs between
+            # batches): no collective can be started unilaterally -- the range is fixed from this rank's data
+            self.local_fallback = True
+            self.batcher.update_now(i, tensor)
+            self.batcher.fixed[i] = True
             return
-        self._end_batch()
-        if self.local_batch == 0 and not self.ranges_fixed:
-            self._fix_ranges()
-        self.local_batch += 1
-        self.calls = [0] * len(self.quantizers)
-        if self.tfe and self.ranges_fixed:
-            self.stage.zero_()     # the statistics launches ADD their counts to their log entry (one memset per batch)
-
-    def _end_batch(self):
-        """File the staged log of the batch that just ran under its slot."""
-        if self.tfe and self.ranges_fixed and self.local_batch >= 0 and self.staged_batch != self.local_batch:
-            first = self.local_batch * self.max_calls
-            self._ensure_log(first + self.max_calls)
-            self.log[first:first + self.max_calls].copy_(self.stage)
-            self.staged_batch = self.local_batch
-
-    def _ensure_log(self, slots):
-        if self.log is None or slots > self.log_slots:
-            new_slots = max(slots, 2 * self.log_slots, 8 * self.max_calls)
-            new = torch.zeros((new_slots, len(self.quantizers), LOG_WORDS), dtype=torch.int32, device=self.device)
-            if self.log is not None:
-                new[:self.log_slots] = self.log
-            self.log, self.log_slots = new, new_slots
-
-    def _on_update(self, i: int, tensor: torch.Tensor):
-        q = self.quantizers[i]
-        op = q._cppOp[0]   # pylint: disable=protected-access
         call = self.calls[i]
         self.calls[i] += 1
         if call >= self.max_calls:
             raise RuntimeError(f"a quantizer was updated more than max_calls_per_batch={self.max_calls} times in one "
                                "forward pass; raise the limit")
-        if tensor.dtype not in (torch.float32, torch.bfloat16):
-            tensor = tensor.to(torch.float32)
-        op._is_encoding_valid = True   # pylint: disable=protected-access
-        q._stats_dirty = True          # pylint: disable=protected-access
-        if not self.tfe:
-            ops.stats_update_impl(tensor, self.block.arena, self.block.first + i, ops.QUANTIZATION_TF, None, 0)
-            return
-        if not self.ranges_fixed:
-            # first local batch: record (min, max) of this call, keep the tensor for binning once the range is known
-            ops.stats_update_impl(tensor, self.first_block.arena, self.first_block.first + i * self.max_calls + call,
-                                  ops.QUANTIZATION_TF, None, 0)
-            self.deferred[i].append(tensor.detach().clone())
-            return
-        ops.stats_update_impl(tensor, self.block.arena, self.block.first + i, ops.QUANTIZATION_TF_ENHANCED, self.stage,
-                              call * len(self.quantizers) + i, ops.STATS_RANGE_FIXED if self.fixed[i] else 0)
+        ops.stats_update_impl(tensor, self.range_block.arena, self.range_block.first + i * self.max_calls + call,
+                              ops.QUANTIZATION_TF, None, 0)
+        self.held.append((i, call, tensor.detach().clone()))
 
-    # -- exchange 1: ranges --------------------------------------------------------------------------------------
-    def _fix_ranges(self):
-        q_count = len(self.quantizers)
-        rec = self.first_block.bytes_view().view(torch.float64).view(q_count * self.max_calls, -1)
+    def _forward_end(self, batcher):
+        if self.need_round:
+            self._range_round(done=False)
+
+    def _range_round(self, done: bool):
+        """One round of exchange 1 (identical on every rank): gather the (min, max) tables of the forward that just ended,
+        fix the ranges their globally first non-zero calls define, bin the kept tensors."""
+        q_count, c = len(self.quantizers), self.max_calls
+        rec = self.range_block.bytes_view().view(torch.float64).view(q_count * c, -1)
         base = field_index("run_min", 8)          # run_min, run_max are adjacent doubles (include/aimet_b200.h)
-        table = rec[:, base:base + 2].to(torch.float32).view(q_count, self.max_calls, 2)
         # an un-updated record holds (+DBL_MAX, -DBL_MAX) -> (+inf, -inf) in float32: "call did not happen"
-        gathered = _all_gather(table, self.group) if self.world > 1 else table.unsqueeze(0)
-        chosen = choose_first_ranges(gathered)
-        self.first_positions = first_call_positions(gathered)
+        table = rec[:, base:base + 2].to(torch.float32).reshape(-1)
+        payload = torch.cat([table, torch.full((1,), 1.0 if done else 0.0, device=self.device)])
+        gathered = _all_gather(payload, self.group) if self.world > 1 else payload.unsqueeze(0)
+        tables = gathered[:, :-1].reshape(self.world, q_count, c, 2)
+        chosen = choose_first_ranges(tables)
         ops.stats_init_range_impl(self.block.arena, self.block.first, q_count, chosen)
-        self.ranges_fixed = True
-        self.fixed = ((chosen[:, 0] != 0) | (chosen[:, 1] != 0)).tolist()     # the one host read-back of the job
-        # now bin the tensors kept from local batch 0 (into the staging log, filed by _end_batch)
-        self.stage.zero_()
-        for i, kept in enumerate(self.deferred):
-            for call, tensor in enumerate(kept):
-                ops.stats_update_impl(tensor, self.block.arena, self.block.first + i, ops.QUANTIZATION_TF_ENHANCED,
-                                      self.stage, call * q_count + i, ops.STATS_RANGE_FIXED if self.fixed[i] else 0)
-        self.deferred = [[] for _ in range(q_count)]
-        self._end_batch()
+        happened = torch.isfinite(tables[..., 0]).any(dim=2).any(dim=0)                        # [Q] called on some rank
+        host = torch.cat([((chosen[:, 0] != 0) | (chosen[:, 1] != 0)).to(torch.float32), happened.to(torch.float32),
+                          first_call_positions(tables).to(torch.float32), gathered[:, -1]]).tolist()   # one read-back
+        newly, called = host[:q_count], host[q_count:2 * q_count]
+        first_pos, all_done = host[2 * q_count:3 * q_count], all(f != 0 for f in host[3 * q_count:])
+        batcher = self.batcher
+        for i in range(q_count):
+            if newly[i] and not batcher.fixed[i]:
+                batcher.fixed[i] = True
+                batcher.native[i]._range_fixed = True   # pylint: disable=protected-access
+            self.called_anywhere[i] = self.called_anywhere[i] or bool(called[i])
+        for i, call, kept in self.held:
+            # calls that precede the chosen first call in global order saw only zeros: the reference skips them
+            if batcher.fixed[i] and self.rank * c + call >= first_pos[i]:
+                if kept.data_ptr() % 16 == 0 and kept.numel() * kept.element_size() >= 16:
+                    batcher.enqueue(i, kept, owned=True)
+                else:
+                    batcher.update_now(i, kept)
+        self.held = []
+        self.calls = [0] * q_count
+        self.rounds += 1
+        waiting = any(self.called_anywhere[i] and not batcher.fixed[i] for i in range(q_count))
+        self.need_round = waiting and not all_done
+        if self.need_round:
+            self.range_block.reset()
 
     # -- exchange 2: statistics ------------------------------------------------------------------------------------
-    def _merge(self):
+    def _merge_tf(self):
         q_count = len(self.quantizers)
-        if not self.tfe:
-            rec = self.block.bytes_view().view(torch.float64).view(q_count, -1)
-            base = field_index("run_min", 8)
-            mins, maxs = rec[:, base].clone(), rec[:, base + 1].clone()
-            updated = torch.tensor([float(q._cppOp[0]._is_encoding_valid) for q in self.quantizers],   # pylint: disable=protected-access
-                                   device=self.device, dtype=torch.float64)
-            if self.world > 1:
-                _all_reduce(mins, dist.ReduceOp.MIN, self.group)
-                _all_reduce(maxs, dist.ReduceOp.MAX, self.group)
-                _all_reduce(updated, dist.ReduceOp.MAX, self.group)
-            rec[:, base] = mins
-            rec[:, base + 1] = maxs
-            flags = self.block.bytes_view().view(torch.int32).view(q_count, -1)
-            flags[:, field_index("stats_updated", 4)] = updated.to(torch.int32)
-            for q, u in zip(self.quantizers, updated.tolist()):
-                q._cppOp[0]._is_encoding_valid = bool(u)   # pylint: disable=protected-access
-            return
-        if not self.ranges_fixed:          # the callback ran a single batch (or none)
-            if self.local_batch >= 0:
-                self._fix_ranges()
-        self._end_batch()
-        local_batches = torch.tensor([self.local_batch + 1], device=self.device, dtype=torch.int64)
+        rec = self.block.bytes_view().view(torch.float64).view(q_count, -1)
+        base = field_index("run_min", 8)
+        mins, maxs = rec[:, base].clone(), rec[:, base + 1].clone()
+        updated = torch.tensor([float(q._cppOp[0]._is_encoding_valid) for q in self.quantizers],   # pylint: disable=protected-access
+                               device=self.device, dtype=torch.float64)
         if self.world > 1:
-            _all_reduce(local_batches, dist.ReduceOp.MAX, self.group)
-        n_local = int(local_batches.item())
-        if n_local == 0:
+            _all_reduce(mins, dist.ReduceOp.MIN, self.group)
+            _all_reduce(maxs, dist.ReduceOp.MAX, self.group)
+            _all_reduce(updated, dist.ReduceOp.MAX, self.group)
+        rec[:, base] = mins
+        rec[:, base + 1] = maxs
+        flags = self.block.bytes_view().view(torch.int32).view(q_count, -1)
+        flags[:, field_index("stats_updated", 4)] = updated.to(torch.int32)
+        for q, u in zip(self.quantizers, updated.tolist()):
+            q._cppOp[0]._is_encoding_valid = bool(u)   # pylint: disable=protected-access
+
+    def _merge(self):
+        if not self.tfe:
+            self._merge_tf()
             return
-        slots = n_local * self.max_calls
-        self._ensure_log(slots)
-        local_log = self.log[:slots].contiguous()
-        # the reference SKIPS all-zero batches seen before the range was fixed: entries that precede the chosen first
-        # call were binned here with a range they would not have had yet -> void them (count 0 == skipped in the replay)
-        if hasattr(self, "first_positions"):
-            pos = self.rank * self.max_calls + torch.arange(self.max_calls, device=self.device)      # batch 0 of this rank
-            void = pos[:, None] < self.first_positions[None, :].to(self.device)                        # [calls, Q]
-            local_log[:self.max_calls][void] = 0
-        gathered = _all_gather(local_log, self.group) if self.world > 1 else local_log.unsqueeze(0)
-        offsets = global_replay_offsets(self.world, n_local, self.max_calls, q_count).to(self.device)
-        ops.stats_fold_batches_impl(self.block.arena, self.block.first, q_count, gathered, offsets)
-        counts = gathered.view(self.world * slots, q_count, LOG_WORDS)[:, :, 512:].to(torch.int64).sum(dim=(0, 2))
-        for q, n in zip(self.quantizers, counts.tolist()):
-            q._cppOp[0]._is_encoding_valid = q._cppOp[0]._is_encoding_valid or n > 0   # pylint: disable=protected-access
+        q_count = len(self.quantizers)
+        if self.batcher.forward < 0:
+            # a rank that was dealt no batch: its wrappers never ran, so nothing has derived its parameter encodings
+            from .quantsim.qc_quantize_op import StaticGridQuantWrapper
+            with torch.no_grad():
+                for _, w in self.sim.quant_wrappers():
+                    if isinstance(w, StaticGridQuantWrapper):
+                        w.ensure_param_encodings()
+        # ranks that are out of batches join the range rounds the others may still run (same collective sequence everywhere)
+        while self.need_round:
+            self._range_round(done=True)
+        self.batcher.flush()
+        sink = self.sink
+        used = torch.tensor([sink.used], device=self.device, dtype=torch.int64)
+        if self.world > 1:
+            _all_reduce(used, dist.ReduceOp.MAX, self.group)
+        rows = int(used.item())
+        if rows == 0:
+            return
+        # one buffer per rank: the log rows, then their (local batch, record) tags and this rank's "was called" flags
+        tag_words = 2 * rows + q_count
+        tag_rows = (tag_words + LOG_WORDS - 1) // LOG_WORDS
+        payload = torch.zeros((rows + tag_rows, LOG_WORDS), dtype=torch.int32, device=self.device)
+        payload[:sink.used] = sink.rows[:sink.used]
+        tags = torch.full((rows, 2), -1, dtype=torch.int32)
+        if sink.used:
+            tags[:sink.used] = torch.tensor(sink.meta, dtype=torch.int32).view(-1, 2)
+        called = torch.tensor([int(q._cppOp[0]._is_encoding_valid) for q in self.quantizers], dtype=torch.int32)   # pylint: disable=protected-access
+        payload[rows:].view(-1)[:tag_words] = torch.cat([tags.view(-1), called]).to(self.device, non_blocking=True)
+        gathered = _all_gather(payload, self.group) if self.world > 1 else payload.unsqueeze(0)
+        tail = gathered[:, rows:].reshape(self.world, -1)[:, :tag_words].cpu()                 # the read-back of the merge
+        meta = tail[:, :2 * rows].reshape(self.world, rows, 2)
+        called_anywhere = tail[:, 2 * rows:].max(dim=0).values.tolist()
+        entry_rows, record_begin = replay_plan(meta, q_count)
+        # rows of rank w sit at w * (rows + tag_rows) + r in the gathered buffer
+        stride = rows + tag_rows
+        entry_rows = (entry_rows // rows) * stride + entry_rows % rows
+        ops.stats_fold_log_impl(self.block.arena, self.block.first, q_count, gathered.view(-1, LOG_WORDS),
+                                entry_rows.to(self.device), record_begin.to(self.device))
+        flags = self.block.bytes_view().view(torch.int32).view(q_count, -1)
+        flags[:, field_index("stats_updated", 4)] = torch.tensor(called_anywhere, dtype=torch.int32).to(self.device)
+        for q, u in zip(self.quantizers, called_anywhere):
+            q._cppOp[0]._is_encoding_valid = bool(u)   # pylint: disable=protected-access
+            q._stats_dirty = True                      # pylint: disable=protected-access
 
     # -- public ----------------------------------------------------------------------------------------------------
     def compute_encodings_for_batches(self, batches, cuda_graph: bool = True):
@@ -290,30 +329,15 @@ class ShardedCalibrator:
         QuantizationSimModel.prepare_sim_for_compute_encodings(sim)
         if not getattr(sim, "_act_block_quantizers", None):
             raise RuntimeError("sharded calibration needs the model on a CUDA device")
-        self._install()
-        self.manual_batches = True
+        self._attach(staging=cuda_graph)
         try:
-            def start_batch():
-                self.local_batch += 1
-                self.calls = [0] * len(self.quantizers)
-                if self.tfe and self.ranges_fixed:
-                    self.stage.zero_()          # before the forward, eager or replayed: the launches add to their entries
-
-            def after_each(n):
-                if n == 0:
-                    if not self.ranges_fixed:
-                        self._fix_ranges()      # exchange 1, then bins the kept tensors of batch 0 and files them
-                else:
-                    self._end_batch()
-                start_batch()                   # the next forward (eager or replayed) belongs to the next batch
-
+            after_each = (lambda n: self.sink.commit(n)) if (self.tfe and cuda_graph) else None
             with in_eval_mode(sim.model), torch.no_grad():
-                start_batch()
-                n = run_batches(sim.model, batches, cuda_graph, after_each=after_each)
-                self.local_batch = n - 1        # after_each advanced one past the last batch
+                run_batches(sim.model, batches, cuda_graph, after_each=after_each,
+                            after_first=None if self.tfe else sim._learn_fixed_ranges)   # pylint: disable=protected-access
             self._merge()
         finally:
-            self._uninstall()
+            self._detach()
         QuantizationSimModel.compute_layer_encodings_for_sim(sim)
 
     def compute_encodings(self, forward_pass_callback, forward_pass_callback_args):
@@ -322,7 +346,7 @@ class ShardedCalibrator:
         QuantizationSimModel.prepare_sim_for_compute_encodings(sim)
         if not getattr(sim, "_act_block_quantizers", None):
             raise RuntimeError("sharded calibration needs the model on a CUDA device")
-        self._install()
+        self._attach(staging=False)
         prefetch = _ParamExportPrefetch(sim)     # parameter encodings are rank-local and final after the first forward
         try:
             with in_eval_mode(sim.model), torch.no_grad():
@@ -330,5 +354,5 @@ class ShardedCalibrator:
             self._merge()
         finally:
             prefetch.close()
-            self._uninstall()
+            self._detach()
         QuantizationSimModel.compute_layer_encodings_for_sim(sim)

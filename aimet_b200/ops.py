@@ -450,6 +450,21 @@ def stats_fold_batches_impl(states, first, count, batch_log, batch_offsets):
     LAUNCHES["fold"] += 1
 
 
+def stats_fold_log_impl(states, first, count, log, entry_rows, record_begin):
+    """Rebuild `count` records from per-call log rows: record s replays rows entry_rows[record_begin[s]:record_begin[s+1]]
+    of `log` in that order (ab_stats_fold_log)."""
+    _require_cuda(states, log, entry_rows, record_begin)
+    for t in (entry_rows, record_begin):
+        if t.dtype != torch.int64 or not t.is_contiguous():
+            raise ValueError("entry_rows / record_begin must be contiguous int64 CUDA tensors")
+    if record_begin.numel() != count + 1 or not log.is_contiguous():
+        raise ValueError("record_begin must have count + 1 entries and the log must be contiguous")
+    with _on_device(states):
+        _lib.check(_L.ab_stats_fold_log(_state_ptr(states, first), int(count), log.data_ptr(), entry_rows.data_ptr(),
+                                        record_begin.data_ptr(), _stream(states)))
+    LAUNCHES["fold"] += 1
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # range learning (learned grid): fused forward / backward of the reference's QuantizeDequantizeFunc
 # ---------------------------------------------------------------------------------------------------------------------

@@ -319,6 +319,18 @@ class StaticGridQuantWrapper(EncodingImportMixin, nn.Module):
                 param.data = q.quantize_dequantize(param.data, round_mode)
         return shadow_params
 
+    def ensure_param_encodings(self):
+        """Derive the encodings of this wrapper's parameters without running the wrapped module: what the first forward of a
+        calibration job does on its way (reference :753-798). Sharded calibration needs it on a rank that was dealt no
+        batch (the weights, hence these encodings, are the same on every rank)."""
+        for name, param in self.get_named_parameters():
+            q = self.param_quantizers[name]
+            if q.enabled and q.bitwidth != 32 and not q._has_encoding():   # pylint: disable=protected-access
+                if not q.refresh_encoding_from(param.data):
+                    q.reset_encoding_stats()
+                    q.update_encoding_stats(param.data)
+                    q.compute_encoding()
+
     def compute_encoding(self):
         """reference :811-826"""
         for q in self.input_quantizers:

@@ -35,24 +35,59 @@ _INITIALIZED_WORD = field_index("initialized", 4)
 
 class LogSink:
     """Where the raw counts of every call go when the job keeps a per-call log instead of folding locally (multi-GPU exact
-    merge, aimet_b200.distributed): rows of LOG_WORDS int32 words, handed out in call order."""
+    merge, aimet_b200.distributed): rows of LOG_WORDS int32 words, handed out in call order; `meta[k]` = (local batch,
+    record index) of row k. With `staging_rows`, rows are first handed out from a fixed staging area -- constant
+    addresses, so the step can live in a CUDA graph -- and `commit` files them under the batch that just ran."""
 
-    def __init__(self, device, capacity=1024):
+    def __init__(self, device, capacity=2048, staging_rows=0):
         self.device = device
         self.rows = torch.zeros((capacity, ops.LOG_WORDS), dtype=torch.int32, device=device)
         self.used = 0
-        self.meta = []            # (local_batch, record index) of row k
+        self.meta = []
+        self.staging = torch.zeros((staging_rows, ops.LOG_WORDS), dtype=torch.int32, device=device) \
+            if staging_rows else None
+        self.staged = 0
+        self.staged_records = []
+        self.last_step_records = []
 
-    def take(self, n, metas):
+    def _reserve(self, n):
         if self.used + n > self.rows.shape[0]:
             grown = torch.zeros((max(2 * self.rows.shape[0], self.used + n), ops.LOG_WORDS), dtype=torch.int32,
                                 device=self.device)
             grown[:self.used] = self.rows[:self.used]
             self.rows = grown
+
+    def take(self, n, metas):
+        """-> int32 view [n, LOG_WORDS] of zeroed rows for the next n calls."""
+        if self.staging is not None:
+            if self.staged + n > self.staging.shape[0]:
+                raise RuntimeError("more statistics calls in one forward pass than the staging log holds")
+            first = self.staged
+            self.staged += n
+            self.staged_records.extend(r for _, r in metas)
+            return self.staging[first:first + n]
+        self._reserve(n)
         first = self.used
         self.used += n
         self.meta.extend(metas)
-        return self.rows[first:first + n], first
+        return self.rows[first:first + n]
+
+    def commit(self, local_batch):
+        """Staging mode, after every forward (eager or replayed): file the staged rows under `local_batch`. A replayed
+        forward ran no Python, so it staged the same calls as the captured one."""
+        if self.staging is None:
+            return
+        if self.staged:
+            self.last_step_records, self.staged_records = self.staged_records, []
+        n = len(self.last_step_records)
+        self.staged = 0
+        if n == 0:
+            return
+        self._reserve(n)
+        self.rows[self.used:self.used + n].copy_(self.staging[:n])
+        self.staging[:n].zero_()
+        self.meta.extend((local_batch, r) for r in self.last_step_records)
+        self.used += n
 
 
 class StatsBatcher:
@@ -75,15 +110,20 @@ class StatsBatcher:
         self.scratch = None if sink is not None else \
             torch.zeros((ops.MULTI_MAX_SEGMENTS, ops.LOG_WORDS), dtype=torch.int32, device=self.block.device)
         self._handles = []
-        self.on_probe_end = None          # optional callable(batcher) run once, when the first forward has ended
+        # sharded calibration (aimet_b200.distributed): histogram ranges come from a global exchange, not from this rank's
+        # first batch. `collect(i, tensor)` takes the calls on records whose range is not known yet; `range_exchange(self)`
+        # runs at the end of every forward, before the flush: it may fix ranges (`fixed`) and enqueue tensors it kept.
+        self.collect = None
+        self.range_exchange = None
 
     # ---- wiring ------------------------------------------------------------------------------------------------
     @classmethod
     def attach(cls, sim, sink=None):
         """A batcher hooked into `sim` for one calibration job, or None where deferral does not apply (no CUDA records,
-        a scheme that keeps no histogram, switched off)."""
+        a scheme that keeps no histogram, switched off). With a `sink` (sharded calibration) the batcher is the logging
+        mechanism itself and is attached even when deferral is switched off: every call is then issued immediately."""
         quantizers = getattr(sim, "_act_block_quantizers", None)
-        if not ENABLED or not quantizers or getattr(sim, "_act_block", None) is None:
+        if (not ENABLED and sink is None) or not quantizers or getattr(sim, "_act_block", None) is None:
             return None
         if not all(ops.keeps_histogram(q._cppOp[0]._code) for q in quantizers):   # pylint: disable=protected-access
             return None
@@ -110,6 +150,8 @@ class StatsBatcher:
 
     def _end_forward(self):
         self.in_forward = False
+        if self.range_exchange is not None:
+            self.range_exchange(self)
         if self.probing and self.forward == 0:
             self._finish_probe()
         self.flush()
@@ -123,15 +165,14 @@ class StatsBatcher:
             if t._version != version:   # pylint: disable=protected-access
                 unstable[i] = True
         self.probe = []
-        words = self.block.bytes_view().view(torch.int32).view(n, -1)
-        flags = words[:, _INITIALIZED_WORD].cpu().tolist()      # the one host read-back of the job
+        if self.range_exchange is None:
+            words = self.block.bytes_view().view(torch.int32).view(n, -1)
+            flags = words[:, _INITIALIZED_WORD].cpu().tolist()      # the one host read-back of the job
+            self.fixed = [bool(f) for f in flags]
         for i in range(n):
-            self.fixed[i] = bool(flags[i])
             self.native[i]._range_fixed = self.fixed[i]          # pylint: disable=protected-access
-            self.defer[i] = self.fixed[i] and called[i] and not unstable[i]
+            self.defer[i] = ENABLED and self.fixed[i] and called[i] and not unstable[i]
         self.probing = False
-        if self.on_probe_end is not None:
-            self.on_probe_end(self)
 
     # ---- the call ------------------------------------------------------------------------------------------------
     def _on_update(self, i, tensor):
@@ -145,23 +186,33 @@ class StatsBatcher:
         op._updates += 1                  # pylint: disable=protected-access
         q._stats_dirty = True             # pylint: disable=protected-access
         es = tensor.element_size()
-        if (self.defer[i] or (owned and self.fixed[i])) and tensor.data_ptr() % 16 == 0 and tensor.numel() * es >= 16:
-            self.pending.append((tensor, i, tensor._version, owned))   # pylint: disable=protected-access
-            self.pending_records.add(i)
-            self.pending_bytes += tensor.numel() * es
-            if len(self.pending) >= ops.MULTI_MAX_SEGMENTS or self.pending_bytes >= FLUSH_BYTES:
-                self.flush()
+        if self.collect is not None and not self.fixed[i]:
+            if self.probing and not owned:
+                self.probe.append((i, tensor, tensor._version))   # pylint: disable=protected-access
+            self.collect(i, tensor)
             return
-        if i in self.pending_records:
-            self.flush()                  # calls on one record are folded in call order
-        row, slot = None, 0
-        if self.sink is not None:
-            row, slot = self.sink.take(1, [(self.forward, i)])
-            slot = 0
-        ops.stats_update_impl(tensor, self.block.arena, self.block.first + i, ops.QUANTIZATION_TF_ENHANCED, row, slot,
-                              ops.STATS_RANGE_FIXED if self.fixed[i] else 0)
+        if (self.defer[i] or (owned and self.fixed[i])) and tensor.data_ptr() % 16 == 0 and tensor.numel() * es >= 16:
+            self.enqueue(i, tensor, owned)
+            return
+        self.update_now(i, tensor)        # (flushes first when the record has queued calls: call order is fold order)
         if self.probing and not owned:
             self.probe.append((i, tensor, tensor._version))   # pylint: disable=protected-access
+
+    def enqueue(self, i, tensor, owned):
+        """Queue one call for the next flush. `owned`: the tensor is a private copy nobody else can write to."""
+        self.pending.append((tensor, i, tensor._version, owned))   # pylint: disable=protected-access
+        self.pending_records.add(i)
+        self.pending_bytes += tensor.numel() * tensor.element_size()
+        if len(self.pending) >= ops.MULTI_MAX_SEGMENTS or self.pending_bytes >= FLUSH_BYTES:
+            self.flush()
+
+    def update_now(self, i, tensor):
+        """One call issued immediately through the single-tensor kernels (a range must be fixed in sharded mode)."""
+        if i in self.pending_records:
+            self.flush()
+        row = self.sink.take(1, [(self.forward, i)]) if self.sink is not None else None
+        ops.stats_update_impl(tensor, self.block.arena, self.block.first + i, ops.QUANTIZATION_TF_ENHANCED, row, 0,
+                              ops.STATS_RANGE_FIXED if self.fixed[i] else 0)
 
     def flush(self):
         """Issue every queued call: one histogram launch + one fold launch per run of up to 128 same-dtype tensors."""
@@ -186,7 +237,7 @@ class StatsBatcher:
             tensors = [c[0] for c in chunk]
             records = [c[1] for c in chunk]
             if self.sink is not None:
-                rows, _ = self.sink.take(len(chunk), [(self.forward, r) for r in records])
+                rows = self.sink.take(len(chunk), [(self.forward, r) for r in records])
                 ops.stats_update_multi_impl(tensors, records, self.block.arena, self.block.first, rows, log_only=True)
             else:
                 ops.stats_update_multi_impl(tensors, records, self.block.arena, self.block.first, self.scratch)

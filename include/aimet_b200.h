@@ -351,6 +351,15 @@ int ab_stats_init_range(ab_stats_state* states, int64_t count, const float* minm
 int ab_stats_fold_batches(ab_stats_state* states, int64_t count, const uint32_t* batch_log,
                           const int64_t* batch_offsets, int64_t num_batches, void* stream);
 
+/* The same replay over a log of per-CALL entries (what ab_stats_update with a log entry and ab_stats_update_multi with
+ * AB_STATS_MULTI_LOG_ONLY write: AB_PDF_SIZE counts + the element count), each record replaying its own entries in the
+ * order given:
+ * log          : DEVICE uint32 buffer of rows of AB_PDF_SIZE + 2 words (e.g. the all-gathered logs of all ranks)
+ * entry_rows   : DEVICE int64[], row numbers inside `log`, grouped by record, each group in replay order
+ * record_begin : DEVICE int64[count + 1], CSR index: record s replays entry_rows[record_begin[s] .. record_begin[s+1]) */
+int ab_stats_fold_log(ab_stats_state* states, int64_t count, const uint32_t* log, const int64_t* entry_rows,
+                      const int64_t* record_begin, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -130,3 +130,107 @@ def test_global_replay_offsets_order():
     off = global_replay_offsets(world=2, local_batches=2, calls=2, num_quantizers=1) // 514
     # slots are [rank][local batch][call]; global order is batch 0 (rank 0), batch 1 (rank 1), batch 2 (rank 0), ...
     assert off.tolist() == [0, 1, 4, 5, 2, 3, 6, 7]
+
+
+def test_replay_plan_orders_calls_as_a_single_process_would():
+    """Per-call log rows tagged (local batch, record): rank w's local batch i is global batch i * W + w; inside a batch the
+    calls of a record keep their row order; padding rows (record -1) are ignored."""
+    from aimet_b200.distributed import replay_plan
+    # W = 2, R = 5 rows per rank. rank 0: batch 0 -> records 0, 1, 0 ; batch 1 -> record 0 ; one padding row
+    #                              rank 1: batch 0 -> records 1, 0    ; batch 1 -> records 0, 1, 1
+    meta = torch.tensor([[[0, 0], [0, 1], [0, 0], [1, 0], [-1, -1]],
+                         [[0, 1], [0, 0], [1, 0], [1, 1], [1, 1]]], dtype=torch.int32)
+    rows, begin = replay_plan(meta, num_records=3)
+    assert begin.tolist() == [0, 5, 9, 9]                       # record 2 never called
+    # record 0: global batch 0 (rank 0 rows 0, 2), batch 1 (rank 1 row 1 -> 5 + 1), batch 2 (rank 0 row 3), batch 3 (rank 1 row 2)
+    assert rows[:5].tolist() == [0, 2, 6, 3, 7]
+    # record 1: batch 0 (rank 0 row 1), batch 1 (rank 1 row 0), batch 3 (rank 1 rows 3, 4)
+    assert rows[5:9].tolist() == [1, 5, 8, 9]
+
+
+def plan_worker(rank, port, result_queue):
+    """Two ranks log per-call rows (different numbers of calls per batch for quantizer 0), exchange them with ONE gather of
+    rows + tags as ShardedCalibrator._merge does, and replay on the host through replay_plan."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    try:
+        from aimet_b200.distributed import _all_gather, choose_first_ranges, first_call_positions, replay_plan
+        from oracle.bindings import Oracle, OracleTfe
+        o = Oracle()
+        table = torch.full((Q, CALLS, 2), float("inf"))
+        table[..., 1] = float("-inf")
+        for q in range(Q):
+            for c in range(calls_of(q)):
+                mn, mx = o.get_min_max(make_batch(rank, q, c))
+                table[q, c, 0], table[q, c, 1] = mn, mx
+        gathered = _all_gather(table, None)
+        chosen = choose_first_ranges(gathered)
+        first_pos = first_call_positions(gathered).tolist()
+        states = []
+        for q in range(Q):
+            s = OracleTfe(o)
+            s.init_pdf(float(chosen[q, 0]), float(chosen[q, 1]))
+            states.append(s)
+        rows, tags = [], []
+        for i in range(N_LOCAL):
+            b = i * WORLD + rank
+            for q in range(Q):
+                bucket, offset = states[q].bucket_params()
+                for c in range(calls_of(q)):
+                    if i == 0 and rank * CALLS + c < first_pos[q]:
+                        continue                       # all-zero call before the range existed: never logged
+                    x = make_batch(b, q, c)
+                    row = torch.zeros(LOG_WORDS, dtype=torch.int32)
+                    row[:512] = torch.from_numpy(o.histogram(x, bucket, offset).astype(np.int32))
+                    row[512] = x.size
+                    rows.append(row)
+                    tags.append((i, q))
+        used = torch.tensor([len(rows)])
+        dist.all_reduce(used, op=dist.ReduceOp.MAX)
+        r_max = int(used)
+        payload = torch.zeros((r_max + 1, LOG_WORDS), dtype=torch.int32)
+        payload[:len(rows)] = torch.stack(rows)
+        t = torch.full((r_max, 2), -1, dtype=torch.int32)
+        t[:len(tags)] = torch.tensor(tags, dtype=torch.int32)
+        payload[r_max, :2 * r_max] = t.view(-1)
+        everything = _all_gather(payload, None)
+        meta = everything[:, r_max, :2 * r_max].reshape(WORLD, r_max, 2)
+        entry_rows, begin = replay_plan(meta, Q)
+        flat = everything.reshape(-1, LOG_WORDS).numpy().view(np.uint32)
+        merged = []
+        for q in range(Q):
+            s = OracleTfe(o)
+            s.init_pdf(float(chosen[q, 0]), float(chosen[q, 1]))
+            for e in entry_rows[begin[q]:begin[q + 1]].tolist():
+                w, r = divmod(e, r_max)
+                entry = flat[w * (r_max + 1) + r]
+                s.fold_histogram(entry[:512].copy(), int(entry[512]))
+            merged.append((s.histogram()[1].tolist(), s.compute(8), s.s.iterations))
+        if rank == 0:
+            result_queue.put(merged)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_per_call_log_merge_equals_sequential_run(oracle):
+    from oracle.bindings import OracleTfe
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=plan_worker, args=(r, port, queue)) for r in range(WORLD)]
+    for p in procs:
+        p.start()
+    merged = queue.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for q in range(Q):
+        s = OracleTfe(oracle)
+        for b in range(WORLD * N_LOCAL):
+            for c in range(calls_of(q)):
+                s.update(make_batch(b, q, c))
+        pdf, enc, iters = merged[q]
+        assert iters == s.s.iterations, q
+        assert np.array_equal(np.array(pdf), s.histogram()[1]), q
+        assert tuple(enc) == s.compute(8), q
