@@ -27,7 +27,13 @@ class StatsSegment(C.Structure):
     _fields_ = [("data", C.c_void_p), ("count", C.c_int64), ("state_index", C.c_int32), ("reserved", C.c_int32)]
 
 
+class RefreshItem(C.Structure):
+    """ab_refresh_item: one parameter tensor of a multi-tensor encoding refresh."""
+    _fields_ = [("data", C.c_void_p), ("num_segments", C.c_int64), ("segment_len", C.c_int64), ("first_record", C.c_int64)]
+
+
 PDF_SIZE = 512
+REFRESH_MULTI_MAX_ITEMS = 96
 STATS_MULTI_MAX_SEGMENTS = 128
 STATS_MULTI_LOG_ONLY = 1
 AB_OK, AB_ERR_INVALID, AB_ERR_CUDA, AB_ERR_UNSUPPORTED = 0, -1, -2, -3
@@ -66,6 +72,8 @@ PROTOTYPES = {
     "ab_compute_encodings_percentile": (_int, [_vp, _i64, _flt, _int, _int, _int, _int, _vp, _vp, _vp]),
     "ab_debug_hist_timer": (_i64, [_vp, _i64]),
     "ab_stats_refresh_encodings": (_int, [_vp, _i64, _i64, _int, _int, _vp, _int, _int, _int, _int, _vp, _vp, _vp, _vp]),
+    "ab_stats_refresh_encodings_multi": (_int, [C.POINTER(RefreshItem), _int, _int, _int, _vp, _int, _int, _int, _int, _vp, _vp,
+                                                _vp, _vp]),
     "ab_stats_init_range": (_int, [_vp, _i64, _vp, _vp]),
     "ab_stats_fold_batches": (_int, [_vp, _i64, _vp, _vp, _i64, _vp]),
     "ab_stats_fold_log": (_int, [_vp, _i64, _vp, _vp, _vp, _vp]),

@@ -879,128 +879,197 @@ __global__ void __launch_bounds__(kHistThreads, 1)
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kSegThreads = 256;
 
+// updateStats of ONE segment x[0 .. seg_len) on its record, by one CTA of kSegThreads threads. s_hist: kBins words.
+template <typename T>
+__device__ __forceinline__ void segment_update(const T* __restrict__ x, int64_t seg_len, int quant_mode, ab_stats_state* st,
+                                               uint32_t* s_hist, float* s_lo_hi)
+{
+    constexpr int kV   = Elem<T>::kPerVec;
+    const bool vec     = (reinterpret_cast<uintptr_t>(x) & 15u) == 0;
+    const int64_t nvec = vec ? seg_len / kV : 0;
+    const bool need_mm = (quant_mode == AB_QUANTIZATION_TF) || !st->initialized;
+
+    __syncthreads();   // previous segment's fold has finished with s_hist / s_lo_hi
+    if (st->pending)   // a batch parked by hist_kernel: fold it before this call's own batch
+    {
+        fold_pending(st, threadIdx.x, kSegThreads);
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            st->iterations = st->iterations + 1;
+            st->pending    = 0;
+        }
+        __syncthreads();
+    }
+    if (need_mm)
+    {
+        float lo = INFINITY, hi = -INFINITY;
+        for (int64_t v = threadIdx.x; v < nvec; v += kSegThreads)
+        {
+            float f[kV];
+            Elem<T>::unpack(__ldg(reinterpret_cast<const uint4*>(x) + v), f);
+#pragma unroll
+            for (int k = 0; k < kV; ++k)
+                lo = fminf(lo, f[k]), hi = fmaxf(hi, f[k]);
+        }
+        for (int64_t i = nvec * kV + threadIdx.x; i < seg_len; i += kSegThreads)
+        {
+            const float xv = Elem<T>::load(x + i);
+            lo = fminf(lo, xv), hi = fmaxf(hi, xv);
+        }
+        block_minmax(lo, hi);
+        if (threadIdx.x == 0)
+            s_lo_hi[0] = lo, s_lo_hi[1] = hi;
+    }
+    for (int i = threadIdx.x; i < kBins; i += kSegThreads)
+        s_hist[i] = 0;
+    __syncthreads();
+    const float s_lo = s_lo_hi[0], s_hi = s_lo_hi[1];
+
+    if (quant_mode == AB_QUANTIZATION_TF)
+    {
+        if (threadIdx.x == 0)
+        {
+            st->run_min       = em::smin(st->run_min, (double) s_lo);
+            st->run_max       = em::smax(st->run_max, (double) s_hi);
+            st->stats_updated = 1;
+        }
+        return;
+    }
+
+    // tf_enhanced
+    Range rg;
+    double x_left0 = 0, bucket_d = 0;
+    const bool was_init = st->initialized != 0;
+    if (was_init)
+    {
+        rg.bucket = st->bucket_size, rg.offset = st->pdf_offset, rg.valid = true;
+    }
+    else if (s_lo == 0 && s_hi == 0)
+    {
+        rg.bucket = 1.0f, rg.offset = 0.0f, rg.valid = false;
+    }
+    else
+    {
+        em::init_pdf_range(s_lo, s_hi, x_left0, bucket_d, rg.bucket, rg.offset);
+        rg.valid = true;
+    }
+    if (rg.valid)
+    {
+        for (int64_t v = threadIdx.x; v < nvec; v += kSegThreads)
+        {
+            float f[kV];
+            Elem<T>::unpack(__ldg(reinterpret_cast<const uint4*>(x) + v), f);
+#pragma unroll
+            for (int k = 0; k < kV; ++k)
+            {
+                const int b = bin_index(f[k], rg.bucket, rg.offset);
+                if (b >= 0)
+                    atomicAdd(s_hist + b, 1u);
+            }
+        }
+        for (int64_t i = nvec * kV + threadIdx.x; i < seg_len; i += kSegThreads)
+        {
+            const int b = bin_index(Elem<T>::load(x + i), rg.bucket, rg.offset);
+            if (b >= 0)
+                atomicAdd(s_hist + b, 1u);
+        }
+        __syncthreads();
+        const int iterations = st->iterations;
+        for (int i = threadIdx.x; i < kBins; i += kSegThreads)
+            fold_bin(&st->pdf[i], s_hist[i], (double) seg_len, iterations);
+        __syncthreads();   // every thread has read st->iterations before it changes
+        if (threadIdx.x == 0)
+        {
+            if (!was_init)
+            {
+                st->x_left0       = x_left0;
+                st->bucket_size_d = bucket_d;
+                st->bucket_size   = rg.bucket;
+                st->pdf_offset    = rg.offset;
+                st->initialized   = 1;
+            }
+            st->iterations = iterations + 1;
+        }
+    }
+    if (threadIdx.x == 0)
+        st->stats_updated = 1;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kSegThreads)
     segmented_kernel(const T* __restrict__ in, int64_t num_segments, int64_t seg_len, int quant_mode,
                      ab_stats_state* states)
 {
     __shared__ uint32_t s_hist[kBins];
-    __shared__ float s_lo, s_hi;
-    constexpr int kV = Elem<T>::kPerVec;
-
+    __shared__ float s_lo_hi[2];
     for (int64_t seg = blockIdx.x; seg < num_segments; seg += gridDim.x)
+        segment_update(in + seg * seg_len, seg_len, quant_mode, states + seg, s_hist, s_lo_hi);
+}
+
+// The same for the segments of MANY tensors in one launch: record r belongs to the item whose [first, first + count) range
+// holds it (a refresh of all parameter encodings of a model: ab_stats_refresh_encodings_multi).
+constexpr int kMaxItems = AB_REFRESH_MULTI_MAX_ITEMS;
+struct ItemTable
+{
+    const void* data[kMaxItems];
+    int64_t segment_len[kMaxItems];
+    int32_t first[kMaxItems + 1];   // first record of item i; [num_items] = total records
+    int32_t skip[kMaxItems];        // 1: handled by the single-tensor kernels (one large per-tensor segment)
+    int32_t num_items;
+};
+static_assert(sizeof(ItemTable) <= 3200, "must travel as a kernel parameter");
+
+__device__ __forceinline__ int item_of(const ItemTable& t, int64_t record)
+{
+    int lo = 0, hi = t.num_items - 1;   // largest i with first[i] <= record
+    while (lo < hi)
     {
-        const T* x         = in + seg * seg_len;
-        ab_stats_state* st = states + seg;
-        const bool vec     = (reinterpret_cast<uintptr_t>(x) & 15u) == 0;
-        const int64_t nvec = vec ? seg_len / kV : 0;
-        const bool need_mm = (quant_mode == AB_QUANTIZATION_TF) || !st->initialized;
-
-        __syncthreads();   // previous segment's fold has finished with s_hist / s_lo / s_hi
-        if (st->pending)   // a batch parked by hist_kernel: fold it before this call's own batch
-        {
-            fold_pending(st, threadIdx.x, kSegThreads);
-            __syncthreads();
-            if (threadIdx.x == 0)
-            {
-                st->iterations = st->iterations + 1;
-                st->pending    = 0;
-            }
-            __syncthreads();
-        }
-        if (need_mm)
-        {
-            float lo = INFINITY, hi = -INFINITY;
-            for (int64_t v = threadIdx.x; v < nvec; v += kSegThreads)
-            {
-                float f[kV];
-                Elem<T>::unpack(__ldg(reinterpret_cast<const uint4*>(x) + v), f);
-#pragma unroll
-                for (int k = 0; k < kV; ++k)
-                    lo = fminf(lo, f[k]), hi = fmaxf(hi, f[k]);
-            }
-            for (int64_t i = nvec * kV + threadIdx.x; i < seg_len; i += kSegThreads)
-            {
-                const float xv = Elem<T>::load(x + i);
-                lo = fminf(lo, xv), hi = fmaxf(hi, xv);
-            }
-            block_minmax(lo, hi);
-            if (threadIdx.x == 0)
-                s_lo = lo, s_hi = hi;
-        }
-        for (int i = threadIdx.x; i < kBins; i += kSegThreads)
-            s_hist[i] = 0;
-        __syncthreads();
-
-        if (quant_mode == AB_QUANTIZATION_TF)
-        {
-            if (threadIdx.x == 0)
-            {
-                st->run_min       = em::smin(st->run_min, (double) s_lo);
-                st->run_max       = em::smax(st->run_max, (double) s_hi);
-                st->stats_updated = 1;
-            }
-            continue;
-        }
-
-        // tf_enhanced
-        Range rg;
-        double x_left0 = 0, bucket_d = 0;
-        const bool was_init = st->initialized != 0;
-        if (was_init)
-        {
-            rg.bucket = st->bucket_size, rg.offset = st->pdf_offset, rg.valid = true;
-        }
-        else if (s_lo == 0 && s_hi == 0)
-        {
-            rg.bucket = 1.0f, rg.offset = 0.0f, rg.valid = false;
-        }
+        const int mid = (lo + hi + 1) >> 1;
+        if (t.first[mid] <= record)
+            lo = mid;
         else
-        {
-            em::init_pdf_range(s_lo, s_hi, x_left0, bucket_d, rg.bucket, rg.offset);
-            rg.valid = true;
-        }
-        if (rg.valid)
-        {
-            for (int64_t v = threadIdx.x; v < nvec; v += kSegThreads)
-            {
-                float f[kV];
-                Elem<T>::unpack(__ldg(reinterpret_cast<const uint4*>(x) + v), f);
-#pragma unroll
-                for (int k = 0; k < kV; ++k)
-                {
-                    const int b = bin_index(f[k], rg.bucket, rg.offset);
-                    if (b >= 0)
-                        atomicAdd(s_hist + b, 1u);
-                }
-            }
-            for (int64_t i = nvec * kV + threadIdx.x; i < seg_len; i += kSegThreads)
-            {
-                const int b = bin_index(Elem<T>::load(x + i), rg.bucket, rg.offset);
-                if (b >= 0)
-                    atomicAdd(s_hist + b, 1u);
-            }
-            __syncthreads();
-            const int iterations = st->iterations;
-            for (int i = threadIdx.x; i < kBins; i += kSegThreads)
-                fold_bin(&st->pdf[i], s_hist[i], (double) seg_len, iterations);
-            __syncthreads();   // every thread has read st->iterations before it changes
-            if (threadIdx.x == 0)
-            {
-                if (!was_init)
-                {
-                    st->x_left0       = x_left0;
-                    st->bucket_size_d = bucket_d;
-                    st->bucket_size   = rg.bucket;
-                    st->pdf_offset    = rg.offset;
-                    st->initialized   = 1;
-                }
-                st->iterations = iterations + 1;
-            }
-        }
-        if (threadIdx.x == 0)
-            st->stats_updated = 1;
+            hi = mid - 1;
     }
+    return lo;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kSegThreads)
+    segmented_multi_kernel(const __grid_constant__ ItemTable t, int quant_mode, ab_stats_state* states)
+{
+    __shared__ uint32_t s_hist[kBins];
+    __shared__ float s_lo_hi[2];
+    const int64_t total = t.first[t.num_items];
+    for (int64_t rec = blockIdx.x; rec < total; rec += gridDim.x)
+    {
+        const int i = item_of(t, rec);
+        if (t.skip[i])
+            continue;
+        const int64_t len = t.segment_len[i];
+        segment_update(reinterpret_cast<const T*>(t.data[i]) + (rec - t.first[i]) * len, len, quant_mode, states + rec,
+                       s_hist, s_lo_hi);
+    }
+}
+
+// per-channel QDQ parameter blocks of many tensors from their encoding rows: item i's float[4][C_i] block starts at
+// params + 4 * first[i]; the step count is decided from the item's channel 0 (ATQ:286-294), as per_channel_params_kernel does
+__global__ void per_channel_params_multi_kernel(const __grid_constant__ ItemTable t, const double* __restrict__ enc5, int bw,
+                                                float* __restrict__ params)
+{
+    const int64_t total = t.first[t.num_items];
+    const int64_t rec   = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (rec >= total)
+        return;
+    const int i        = item_of(t, rec);
+    const int64_t f    = t.first[i];
+    const int64_t nch  = t.first[i + 1] - f;
+    const int64_t c    = rec - f;
+    double steps       = em::pow2(bw) - 1;
+    if (enc5[f * 5] == -enc5[f * 5 + 1])
+        steps -= 1;
+    float* p = params + 4 * f;
+    em::per_channel_param(enc5[rec * 5], enc5[rec * 5 + 1], (float) steps, p[c], p[nch + c], p[2 * nch + c], p[3 * nch + c]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1594,6 +1663,106 @@ int ab_stats_update_segmented(const void* in, int64_t num_segments, int64_t segm
         k<<<grid, kSegThreads, 0, st>>>((const __nv_bfloat16*) in, num_segments, segment_len, quant_mode, states);
     }
     AB_CUDA_CHECK(cudaGetLastError());
+    return AB_OK;
+}
+
+// reset -> updateStats -> computeEncoding (-> per-channel parameter blocks) for MANY parameter tensors with a handful of
+// launches: what every wrapper of a model does with its weights before a training-mode forward, and once per calibration job
+// (TEt/.../v1/qc_quantize_op.py:753-798) -- 4 launches per weight through ab_stats_refresh_encodings, 81 weights in
+// MobileNet-v2, 54 in ResNet-50.
+int ab_stats_refresh_encodings_multi(const ab_refresh_item* items, int num_items, int dtype, int quant_mode,
+                                     ab_stats_state* states, int bw, int use_symmetric, int use_strict_symmetric,
+                                     int use_unsigned_symmetric, double* enc_out, float* qdq4_out, float* params_out,
+                                     void* stream)
+{
+    if (num_items < 0 || num_items > AB_REFRESH_MULTI_MAX_ITEMS ||
+        (num_items > 0 && (items == nullptr || states == nullptr || enc_out == nullptr)))
+    {
+        set_error("null pointer, or more than %d items", AB_REFRESH_MULTI_MAX_ITEMS);
+        return AB_ERR_INVALID;
+    }
+    if (dtype != AB_F32 && dtype != AB_BF16)
+    {
+        set_error("unsupported dtype %d", dtype);
+        return AB_ERR_INVALID;
+    }
+    if (num_items == 0)
+        return AB_OK;
+    const int stats = stats_mode(quant_mode);
+    if (stats != AB_QUANTIZATION_TF && stats != AB_QUANTIZATION_TF_ENHANCED)
+    {
+        set_error("unsupported quantization mode %d", quant_mode);
+        return AB_ERR_INVALID;
+    }
+    constexpr int64_t kLargeSegment = 128 * 1024;   // a single segment this long gets the grid-wide single-tensor kernels
+    ItemTable t;
+    memset(&t, 0, sizeof(t));
+    t.num_items   = num_items;
+    int64_t total = 0;
+    bool any_small = false;
+    for (int i = 0; i < num_items; ++i)
+    {
+        if (items[i].data == nullptr || items[i].num_segments < 1 || items[i].segment_len < 1 ||
+            items[i].first_record != total)
+        {
+            set_error("item %d: null data, empty tensor, or records that do not follow the previous item's", i);
+            return AB_ERR_INVALID;
+        }
+        t.data[i]        = items[i].data;
+        t.segment_len[i] = items[i].segment_len;
+        t.first[i]       = (int32_t) total;
+        t.skip[i]        = (items[i].num_segments == 1 && items[i].segment_len >= kLargeSegment) ? 1 : 0;
+        any_small |= !t.skip[i];
+        total += items[i].num_segments;
+        if (total > 0x7fffffff)
+        {
+            set_error("too many records in one call");
+            return AB_ERR_INVALID;
+        }
+    }
+    t.first[num_items] = (int32_t) total;
+    cudaStream_t st    = (cudaStream_t) stream;
+    int rc             = ab_stats_reset(states, total, stream);
+    if (rc != AB_OK)
+        return rc;
+    if (any_small)
+    {
+        if (dtype == AB_F32)
+        {
+            auto k   = segmented_multi_kernel<float>;
+            int grid = resident_grid(k, kSegThreads, 0);
+            k<<<total < grid ? (int) total : grid, kSegThreads, 0, st>>>(t, stats, states);
+        }
+        else
+        {
+            auto k   = segmented_multi_kernel<__nv_bfloat16>;
+            int grid = resident_grid(k, kSegThreads, 0);
+            k<<<total < grid ? (int) total : grid, kSegThreads, 0, st>>>(t, stats, states);
+        }
+        AB_CUDA_CHECK(cudaGetLastError());
+    }
+    for (int i = 0; i < num_items; ++i)
+        if (t.skip[i])
+        {
+            rc = ab_stats_update(items[i].data, items[i].segment_len, dtype, stats, states + t.first[i], nullptr, 0, stream);
+            if (rc != AB_OK)
+                return rc;
+        }
+    rc = quant_mode == AB_QUANTIZATION_PERCENTILE
+             ? AB_ERR_UNSUPPORTED
+             : ab_compute_encodings(states, total, quant_mode, bw, use_symmetric, use_strict_symmetric, use_unsigned_symmetric,
+                                    enc_out, qdq4_out, stream);
+    if (rc != AB_OK)
+    {
+        if (rc == AB_ERR_UNSUPPORTED)
+            set_error("the percentile scheme is refreshed per tensor (it needs its percentile value)");
+        return rc;
+    }
+    if (params_out != nullptr)
+    {
+        per_channel_params_multi_kernel<<<(unsigned) ((total + 127) / 128), 128, 0, st>>>(t, enc_out, bw, params_out);
+        AB_CUDA_CHECK(cudaGetLastError());
+    }
     return AB_OK;
 }
 

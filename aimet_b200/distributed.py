@@ -324,6 +324,7 @@ class ShardedCalibrator:
     def compute_encodings_for_batches(self, batches, cuda_graph: bool = True):
         """Like compute_encodings with the callback `for x in batches: model(x)` over THIS rank's batches, with the
         steady state replayed from a CUDA graph (see QuantizationSimModel.compute_encodings_for_batches)."""
+        from .quantsim.qc_quantize_op import CalibrationJob
         from .quantsim.quantsim import QuantizationSimModel, in_eval_mode, run_batches
         sim = self.sim
         QuantizationSimModel.prepare_sim_for_compute_encodings(sim)
@@ -332,7 +333,7 @@ class ShardedCalibrator:
         self._attach(staging=cuda_graph)
         try:
             after_each = (lambda n: self.sink.commit(n)) if (self.tfe and cuda_graph) else None
-            with in_eval_mode(sim.model), torch.no_grad():
+            with in_eval_mode(sim.model), torch.no_grad(), CalibrationJob(sim):
                 run_batches(sim.model, batches, cuda_graph, after_each=after_each,
                             after_first=None if self.tfe else sim._learn_fixed_ranges)   # pylint: disable=protected-access
             self._merge()
@@ -341,6 +342,7 @@ class ShardedCalibrator:
         QuantizationSimModel.compute_layer_encodings_for_sim(sim)
 
     def compute_encodings(self, forward_pass_callback, forward_pass_callback_args):
+        from .quantsim.qc_quantize_op import CalibrationJob
         from .quantsim.quantsim import QuantizationSimModel, _ParamExportPrefetch, in_eval_mode
         sim = self.sim
         QuantizationSimModel.prepare_sim_for_compute_encodings(sim)
@@ -349,7 +351,7 @@ class ShardedCalibrator:
         self._attach(staging=False)
         prefetch = _ParamExportPrefetch(sim)     # parameter encodings are rank-local and final after the first forward
         try:
-            with in_eval_mode(sim.model), torch.no_grad():
+            with in_eval_mode(sim.model), torch.no_grad(), CalibrationJob(sim):
                 forward_pass_callback(sim.model, forward_pass_callback_args)
             self._merge()
         finally:

@@ -420,6 +420,42 @@ def stats_refresh_encodings_impl(x, states, first, num_segments, segment_len, qu
     return enc, qdq4, params
 
 
+REFRESH_MAX_ITEMS = _lib.REFRESH_MULTI_MAX_ITEMS
+
+
+def stats_refresh_multi_impl(tensors, num_segments, states, first, quant_mode, bw, sym, strict, unsigned_sym,
+                             enc, qdq4=None, params=None, first_record=0):
+    """reset + updateStats + computeEncoding (+ per-channel parameter blocks) for up to REFRESH_MAX_ITEMS parameter tensors
+    in a handful of launches (ab_stats_refresh_encodings_multi). tensors[k]: contiguous CUDA tensor whose num_segments[k]
+    equal segments update consecutive records, starting at `first + first_record` for k = 0 and following on from there.
+    enc / qdq4 / params: the output tables for ALL records of the block ([N, 5] float64, [N, 4] float32, [4 N] float32);
+    this call fills their rows from `first_record` on."""
+    n = len(tensors)
+    if n == 0:
+        return
+    if n > REFRESH_MAX_ITEMS:
+        raise ValueError(f"at most {REFRESH_MAX_ITEMS} tensors per call")
+    _require_cuda(states, enc, qdq4, params, *tensors)
+    items = (_lib.RefreshItem * n)()
+    at = 0
+    for k, (t, segs) in enumerate(zip(tensors, num_segments)):
+        if t.dtype != tensors[0].dtype or not t.is_contiguous() or t.numel() % segs or t.numel() == 0:
+            raise ValueError("tensors must be contiguous, non-empty, of one dtype and divisible into their segments")
+        it = items[k]
+        it.data, it.num_segments, it.segment_len, it.first_record = t.data_ptr(), segs, t.numel() // segs, at
+        at += segs
+    with _on_device(states):
+        _lib.check(_L.ab_stats_refresh_encodings_multi(
+            items, n, _dtype_code(tensors[0]), int(quant_mode), _state_ptr(states, first + first_record), int(bw),
+            int(bool(sym)), int(bool(strict)), int(bool(unsigned_sym)), enc.data_ptr() + first_record * 40,
+            None if qdq4 is None else qdq4.data_ptr() + first_record * 16,
+            None if params is None else params.data_ptr() + first_record * 16, _stream(states)))
+    LAUNCHES["reset"] += 1
+    LAUNCHES["segmented"] += 1
+    LAUNCHES["search"] += 1
+    return at
+
+
 def compute_encodings_into(states, first, count, quant_mode, bw, sym, strict, unsigned_sym, out, percentile=None):
     """Same as compute_encodings_impl, but writes into `out` (float64 CUDA, [count, 5], contiguous): lets a caller
     enqueue many searches and read them back with one copy."""

@@ -11,7 +11,7 @@ from torch import nn
 
 from .. import libpymo
 from .defs import MAP_ROUND_MODE_TO_PYMO, QuantizationDataType, QuantScheme
-from .tensor_quantizer import (StaticGridPerChannelQuantizer, StaticGridPerTensorQuantizer, compute_dloss_by_dx)
+from .tensor_quantizer import (_LAZY, StaticGridPerChannelQuantizer, StaticGridPerTensorQuantizer, compute_dloss_by_dx)
 
 import os
 
@@ -92,6 +92,32 @@ _NEVER_IN_PLACE = (nn.modules.conv._ConvNd, nn.Linear, nn.modules.batchnorm._Bat
                    nn.modules.pooling._AdaptiveAvgPoolNd, nn.modules.pooling._AdaptiveMaxPoolNd, nn.Flatten, nn.Identity)  # pylint: disable=protected-access
 
 
+class ForwardToken:
+    """One model forward in flight (set by the sim's forward hooks): parameter encodings stamped with `current` while
+    `active` were refreshed for this very forward by quantsim.param_plan, all parameters of the model in one native call."""
+    current = 0
+    active = False
+
+
+_FORWARD = ForwardToken
+
+
+class CalibrationJob:
+    """Set by QuantizationSimModel.compute_encodings (and the sharded calibrator) around the user's calibration callback."""
+    active = False
+
+    def __init__(self, sim):
+        self.sim = sim
+
+    def __enter__(self):
+        self.previous, CalibrationJob.active = CalibrationJob.active, True
+        return self
+
+    def __exit__(self, *exc):
+        CalibrationJob.active = self.previous
+        for _, w in self.sim.quant_wrappers():
+            for q in getattr(w, "param_quantizers", {}).values():
+                q.__dict__.pop("_qdq_cache", None)
 ALWAYS_GATE_AND_CLONE = False   # test hook: the reference's unconditional gating + clone in every wrapper
 
 
@@ -311,12 +337,26 @@ class StaticGridQuantWrapper(EncodingImportMixin, nn.Module):
             if q.enabled and q.bitwidth != 32:
                 shadow_params[name] = param.data
                 if self._module_to_wrap.training or not q._has_encoding():   # pylint: disable=protected-access
-                    if not q.refresh_encoding_from(param.data):                # one native call where possible
+                    if _FORWARD.active and q.__dict__.get("_fresh_token") == _FORWARD.current and q._has_encoding():   # pylint: disable=protected-access
+                        pass   # refreshed for this very forward, together with all other parameters (param_plan)
+                    elif not q.refresh_encoding_from(param.data):              # one native call where possible
                         q.reset_encoding_stats()
                         q.update_encoding_stats(param.data)
                         q.compute_encoding()
                 round_mode = q.round_mode if self.training else libpymo.RoundingMode.ROUND_NEAREST
-                param.data = q.quantize_dequantize(param.data, round_mode)
+                if CalibrationJob.active and not self.training and not torch.is_grad_enabled() and \
+                        q._encoding is _LAZY and round_mode == libpymo.RoundingMode.ROUND_NEAREST:   # pylint: disable=protected-access
+                    # Inside one calibration job (eval mode, no_grad) neither the weights nor their encodings change from
+                    # batch to batch: the quantize-dequantized weight of the first batch serves the others (the reference
+                    # re-quantizes all weights on every forward; 53 launches per ResNet-50 step). Keyed on the parameter's
+                    # storage and version and on the identity of the device-resident encoding table.
+                    key = (param.data.data_ptr(), param._version, id(q._enc_dev))   # pylint: disable=protected-access
+                    cached = q.__dict__.get("_qdq_cache")
+                    if cached is None or cached[0] != key:
+                        cached = q._qdq_cache = (key, q.quantize_dequantize(param.data, round_mode))   # pylint: disable=protected-access
+                    param.data = cached[1]
+                else:
+                    param.data = q.quantize_dequantize(param.data, round_mode)
         return shadow_params
 
     def ensure_param_encodings(self):

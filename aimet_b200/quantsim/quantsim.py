@@ -18,7 +18,7 @@ from torch import nn
 from . import config as qconfig
 from .defs import MAP_ROUND_MODE_TO_PYMO, QuantizationDataType, QuantScheme
 from .learned_grid import LearnedGridQuantWrapper, construct_and_initialize_trainable_wrapper
-from .qc_quantize_op import QcQuantizeOpMode, StaticGridQuantWrapper
+from .qc_quantize_op import CalibrationJob, QcQuantizeOpMode, StaticGridQuantWrapper
 
 ENCODING_VERSION = "0.6.1"   # reference aimet_common/quantsim.py:55-57
 _RANGE_LEARNING_SCHEMES = (QuantScheme.training_range_learning_with_tf_init,
@@ -115,6 +115,37 @@ def run_batches(model, batches, cuda_graph: bool, after_first=None, after_each=N
     return n
 
 
+class _ModelForwardHooks:
+    """Forward pre / post hooks of `sim.model`: in training mode every wrapper re-derives its parameter encodings before
+    every forward (reference qc_quantize_op.py:753-798); the pre hook does that for ALL parameters of the model in one
+    native call (quantsim.param_plan) and stamps them as fresh for this forward. Holds the sim weakly; copies of the model
+    (deepcopy, unpickling) keep an inert instance."""
+
+    def __init__(self, sim):
+        import weakref
+        self._sim = weakref.ref(sim)
+
+    def __deepcopy__(self, memo):
+        return self
+
+    def __getstate__(self):
+        return {}
+
+    def __setstate__(self, state):
+        self._sim = lambda: None
+
+    def pre(self, module, args):   # pylint: disable=unused-argument
+        sim = self._sim()
+        if sim is not None and module is sim.model:
+            sim._begin_model_forward()   # pylint: disable=protected-access
+
+    def post(self, module, args, output):   # pylint: disable=unused-argument
+        from .param_plan import ForwardToken
+        sim = self._sim()
+        if sim is not None and module is sim.model:
+            ForwardToken.active = False
+
+
 class QuantizationSimModel:
     """Adds quantization-simulation wrappers to a model, calibrates them and exports the encodings."""
 
@@ -149,12 +180,54 @@ class QuantizationSimModel:
         for w in self._wrappers.values():
             if "bias" in w.param_quantizers:
                 w.param_quantizers["bias"].enabled = False
+        self._register_model_hooks()
 
     def __getstate__(self):
         state = self.__dict__.copy()
         state.pop("_act_block", None)               # device-resident statistics are not part of a checkpoint
         state.pop("_act_block_quantizers", None)
+        state.pop("_param_plan", None)
+        state.pop("_model_hooks", None)
         return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self._register_model_hooks()
+
+    def _register_model_hooks(self):
+        hooks = self._model_hooks = _ModelForwardHooks(self)
+        self.model.register_forward_pre_hook(hooks.pre)
+        self.model.register_forward_hook(hooks.post, always_call=True)
+
+    # ---- all parameter encodings at once -------------------------------------------------------------------------
+    def _plan(self):
+        """The sim's ParamPlan, or None when the model's parameters are not on a CUDA device."""
+        from .param_plan import ParamPlan
+        device = next((p.device for p in self.model.parameters()), None)
+        if device is None or device.type != "cuda":
+            return None
+        plan = self.__dict__.get("_param_plan")
+        if plan is None:
+            plan = self._param_plan = ParamPlan(self)
+        return plan
+
+    def _begin_model_forward(self):
+        """Pre hook of every forward of self.model. Training mode: refresh, in one native call, the encodings of every
+        planned parameter whose wrapped module is in training mode, and stamp them fresh for this forward."""
+        from .param_plan import ForwardToken
+        ForwardToken.current += 1
+        ForwardToken.active = False
+        if not any(w._module_to_wrap.training for w in self._wrappers.values()   # pylint: disable=protected-access
+                   if isinstance(w, StaticGridQuantWrapper) and w.param_quantizers):
+            return
+        plan = self._plan()
+        if plan is None:
+            return
+        plan.ensure()
+        with torch.no_grad():
+            plan.refresh(only=lambda e: e.wrapper._module_to_wrap.training or not e.q._has_encoding(),   # pylint: disable=protected-access
+                         stamp=ForwardToken.current)
+        ForwardToken.active = True
 
     # ---- model surgery -----------------------------------------------------------------------------------------
     @staticmethod
@@ -202,6 +275,7 @@ class QuantizationSimModel:
         self._wrappers = {orig: w for orig, w in self._wrappers.items() if w not in doomed}
         self.__dict__.pop("_act_block", None)               # the activation statistics block is rebuilt on the next bind
         self.__dict__.pop("_act_block_quantizers", None)
+        self.__dict__.pop("_param_plan", None)
 
     # ---- calibration -------------------------------------------------------------------------------------------
     @staticmethod
@@ -210,9 +284,18 @@ class QuantizationSimModel:
             raise RuntimeError("the wrappers have already been replaced by range-learning wrappers; their encodings are "
                                "trainable parameters now and are not re-calibrated")
         sim._bind_activation_states()   # pylint: disable=protected-access
+        plan = sim._plan()              # pylint: disable=protected-access
+        if plan is not None:
+            plan.ensure()
+            plan.mark_reset_pending()   # their records are reset block-wide by the refresh below, not one launch each
         for _, layer in sim.quant_wrappers():
             layer.reset_encodings()
             layer.set_mode(QcQuantizeOpMode.ANALYSIS)
+        if plan is not None:
+            # The parameters are known now: derive all their encodings in one native call instead of four launches per
+            # weight inside the first forward (the wrappers find them ready; same values either way).
+            with torch.no_grad():
+                plan.refresh()
         if sim._quant_scheme == QuantScheme.post_training_percentile:   # pylint: disable=protected-access
             for _, layer in sim.quant_wrappers():                       # reference :397-400
                 layer.set_percentile_value(sim._percentile_value)       # pylint: disable=protected-access
@@ -293,7 +376,7 @@ class QuantizationSimModel:
         prefetch = _ParamExportPrefetch(self)
         batcher = StatsBatcher.attach(self)     # activation statistics: deferred, one launch per forward (or None)
         try:
-            with in_eval_mode(self.model), torch.no_grad():
+            with in_eval_mode(self.model), torch.no_grad(), CalibrationJob(self):
                 _ = forward_pass_callback(self.model, forward_pass_callback_args)
             if batcher is not None:
                 batcher.flush()
@@ -316,7 +399,7 @@ class QuantizationSimModel:
         QuantizationSimModel.prepare_sim_for_compute_encodings(self)
         batcher = StatsBatcher.attach(self)
         try:
-            with in_eval_mode(self.model), torch.no_grad():
+            with in_eval_mode(self.model), torch.no_grad(), CalibrationJob(self):
                 # the batcher learns the fixed ranges itself at the end of the first forward
                 run_batches(self.model, batches, cuda_graph,
                             after_first=None if batcher is not None else self._learn_fixed_ranges)
@@ -573,7 +656,8 @@ class _ParamExportPrefetch:
 
     def _on_forward(self, _module, _inputs):
         self._forwards += 1
-        if self._done or self._forwards < 2 or torch.cuda.is_current_stream_capturing():
+        # (the parameter encodings of planned quantizers exist before the first forward: quantsim.param_plan)
+        if self._done or torch.cuda.is_current_stream_capturing():
             return
         if self._pending is None:
             from .tensor_quantizer import _LAZY

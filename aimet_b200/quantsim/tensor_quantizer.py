@@ -244,6 +244,7 @@ class StaticGridTensorQuantizer:
             data = tensor if self._ch_axis == 0 else tensor.movedim(self._ch_axis, 0)
             data = data.contiguous(memory_format=torch.contiguous_format)
             seg_len = data.numel() // n
+        self.__dict__.pop("_reset_is_pending", None)     # this call resets the records itself
         enc, qdq4, params = ops.stats_refresh_encodings_impl(data, arena, first, n, seg_len, op0._code, self.bitwidth,   # pylint: disable=protected-access
                                                              self.use_symmetric_encodings, self.use_strict_symmetric,
                                                              self.use_unsigned_symmetric)
@@ -272,10 +273,23 @@ class StaticGridTensorQuantizer:
 
     def reset_encoding_stats(self):
         if not self._is_encoding_frozen:
-            self._reset_ops()
+            if self.__dict__.get("_reset_is_pending"):
+                # planned parameter quantizer (quantsim.param_plan): the refresh that follows resets the whole block of
+                # records in one launch -- only the host-side bookkeeping happens here
+                self._mark_ops_invalid()
+            else:
+                self._reset_ops()
             self._encoding = None
             self._drop_device_encoding()
             self._stats_dirty = True
+
+    def _mark_ops_invalid(self):
+        group = getattr(self, "_group", None)
+        if group is not None and group.detached == 0:
+            group.valid = False
+        else:
+            for op in self._cppOp:
+                op._is_encoding_valid = False   # pylint: disable=protected-access
 
     def _reset_ops(self):
         for op in self._cppOp:
@@ -344,6 +358,8 @@ class StaticGridPerTensorQuantizer(StaticGridTensorQuantizer):
         if self.enabled and not self._is_encoding_frozen:
             if self.bitwidth == 32:
                 return
+            if self.__dict__.pop("_reset_is_pending", None):
+                self._reset_ops()        # the block-wide reset never came: do this quantizer's own now
             hook = getattr(self, "_calib_hook", None)
             if hook is not None and self.encoding_min_max_fixed_vals is None:
                 hook(tensor)        # sharded calibration (aimet_b200.distributed) records / logs the call itself
@@ -401,6 +417,8 @@ class StaticGridPerChannelQuantizer(StaticGridTensorQuantizer):
         if self.enabled and not self._is_encoding_frozen:
             if self.bitwidth == 32:
                 return
+            if self.__dict__.pop("_reset_is_pending", None):
+                self._reset_ops()        # the block-wide reset never came: do this quantizer's own now
             self._stats_dirty = True
             if self.encoding_min_max_fixed_vals is not None:
                 tensor = torch.tensor([self.encoding_min_max_fixed_vals[0], self.encoding_min_max_fixed_vals[1]])

@@ -286,6 +286,26 @@ int ab_stats_refresh_encodings(const void* in, int64_t num_segments, int64_t seg
                                int use_unsigned_symmetric, double* enc_out, float* qdq4_out, float* params_out,
                                void* stream);
 
+/* The same for MANY tensors with a handful of launches in total (one reset, one statistics launch over all segments of all
+ * tensors, one grid search over all records, one parameter-block launch) instead of four per tensor: the parameter
+ * quantizers of a whole model before a training-mode forward / once per calibration job. All tensors share `dtype`, the
+ * scheme and the encoding flags. Item i's records are states[first_record .. first_record + num_segments); the items must
+ * tile the record range [0, total) in order. enc_out: total x 5 doubles; qdq4_out (optional): total x 4 floats;
+ * params_out (optional): 4 * total floats, item i's float[4][num_segments] block at params_out + 4 * first_record.
+ * Same kernels' arithmetic, same results as ab_stats_refresh_encodings per tensor. */
+typedef struct
+{
+    const void* data;     /* DEVICE, contiguous: num_segments x segment_len elements */
+    int64_t num_segments; /* 1: one per-tensor quantizer; C: one record per channel */
+    int64_t segment_len;
+    int64_t first_record;
+} ab_refresh_item;
+#define AB_REFRESH_MULTI_MAX_ITEMS 96
+int ab_stats_refresh_encodings_multi(const ab_refresh_item* items, int num_items, int dtype, int quant_mode,
+                                     ab_stats_state* states, int bw, int use_symmetric, int use_strict_symmetric,
+                                     int use_unsigned_symmetric, double* enc_out, float* qdq4_out, float* params_out,
+                                     void* stream);
+
 /* PercentileEncodingAnalyzer<float>::computeEncoding (DlQ/src/PercentileEncodingAnalyzer.cpp:77-196) for `count` consecutive
  * records whose statistics were collected with AB_QUANTIZATION_PERCENTILE (or TF_ENHANCED: the PDF is the same).
  * `percentile` is what setPercentileValue received (:203-206; 100 = the observed range). Outputs as ab_compute_encodings. */

@@ -147,3 +147,42 @@ def test_multi_update_rejects_what_it_cannot_do(ops):
         ops.stats_update_multi_impl([base, base.to(torch.bfloat16)], [0, 0], blk.arena, blk.first, counts)
     with pytest.raises(ValueError):
         ops.stats_update_multi_impl([base] * 129, [0] * 129, blk.arena, blk.first, counts)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("mode,sym", [(1, True), (1, False), (0, True)])
+def test_multi_parameter_refresh_equals_one_call_per_tensor(ops, dtype, mode, sym):
+    """ab_stats_refresh_encodings_multi (all weights of a model in a handful of launches) against ab_stats_refresh_encodings
+    per weight: records, encodings, per-tensor and per-channel kernel parameters byte-identical. Shapes: per-channel conv
+    weights (ragged channel lengths), per-tensor weights below and above the large-segment threshold, a 1-element tail."""
+    torch.manual_seed(3)
+    shapes = [(64, 147), (1, 4096), (256, 64), (1, 200_001), (96, 1, 9), (1000, 17), (1, 7), (1, 131072), (33, 577)]
+    tensors = [(torch.randn(s, device="cuda") * (0.05 + 0.01 * k)).to(dtype).contiguous() for k, s in enumerate(shapes)]
+    segs = [s[0] for s in shapes]
+    total = sum(segs)
+    blk_m, blk_s = new_state(total), new_state(total)
+    enc_m = torch.zeros((total, 5), dtype=torch.float64, device="cuda")
+    qdq4_m = torch.zeros((total, 4), dtype=torch.float32, device="cuda")
+    par_m = torch.zeros(4 * total, dtype=torch.float32, device="cuda")
+    for _ in range(2):          # twice: the second call starts from used records
+        ops.stats_refresh_multi_impl(tensors, segs, blk_m.arena, blk_m.first, mode, 8, sym, False, False, enc_m, qdq4_m, par_m)
+    at = 0
+    for t, n in zip(tensors, segs):
+        enc, qdq4, params = ops.stats_refresh_encodings_impl(t, blk_s.arena, blk_s.first + at, n, t.numel() // n, mode, 8, sym,
+                                                             False, False)
+        assert torch.equal(enc, enc_m[at:at + n]), (tuple(t.shape), "encodings")
+        if n == 1:
+            assert torch.equal(qdq4, qdq4_m[at:at + 1])
+        else:
+            assert torch.equal(params, par_m[4 * at:4 * (at + n)]), (tuple(t.shape), "per-channel parameters")
+        at += n
+    a, b = blk_m.read(), blk_s.read()
+    for field in ("pdf", "iterations", "initialized", "stats_updated", "x_left0", "bucket_size_d", "bucket_size",
+                  "pdf_offset", "run_min", "run_max"):
+        assert np.array_equal(a[field], b[field]), field
+    # a sub-range refresh (first_record > 0) touches only its own records
+    keep = blk_m.read()
+    ops.stats_refresh_multi_impl(tensors[2:4], segs[2:4], blk_m.arena, blk_m.first, mode, 8, sym, False, False, enc_m, qdq4_m,
+                                 par_m, first_record=segs[0] + segs[1])
+    again = blk_m.read()
+    assert np.array_equal(keep["pdf"], again["pdf"]) and np.array_equal(keep["iterations"], again["iterations"])
