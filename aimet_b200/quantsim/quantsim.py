@@ -288,6 +288,10 @@ class QuantizationSimModel:
         if plan is not None:
             plan.ensure()
             plan.mark_reset_pending()   # their records are reset block-wide by the refresh below, not one launch each
+        if getattr(sim, "_act_block", None) is not None:
+            sim._act_block.reset()      # all activation records in one launch  # pylint: disable=protected-access
+            for q in sim._act_block_quantizers:   # pylint: disable=protected-access
+                q._reset_done_blockwide = True    # pylint: disable=protected-access
         for _, layer in sim.quant_wrappers():
             layer.reset_encodings()
             layer.set_mode(QcQuantizeOpMode.ANALYSIS)

@@ -273,9 +273,10 @@ class StaticGridTensorQuantizer:
 
     def reset_encoding_stats(self):
         if not self._is_encoding_frozen:
-            if self.__dict__.get("_reset_is_pending"):
+            if self.__dict__.get("_reset_is_pending") or self.__dict__.pop("_reset_done_blockwide", False):
                 # planned parameter quantizer (quantsim.param_plan): the refresh that follows resets the whole block of
-                # records in one launch -- only the host-side bookkeeping happens here
+                # records in one launch; activation quantizer of a sim: prepare_sim_for_compute_encodings has just reset
+                # the sim's whole activation block in one launch -- only the host-side bookkeeping happens here
                 self._mark_ops_invalid()
             else:
                 self._reset_ops()
@@ -289,7 +290,7 @@ class StaticGridTensorQuantizer:
             group.valid = False
         else:
             for op in self._cppOp:
-                op._is_encoding_valid = False   # pylint: disable=protected-access
+                op._reset_host_state()   # pylint: disable=protected-access
 
     def _reset_ops(self):
         for op in self._cppOp:

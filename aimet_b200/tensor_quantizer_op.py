@@ -83,12 +83,17 @@ class AimetTensorQuantizer:
             self._block, self._index = StateArena.for_device(device).allocate(1), 0
 
     # ---- reference API ---------------------------------------------------------------------------------------
-    def resetEncodingStats(self):
-        """AimetTensorQuantizer.cpp:85-92 (a new analyzer: the percentile value falls back to its default as well)"""
+    def _reset_host_state(self):
+        """The host half of resetEncodingStats; the caller has reset (or is about to reset) the record itself, together with
+        its neighbours, in one launch."""
         self._is_encoding_valid = False
         if self._percentile is not None:
             self._percentile = 100.0
         self._range_fixed, self._probe, self._updates = False, None, 0
+
+    def resetEncodingStats(self):
+        """AimetTensorQuantizer.cpp:85-92 (a new analyzer: the percentile value falls back to its default as well)"""
+        self._reset_host_state()
         if self._block is not None:
             ops.stats_reset_impl(self._block.arena, self._block.first + self._index, 1)
 

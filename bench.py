@@ -57,6 +57,8 @@ def parse_args():
     ap.add_argument("--no-kernels", action="store_true", help="skip the kernel sweep (`kernels` block)")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity passes (`parity` block)")
     ap.add_argument("--no-strong", action="store_true", help="skip the extra 2048-image strong-scaling job")
+    ap.add_argument("--no-reference-python", action="store_true",
+                    help="skip the leg that runs the reference's own Python (baseline/_ref) on the CUDA drop-ins")
     ap.add_argument("--images-per-step", type=int, default=BATCH,
                     help="calibration batch (SURVEY section 8d fixes 32 for the headline; larger batches mean larger "
                          "tensors per statistics launch -- a sensitivity knob, not the headline config)")
@@ -343,7 +345,7 @@ def kernel_sweep(device, peak, sizes_mb=(1, 16, 64, 256, 1024), window_mb=512):
         """fn(i) launches on slice i and returns its output tensor (or None)."""
         launches = max(4, len(slices))          # one pass over the whole window: nothing a launch reads is still in L2
         for i in range(min(3, launches)):
-            fn(i)
+            fn(i % len(slices))
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
@@ -691,6 +693,8 @@ def run_ours(args):
                                       "algorithmic bytes / time (QDQ 2s, STE 3s, statistics 1s bytes per element)"}
         except Exception as exc:   # pylint: disable=broad-except
             line["kernels"] = {"error": str(exc)[:300]}
+    if world == 1 and not args.no_reference_python:
+        line["reference_python_api"] = reference_python_leg()
     if world == 1 and not args.no_cpu_baseline:
         try:
             v, info = cpu_job(args.cpu_baseline_steps, 1)
@@ -705,6 +709,34 @@ def run_ours(args):
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def reference_python_leg(steps=2):
+    """The same workload through the REFERENCE's own, unmodified Python (aimet_torch.v1.quantsim.QuantizationSimModel staged
+    under baseline/_ref: its ConnectedGraph, wrappers and per-channel loops -- 26 560 updateStats + 53 163 getEncoding calls
+    per ResNet-50 job) on top of aimet_b200's drop-ins for its two native modules, in a process of its own
+    (tests/ref_python_driver.py --backend native; parity of that path: tests/test_gpu_reference_python.py). Reported next to
+    the headline, which goes through this repo's host layer (batched per-channel calls, device-resident encodings)."""
+    driver = os.path.join(ROOT, "tests", "ref_python_driver.py")
+    if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "aimet_torch")):
+        return {"unavailable": "baseline/_ref not staged (tools/make_ref_python.py needs the reference checkout)"}
+    try:
+        res = subprocess.run([sys.executable, driver, "--backend", "native", "--model", "resnet50", "--config", "per_channel",
+                              "--scheme", "tf_enhanced", "--batch", str(BATCH), "--image", str(IMAGE[1]), "--steps", str(steps),
+                              "--warmup", "1"], cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                             timeout=600)
+        if res.returncode != 0:
+            return {"error": res.stderr[-400:]}
+        r = json.loads(res.stdout.strip().splitlines()[-1])
+        n = r["native"]
+        return {"api": "reference_python", "value": n["img_s"], "unit": UNIT, "steps": steps, "images_per_step": BATCH,
+                "seconds": n["seconds"], "aimet_b200_launches": n["aimet_b200_launches"],
+                "num_activation_encodings": n["num_activation_encodings"], "num_param_encodings": n["num_param_encodings"],
+                "encodings_sha256": n["encodings_sha256"], "quantsim_module": r["quantsim_module"],
+                "note": "complete job of `steps` batches; one native call per weight CHANNEL and a device->host read per "
+                        "getEncoding, as the reference's Python makes them"}
+    except Exception as exc:   # pylint: disable=broad-except
+        return {"error": str(exc)[:300]}
 
 
 def measure_roofline(sim, job, resident, steps, barrier, device, rank):
