@@ -267,6 +267,10 @@ class StaticGridQuantWrapper(EncodingImportMixin, nn.Module):
         return self._module_to_wrap
 
     def get_named_parameters(self):
+        """reference :257-268. A replica made by torch.nn.DataParallel keeps its parameters in `_former_parameters` (plain
+        tensors, views of the broadcast copies) and carries `_is_replica`."""
+        if getattr(self, "_is_replica", False):
+            return list(getattr(self._module_to_wrap, "_former_parameters", {}).items())
         params = self._module_to_wrap._parameters   # pylint: disable=protected-access
         if not self._module_to_wrap._modules:        # leaf module: its own parameters are all there is
             return [(k, v) for k, v in params.items() if v is not None]
@@ -306,22 +310,57 @@ class StaticGridQuantWrapper(EncodingImportMixin, nn.Module):
         """reference :705-745"""
         quantized_inputs = self._quantize_activation(self.input_quantizers, list(inputs))
         shadow_params = self._quantize_dequantize_params()
-        # The reference routes the inputs through the gating function and clones them in every wrapper whenever grad mode
-        # is on (:716-726). The gating function only touches the gradients of parameters whose quantizer is enabled, so a
-        # wrapper without any (activations, batch norms, pooling ...) skips it: nothing would happen in its backward. The
-        # clone protects the gating function's outputs -- aliases of the wrapper's inputs -- from a wrapped module that
-        # works in place; a module known not to write to its input gets the alias itself (same values, same gradients, one
-        # copy of the activation less per layer and step).
-        if (shadow_params or ALWAYS_GATE_AND_CLONE) and torch.is_grad_enabled():
-            quantized_inputs = SteGatingFuncForParameters.apply(self, *quantized_inputs)
-            if ALWAYS_GATE_AND_CLONE or not _leaves_its_input_alone(self._module_to_wrap):
+        # The reference routes the inputs through SteGatingFuncForParameters whenever grad mode is on (:716-726): in ITS
+        # backward -- which runs after the wrapped module's -- that function overwrites `param.grad` of every quantized
+        # parameter with grad * [min <= w <= max], and it clones the inputs to protect its aliased outputs from in-place
+        # modules. Here the same gate is a gradient hook on the parameter itself (`_gate_parameter_gradients`): it acts on
+        # the gradient BEFORE it is accumulated into `.grad`, which (i) yields the same `.grad`, (ii) needs no alias of the
+        # inputs, hence no clone per layer and step, and (iii) is what makes the gate survive DistributedDataParallel, whose
+        # reducer copies a gradient into its bucket the moment it is accumulated -- a later write to `param.grad` is
+        # overwritten by the all-reduced bucket. ALWAYS_GATE_AND_CLONE restores the reference's form (test hook).
+        if torch.is_grad_enabled():
+            if ALWAYS_GATE_AND_CLONE:
+                quantized_inputs = SteGatingFuncForParameters.apply(self, *quantized_inputs)
                 quantized_inputs = [inp.clone() if isinstance(inp, torch.Tensor) and inp.requires_grad else inp
                                     for inp in quantized_inputs]
+            elif shadow_params:
+                self._gate_parameter_gradients()
         wrapped_output = self._module_to_wrap(*quantized_inputs, **kwargs)
         self._restore_shadow_params(shadow_params)
         is_seq = isinstance(wrapped_output, (list, tuple))
         outputs = self._quantize_activation(self.output_quantizers, list(wrapped_output) if is_seq else [wrapped_output])
         return outputs[0] if len(outputs) == 1 else outputs
+
+    def _gate_parameter_gradients(self):
+        """Make sure every quantized parameter of the wrapped module carries the straight-through gate as a gradient hook
+        (registered once per parameter tensor; a no-op while its quantizer is disabled)."""
+        import weakref
+        hooks = self.__dict__.setdefault("_ste_hooks", {})
+        for name, param in self.get_named_parameters():
+            if not param.requires_grad:
+                continue
+            known = hooks.get(name)
+            live = getattr(param, "_backward_hooks", None) or {}
+            if known is not None and known[0] is param and known[1].id in live:
+                continue
+            ref = weakref.ref(self)
+
+            def gate(grad, name=name, ref=ref, pref=weakref.ref(param)):
+                wrapper, p = ref(), pref()
+                if wrapper is None or p is None or ALWAYS_GATE_AND_CLONE:
+                    return grad
+                q = wrapper.param_quantizers.get(name)
+                if q is None or not q.enabled or q.bitwidth == 32 or q.data_type == QuantizationDataType.float or \
+                        not q._has_encoding():   # pylint: disable=protected-access
+                    return grad
+                return ste_for_quantizer(p.data, grad, q)
+
+            hooks[name] = (param, param.register_hook(gate))
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state.pop("_ste_hooks", None)          # gradient hooks are not serialised with the tensors: re-registered on use
+        return state
 
     def _restore_shadow_params(self, shadow_params):
         for name, param in self.get_named_parameters():
@@ -355,6 +394,8 @@ class StaticGridQuantWrapper(EncodingImportMixin, nn.Module):
                     if cached is None or cached[0] != key:
                         cached = q._qdq_cache = (key, q.quantize_dequantize(param.data, round_mode))   # pylint: disable=protected-access
                     param.data = cached[1]
+                elif getattr(self, "_is_replica", False):
+                    param.data = q.quantize_dequantize(param.data.clone(), round_mode)   # reference :785-786
                 else:
                     param.data = q.quantize_dequantize(param.data, round_mode)
         return shadow_params

@@ -658,18 +658,21 @@ class _ParamExportPrefetch:
             self._handle.remove()
         self._pending = None
 
+    BUDGET_S = 2.0e-3      # host time spent on dictionaries per forward
+
     def _on_forward(self, _module, _inputs):
+        import time
         self._forwards += 1
-        # (the parameter encodings of planned quantizers exist before the first forward: quantsim.param_plan)
         if self._done or torch.cuda.is_current_stream_capturing():
             return
         if self._pending is None:
+            # (the parameter encodings of planned quantizers exist before the first forward: quantsim.param_plan)
             from .tensor_quantizer import _LAZY
             qs = [q for _, w in self._sim.quant_wrappers() if isinstance(w, StaticGridQuantWrapper)
                   for q in w.param_quantizers.values()
                   if q.enabled and getattr(q, "_encoding", None) is _LAZY and q._enc_dev is not None]   # pylint: disable=protected-access
             if len(qs) < 2 or len({q._enc_dev.device for q in qs}) != 1:                                 # pylint: disable=protected-access
-                self._done = True
+                self._done = self._forwards >= 2
                 return
             tables = [q._enc_dev for q in qs]                                                            # pylint: disable=protected-access
             gathered = torch.cat(tables)
@@ -677,26 +680,36 @@ class _ParamExportPrefetch:
             host.copy_(gathered, non_blocking=True)
             event = torch.cuda.Event()
             event.record()
-            self._pending = (qs, tables, host, event)
+            self._pending = [qs, tables, host, event, 0, 0]      # ..., next quantizer, its first row
             return
-        qs, tables, host, event = self._pending
+        # The first forwards of a job are issued with the device waiting for the host (the statistics batcher reads the
+        # range flags back at the end of forward 0): building dictionaries there would stall the GPU. From the third
+        # forward on the host runs ahead of the device again; a slice of the work per forward uses that lead up.
+        if self._forwards < 3:
+            return
+        qs, tables, host, event, nxt, at = self._pending
         if not event.query():
             return
         rows = host.numpy()
-        at = 0
-        for q, table in zip(qs, tables):
+        deadline = time.perf_counter() + self.BUDGET_S
+        while nxt < len(qs):
+            q, table = qs[nxt], tables[nxt]
             n = table.shape[0]
-            a = rows[at:at + n]
+            if q._enc_dev is table:              # pylint: disable=protected-access  (else: recomputed meanwhile, leave it)
+                a = rows[at:at + n]
+                sym = str(q.use_symmetric_encodings)
+                q._export_cache = (table, sym, [                                                         # pylint: disable=protected-access
+                    {"min": mn, "max": mx, "scale": sc, "offset": off, "bitwidth": bw, "is_symmetric": sym, "dtype": "int"}
+                    for mn, mx, sc, off, bw in zip(a[:, 0].tolist(), a[:, 1].tolist(), a[:, 2].tolist(),
+                                                   a[:, 3].astype("int64").tolist(), a[:, 4].astype("int64").tolist())])
             at += n
-            if q._enc_dev is not table:          # pylint: disable=protected-access
-                continue                         # recomputed in the meantime: leave it to the exporter
-            sym = str(q.use_symmetric_encodings)
-            q._export_cache = (table, sym, [                                                             # pylint: disable=protected-access
-                {"min": mn, "max": mx, "scale": sc, "offset": off, "bitwidth": bw, "is_symmetric": sym, "dtype": "int"}
-                for mn, mx, sc, off, bw in zip(a[:, 0].tolist(), a[:, 1].tolist(), a[:, 2].tolist(),
-                                               a[:, 3].astype("int64").tolist(), a[:, 4].astype("int64").tolist())])
-        self._pending = None
-        self._done = True
+            nxt += 1
+            if time.perf_counter() > deadline:
+                break
+        self._pending[4], self._pending[5] = nxt, at
+        if nxt >= len(qs):
+            self._pending = None
+            self._done = True
 
 
 class GraphedForward:

@@ -45,12 +45,16 @@ def job():
         dist.barrier()
     t = time.perf_counter()
     QuantizationSimModel.prepare_sim_for_compute_encodings(sim)
-    cal = None
+    cal = batcher = None
     if world > 1:
         cal = ShardedCalibrator(sim)
-        cal._install()
-    t = tick("prepare", t, out)
-    with in_eval_mode(sim.model), torch.no_grad():
+        cal._attach(staging=False)
+    else:
+        from aimet_b200.quantsim.stats_batcher import StatsBatcher
+        batcher = StatsBatcher.attach(sim)
+    t = tick("prepare (reset + all parameter encodings)", t, out)
+    from aimet_b200.quantsim.qc_quantize_op import CalibrationJob
+    with in_eval_mode(sim.model), torch.no_grad(), CalibrationJob(sim):
         sim.model(xs[0])
         t = tick("forward[0]", t, out)
         if steps > 1:
@@ -61,8 +65,11 @@ def job():
         t = tick(f"forward[2..{steps - 1}]", t, out)
     if cal is not None:
         cal._merge()
-        cal._uninstall()
+        cal._detach()
         t = tick("merge", t, out)
+    elif batcher is not None:
+        batcher.flush()
+        batcher.detach()
     QuantizationSimModel.compute_layer_encodings_for_sim(sim)
     t = tick("encodings on device", t, out)
     sim.get_activation_param_encodings()
