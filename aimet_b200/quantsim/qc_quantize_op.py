@@ -324,7 +324,12 @@ class StaticGridQuantWrapper(EncodingImportMixin, nn.Module):
                 quantized_inputs = [inp.clone() if isinstance(inp, torch.Tensor) and inp.requires_grad else inp
                                     for inp in quantized_inputs]
             elif shadow_params:
-                self._gate_parameter_gradients()
+                # The reference's gating function only ever runs its backward when one of the wrapper's inputs requires
+                # grad (an autograd function without a differentiable input is not part of the graph): the parameters of a
+                # model's FIRST layer, fed by the data tensor, are therefore not gated there. Kept, for identical gradients.
+                self._gate_armed = any(isinstance(t, torch.Tensor) and t.requires_grad for t in quantized_inputs)
+                if self._gate_armed:
+                    self._gate_parameter_gradients()
         wrapped_output = self._module_to_wrap(*quantized_inputs, **kwargs)
         self._restore_shadow_params(shadow_params)
         is_seq = isinstance(wrapped_output, (list, tuple))
@@ -347,7 +352,7 @@ class StaticGridQuantWrapper(EncodingImportMixin, nn.Module):
 
             def gate(grad, name=name, ref=ref, pref=weakref.ref(param)):
                 wrapper, p = ref(), pref()
-                if wrapper is None or p is None or ALWAYS_GATE_AND_CLONE:
+                if wrapper is None or p is None or ALWAYS_GATE_AND_CLONE or not wrapper.__dict__.get("_gate_armed"):
                     return grad
                 q = wrapper.param_quantizers.get(name)
                 if q is None or not q.enabled or q.bitwidth == 32 or q.data_type == QuantizationDataType.float or \
