@@ -57,6 +57,7 @@ PROTOTYPES = {
     "ab_qdq_per_tensor_fwd": (_int, [_vp, _vp, _i64, _int, _dbl, _dbl, _int, _int, _u64, _vp]),
     "ab_qdq_per_tensor_fwd_dev": (_int, [_vp, _vp, _i64, _int, _vp, _int, _u64, _vp]),
     "ab_quantize_to_grid": (_int, [_vp, _vp, _i64, _int, _dbl, _dbl, _int, _int, _int, _u64, _vp]),
+    "ab_quantize_to_packed": (_int, [_vp, _vp, _i64, _int, _dbl, _dbl, _int, _int, _vp]),
     "ab_qdq_per_channel_fwd": (_int, [_vp, _vp, _i64, _i64, _i64, _int, _vp, _int, _u64, _vp]),
     "ab_per_channel_params_dev": (_int, [_vp, _i64, _int, _vp, _vp]),
     "ab_qdq_broadcast_fwd": (_int, [_vp, _vp, _i64, _int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _vp, _vp, _vp, _vp,

@@ -146,6 +146,19 @@ def quantize_to_grid_impl(x, enc_min, enc_max, bw, round_mode=0, shift_to_signed
     return out
 
 
+def quantize_to_packed_impl(x, enc_min, enc_max, bw, shift_to_signed=False):
+    """quantizeTensorPacked: the integer grid values as a flat uint8 CUDA tensor of max(bw, 8) / 8 bytes per element (view it
+    as int8 / uint16 / int16 / int32 ... with `.view(dtype)`), as the reference fills its std::vector<uint8_t>."""
+    _require_cuda(x)
+    x = x.contiguous()
+    out = torch.empty(x.numel() * max(int(bw), 8) // 8, dtype=torch.uint8, device=x.device)
+    with _on_device(x):
+        _lib.check(_L.ab_quantize_to_packed(x.data_ptr(), out.data_ptr(), x.numel(), _dtype_code(x), float(enc_min),
+                                            float(enc_max), int(bw), int(bool(shift_to_signed)), _stream(x)))
+    LAUNCHES["quantize"] += 1
+    return out
+
+
 def qdq_per_channel_impl(x, params, num_channel, num_element_per_channel, round_mode=0, seed=0):
     _require_cuda(x, params)
     if params.dtype != torch.float32 or params.numel() != 4 * num_channel or not params.is_contiguous():

@@ -166,6 +166,15 @@ int ab_qdq_per_tensor_fwd_dev(const void* in, void* out, int64_t count, int dtyp
 int ab_quantize_to_grid(const void* in, void* out, int64_t count, int dtype, double enc_min, double enc_max, int bw,
                         int round_mode, int shift_to_signed, uint64_t seed, void* stream);
 
+/* ITensorQuantizationSim::quantizeTensorPacked (DlQ/src/TensorQuantizationSim.cpp:128-139 -> quantizeToFxpPackedCpu,
+ * DlQ/src/trim_functions.cpp:221-388; "GPU packed quantization not supported" in the reference, :194-196): the integer grid
+ * value of every element, nearest rounding, computed in double on the double encoding, stored in `out` (DEVICE) as
+ * max(bw, 8) / 8 bytes per element: uint8 (one value per byte below 8 bit, as the reference stores them), uint16 or uint32;
+ * with shift_to_signed the value minus 2^(bw-1) - 1 as int8 (low bw bits below 8 bit) / int16 / int32.
+ * bw must be 1, 2, 4, 8, 16 or 32 (AB_ERR_INVALID otherwise: the reference throws). */
+int ab_quantize_to_packed(const void* in, void* out, int64_t count, int dtype, double enc_min, double enc_max, int bw,
+                          int shift_to_signed, void* stream);
+
 /* ITensorQuantizationSim::quantizeDequantizeTensorPerChannel (DlQ/src/TensorQuantizationSim.cpp:281-318 ->
  * trim_functions.cpp:697-709 ; GPU twin trim_functions.cu:78-92,169-172).
  * channel(i) = (i / num_element_per_channel) % num_channel. `params` is a DEVICE array of 4*num_channel floats

@@ -66,6 +66,8 @@ class Oracle:
         L.qo_partial_encoding.argtypes = [C.c_int, C.POINTER(Encoding), C.c_int, C.c_int, C.c_int]
         L.qo_qdq_tensor.argtypes = [_fp, C.c_size_t, _fp, C.c_double, C.c_double, C.c_int]
         L.qo_quantize_tensor.argtypes = [_fp, C.c_size_t, _fp, C.c_double, C.c_double, C.c_int, C.c_int]
+        L.qo_quantize_packed.restype = C.c_int64
+        L.qo_quantize_packed.argtypes = [_fp, C.c_size_t, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int]
         L.qo_per_channel_prepare.argtypes = [_dp, _dp, C.c_int, C.c_int, _fp, _fp, _fp, _fp]
         L.qo_qdq_per_channel.argtypes = [_fp, C.c_size_t, C.c_size_t, C.c_size_t, _fp, _fp, _fp, _fp, _fp]
         L.qo_qdq_broadcast.argtypes = [_fp, _fp, C.c_int64, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _fp, _fp,
@@ -127,6 +129,13 @@ class Oracle:
         out = np.empty_like(x)
         self.L.qo_quantize_tensor(_f(x), x.size, _f(out), mn, mx, bw, int(shift_to_signed))
         return out
+
+    def quantize_packed(self, x, mn, mx, bw, shift_to_signed):
+        """-> uint8 array of max(bw, 8) / 8 bytes per element (quantizeTensorPacked), or None for an unsupported bitwidth"""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        out = np.zeros(x.size * max(bw, 8) // 8, dtype=np.uint8)
+        n = self.L.qo_quantize_packed(_f(x), x.size, out.ctypes.data_as(C.c_void_p), mn, mx, bw, int(shift_to_signed))
+        return None if n < 0 else out[:n]
 
     def per_channel_prepare(self, mins, maxs, bw):
         mins = np.ascontiguousarray(mins, dtype=np.float64)
@@ -293,6 +302,9 @@ class Reference:
         L.ref_qdq.argtypes = [_fp, C.c_size_t, _fp, C.c_double, C.c_double, C.c_int, C.c_int]
         L.ref_quantize.argtypes = [_fp, C.c_size_t, _fp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int]
         L.ref_qdq_per_channel.argtypes = [_fp, C.c_size_t, C.c_size_t, C.c_size_t, _fp, _fp, _fp, _fp, _fp, C.c_int]
+        if hasattr(L, "ref_quantize_packed"):      # (a library built before this entry point existed lacks it)
+            L.ref_quantize_packed.restype = C.c_int64
+            L.ref_quantize_packed.argtypes = [_fp, C.c_size_t, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int]
         L.ref_qdq_broadcast.argtypes = [_fp, _fp, C.c_int64, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _fp, _fp,
                                         _fp, _fp]
         L.ref_tq_new.restype = C.c_void_p
@@ -325,6 +337,12 @@ class Reference:
         out = np.empty_like(x)
         self.L.ref_quantize(_f(x), x.size, _f(out), mn, mx, bw, ROUND_NEAREST, int(shift_to_signed))
         return out
+
+    def quantize_packed(self, x, mn, mx, bw, shift_to_signed):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        out = np.zeros(x.size * max(bw, 8) // 8 + 8, dtype=np.uint8)
+        n = self.L.ref_quantize_packed(_f(x), x.size, out.ctypes.data_as(C.c_void_p), mn, mx, bw, int(shift_to_signed))
+        return None if n < 0 else out[:n]
 
     def qdq_per_channel(self, x, num_channel, num_per_channel, emin, emax, edelta, eoffset):
         x = np.ascontiguousarray(x, dtype=np.float32)

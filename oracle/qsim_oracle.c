@@ -212,6 +212,71 @@ void qo_quantize_tensor(const float* in, size_t n, float* out, double enc_min, d
     }
 }
 
+/* quantizeTensorPacked + quantizeToFxpPackedCpu (TensorQuantizationSim.cpp:128-139, trim_functions.cpp:221-388), nearest
+ * rounding. All arithmetic in DOUBLE on the double encoding (unlike the float kernels above). One value per byte below 8 bit
+ * (the reference's sub-byte packing is compiled out), uint16 / uint32 above; shiftToSigned subtracts 2^(bw-1) - 1 (NOT
+ * 2^(bw-1) as quantizeToFxp does) and stores int8 / int16 / int32. Returns bytes written, -1 for an unsupported bitwidth.
+ * The float -> integer casts are x86's cvttsd2si on values already clamped into range, except NaN inputs, which the
+ * reference lets through its std::min / std::max chain (they return the first argument when a comparison with NaN is
+ * false) and then casts -- reproduced as the instruction behaves: the "integer indefinite" value, truncated. */
+static int64_t cvtt_i64(double v)
+{
+    if (!(v == v) || v >= 9223372036854775808.0 || v < -9223372036854775808.0)
+        return INT64_MIN;
+    return (int64_t) v;
+}
+static int32_t cvtt_i32(double v)
+{
+    if (!(v == v) || v >= 2147483648.0 || v < -2147483649.0)
+        return INT32_MIN;
+    return (int32_t) v;
+}
+static double std_min(double a, double b) { return (b < a) ? b : a; }
+static double std_max(double a, double b) { return (a < b) ? b : a; }
+
+int64_t qo_quantize_packed(const float* in, size_t n, uint8_t* out, double enc_min, double enc_max, int bw,
+                           int shift_to_signed)
+{
+    qo_encoding e;
+    qo_fill_encoding_info(bw, enc_min, enc_max, &e);
+    if (!(bw == 1 || bw == 2 || bw == 4 || bw == 8 || bw == 16 || bw == 32))
+        return -1;
+    const int bytes_per = (bw > 8 ? bw : 8) / 8;
+    for (size_t i = 0; i < n; ++i)
+    {
+        double q = std_max(std_min((double) in[i], e.max), e.min);
+        q        = q / e.delta - e.offset;
+        q        = round(q);
+        if (!shift_to_signed)
+        {
+            if (bw < 8)
+            {
+                const uint8_t shr = (uint8_t) cvtt_i32(q);                      /* (uint8_t) data_quantized */
+                out[i]            = (uint8_t) cvtt_i32(std_max(std_min((double) shr, pow(2, bw) - 1), 0.0));
+            }
+            else if (bw == 8)
+                out[i] = (uint8_t) cvtt_i32(std_max(std_min(q, 255.0), 0.0));
+            else if (bw == 16)
+                ((uint16_t*) out)[i] = (uint16_t) cvtt_i32(std_max(std_min(q, 65535.0), 0.0));
+            else
+                ((uint32_t*) out)[i] = (uint32_t) cvtt_i64(std_max(std_min(q, 4294967295.0), 0.0));
+        }
+        else
+        {
+            q -= pow(2, bw - 1) - 1;
+            if (bw < 8)
+                ((int8_t*) out)[i] = (int8_t) ((int8_t) cvtt_i32(q) & (int8_t) (pow(2, bw) - 1));
+            else if (bw == 8)
+                ((int8_t*) out)[i] = (int8_t) cvtt_i32(std_max(std_min(q, 127.0), -128.0));
+            else if (bw == 16)
+                ((int16_t*) out)[i] = (int16_t) cvtt_i32(std_max(std_min(q, 32767.0), -32768.0));
+            else
+                ((int32_t*) out)[i] = cvtt_i32(std_max(std_min(q, 2147483647.0), -2147483648.0));
+        }
+    }
+    return (int64_t) n * bytes_per;
+}
+
 void qo_per_channel_prepare(const double* enc_min, const double* enc_max, int num_channel, int bw, float* o_min,
                             float* o_max, float* o_delta, float* o_offset)
 {

@@ -55,6 +55,8 @@ int qo_partial_encoding(int bw, qo_encoding* e, int sym, int unsigned_sym, int s
 /* ---- element-wise kernels ---- */
 void qo_qdq(const float* in, size_t n, float* out, const qo_encoding* e);          /* src/trim_functions.cpp:140-182 */
 void qo_qdq_tensor(const float* in, size_t n, float* out, double enc_min, double enc_max, int bw); /* TensorQuantizationSim.cpp:104-114 */
+int64_t qo_quantize_packed(const float* in, size_t n, uint8_t* out, double enc_min, double enc_max, int bw,
+                           int shift_to_signed);
 void qo_quantize_tensor(const float* in, size_t n, float* out, double enc_min, double enc_max, int bw,
                         int shift_to_signed);                                       /* TensorQuantizationSim.cpp:116-126; trim_functions.cpp:202-218 */
 /* TrainingExtensions/torch/src/AimetTensorQuantizer.cpp:236-299 (torch fp32 CPU ops restated) */

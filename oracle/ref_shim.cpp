@@ -109,6 +109,27 @@ void ref_quantize(const float* in, size_t n, float* out, double enc_min, double 
                         shift_to_signed != 0);
 }
 
+// ITensorQuantizationSim::quantizeTensorPacked (TensorQuantizationSim.cpp:128-139). out: max(bw, 8) / 8 bytes per element.
+// Returns the number of bytes written, or -1 where the reference throws (a bitwidth that is not 1, 2, 4, 8, 16 or 32).
+int64_t ref_quantize_packed(const float* in, size_t n, uint8_t* out, double enc_min, double enc_max, int bw, int shift_to_signed)
+{
+    // (the reference throws for other bitwidths from inside its worker threads, i.e. it terminates the process)
+    if (!(bw == 1 || bw == 2 || bw == 4 || bw == 8 || bw == 16 || bw == 32))
+        return -1;
+    auto sim = getTensorQuantizationSim<float>();
+    std::vector<uint8_t> packed;
+    try
+    {
+        sim->quantizeTensorPacked(in, n, packed, enc_min, enc_max, bw, ROUND_NEAREST, false, shift_to_signed != 0);
+    }
+    catch (const std::exception&)
+    {
+        return -1;
+    }
+    std::memcpy(out, packed.data(), packed.size());
+    return (int64_t) packed.size();
+}
+
 void ref_qdq_broadcast(const float* in, float* out, int64_t num_element, int64_t num_dims, const int64_t* input_strides,
                        const int64_t* encoding_strides, const float* enc_min, const float* enc_max,
                        const float* enc_delta, const float* enc_offset)
