@@ -8,3 +8,4 @@ from .tensor_quantizer import (Quantize, QuantizeDequantize, StaticGridPerChanne
 from .learned_grid import (LearnedGridQuantWrapper, LearnedGridTensorQuantizer,  # noqa: F401
                            set_encoding_min_max_gating_threshold)
 from .quant_analyzer import CallbackFunc, QuantAnalyzer  # noqa: F401,E402
+from .adaround import Adaround, AdaroundParameters  # noqa: F401,E402

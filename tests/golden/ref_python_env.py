@@ -150,6 +150,12 @@ class AimetTensorQuantizer:
         h = self.a.histogram()
         return list(zip(h[0].tolist(), h[1].tolist()))
 
+    def makeDeltaOffsetTensor(self, device, encodings):
+        # AimetTensorQuantizer.cpp:209-234: float32 [2, C] from the doubles, moved to `device`, rows returned
+        t = torch.tensor([[e.delta for e in encodings], [e.offset for e in encodings]], dtype=torch.float64).to(torch.float32)
+        t = t.to(device)
+        return t[0], t[1]
+
     def setPercentileValue(self, p):
         if self.scheme == int(QuantizationMode.QUANTIZATION_PERCENTILE):   # AimetTensorQuantizer.cpp:200-207
             self.a.set_percentile(p)
