@@ -27,6 +27,17 @@ class StatsSegment(C.Structure):
     _fields_ = [("data", C.c_void_p), ("count", C.c_int64), ("state_index", C.c_int32), ("reserved", C.c_int32)]
 
 
+class QcQuantizeInfo(C.Structure):
+    """ab_qc_quantize_info: what the reference's ONNX op keeps per quantizer (QcQuantizeInfo.h:47-73)."""
+    _fields_ = [("states", C.c_void_p), ("encodings", C.POINTER(Encoding)), ("num_encodings", C.c_int), ("op_mode", C.c_int),
+                ("quant_mode", C.c_int), ("use_symmetric_encoding", C.c_int), ("enabled", C.c_int),
+                ("is_int_data_type", C.c_int), ("use_per_channel_mode", C.c_int), ("channel_axis", C.c_int),
+                ("block_axis", C.c_int), ("block_size", C.c_int)]
+
+
+OP_UPDATE_STATS, OP_ONE_SHOT_QDQ, OP_QDQ, OP_PASS_THROUGH = 0, 1, 2, 3
+
+
 class RefreshItem(C.Structure):
     """ab_refresh_item: one parameter tensor of a multi-tensor encoding refresh."""
     _fields_ = [("data", C.c_void_p), ("num_segments", C.c_int64), ("segment_len", C.c_int64), ("first_record", C.c_int64)]
@@ -78,6 +89,8 @@ PROTOTYPES = {
     "ab_stats_init_range": (_int, [_vp, _i64, _vp, _vp]),
     "ab_stats_fold_batches": (_int, [_vp, _i64, _vp, _vp, _i64, _vp]),
     "ab_stats_fold_log": (_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
+    "ab_qc_quantize_op_workspace_bytes": (C.c_size_t, [_int]),
+    "ab_qc_quantize_op_compute": (_int, [C.POINTER(QcQuantizeInfo), _vp, _vp, C.POINTER(C.c_int64), _int, _int, _vp, _vp]),
     "ab_lg_workspace_bytes": (_i64, [_i64]),
     "ab_lg_qdq_fwd": (_int, [_vp, _vp, _i64, _i64, _i64, _int, _vp, _vp, _int, _int, _int, _int, _vp, _vp]),
     "ab_lg_qdq_bwd": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _int, _vp, _vp, _int, _int, _int, _vp, _vp, _vp, _vp]),

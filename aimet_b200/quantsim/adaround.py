@@ -338,7 +338,7 @@ class AdaroundOptimizer:
         out_soft = cls._compute_output_with_adarounded_weights(quant_module, inp_data)
         if act_func is not None:
             out_data, out_soft, out_hard = act_func(out_data), act_func(out_soft), act_func(out_hard)
-        return float(functional.mse_loss(out_hard, out_data)), float(functional.mse_loss(out_soft, out_data))
+        return float(functional.mse_loss(out_hard, out_data).detach()), float(functional.mse_loss(out_soft, out_data).detach())
 
     @staticmethod
     def _compute_output_with_adarounded_weights(quant_module: AdaroundWrapper, inp_data: torch.Tensor):

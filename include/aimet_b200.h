@@ -389,6 +389,45 @@ int ab_stats_fold_batches(ab_stats_state* states, int64_t count, const uint32_t*
 int ab_stats_fold_log(ab_stats_state* states, int64_t count, const uint32_t* log, const int64_t* entry_rows,
                       const int64_t* record_begin, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * The compute body of the reference's ONNX Runtime custom op "QcQuantizeOp" (TrainingExtensions/onnx/src/QcQuantizeOp.cpp:
+ * 64-143 -> AimetOpUtils.h:98-322): what QcQuantizeOpCuda::Compute does between its input and output buffers, for the
+ * integer data type. `ab_qc_quantize_info` carries what the reference's QcQuantizeInfo (QcQuantizeInfo.h:47-73) does; the
+ * op modes have TensorQuantizerOpMode's values (DlQ/include/DlQuantization/TensorQuantizerOpFacade.h:48-54).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef enum
+{
+    AB_OP_UPDATE_STATS = 0,
+    AB_OP_ONE_SHOT_QDQ = 1,
+    AB_OP_QDQ          = 2,
+    AB_OP_PASS_THROUGH = 3
+} ab_op_mode;
+
+typedef struct
+{
+    ab_stats_state* states; /* DEVICE: one record per encoding (replaces tensorQuantizerRef); may be NULL for QDQ / pass-through */
+    ab_encoding* encodings; /* HOST: num_encodings entries; min / max / delta / offset are rewritten by the one-shot mode */
+    int num_encodings;      /* 1, the channel count, or channels x blocks */
+    int op_mode;            /* ab_op_mode; the one-shot mode switches itself to AB_OP_QDQ after running once */
+    int quant_mode;         /* ab_quant_mode of the statistics */
+    int use_symmetric_encoding;
+    int enabled;
+    int is_int_data_type;
+    int use_per_channel_mode;
+    int channel_axis;
+    int block_axis;
+    int block_size;         /* 0: plain per-channel */
+} ab_qc_quantize_info;
+
+/* bytes of DEVICE scratch ab_qc_quantize_op_compute needs for `num_encodings` encodings (the reference cudaMallocs per call) */
+size_t ab_qc_quantize_op_workspace_bytes(int num_encodings);
+
+/* shape / ndim: the input tensor's dimensions (contiguous). Statistics are supported per tensor, per channel when no
+ * dimension precedes the channel axis, and per contiguous block; quantize-dequantize for every layout the reference handles.
+ * Unlike the reference's CUDA op no stream synchronisation happens in updateStats mode. */
+int ab_qc_quantize_op_compute(ab_qc_quantize_info* info, const void* in, void* out, const int64_t* shape, int ndim, int dtype,
+                              void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
