@@ -426,6 +426,37 @@ def kernel_sweep(device, peak, sizes_mb=(1, 16, 64, 256, 1024), window_mb=512):
             measure("stats_tfe_hist_steady", dname, mb,
                     lambda i: ops.stats_update_impl(xs[i], blk.arena, blk.first, ops.QUANTIZATION_TF_ENHANCED, None, 0,
                                                     ops.STATS_RANGE_FIXED), es * n, xs)
+            if mb in (64, 1024):
+                # range learning: fused forward (2 s B / element) and backward (3 s B / element, the
+                # backward also produces grad_min / grad_max), per tensor asymmetric and per channel signed symmetric
+                c_lg = 2048
+                per = n // c_lg
+                for cname, cnt, shape, mode in (("per_tensor_asym", 1, (n,), ops.LG_ASYMMETRIC),
+                                                ("per_channel_sym_c2048", c_lg, (c_lg, per), ops.LG_SIGNED_SYMMETRIC)):
+                    mn = torch.full((cnt,), -4.0, dtype=dtype, device=device)
+                    mx = torch.full((cnt,), 8.0 if mode == ops.LG_ASYMMETRIC else 4.0, dtype=dtype, device=device)
+                    m = c_lg * per if cnt > 1 else n
+                    measure(f"range_learning_fwd_{cname}_bw8", dname, mb,
+                            lambda i, mn=mn, mx=mx, mode=mode, shape=shape, m=m:
+                            ops.lg_qdq_fwd_impl(xs[i][:m].view(shape), mn, mx, 8, mode, False, 0, gate=True), 2 * es * m, xs)
+                    measure(f"range_learning_bwd_{cname}_bw8", dname, mb,
+                            lambda i, mn=mn, mx=mx, mode=mode, shape=shape, m=m:
+                            ops.lg_qdq_bwd_impl(xs[i][:m].view(shape), gs[i % len(gs)][:m].view(shape), mn, mx, 8, mode,
+                                                False, 0), 3 * es * m, xs)
+                # blockwise QDQ with one encoding per `block` consecutive elements (ONNX path)
+                for block in (16, 64):
+                    rows_b = n // 4096
+                    nb = 4096 // block
+                    e_shape = (rows_b, nb, 1)
+                    e_min = torch.full(e_shape, -4.0, device=device)
+                    e_max = torch.full(e_shape, 8.0, device=device)
+                    e_delta = torch.full(e_shape, 12.0 / 255.0, device=device)
+                    e_off = torch.full(e_shape, -85.0, device=device)
+                    m = rows_b * 4096
+                    measure(f"qdq_blockwise_block{block}", dname, mb,
+                            lambda i, e=(e_min, e_max, e_delta, e_off), m=m, rows_b=rows_b, nb=nb, block=block:
+                            ops.qdq_broadcast_impl(xs[i][:m].view(rows_b, nb, block), *e),
+                            2 * es * m + 16 * rows_b * nb, xs, {"encodings": rows_b * nb})
             if n > total:
                 del big
             del xs, gs

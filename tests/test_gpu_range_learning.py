@@ -131,6 +131,13 @@ SEEDED = [
     ((96, 33, 3), torch.bfloat16, 8, rl.SIGNED_SYMMETRIC, False, 0),
     ((40, 130), torch.bfloat16, 4, rl.ASYMMETRIC, False, 0),
     ((2000,), torch.bfloat16, 8, rl.ASYMMETRIC, False, 0),
+    # channel runs longer than a CTA tile: the block-uniform "whole tile in one channel" path, mixed tiles at the run ends
+    ((6, 20480), torch.bfloat16, 8, rl.SIGNED_SYMMETRIC, False, 0),
+    ((5, 24576), torch.bfloat16, 8, rl.ASYMMETRIC, False, 0),
+    ((3, 40960), torch.bfloat16, 4, rl.SIGNED_SYMMETRIC, True, 0),
+    ((2, 3, 16384), torch.float32, 8, rl.ASYMMETRIC, False, 1),
+    ((3, 20480), torch.float32, 8, rl.SIGNED_SYMMETRIC, False, 0),
+    ((4, 12296), torch.bfloat16, 12, rl.ASYMMETRIC, False, 0),      # bf16 above 8 bit: every operation rounded (policy 1)
 ]
 
 
@@ -189,6 +196,86 @@ def test_non_finite_inputs_and_unaligned_views(ops):
         assert bits_equal(y, y_ref)
         assert bits_equal(gx, gx_ref)
         assert torch.isnan(gmin).all() and torch.isnan(gmax).all()   # a NaN input poisons the sums, as in the reference
+
+
+@pytest.mark.parametrize("per_channel", [False, True])
+@pytest.mark.parametrize("mode", [rl.ASYMMETRIC, rl.SIGNED_SYMMETRIC])
+def test_bf16_packed_path_special_values(ops, mode, per_channel):
+    """The packed bf16 kernels (two elements per instruction) on aligned tensors: NaN, +-inf, -0, the largest finite bf16,
+    and, for the symmetric gradients, an |x| whose quotient by delta overflows bf16 (0 * inf = NaN in the reference) next to
+    one that just does not."""
+    g = torch.Generator().manual_seed(9)
+    c, per = (4, 16384) if per_channel else (1, 65536)
+    base = torch.randn(c, per, generator=g) * 1.2
+    grad = torch.randn(c, per, generator=g).to(torch.bfloat16)
+    mn = (-2.0 * torch.ones(c)).to(torch.bfloat16)
+    mx = (2.0 * torch.ones(c) if mode != rl.ASYMMETRIC else 2.5 * torch.ones(c)).to(torch.bfloat16)
+    axis = 0
+
+    def run(x):
+        x = x.to(torch.bfloat16)
+        xs = x if per_channel else x.reshape(-1)
+        gs = grad if per_channel else grad.reshape(-1)
+        y_ref, saved = rl.forward(xs, mn, mx, 8, mode, False, axis)
+        gx_ref, gmin_ref, gmax_ref = rl.backward(gs, saved)
+        y = ops.lg_qdq_fwd_impl(xs.cuda(), mn.cuda(), mx.cuda(), 8, mode, False, axis)
+        gx, gmin, gmax = ops.lg_qdq_bwd_impl(xs.cuda(), gs.cuda(), mn.cuda(), mx.cuda(), 8, mode, False, axis)
+        assert bits_equal(y, y_ref)
+        assert bits_equal(gx, gx_ref.to(torch.bfloat16))
+        return (gmin.float().cpu().reshape(-1), gmax.float().cpu().reshape(-1), gmin_ref.float().reshape(-1),
+                gmax_ref.float().reshape(-1), saved)
+
+    # (1) finite only, incl. -0, the largest bf16 and values far outside the grid whose quotient stays finite
+    x = base.clone()
+    x[:, 3::89] = -0.0
+    x[:, 5::1013] = 3.3895e38
+    x[:, 6::1013] = -1e30
+    gmin, gmax, gmin_ref, gmax_ref, saved = run(x)
+    delta = float(saved["delta"].reshape(-1)[0])
+    overflow = mode != rl.ASYMMETRIC and 3.3895e38 / abs(delta) > 3.39e38
+    if overflow:
+        assert torch.isnan(gmin_ref).all() and torch.isnan(gmin).all() and torch.isnan(gmax).all()
+    else:
+        assert torch.isfinite(gmin_ref).all()
+        assert torch.allclose(gmin, gmin_ref, rtol=2e-2, atol=2e-2) and torch.allclose(gmax, gmax_ref, rtol=2e-2, atol=2e-2)
+    # (2) only channel 1 (or the tensor) holds an infinity: its gradients are NaN, the other channels' are not
+    x = base.clone()
+    x[min(1, c - 1), 77] = float("inf")
+    x[min(1, c - 1), 4099] = float("-inf")
+    gmin, gmax, gmin_ref, gmax_ref, _ = run(x)
+    assert torch.equal(torch.isnan(gmin), torch.isnan(gmin_ref)) and torch.equal(torch.isnan(gmax), torch.isnan(gmax_ref))
+    assert torch.isnan(gmin_ref).any()
+    ok = ~torch.isnan(gmin_ref)
+    assert torch.allclose(gmin[ok], gmin_ref[ok], rtol=2e-2, atol=2e-2)
+    # (3) NaN inputs
+    x = base.clone()
+    x[:, 11::97] = float("nan")
+    gmin, gmax, gmin_ref, gmax_ref, _ = run(x)
+    assert torch.isnan(gmin).all() and torch.isnan(gmax).all() and torch.isnan(gmin_ref).all()
+    # (4) a non-finite gradient: grad_x = mask * grad keeps inf where the mask is set and gives NaN where it is not
+    grad[:, 13::211] = float("inf")
+    gmin, gmax, gmin_ref, gmax_ref, _ = run(base)
+    assert torch.equal(torch.isnan(gmin), torch.isnan(gmin_ref))
+
+
+def test_bf16_symmetric_quotient_overflow_threshold(ops):
+    """Symmetric gradients multiply mask * (x / delta) by the gradient: where the mask is clear and x / delta rounds to a bf16
+    infinity, the reference gets 0 * inf = NaN. A tiny delta puts that threshold inside the finite bf16 range: values just
+    below it must leave the gradients finite, the first value at it must turn them NaN."""
+    mx = torch.tensor([2.0 ** -60 * 127]).to(torch.bfloat16)       # delta = 2^-60 (the packed path takes |delta| >= 2^-64)
+    mn = -mx
+    g = torch.Generator().manual_seed(3)
+    grad = torch.randn(8192, generator=g).to(torch.bfloat16)
+    for magnitude, expect_nan in ((2.0 ** 67 * 1.9921875, False), (2.0 ** 68, True), (-(2.0 ** 68), True)):
+        x = (torch.randn(8192, generator=g) * 2.0 ** -60 * 50).to(torch.bfloat16)
+        x[4001] = magnitude
+        y_ref, saved = rl.forward(x, mn, mx, 8, rl.SIGNED_SYMMETRIC, False, 0)
+        _, gmin_ref, _ = rl.backward(grad, saved)
+        assert bool(torch.isnan(gmin_ref).all()) == expect_nan, magnitude
+        y = ops.lg_qdq_fwd_impl(x.cuda(), mn.cuda(), mx.cuda(), 8, rl.SIGNED_SYMMETRIC, False, 0)
+        _, gmin, gmax = ops.lg_qdq_bwd_impl(x.cuda(), grad.cuda(), mn.cuda(), mx.cuda(), 8, rl.SIGNED_SYMMETRIC, False, 0)
+        assert bits_equal(y, y_ref)
+        assert bool(torch.isnan(gmin).all()) == expect_nan and bool(torch.isnan(gmax).all()) == expect_nan, magnitude
 
 
 def test_workspace_is_rearmed_and_optional_outputs(ops):
