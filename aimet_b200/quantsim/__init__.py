@@ -9,3 +9,5 @@ from .learned_grid import (LearnedGridQuantWrapper, LearnedGridTensorQuantizer, 
                            set_encoding_min_max_gating_threshold)
 from .quant_analyzer import CallbackFunc, QuantAnalyzer  # noqa: F401,E402
 from .adaround import Adaround, AdaroundParameters  # noqa: F401,E402
+from .auto_quant import AutoQuant  # noqa: F401,E402
+from .batch_norm_fold import fold_all_batch_norms  # noqa: F401,E402

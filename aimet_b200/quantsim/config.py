@@ -133,6 +133,16 @@ def build_op_graph(model: nn.Module) -> List[Op]:
         if node.op in ("output", "get_attr"):
             node_to_op[node] = None
             continue
+        if node.op == "call_module" and type(modules[node.target]) is nn.Identity and node.args and \
+                isinstance(node.args[0], torch.fx.Node):   # pylint: disable=unidiomatic-typecheck
+            # transparent, as in the reference's ConnectedGraph (an Identity leaves no op in the jit trace): what follows a
+            # folded-away batch norm still forms a supergroup with what precedes it
+            src = node.args[0]
+            if src in placeholders:
+                placeholders.add(node)
+            else:
+                node_to_op[node] = node_to_op.get(src)
+            continue
         if node.op == "call_module":
             mod = modules[node.target]
             types = MODULE_OP_TYPES.get(type(mod), [type(mod).__name__])
