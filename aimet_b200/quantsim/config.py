@@ -100,11 +100,47 @@ class Op:
         return f"Op({self.name}:{self.type})"
 
 
+def _is_torch_nn_module(m: nn.Module) -> bool:
+    """reference aimet_torch/utils.py:919-927"""
+    return type(m) in torch.nn.__dict__.values()
+
+
+def _interior_op_count(m: nn.Module) -> int:
+    """Number of operations in the forward of a childless module, or 1 when it cannot be traced on its own."""
+    try:
+        graph = torch.fx.Tracer().trace(m)
+    except Exception:   # pylint: disable=broad-except
+        return 1
+    return sum(1 for n in graph.nodes if n.op in ("call_function", "call_method"))
+
+
+def _is_pass_through(m: nn.Module) -> bool:
+    """Modules whose eval-mode forward hands its input on untouched leave no operation in the reference's jit trace: the
+    ConnectedGraph connects their producer straight to their consumer (and keeps an isolated op for the module)."""
+    if type(m) is nn.Identity:   # pylint: disable=unidiomatic-typecheck
+        return True
+    return type(m).__name__ == "StochasticDepth"   # the reference traces the model in eval mode, whatever mode it is in
+
+
 class _LeafTracer(torch.fx.Tracer):
-    """Modules without children are leaves (the reference wraps exactly those: v1/quantsim.py:1440-1454)."""
+    """Modules without children are leaves (the reference wraps exactly those: v1/quantsim.py:1440-1454) and one op of the
+    graph -- except a childless module that is not a torch.nn class and runs more than one operation in its forward: the
+    reference's ConnectedGraph parses into those (meta/connectedgraph.py:502-512, 1315-1329), so their interior shows up
+    as module-less functional ops and the module itself (still wrapped) has no op of its own. torchvision's LayerNorm2d
+    (permute, layer_norm, permute) is the common case."""
+
+    def __init__(self):
+        super().__init__()
+        self._verdict = {}
 
     def is_leaf_module(self, m, module_qualified_name):
-        return len(list(m.children())) == 0 or super().is_leaf_module(m, module_qualified_name)
+        if len(list(m.children())) != 0:
+            return super().is_leaf_module(m, module_qualified_name)
+        if _is_torch_nn_module(m) or _is_pass_through(m):
+            return True
+        if type(m) not in self._verdict:
+            self._verdict[type(m)] = _interior_op_count(m) <= 1
+        return self._verdict[type(m)]
 
 
 def build_op_graph(model: nn.Module) -> List[Op]:
@@ -133,8 +169,8 @@ def build_op_graph(model: nn.Module) -> List[Op]:
         if node.op in ("output", "get_attr"):
             node_to_op[node] = None
             continue
-        if node.op == "call_module" and type(modules[node.target]) is nn.Identity and node.args and \
-                isinstance(node.args[0], torch.fx.Node):   # pylint: disable=unidiomatic-typecheck
+        if node.op == "call_module" and _is_pass_through(modules[node.target]) and node.args and \
+                isinstance(node.args[0], torch.fx.Node):
             # transparent, as in the reference's ConnectedGraph (an Identity leaves no op in the jit trace): what follows a
             # folded-away batch norm still forms a supergroup with what precedes it
             src = node.args[0]

@@ -240,8 +240,10 @@ class QuantizationSimModel:
             if isinstance(child, _WRAPPER_TYPES):
                 continue
             if len(list(child.children())) == 0:
-                if self._is_quantizable_module(child) and child in inout:
-                    n_in, n_out = inout[child]
+                if self._is_quantizable_module(child):
+                    # a module that the forward pass never reaches is wrapped too, with one input and one output
+                    # (reference :1409-1411)
+                    n_in, n_out = inout.get(child, (1, 1))
                     w = StaticGridQuantWrapper(child, self._default_param_bw, self._default_output_bw,
                                                MAP_ROUND_MODE_TO_PYMO[self._rounding_mode], self._quant_scheme,
                                                num_inputs=n_in, num_outputs=n_out)
