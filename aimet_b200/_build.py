@@ -12,8 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.environ.get("AIMET_B200_LIB") or os.path.join(LIB_DIR, "libaimet_b200.so")   # override: kernel-variant experiments
-SOURCES = ["qdq.cu", "stats.cu", "tfe_search.cu", "learned_grid.cu", "broadcast.cu", "packed.cu", "qc_op.cu"]
-HEADERS = ["common.cuh", "encoding_math.h", "tfe_math.h", "percentile_math.h", "mse_math.h", os.path.join("..", "..", "include", "aimet_b200.h")]
+SOURCES = ["qdq.cu", "stats.cu", "tfe_search.cu", "learned_grid.cu", "broadcast.cu", "packed.cu", "qc_op.cu", "entropy.cu"]
+HEADERS = ["common.cuh", "encoding_math.h", "tfe_math.h", "percentile_math.h", "mse_math.h", "entropy_math.h", os.path.join("..", "..", "include", "aimet_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -91,6 +91,9 @@ PROTOTYPES = {
     "ab_stats_fold_log": (_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
     "ab_qc_quantize_op_workspace_bytes": (C.c_size_t, [_int]),
     "ab_qc_quantize_op_compute": (_int, [C.POINTER(QcQuantizeInfo), _vp, _vp, C.POINTER(C.c_int64), _int, _int, _vp, _vp]),
+    "ab_entropy_update": (_int, [_vp, _i64, _int, _vp, _vp]),
+    "ab_entropy_compute_encoding": (_int, [_vp, _int, _int, _int, _int, _encp, _vp]),
+    "ab_entropy_histogram": (_int, [_vp, _dblp, _dblp, C.POINTER(C.c_int), _vp]),
     "ab_lg_workspace_bytes": (_i64, [_i64]),
     "ab_lg_qdq_fwd": (_int, [_vp, _vp, _i64, _i64, _i64, _int, _vp, _vp, _int, _int, _int, _int, _vp, _vp]),
     "ab_lg_qdq_bwd": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _int, _vp, _vp, _int, _int, _int, _vp, _vp, _vp, _vp]),

@@ -10,7 +10,7 @@ import json
 import os
 from collections import OrderedDict, defaultdict
 from contextlib import contextmanager
-from typing import Callable, Dict, List, Tuple
+from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
 from torch import nn
@@ -605,7 +605,7 @@ class QuantizationSimModel:
         return GraphedForward(self.model, sample_inputs, warmup)
 
     def capture_train_step(self, loss_fn: Callable, optimizer: torch.optim.Optimizer, sample_inputs, sample_target,
-                           warmup: int = 3) -> "GraphedTrainStep":
+                           warmup: int = 3, model: Optional[nn.Module] = None) -> "GraphedTrainStep":
         """One quantization-aware training step -- forward through the wrappers, loss, backward with the straight-through
         gates, optimizer step -- captured in a CUDA graph (no counterpart in the reference; the B200 idiom for a
         launch-bound loop). A QAT step issues ~2x the kernels of the plain step from ~140 Python wrappers and ~120 autograd
@@ -613,8 +613,14 @@ class QuantizationSimModel:
         the host cost is gone. Everything the step does is device-side and allocation-free where torch is not the allocator
         (the parameter encodings of the whole model are re-derived by one native call into preallocated tables), which is
         what makes it capturable. Returns a callable `step(*inputs, target) -> loss tensor` (static, overwritten by the
-        next call). Capture again after anything that changes quantizer configuration or enabled flags."""
-        return GraphedTrainStep(self.model, loss_fn, optimizer, sample_inputs, sample_target, warmup)
+        next call). Capture again after anything that changes quantizer configuration or enabled flags.
+
+        `model`: the module the step calls, when that is a wrapper around `self.model` -- a DistributedDataParallel
+        instance, so that its reducer's all-reduces are captured with the backward. torch's rules for that apply: build the
+        DDP wrapper on a side stream, run at least 11 eager DDP iterations before capture (`warmup >= 11`), and switch off
+        NCCL's asynchronous error handling (TORCH_NCCL_ASYNC_ERROR_HANDLING=0) before the process group is created."""
+        return GraphedTrainStep(model if model is not None else self.model, loss_fn, optimizer, sample_inputs, sample_target,
+                                warmup)
 
     @staticmethod
     def get_original_model(model: nn.Module, qdq_weights: bool = False) -> nn.Module:

@@ -428,6 +428,28 @@ size_t ab_qc_quantize_op_workspace_bytes(int num_encodings);
 int ab_qc_quantize_op_compute(ab_qc_quantize_info* info, const void* in, void* out, const int64_t* shape, int ndim, int dtype,
                               void* workspace, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * The entropy scheme: QuantizationMode::QUANTIZATION_ENTROPY = 5 of the reference's libpymo
+ * (ModelOptimizations/PyModelOptimizations/PyModelOptimizations.cpp:148-156), EntropyEncodingAnalyzer<float>
+ * (DlQ/src/EntropyEncodingAnalyzer.cpp). `state` is an ab_stats_state record initialised by ab_stats_reset and used with
+ * these three functions only.
+ *  ab_entropy_update           : updateStats (:80-96) -> updateTensorHistogram (DlQ/src/math_functions.cpp:440-560): min / max
+ *                                of the tensor, range growth with redistribution of the older counts, binning. Three launches
+ *                                on `stream`, no host synchronisation (the reference's GPU build copies the tensor to the
+ *                                host and bins it there).
+ *  ab_entropy_compute_encoding : computeEncoding (:98-143) -> _optimizeKL (:221-428) -> getComputedEncodings. Reads the
+ *                                512-bin histogram back (synchronises `stream`) and runs the KL search on the HOST: the
+ *                                result is defined by the C library's log (csrc/entropy_math.h). `out` is HOST memory.
+ *  ab_entropy_histogram        : the raw TensorProfilingParams {histogram[512], min, max}; info[3] = {initialized,
+ *                                stats_updated, iterations} (may be NULL). The reference's own getStatsHistogram for this
+ *                                scheme (:54-78) trips its size assertion, so there is no PDF view to mirror.
+ * ------------------------------------------------------------------------------------------------------------ */
+#define AB_QUANTIZATION_ENTROPY 5
+int ab_entropy_update(const void* in, int64_t count, int dtype, ab_stats_state* state, void* stream);
+int ab_entropy_compute_encoding(const ab_stats_state* state, int bw, int use_symmetric, int use_strict_symmetric,
+                                int use_unsigned_symmetric, ab_encoding* out, void* stream);
+int ab_entropy_histogram(const ab_stats_state* state, double* hist512, double* min_max, int* info, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

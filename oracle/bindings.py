@@ -37,6 +37,11 @@ class TfState(C.Structure):
     _fields_ = [("stats_updated", C.c_int), ("min", C.c_double), ("max", C.c_double)]
 
 
+class EntropyState(C.Structure):
+    _fields_ = [("initialized", C.c_int), ("stats_updated", C.c_int), ("iterations", C.c_int), ("min", C.c_double),
+                ("max", C.c_double), ("histogram", C.c_double * PDF_SIZE)]
+
+
 _fp = C.POINTER(C.c_float)
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -102,6 +107,11 @@ class Oracle:
         L.qo_tfe_cost.argtypes = [C.POINTER(TfeState), C.c_int, C.c_float, C.c_int]
         L.qo_tfe_candidates.restype = C.c_int
         L.qo_tfe_candidates.argtypes = [C.POINTER(TfeState), C.c_int, C.c_int, C.c_int, C.c_int, _fp, _ip, _fp]
+        L.qo_entropy_init.argtypes = [C.POINTER(EntropyState)]
+        L.qo_entropy_update.argtypes = [C.POINTER(EntropyState), _fp, C.c_size_t]
+        L.qo_entropy_compute.restype = Encoding
+        L.qo_entropy_compute.argtypes = [C.POINTER(EntropyState), C.c_int, C.c_int, C.c_int, C.c_int]
+        L.qo_rescale_histogram.argtypes = [_dp, C.c_double, C.c_double, C.c_double, C.c_double, _dp]
 
     # -- encodings ------------------------------------------------------------------------------
     def tf_encoding(self, bw, mn, mx, sym=False, strict=False, unsigned=False):
@@ -218,6 +228,26 @@ class OracleTf:
         return self.o.L.qo_tf_compute(C.byref(self.s), bw, int(sym), int(strict), int(unsigned)).astuple()
 
 
+class OracleEntropy:
+    """EntropyEncodingAnalyzer<float> restated (qo_entropy_*)."""
+
+    def __init__(self, oracle):
+        self.o, self.s = oracle, EntropyState()
+        oracle.L.qo_entropy_init(C.byref(self.s))
+
+    def update(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1)
+        self.o.L.qo_entropy_update(C.byref(self.s), _f(x), x.size)
+
+    def compute(self, bw, sym=False, strict=False, unsigned=False):
+        return self.o.L.qo_entropy_compute(C.byref(self.s), bw, int(sym), int(strict), int(unsigned)).astuple()
+
+    def raw(self):
+        """(histogram[512] or None, min, max, iterations)"""
+        hist = np.array(self.s.histogram[:]) if self.s.initialized else None
+        return hist, self.s.min, self.s.max, self.s.iterations
+
+
 class OracleTfe:
     def __init__(self, oracle):
         self.o, self.s = oracle, TfeState()
@@ -316,6 +346,13 @@ class Reference:
         L.ref_tq_is_valid.argtypes = [C.c_void_p]
         L.ref_tq_reset.argtypes = [C.c_void_p]
         L.ref_tq_partial.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, C.c_int, C.c_int]
+        if hasattr(L, "ref_tpp_new"):
+            L.ref_tpp_new.restype = C.c_void_p
+            L.ref_tpp_free.argtypes = [C.c_void_p]
+            L.ref_tpp_update.argtypes = [C.c_void_p, _fp, C.c_int]
+            L.ref_tpp_get.restype = C.c_int
+            L.ref_tpp_get.argtypes = [C.c_void_p, _dp, _dp, _ip]
+            L.ref_rescale_histogram.argtypes = [_dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, _dp]
 
     @staticmethod
     def _enc(out5):
@@ -396,3 +433,25 @@ class RefAnalyzer:
         pdf = np.zeros(PDF_SIZE)
         n = self.r.L.ref_analyzer_histogram(self.h, _d(xl), _d(pdf))
         return (xl, pdf) if n == PDF_SIZE else None
+
+
+class RefTensorHistogram:
+    """The reference's updateTensorHistogram on a TensorProfilingParams of its own (the entropy scheme's raw statistics)."""
+
+    def __init__(self, ref):
+        self.r = ref
+        self.h = ref.L.ref_tpp_new()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.r.L.ref_tpp_free(self.h)
+            self.h = None
+
+    def update(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1)
+        self.r.L.ref_tpp_update(self.h, _f(x), x.size)
+
+    def raw(self):
+        hist, mm, it = np.zeros(PDF_SIZE), np.zeros(2), C.c_int(0)
+        n = self.r.L.ref_tpp_get(self.h, _d(hist), _d(mm), C.byref(it))
+        return (hist if n == PDF_SIZE else None), mm[0], mm[1], it.value

@@ -847,3 +847,312 @@ void qo_qdq_broadcast(const float* in, float* out, int64_t num_element, int64_t 
         qo_qdq(in + i, 1, out + i, &e);
     }
 }
+
+
+/* =====================================================================================================================
+ * Entropy scheme (src/EntropyEncodingAnalyzer.cpp). DTYPE = float throughout, as libpymo instantiates it.
+ * ===================================================================================================================== */
+void qo_entropy_init(qo_entropy_state* s)
+{
+    memset(s, 0, sizeof(*s));
+}
+
+/* getBin, math_functions.cpp:466-470: every argument is narrowed to float; the quotient goes through a float -> size_t cast,
+ * written here exactly as there so that the compiler emits the same conversion */
+static size_t entropy_get_bin(size_t n_bins, float bin_width, float min_value, float value)
+{
+    size_t q;
+    if (bin_width == 0)
+        return 0;
+    q = (size_t) ((value - min_value) / bin_width);
+    return q < n_bins - 1 ? q : n_bins - 1;
+}
+
+/* updateTensorHistogram_cpu, math_functions.cpp:472-560 */
+void qo_entropy_update(qo_entropy_state* s, const float* data, size_t n)
+{
+    double min_input, max_input;
+    float bin_width;
+    size_t i;
+    s->stats_updated = 1;                      /* EntropyEncodingAnalyzer.cpp:84 */
+    min_input        = qo_get_min(data, n);
+    max_input        = qo_get_max(data, n);
+    if (min_input == 0 && max_input == 0)      /* :478-483 */
+        return;
+    if (min_input == max_input)                /* :486-489: std::max(maxInput, minInput + (float) 0.01) */
+    {
+        double cand = min_input + (float) 0.01;
+        max_input   = max_input < cand ? cand : max_input;
+    }
+    if (!s->initialized)                       /* :492-497 */
+    {
+        for (i = 0; i < QO_PDF_SIZE; ++i)
+            s->histogram[i] = 0;
+        s->min = min_input, s->max = max_input;
+        s->initialized = 1;
+    }
+    if (min_input < s->min || max_input > s->max)   /* :500-548 */
+    {
+        double new_min  = s->min < min_input ? s->min : min_input;   /* std::min(minInput, tpp.min) */
+        double new_max  = max_input < s->max ? s->max : max_input;   /* std::max(maxInput, tpp.max) */
+        double dest_w   = (new_max - new_min) / QO_PDF_SIZE;
+        double src_w    = (s->max - s->min) / QO_PDF_SIZE;
+        double scaled[QO_PDF_SIZE];
+        for (i = 0; i < QO_PDF_SIZE; ++i)
+            scaled[i] = 0;
+        for (i = 0; i < QO_PDF_SIZE; ++i)
+        {
+            double src_begin, dest_end, cnt, r;
+            size_t dest_bin, b;
+            if (s->histogram[i] == 0)
+                continue;
+            src_begin = s->min + src_w * i;
+            dest_bin  = (size_t) ((src_begin - new_min) / dest_w);
+            dest_end  = new_min + dest_w * (dest_bin + 1);
+            r         = round((dest_end - src_begin) / src_w * s->histogram[i]);
+            cnt       = s->histogram[i] < r ? s->histogram[i] : r;   /* std::min(round(..), histogram[i]) */
+            b         = entropy_get_bin(QO_PDF_SIZE, dest_w, new_min, src_begin);
+            scaled[b] += cnt;
+            if (cnt < s->histogram[i])
+            {
+                b = entropy_get_bin(QO_PDF_SIZE, dest_w, new_min, src_begin + dest_w);
+                scaled[b] += s->histogram[i] - cnt;
+            }
+        }
+        for (i = 0; i < QO_PDF_SIZE; ++i)
+            s->histogram[i] = scaled[i];
+        s->min = new_min, s->max = new_max;
+    }
+    bin_width = (s->max - s->min) / QO_PDF_SIZE;   /* :550 */
+    for (i = 0; i < n; ++i)
+        s->histogram[entropy_get_bin(QO_PDF_SIZE, bin_width, s->min, data[i])] += 1;
+    s->iterations++;
+}
+
+/* rescaleHistogram, math_functions.cpp:562-640 */
+void qo_rescale_histogram(const double* src, double src_min, double src_max, double dst_min, double dst_max, double* dst)
+{
+    const size_t n = QO_PDF_SIZE;
+    double src_w, dest_w;
+    size_t si, d;
+    if (src_min == dst_min && src_max == dst_max)
+    {
+        memcpy(dst, src, n * sizeof(double));
+        return;
+    }
+    src_w  = (src_max - src_min) / n;
+    dest_w = (dst_max - dst_min) / n;
+    for (d = 0; d < n; ++d)
+        dst[d] = 0;
+    for (si = 0; si < n; ++si)
+    {
+        double val = src[si], s_start, s_stop, f0, f1, rem;
+        size_t d0, d1;
+        if (val == 0)
+            continue;
+        s_start = src_min + si * src_w;
+        s_stop  = src_min + (si + 1) * src_w;
+        f0      = floor((s_start - dst_min) / dest_w);
+        f1      = ceil((s_stop - dst_min) / dest_w);
+        d0      = (size_t) (f0 < 0.0 ? 0.0 : f0);   /* std::max(f, 0.0) */
+        d1      = (size_t) (f1 < 0.0 ? 0.0 : f1);
+        if (d0 >= n)
+            d0 = n - 1;
+        if (d1 >= n)
+            d1 = n - 1;
+        rem = val;
+        for (d = d0; d <= d1; ++d)
+        {
+            double d_start = dst_min + d * dest_w;
+            double d_stop  = dst_min + (d + 1) * dest_w;
+            double o_start = s_start < d_start ? d_start : s_start;
+            double o_stop  = d_stop < s_stop ? d_stop : s_stop;
+            double ratio   = (o_stop - o_start) / src_w;
+            double dist;
+            ratio = ratio >= 0.0f ? ratio : 0.0f;
+            ratio = ratio <= 1.0f ? ratio : 1.0f;
+            dist  = round(ratio * val);
+            dist  = dist <= rem ? dist : rem;
+            dst[d] += dist;
+            rem -= dist;
+        }
+    }
+}
+
+/* std::accumulate(first, last, 0.f): the accumulator has the type of the initial value, float */
+static double entropy_accumulate(const double* p, size_t n)
+{
+    float acc = 0.f;
+    size_t i;
+    for (i = 0; i < n; ++i)
+        acc = acc + p[i];
+    return acc;
+}
+
+/* _conditionHistogram, EntropyEncodingAnalyzer.cpp:151-194 */
+static void entropy_condition(double* hist, size_t length)
+{
+    const double eps_zero = 0.0001;
+    size_t zeros = 0, i;
+    int is_zero[QO_PDF_SIZE];
+    double eps_non;
+    if (length == 0)
+        return;
+    for (i = 0; i < length; ++i)
+    {
+        is_zero[i] = hist[i] == 0.f;
+        zeros += is_zero[i];
+    }
+    if (zeros == length)
+        return;
+    eps_non = eps_zero * (double) zeros / (double) (length - zeros);
+    if (eps_non >= 1.0)
+        return;
+    for (i = 0; i < length; ++i)
+    {
+        hist[i] += eps_zero * is_zero[i];
+        hist[i] -= eps_non * (1 - is_zero[i]);
+    }
+}
+
+/* _computeKL, :196-219 */
+static double entropy_kl(double* P, double* Q, size_t length)
+{
+    double sum_p = entropy_accumulate(P, length), sum_q = entropy_accumulate(Q, length), divergence = 0;
+    size_t i;
+    for (i = 0; i < length; ++i)
+    {
+        P[i] /= sum_p;
+        Q[i] /= sum_q;
+        if (P[i] > 0 && Q[i] > 0)
+            divergence += P[i] * log(P[i] / Q[i]);
+    }
+    return divergence;
+}
+
+/* _optimizeKL, :221-428 */
+static void entropy_optimize_kl(const qo_entropy_state* s, int bw, int sym, int strict, int unsigned_sym, float* o_min,
+                                float* o_max)
+{
+    double hist_min = s->min, hist_max = s->max, hist[QO_PDF_SIZE], P[QO_PDF_SIZE], Q[QO_PDF_SIZE];
+    const size_t num_bins = QO_PDF_SIZE, num_q = 255;
+    double bin_w, best = INFINITY, t_min, t_max;
+    size_t start = 0, stop = num_bins - 1, i;
+    if (sym && (hist_min < 0.0 || !unsigned_sym))   /* :229-241 */
+    {
+        double a = fabs(hist_max), b = fabs(hist_min);
+        float abs_max = a < b ? b : a;   /* std::max(std::abs(histMax), std::abs(histMin)) narrowed to DTYPE */
+        float abs_min = -abs_max;
+        qo_rescale_histogram(s->histogram, hist_min, hist_max, abs_min, abs_max, hist);
+        hist_min = abs_min, hist_max = abs_max;
+    }
+    else
+        memcpy(hist, s->histogram, sizeof(hist));
+    if (bw != 8)   /* :251-254 (the bin-count conditions cannot hold for 512 bins) */
+    {
+        *o_min = hist_min, *o_max = hist_max;
+        return;
+    }
+    bin_w = (hist_max - hist_min) / (double) num_bins;
+    t_min = hist_min, t_max = hist_max;
+    while ((stop - start + 1) >= num_q)
+    {
+        const size_t win = stop - start + 1;
+        const double* wp = hist + start;
+        double left = 0, right = 0, merged, sum_p, sum_q, divergence;
+        size_t q;
+        for (i = 0; i < win; ++i)
+            P[i] = 0, Q[i] = 0;
+        for (i = 0; i <= start; ++i)
+            left += hist[i];
+        P[0] += left;
+        for (i = start + 1; i < stop; ++i)
+            P[i - start] = hist[i];
+        for (i = stop; i < num_bins; ++i)
+            right += hist[i];
+        P[win - 1] += right;
+        merged = (double) win / (double) num_q;
+        for (q = 0; q < num_q; ++q)
+        {
+            const size_t i0 = ceil(q * merged);
+            const size_t i1 = (q < num_q - 1) ? (size_t) ceil((q + 1) * merged) : win;
+            double sum = 0, norm = 0;
+            for (i = i0; i < i1; ++i)
+            {
+                sum += wp[i];
+                norm += (wp[i] != 0);
+            }
+            if (norm != 0)
+                for (i = i0; i < i1; ++i)
+                    if (wp[i])
+                        Q[i] = sum / norm;
+        }
+        sum_p = entropy_accumulate(P, win);
+        sum_q = entropy_accumulate(Q, win);
+        if (sum_p == 0 || sum_q == 0)
+            break;
+        entropy_condition(P, win);
+        entropy_condition(Q, win);
+        divergence = entropy_kl(P, Q, win);
+        if (divergence < best)
+        {
+            best  = divergence;
+            t_min = hist_min + start * bin_w;
+            t_max = hist_min + (stop + 1) * bin_w;
+        }
+        if (sym || strict)
+        {
+            start++;
+            stop--;
+        }
+        else
+        {
+            double loss[3];
+            int k = 0, j;
+            loss[0] = hist[start] + hist[stop];
+            loss[1] = hist[start] + hist[start + 1];
+            loss[2] = hist[stop] + hist[stop - 1];
+            for (j = 1; j < 3; ++j)   /* std::min_element: first minimum */
+                if (loss[j] < loss[k])
+                    k = j;
+            if ((k == 0 && (hist_min + (start + 1) * bin_w) > 0) || (k == 1 && (hist_min + (start + 2) * bin_w) > 0))
+                k = 2;
+            else if ((k == 0 && (hist_min + stop * bin_w) < 0) || (k == 2 && (hist_min + (stop - 1) * bin_w) < 0))
+                k = 1;
+            if (k == 0)
+                start++, stop--;
+            else if (k == 1)
+                start += 2;
+            else
+                stop -= 2;
+        }
+    }
+    *o_min = t_min, *o_max = t_max;
+}
+
+/* computeEncoding, :98-143 */
+qo_encoding qo_entropy_compute(const qo_entropy_state* s, int bw, int sym, int strict, int unsigned_sym)
+{
+    qo_encoding e = {0, 0, 0, 0, 0};
+    float num_steps = pow(2, bw) - 1, a_min, a_max;
+    if (sym && strict)
+        num_steps -= 1;
+    if (!s->initialized)
+    {
+        if (s->stats_updated)
+        {
+            e.min    = -1;
+            e.max    = 1;
+            e.delta  = (e.max - e.min) / (int) num_steps;
+            e.offset = floor(e.min / e.delta);
+            e.min    = e.offset * e.delta;
+            e.max    = e.min + (int) num_steps * e.delta;
+            e.bw     = bw;
+        }
+        return e;
+    }
+    entropy_optimize_kl(s, bw, sym, strict, unsigned_sym, &a_min, &a_max);
+    a_min = (0.f < a_min) ? 0.f : a_min;   /* std::min(aMin, 0.f) */
+    a_max = (a_max < 0.f) ? 0.f : a_max;   /* std::max(aMax, 0.f) */
+    return qo_tf_encoding(bw, a_min, a_max, sym, strict, unsigned_sym);
+}

@@ -105,6 +105,21 @@ double qo_tfe_cost(const qo_tfe_state* s, int bw, float delta, int offset);
 int qo_tfe_candidates(const qo_tfe_state* s, int bw, int sym, int strict, int unsigned_sym, float* deltas,
                       int* offsets, float* num_steps_out);
 
+/* ---- entropy scheme: src/EntropyEncodingAnalyzer.cpp, TensorProfilingParams src/math_functions.hpp:71-77 ---- */
+typedef struct
+{
+    int initialized;   /* histogram.size() != 0 */
+    int stats_updated; /* _statsUpdated */
+    int iterations;
+    double min, max;
+    double histogram[QO_PDF_SIZE];
+} qo_entropy_state;
+void qo_entropy_init(qo_entropy_state* s);
+void qo_entropy_update(qo_entropy_state* s, const float* data, size_t n);   /* :80-96 -> math_functions.cpp:472-560 */
+qo_encoding qo_entropy_compute(const qo_entropy_state* s, int bw, int sym, int strict, int unsigned_sym); /* :98-143 */
+/* rescaleHistogram, math_functions.cpp:562-640 (512 bins) */
+void qo_rescale_histogram(const double* src, double src_min, double src_max, double dst_min, double dst_max, double* dst);
+
 #ifdef __cplusplus
 }
 #endif

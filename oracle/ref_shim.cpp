@@ -21,6 +21,7 @@
 #include "DlQuantization/Quantization.hpp"
 #include "DlQuantization/QuantizerFactory.hpp"
 #include "DlQuantization/TensorQuantizer.h"
+#include "math_functions.hpp"
 
 using namespace DlQuantization;
 
@@ -208,6 +209,44 @@ int ref_tq_partial(void* h, int bw, double* enc5, int sym, int unsigned_sym, int
 }
 // The input the reference's own fixture builds (DlQuantization/test/TestTensorQuantizer.cpp:92-103):
 // std::normal_distribution<float>(mean, stddev) driven by std::mt19937(seed). libstdc++-specific, hence generated here.
+// ---- the entropy scheme's raw histogram: updateTensorHistogram on a TensorProfilingParams the test owns
+//      (EntropyEncodingAnalyzer keeps its own private; the analyzer object itself is reachable through ref_analyzer_*) ----
+void* ref_tpp_new()
+{
+    auto* t       = new TensorProfilingParams;
+    t->min        = 0;
+    t->max        = 0;
+    t->iterations = 0;
+    return t;
+}
+void ref_tpp_free(void* h)
+{
+    delete static_cast<TensorProfilingParams*>(h);
+}
+void ref_tpp_update(void* h, const float* data, int n)
+{
+    updateTensorHistogram(data, n, COMP_MODE_CPU, *static_cast<TensorProfilingParams*>(h));
+}
+// returns the histogram size (0 before the first non-zero batch)
+int ref_tpp_get(void* h, double* hist, double* min_max, int* iterations)
+{
+    auto* t    = static_cast<TensorProfilingParams*>(h);
+    min_max[0] = t->min;
+    min_max[1] = t->max;
+    *iterations = t->iterations;
+    for (size_t i = 0; i < t->histogram.size(); ++i)
+        hist[i] = t->histogram[i];
+    return (int) t->histogram.size();
+}
+void ref_rescale_histogram(const double* src, int n, double src_min, double src_max, double dst_min, double dst_max,
+                           double* dst)
+{
+    std::vector<double> s(src, src + n);
+    std::vector<double> d = rescaleHistogram(s, src_min, src_max, dst_min, dst_max);
+    for (int i = 0; i < n; ++i)
+        dst[i] = d[i];
+}
+
 void ref_kat_normal(unsigned seed, float mean, float stddev, unsigned n, float* out)
 {
     std::normal_distribution<float> distribution(mean, stddev);

@@ -25,6 +25,8 @@ torch.cuda.set_device(local_rank)
 dev = torch.device("cuda", local_rank)
 if world > 1:
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ["TORCH_NCCL_ASYNC_ERROR_HANDLING"] = "0"   # torch's rule for capturing DDP's all-reduces in a CUDA graph
+    os.environ["NCCL_ASYNC_ERROR_HANDLING"] = "0"
     dist.init_process_group("nccl", device_id=dev)
 torch.backends.cudnn.benchmark = True
 BATCH, STEPS, WARM = 32, 20, 5
@@ -76,23 +78,39 @@ for dtype in (torch.bfloat16, torch.float32):
     sim = QuantizationSimModel(model, dummy_input=x, quant_scheme="tf_enhanced", default_output_bw=8, default_param_bw=8)
     sim.compute_encodings(lambda m, _: m(x), None)
     sim.model.train()
-    wrapped = torch.nn.parallel.DistributedDataParallel(sim.model, device_ids=[local_rank]) if world > 1 else sim.model
+    if world > 1:
+        side = torch.cuda.Stream()          # torch's rule: a DDP wrapper that will be captured is built on a side stream
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            wrapped = torch.nn.parallel.DistributedDataParallel(sim.model, device_ids=[local_rank])
+        torch.cuda.current_stream().wait_stream(side)
+    else:
+        wrapped = sim.model
     opt = torch.optim.SGD(sim.model.parameters(), lr=1e-3, momentum=0.9)
     ms_sim, launches = timed(eager_step(wrapped, opt, x, y))
     row = {"dtype": str(dtype).split(".")[-1], "gpus": world, "batch_per_gpu": BATCH, "plain_ms": round(ms_plain, 3),
            "quantsim_ms": round(ms_sim, 3), "quantsim_img_s": round(BATCH * world / ms_sim * 1e3, 1),
            "own_launches_per_step": launches}
-    if world == 1:
-        graphed = sim.capture_train_step(loss_fn, opt, (x,), y)
+    try:
+        graphed = sim.capture_train_step(loss_fn, opt, (x,), y, warmup=3 if world == 1 else 11, model=wrapped)
         ms_graph, _ = timed(lambda: graphed(x, target=y))
-        row.update(quantsim_cuda_graph_ms=round(ms_graph, 3), quantsim_cuda_graph_img_s=round(BATCH / ms_graph * 1e3, 1))
+        row.update(quantsim_cuda_graph_ms=round(ms_graph, 3),
+                   quantsim_cuda_graph_img_s=round(BATCH * world / ms_graph * 1e3, 1))
+    except Exception as exc:   # pylint: disable=broad-except
+        row["quantsim_cuda_graph_error"] = repr(exc)[:300]
     rows.append(row)
     if rank == 0:
         print(json.dumps(row), flush=True)
+    graphed = None
     del wrapped, sim, model, opt
     torch.cuda.empty_cache()
 if rank == 0:
     out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", f"qat_ddp_n{world}.json")
     json.dump(rows, open(out, "w"), indent=1)
 if world > 1:
-    dist.destroy_process_group()
+    # a process group whose collectives were captured into CUDA graphs does not always tear down cleanly: synchronise, meet
+    # at a barrier, and leave without running the destructors
+    torch.cuda.synchronize()
+    dist.barrier()
+    sys.stdout.flush()
+    os._exit(0)
