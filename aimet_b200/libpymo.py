@@ -119,7 +119,7 @@ def scheme_code(quant_scheme) -> int:
     percentile are on the hot path; percentile keeps the tf_enhanced statistics (PercentileEncodingAnalyzer.cpp:69-75)
     and differs only in how the encoding is closed (see is_percentile). The reference's factory
     (QuantizerFactory.cpp:72-103) falls back to the TF analyzer for anything it does not know, range learning included,
-    and so do we. The entropy analyzer (a different, rescaling histogram) is out of scope."""
+    and so do we. The entropy analyzer keeps a different, rescaling histogram behind its own entry points (ab_entropy_*)."""
     mode = QuantizationMode(int(quant_scheme))
     if mode in (QuantizationMode.QUANTIZATION_TF_ENHANCED, QuantizationMode.QUANTIZATION_PERCENTILE):
         return ops.QUANTIZATION_TF_ENHANCED
@@ -127,7 +127,9 @@ def scheme_code(quant_scheme) -> int:
         return ops.QUANTIZATION_MSE        # tf_enhanced statistics, MseEncodingAnalyzer's closing search
     if mode in (QuantizationMode.QUANTIZATION_TF, QuantizationMode.QUANTIZATION_RANGE_LEARNING):
         return ops.QUANTIZATION_TF
-    raise NotImplementedError(f"{mode.name} is outside the aimet_b200 hot path (tf / tf_enhanced / percentile / mse only)")
+    if mode == QuantizationMode.QUANTIZATION_ENTROPY:
+        return ops.QUANTIZATION_ENTROPY
+    raise NotImplementedError(f"{mode.name} is not a statistics scheme")
 
 
 def is_percentile(quant_scheme) -> bool:
@@ -162,11 +164,17 @@ class _Analyzer:
     def update(self, tensor: torch.Tensor):
         if self._slot is None or self._slot.device != tensor.device:
             self._slot = StateArena.for_device(tensor.device).allocate(1)
+        if self._code == ops.QUANTIZATION_ENTROPY:
+            ops.entropy_update_impl(tensor, self._slot.arena, self._slot.first)
+            return
         ops.stats_update_impl(tensor, self._slot.arena, self._slot.first, self._code, None, 0)
 
     def compute(self, bw, sym, strict, unsigned_sym) -> TfEncoding:
         if self._slot is None:
             return TfEncoding()   # no statistics at all: the zero encoding
+        if self._code == ops.QUANTIZATION_ENTROPY:
+            return TfEncoding._from_c(ops.entropy_compute_impl(self._slot.arena, self._slot.first, bw, sym, strict,
+                                                               unsigned_sym))
         enc, _ = ops.compute_encodings_impl(self._slot.arena, self._slot.first, 1, self._code, bw, sym, strict,
                                             unsigned_sym,
                                             percentile=self.percentile if is_percentile(self._scheme) else None)
@@ -174,6 +182,9 @@ class _Analyzer:
         return TfEncoding._from_values(v[0], v[1], v[2], v[3], int(v[4]))
 
     def histogram(self):
+        if self._code == ops.QUANTIZATION_ENTROPY:
+            # the reference's EntropyEncodingAnalyzer::getStatsHistogram trips its own size assertion (:54-78)
+            raise AssertionError("pdf.xLeft.size() == pdf.pdf.size()")
         if not ops.keeps_histogram(self._code):
             raise AssertionError("No real histogram data is kept for TF Encoding analyzer")   # TfEncodingAnalyzer.cpp:53-57
         if self._slot is None:

@@ -15,6 +15,7 @@ from . import _lib
 
 ROUND_NEAREST, ROUND_STOCHASTIC = 0, 1
 QUANTIZATION_TF, QUANTIZATION_TF_ENHANCED, QUANTIZATION_PERCENTILE, QUANTIZATION_MSE = 0, 1, 3, 4
+QUANTIZATION_ENTROPY = 5   # its own entry points (ab_entropy_*): a histogram whose range grows, KL search on the host
 
 
 def keeps_histogram(quant_mode) -> bool:
@@ -30,7 +31,7 @@ STATE_BYTES = int(_L.ab_stats_state_bytes())
 # kernel launches issued through this module, by kernel family (bench.py reports their sum as gpu_launches)
 LAUNCHES = {"qdq": 0, "quantize": 0, "qdq_per_channel": 0, "ste_bwd": 0, "minmax": 0, "hist": 0, "segmented": 0,
             "search": 0, "reset": 0, "init_range": 0, "fold": 0, "lg_fwd": 0, "lg_bwd": 0, "qdq_broadcast": 0,
-            "hist_multi": 0, "fold_segments": 0}
+            "hist_multi": 0, "fold_segments": 0, "entropy": 0}
 # when a list, stats_update_impl brackets its launches with CUDA events and appends (bytes, start, stop, quant_mode)
 STATS_TIMING = None
 _EVENT_POOL = []
@@ -392,6 +393,35 @@ def _search(states, first, count, quant_mode, bw, sym, strict, unsigned_sym, enc
         _lib.check(_L.ab_compute_encodings_percentile(_state_ptr(states, first), int(count), float(percentile), int(bw),
                                                       *flags, enc_ptr, qdq4_ptr, _stream(states)))
     LAUNCHES["search"] += 1
+
+
+def entropy_update_impl(x, states, index):
+    """EntropyEncodingAnalyzer::updateStats on record `index` (min / max, range growth, binning: three launches, no sync)."""
+    _require_cuda(x)
+    x = _contig16(x) if x.dtype in (torch.float32, torch.bfloat16) else x.float().contiguous()
+    with _on_device(x):
+        _lib.check(_L.ab_entropy_update(x.data_ptr(), x.numel(), _dtype_code(x), _state_ptr(states, index), _stream(x)))
+    LAUNCHES["entropy"] += 3 if x.numel() else 1
+
+
+def entropy_compute_impl(states, index, bw, sym, strict, unsigned_sym):
+    """EntropyEncodingAnalyzer::computeEncoding: reads the histogram back (synchronises the stream), KL search on the host.
+    Returns an _lib.Encoding."""
+    e = _lib.Encoding()
+    with _on_device(states):
+        _lib.check(_L.ab_entropy_compute_encoding(_state_ptr(states, index), int(bw), int(bool(sym)), int(bool(strict)),
+                                                  int(bool(unsigned_sym)), C.byref(e), _stream(states)))
+    return e
+
+
+def entropy_histogram_impl(states, index):
+    """(histogram[512] float64 or None before the first non-zero batch, min, max, iterations) -- TensorProfilingParams."""
+    import numpy as np
+    hist, mm, info = np.zeros(_lib.PDF_SIZE), np.zeros(2), (C.c_int * 3)()
+    with _on_device(states):
+        _lib.check(_L.ab_entropy_histogram(_state_ptr(states, index), hist.ctypes.data_as(C.POINTER(C.c_double)),
+                                           mm.ctypes.data_as(C.POINTER(C.c_double)), info, _stream(states)))
+    return (hist if info[0] else None), float(mm[0]), float(mm[1]), int(info[2])
 
 
 def compute_encodings_impl(states, first, count, quant_mode, bw, sym, strict, unsigned_sym, want_qdq4=False,

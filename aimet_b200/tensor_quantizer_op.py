@@ -102,6 +102,9 @@ class AimetTensorQuantizer:
         t, _ = _to_device_tensor(input)
         self._is_encoding_valid = True
         self._ensure_state(t.device)
+        if self._code == ops.QUANTIZATION_ENTROPY:
+            ops.entropy_update_impl(t, self._block.arena, self._block.first + self._index)
+            return
         ops.stats_update_impl(t, self._block.arena, self._block.first + self._index, self._code, None, 0,
                               ops.STATS_RANGE_FIXED if self._range_fixed else 0)
         self._updates += 1
@@ -138,6 +141,10 @@ class AimetTensorQuantizer:
         """AimetTensorQuantizer.cpp:180-192 -> (TfEncoding, is_valid)"""
         if not self._is_encoding_valid or self._block is None:
             return libpymo.TfEncoding(), self._is_encoding_valid
+        if self._code == ops.QUANTIZATION_ENTROPY:
+            return libpymo.TfEncoding._from_c(ops.entropy_compute_impl(
+                self._block.arena, self._block.first + self._index, bitwidth, use_symmetric_encodings, use_strict_symmetric,
+                use_unsigned_symmetric)), True
         if use_symmetric_encodings and self._code == ops.QUANTIZATION_TF:
             assert not (use_strict_symmetric and use_unsigned_symmetric)   # TfEncodingAnalyzer.cpp:85-86
         enc, _ = ops.compute_encodings_impl(self._block.arena, self._block.first + self._index, 1, self._code,
