@@ -100,6 +100,20 @@ __global__ void __launch_bounds__(kThreads) entropy_bin_kernel(const T* __restri
         return;
     constexpr int kV  = Elem<T>::kPerVec;
     const float width = st->bucket_size, mn = st->pdf_offset;
+    // (x - min) / width with the hoisted reciprocal (common.cuh: the very FFMA sequence div.rn.f32 executes, hence the same
+    // bits; a numerator too small for it perturbs only quotients far below 1, which truncate to bin 0 either way), and the
+    // float -> size_t cast of a quotient in [0, 2^22) as one round-toward-zero add: no MUFU, no F2I in the loop.
+    const Divisor dv  = make_divisor(width);
+    const bool fast   = dv.fast && width > 0.0f;
+    auto bin_of       = [&](float x) -> int {
+        const float d = __fsub_rn(x, mn);
+        if (!fast)
+            return width == 0.0f ? 0 : ent::bin_of_quotient(__fdiv_rn(d, width));
+        const float q = div_fast(d, dv);
+        if (q >= 0.0f && q < 4194304.0f)
+            return min(__float_as_int(__fadd_rz(q, 8388608.0f)) & 0x7fffff, ent::kBins - 1);
+        return ent::bin_of_quotient(q);
+    };
     for (int i = threadIdx.x; i < ent::kBins * 32; i += kThreads)
         s_bins[i] = 0;
     __syncthreads();
@@ -121,11 +135,11 @@ __global__ void __launch_bounds__(kThreads) entropy_bin_kernel(const T* __restri
                 Elem<T>::unpack(raw[u], f);
 #pragma unroll
                 for (int k = 0; k < kV; ++k)
-                    atomicAdd(&s_bins[ent::get_bin(width, mn, f[k]) * 32 + lane], 1u);
+                    atomicAdd(&s_bins[bin_of(f[k]) * 32 + lane], 1u);
             }
     }
     for (int64_t i = num_vec * kV + (int64_t) blockIdx.x * kThreads + threadIdx.x; i < count; i += stride)
-        atomicAdd(&s_bins[ent::get_bin(width, mn, Elem<T>::load(in + i)) * 32 + lane], 1u);
+        atomicAdd(&s_bins[bin_of(Elem<T>::load(in + i)) * 32 + lane], 1u);
     __syncthreads();
     unsigned long long* batch = reinterpret_cast<unsigned long long*>(&st->hist[0][0]);   // 512 x 64 bit
     for (int b = threadIdx.x; b < ent::kBins; b += kThreads)

@@ -42,6 +42,13 @@ AB_HD uint64_t float_to_size_t(float v)
     return (uint64_t) (int64_t) v;   // truncation toward zero; negative values wrap to huge numbers
 }
 
+// std::min(static_cast<size_t>(q), nBins - 1) for the quotient q of getBin
+AB_HD int bin_of_quotient(float q)
+{
+    const uint64_t b = float_to_size_t(q);
+    return (int) (b < (uint64_t) (kBins - 1) ? b : (uint64_t) (kBins - 1));
+}
+
 // getBin (math_functions.cpp:466-470)
 AB_HD int get_bin(float bin_width, float min_value, float value)
 {
@@ -52,8 +59,7 @@ AB_HD int get_bin(float bin_width, float min_value, float value)
 #else
     const float q = (value - min_value) / bin_width;
 #endif
-    const uint64_t b = float_to_size_t(q);
-    return (int) (b < (uint64_t) (kBins - 1) ? b : (uint64_t) (kBins - 1));
+    return bin_of_quotient(q);
 }
 
 // Range bookkeeping of one updateTensorHistogram call BEFORE its binning loop (math_functions.cpp:478-548).

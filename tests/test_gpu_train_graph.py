@@ -50,3 +50,21 @@ def test_graphed_qat_step_trains_like_the_eager_step():
         assert torch.allclose(a, b, rtol=1e-4, atol=1e-6), n
     for (n, a), (_, b) in zip(sim_e.model.named_buffers(), sim_g.model.named_buffers()):
         assert torch.allclose(a.float(), b.float(), rtol=1e-4, atol=1e-6), n
+
+
+def test_graphed_ddp_qat_step_trains_like_the_eager_ddp_step():
+    """capture_train_step(model=<DDP wrapper>): the reducer's all-reduces are captured with the backward. Runs in a helper
+    process (NCCL needs its environment set before the process group exists)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    res = subprocess.run([sys.executable, os.path.join(here, "ddp_graph_driver.py"), "29541"], stdout=subprocess.PIPE,
+                         stderr=subprocess.STDOUT, text=True, timeout=600, cwd=os.path.dirname(here))
+    line = [ln for ln in res.stdout.splitlines() if ln.startswith("RESULT ")]
+    assert line, res.stdout[-3000:]
+    out = json.loads(line[-1][len("RESULT "):])
+    assert out["graphed"] == pytest.approx(out["eager"], rel=1e-5)
+    assert out["graphed"][-1] != out["graphed"][0]
+    assert out["parameters_close"]
