@@ -31,6 +31,9 @@ namespace ab
 #endif
 constexpr int kThreads = AB_QDQ_THREADS;
 constexpr int kUnroll  = AB_QDQ_UNROLL;   // 128-bit vectors per thread per tile
+#ifndef AB_QDQ_MIN_BLOCKS
+#define AB_QDQ_MIN_BLOCKS 1               // tuning hook: resident CTAs per SM the streaming kernels are compiled for
+#endif
 
 enum class Op
 {
@@ -59,11 +62,12 @@ __device__ __forceinline__ float apply(float x, const Enc4& e, float shift, uint
 // ---------------------------------------------------------------------------------------------------------------
 // per-tensor QDQ / quantize-only.  `in`/`out` are 16-byte aligned here (otherwise per_tensor_scalar_kernel runs).
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T, Op kOp, bool kStochastic, bool kFast>
+template <typename T, Op kOp, bool kStochastic, bool kFast, bool kPos = false>
 __device__ __forceinline__ void per_tensor_body(const T* __restrict__ in, T* __restrict__ out, int64_t count,
                                                 const Enc4& e, const Divisor& dv, float shift, uint64_t seed,
                                                 int reverse)
 {
+    const float m_off = __fsub_rn(12582912.0f, e.offset);   // kPos only
     constexpr int kV        = Elem<T>::kPerVec;
     const int64_t num_vec   = count / kV;
     const int64_t num_tiles = (num_vec + kThreads * kUnroll - 1) / (kThreads * kUnroll);
@@ -95,7 +99,7 @@ __device__ __forceinline__ void per_tensor_body(const T* __restrict__ in, T* __r
 #pragma unroll
                 for (int k = 0; k < kV; ++k)
                     f[k] = !kFast               ? apply<kOp, kStochastic>(f[k], e, shift, seed, (uint64_t) (v * kV + k))
-                           : kOp == Op::kQdq    ? qdq_fast(f[k], e, dv)
+                           : kOp == Op::kQdq    ? (kPos ? qdq_fast_pos(f[k], e, dv, m_off) : qdq_fast(f[k], e, dv))
                                                 : __fsub_rn(quantize_fast(f[k], e, dv), shift);
                 stg_stream(reinterpret_cast<uint4*>(out) + v, Elem<T>::pack(f));
             }
@@ -111,7 +115,7 @@ __device__ __forceinline__ void per_tensor_body(const T* __restrict__ in, T* __r
 }
 
 template <typename T, Op kOp, bool kStochastic>
-__global__ void __launch_bounds__(kThreads) per_tensor_kernel(const T* __restrict__ in, T* __restrict__ out,
+__global__ void __launch_bounds__(kThreads, AB_QDQ_MIN_BLOCKS) per_tensor_kernel(const T* __restrict__ in, T* __restrict__ out,
                                                               int64_t count, TensorArgs args)
 {
     Enc4 e = args.enc;
@@ -123,7 +127,12 @@ __global__ void __launch_bounds__(kThreads) per_tensor_kernel(const T* __restric
     const Divisor dv = make_divisor(e.delta);
     // Nearest rounding with an ordinary grid takes the XU-free path; the choice is uniform over the launch.
     if (!kStochastic && qdq_fast_ok(e, dv))
-        per_tensor_body<T, kOp, kStochastic, true>(in, out, count, e, dv, args.shift, args.seed, args.reverse);
+    {
+        if (kOp == Op::kQdq && qdq_pos_ok(e, dv))
+            per_tensor_body<T, kOp, kStochastic, true, true>(in, out, count, e, dv, args.shift, args.seed, args.reverse);
+        else
+            per_tensor_body<T, kOp, kStochastic, true>(in, out, count, e, dv, args.shift, args.seed, args.reverse);
+    }
     else
         per_tensor_body<T, kOp, kStochastic, false>(in, out, count, e, dv, args.shift, args.seed, args.reverse);
 }
@@ -171,7 +180,7 @@ __device__ __forceinline__ Enc4 load_channel(const float* params, int64_t num_ch
 //   * a vector that lies inside one channel (the common case) does a single 16-byte shared load and runs the straight-line
 //     fast QDQ; only vectors that straddle a channel boundary step element by element.
 template <typename T>
-__global__ void __launch_bounds__(kThreads) per_channel_fast_kernel(const T* __restrict__ in, T* __restrict__ out,
+__global__ void __launch_bounds__(kThreads, AB_QDQ_MIN_BLOCKS) per_channel_fast_kernel(const T* __restrict__ in, T* __restrict__ out,
                                                                     int64_t count, ChannelArgs args)
 {
     constexpr int kV               = Elem<T>::kPerVec;
@@ -213,6 +222,7 @@ __global__ void __launch_bounds__(kThreads) per_channel_fast_kernel(const T* __r
         const uint32_t rem0 = s_rem0, c0 = s_c0;
         const uint32_t span = div_l(rem0 + tile_n - 1) + 1;   // channels the tile touches (rem0 + tile_n < 2^31)
         bool ok             = span <= kSmemChannels;
+        bool pos            = true;
         if (ok)
             for (uint32_t j = threadIdx.x; j < span; j += kThreads)
             {
@@ -221,8 +231,10 @@ __global__ void __launch_bounds__(kThreads) per_channel_fast_kernel(const T* __r
                 s_enc[j]         = make_float4(e.mn, e.mx, e.delta, e.offset);
                 s_rcp[j]         = dv.y;
                 ok               = ok && qdq_fast_ok(e, dv);
+                pos              = pos && qdq_pos_ok(e, dv);
             }
         const bool fast = __syncthreads_and(ok);   // every channel of the tile is staged and takes the fast arithmetic
+        const bool fpos = __syncthreads_and(ok && pos);   // ... and none of them can produce a position below -0.5
 
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u)
@@ -242,9 +254,19 @@ __global__ void __launch_bounds__(kThreads) per_channel_fast_kernel(const T* __r
                 Divisor dv = Divisor {p.z, s_rcp[j], true};
                 if (rem + kV <= L)
                 {
+                    if (fpos)
+                    {
+                        const float m_off = __fsub_rn(12582912.0f, e.offset);
 #pragma unroll
-                    for (int k = 0; k < kV; ++k)
-                        f[k] = qdq_fast(f[k], e, dv);
+                        for (int k = 0; k < kV; ++k)
+                            f[k] = qdq_fast_pos(f[k], e, dv, m_off);
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int k = 0; k < kV; ++k)
+                            f[k] = qdq_fast(f[k], e, dv);
+                    }
                 }
                 else
                 {

@@ -57,6 +57,8 @@ def parse_args():
     ap.add_argument("--no-kernels", action="store_true", help="skip the kernel sweep (`kernels` block)")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity passes (`parity` block)")
     ap.add_argument("--no-strong", action="store_true", help="skip the extra 2048-image strong-scaling job")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the short runs of BASELINE configs[0], [2], [3] (`other_configs` block)")
     ap.add_argument("--no-reference-python", action="store_true",
                     help="skip the leg that runs the reference's own Python (baseline/_ref) on the CUDA drop-ins")
     ap.add_argument("--images-per-step", type=int, default=BATCH,
@@ -688,6 +690,18 @@ def run_ours(args):
     # ---- the same job once more with CUDA events around every statistics call (roofline of the dominant kernel) ----
     roofline = measure_roofline(sim, job, resident, steps, barrier, device, rank)
 
+    # BASELINE configs[2] (MobileNet-v2 QAT) at this N: under DistributedDataParallel when N > 1, so EVERY rank runs it
+    # (a rank that dropped out would hang the others: an error here is fatal at N > 1)
+    qat_leg = None
+    if not args.no_other_configs:
+        from tools import other_configs
+        try:
+            qat_leg = other_configs.qat(device, world, local_rank)
+        except Exception as exc:   # pylint: disable=broad-except
+            if world > 1:
+                raise
+            qat_leg = {"error": repr(exc)[:300]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -737,6 +751,20 @@ def run_ours(args):
                 line["kernels"]["cpu_reference"] = cpu_kernel_baseline()
             except Exception as exc:   # pylint: disable=broad-except
                 line["kernels"]["cpu_reference"] = {"error": str(exc)[:200]}
+    if not args.no_other_configs:
+        # BASELINE.json's other configurations, short versions (tools/other_configs.py): ResNet-18 (configs[0], with the
+        # reference's C++ on the host cores beside it) and the Llama-2-7B-shaped W4A16 kernels (configs[3]) at N = 1;
+        # MobileNet-v2 QAT (configs[2]) at every N, under DistributedDataParallel when N > 1.
+        legs = {}
+        if world == 1:
+            legs["resnet18_w8a8"] = lambda: other_configs.resnet18(device, with_cpu_reference=not args.no_cpu_baseline)
+            legs["llama7b_w4a16"] = lambda: other_configs.llama(device)
+        line["other_configs"] = {"mobilenet_v2_qat": qat_leg}
+        for name, leg in legs.items():
+            try:
+                line["other_configs"][name] = leg()
+            except Exception as exc:   # pylint: disable=broad-except
+                line["other_configs"][name] = {"error": repr(exc)[:300]}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -78,6 +78,12 @@ __global__ void check_div(uint64_t seed, int iters, unsigned long long* bad_div,
                 const float fast = qdq_fast(xs[j], e, dv);
                 if (__float_as_uint(slow) != __float_as_uint(fast) && !(slow == 0.0f && fast == 0.0f))
                     ++nq;
+                if (qdq_pos_ok(e, dv))   // the two-instructions-shorter form for grids whose positions stay above -0.5
+                {
+                    const float pos = qdq_fast_pos(xs[j], e, dv, __fsub_rn(12582912.0f, e.offset));
+                    if (__float_as_uint(slow) != __float_as_uint(pos) && !(slow == 0.0f && pos == 0.0f))
+                        ++nq;
+                }
                 // quantize-only: bit-exact INCLUDING the sign of zero, also for +-0 inputs
                 const float xq = ((g >> (13 + j)) & 15) == 0 ? copysignf(0.0f, xs[j]) : xs[j];
                 if (__float_as_uint(quantize_value<false, true>(xq, e, 0, 0)) != __float_as_uint(quantize_fast(xq, e, dv)))
