@@ -191,8 +191,12 @@ def llama(device, layers=32):
            "matrices": len(weights), "weights": n_weights, "channels": channels}
     for name, mode in (("tf", ops.QUANTIZATION_TF), ("tf_enhanced", ops.QUANTIZATION_TF_ENHANCED)):
         ms = _events(lambda mode=mode: refresh(mode), 2, 1)
-        out[f"weight_encodings_{name}"] = {"ms": round(ms, 2), "read_gbs": round(wbytes / ms / 1e6, 1),
-                                           "frac": round(wbytes / ms / 1e6 / peak, 3)}
+        row = {"ms": round(ms, 2), "channels_per_s": round(channels / ms * 1e3)}
+        if name == "tf":      # one pass over the weights: HBM-bound; the tf_enhanced grid search is FP64-bound instead
+            row.update(read_gbs=round(wbytes / ms / 1e6, 1), frac=round(wbytes / ms / 1e6 / peak, 3))
+        else:
+            row["bound"] = "FP64 grid search (101 candidates x 512 bins per channel), not HBM"
+        out[f"weight_encodings_{name}"] = row
     blocks = []
     for b in range(layers):                      # the parameter blocks of every matrix, then QDQ over all of them
         ws = weights[b * per_block:(b + 1) * per_block]
