@@ -86,7 +86,8 @@ __device__ __forceinline__ float qdq_exact(float x, const Enc4& e)
 // kSimple: the encoding index is the run index itself (a.linear) and a run is a whole number of 128-bit vectors, so no
 // vector straddles a run boundary -- blockwise and per-channel encodings with block sizes that are multiples of 4 (fp32) /
 // 8 (bf16) elements. The per-vector work is then one multiply-high, four loads and the divisor set-up.
-template <typename T, bool kSimple>
+// kShared (with kSimple): runs at least as long as the 32 * kBcUnroll vectors a thread's chunk spans -- see the first branch.
+template <typename T, bool kSimple, bool kShared = false>
 __global__ void __launch_bounds__(kBcThreads)
     broadcast_fast_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t count, BroadcastArgs a)
 {
@@ -94,6 +95,98 @@ __global__ void __launch_bounds__(kBcThreads)
     const int64_t num_vec   = count / kV;
     const int64_t num_tiles = (num_vec + kBcThreads * kBcUnroll - 1) / (kBcThreads * kBcUnroll);
     const uint32_t inner    = (uint32_t) a.inner;
+    if constexpr (kSimple && kShared)
+    {
+        // Long runs that are whole numbers of vectors (per-channel weights, blocks): every WARP takes kBcUnroll consecutive rows of
+        // 32 vectors, so a thread's vectors lie within 32 * kBcUnroll * kV consecutive elements -- inside ONE run whenever
+        // the run is at least that long and the chunk does not straddle its end. Then the thread fetches the encoding and
+        // sets up the divisor once for all its vectors instead of once per vector (the per-vector set-up was 3 of the 17
+        // instructions per bf16 element), and takes the shorter QDQ form where the grid allows it.
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+        {
+            const int64_t v0 = tile * (kBcThreads * kBcUnroll) + (int64_t) warp * (32 * kBcUnroll) + lane;
+            uint4 raw[kBcUnroll];
+#pragma unroll
+            for (int u = 0; u < kBcUnroll; ++u)
+                if (v0 + u * 32 < num_vec)
+                    raw[u] = ldg_stream(reinterpret_cast<const uint4*>(in) + v0 + u * 32);
+            if (v0 >= num_vec)
+                continue;
+            const int64_t v_last = min(v0 + (kBcUnroll - 1) * 32, num_vec - 1 - ((num_vec - 1 - v0) & 31));
+            const uint32_t g0    = fast_div((uint32_t) (v0 * kV), a.inner, a.inner_mul, a.inner_shift);
+            const uint32_t g1    = fast_div((uint32_t) (v_last * kV), a.inner, a.inner_mul, a.inner_shift);
+            if (g0 == g1)
+            {
+                const Enc4 e     = load_enc(a, (int64_t) g0);
+                const Divisor dv = make_divisor(e.delta);
+                const bool ok    = qdq_fast_ok(e, dv);
+                const bool pos   = ok && qdq_pos_ok(e, dv);
+                const float moff = __fsub_rn(12582912.0f, e.offset);
+#pragma unroll
+                for (int u = 0; u < kBcUnroll; ++u)
+                {
+                    if (v0 + u * 32 >= num_vec)
+                        continue;
+                    float f[kV];
+                    Elem<T>::unpack(raw[u], f);
+                    if (pos)
+                    {
+#pragma unroll
+                        for (int k = 0; k < kV; ++k)
+                            f[k] = qdq_fast_pos(f[k], e, dv, moff);
+                    }
+                    else if (ok)
+                    {
+#pragma unroll
+                        for (int k = 0; k < kV; ++k)
+                            f[k] = qdq_fast(f[k], e, dv);
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int k = 0; k < kV; ++k)
+                            f[k] = qdq_exact(f[k], e);
+                    }
+                    stg_stream(reinterpret_cast<uint4*>(out) + v0 + u * 32, Elem<T>::pack(f));
+                }
+            }
+            else
+            {
+#pragma unroll
+                for (int u = 0; u < kBcUnroll; ++u)
+                {
+                    const int64_t v = v0 + u * 32;
+                    if (v >= num_vec)
+                        continue;
+                    float f[kV];
+                    Elem<T>::unpack(raw[u], f);
+                    const Enc4 e     = load_enc(a, (int64_t) fast_div((uint32_t) (v * kV), a.inner, a.inner_mul, a.inner_shift));
+                    const Divisor dv = make_divisor(e.delta);
+                    if (qdq_fast_ok(e, dv))
+                    {
+#pragma unroll
+                        for (int k = 0; k < kV; ++k)
+                            f[k] = qdq_fast(f[k], e, dv);
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int k = 0; k < kV; ++k)
+                            f[k] = qdq_exact(f[k], e);
+                    }
+                    stg_stream(reinterpret_cast<uint4*>(out) + v, Elem<T>::pack(f));
+                }
+            }
+        }
+        if (blockIdx.x == 0)
+        {
+            const int64_t i = num_vec * kV + threadIdx.x;
+            if (i < count)
+                Elem<T>::store(out + i, qdq_exact(Elem<T>::load(in + i), load_enc(a, enc_index64(a, i / a.inner))));
+        }
+        return;
+    }
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
     {
         const int64_t v0 = tile * (kBcThreads * kBcUnroll) + threadIdx.x;
@@ -211,7 +304,10 @@ int launch(const void* in, void* out, int64_t count, const BroadcastArgs& a, boo
     {
         constexpr int kV    = Elem<T>::kPerVec;
         const int64_t tiles = (count / kV + kBcThreads * kBcUnroll - 1) / (kBcThreads * kBcUnroll);
-        if (a.linear && a.inner % kV == 0)
+        if (a.linear && a.inner % kV == 0 && a.inner >= (int64_t) 32 * kBcUnroll * kV)
+            broadcast_fast_kernel<T, true, true>
+                <<<grid_size((const void*) broadcast_fast_kernel<T, true, true>, tiles), kBcThreads, 0, st>>>(x, y, count, a);
+        else if (a.linear && a.inner % kV == 0)
             broadcast_fast_kernel<T, true><<<grid_size((const void*) broadcast_fast_kernel<T, true>, tiles), kBcThreads, 0, st>>>(
                 x, y, count, a);
         else

@@ -180,7 +180,8 @@ __device__ __forceinline__ Enc4 load_channel(const float* params, int64_t num_ch
 //   * a vector that lies inside one channel (the common case) does a single 16-byte shared load and runs the straight-line
 //     fast QDQ; only vectors that straddle a channel boundary step element by element.
 template <typename T>
-__global__ void __launch_bounds__(kThreads, AB_QDQ_MIN_BLOCKS) per_channel_fast_kernel(const T* __restrict__ in, T* __restrict__ out,
+// (5 resident CTAs per SM = 48 registers: 0.87 against 0.78 of the HBM roofline at 64 MB fp32 with the compiler's own 60)
+__global__ void __launch_bounds__(kThreads, AB_QDQ_MIN_BLOCKS > 5 ? AB_QDQ_MIN_BLOCKS : 5) per_channel_fast_kernel(const T* __restrict__ in, T* __restrict__ out,
                                                                     int64_t count, ChannelArgs args)
 {
     constexpr int kV               = Elem<T>::kPerVec;
@@ -731,7 +732,13 @@ int ab_qdq_per_channel_fwd(const void* in, void* out, int64_t num_channel, int64
                       num_channel < (int64_t) 0x7fffffff;
     // bf16 is issue-bound, and there the straight-line run kernel of broadcast.cu (no staging, no barriers: every vector
     // fetches its channel's four parameters through L1) is the faster one: 0.85 against 0.78 of the HBM roofline.
-    if (fast && dtype == AB_BF16 && num_element_per_channel % 8 == 0 && num_element < (int64_t) 0x7fff0000 &&
+    // fp32: the staged kernel below is the faster one on large tensors (0.93-0.95 against 0.89-0.92 from 256 MB up), the run
+    // kernel on small ones, where the staging barriers cost more than they save (16 MB: 6.9 against 8.2 us) -- and weights,
+    // the tensors that are quantized per channel, are small.
+    const bool run_bf16 = dtype == AB_BF16 && num_element_per_channel % 8 == 0;
+    const bool run_fp32 = dtype == AB_F32 && num_element_per_channel % 4 == 0 && num_element_per_channel >= 512 &&
+                          num_element <= (int64_t) 8 << 20;
+    if (fast && (run_bf16 || run_fp32) && num_element < (int64_t) 0x7fff0000 &&
         num_element <= num_channel * num_element_per_channel)
         return launch_run_qdq(in, out, num_element, num_element_per_channel, params, params + num_channel,
                               params + 2 * num_channel, params + 3 * num_channel, dtype, st);
