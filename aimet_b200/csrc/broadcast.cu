@@ -101,7 +101,8 @@ __global__ void __launch_bounds__(kBcThreads)
         // 32 vectors, so a thread's vectors lie within 32 * kBcUnroll * kV consecutive elements -- inside ONE run whenever
         // the run is at least that long and the chunk does not straddle its end. Then the thread fetches the encoding and
         // sets up the divisor once for all its vectors instead of once per vector (the per-vector set-up was 3 of the 17
-        // instructions per bf16 element), and takes the shorter QDQ form where the grid allows it.
+        // instructions per bf16 element), and takes the shorter QDQ form where the grid allows it. A warp whose chunk does
+        // straddle a run end redoes the set-up only where the run changes.
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
         {
@@ -111,12 +112,14 @@ __global__ void __launch_bounds__(kBcThreads)
             for (int u = 0; u < kBcUnroll; ++u)
                 if (v0 + u * 32 < num_vec)
                     raw[u] = ldg_stream(reinterpret_cast<const uint4*>(in) + v0 + u * 32);
+            // does every lane's chunk lie inside one run? (the common case: a single fetch + set-up per thread, no per-vector index)
+            const int64_t v_last = min(v0 + (kBcUnroll - 1) * 32, num_vec - 1 - ((num_vec - 1 - v0) & 31));
+            const uint32_t g0    = fast_div((uint32_t) ((v0 < num_vec ? v0 : 0) * kV), a.inner, a.inner_mul, a.inner_shift);
+            const uint32_t g1    = fast_div((uint32_t) ((v0 < num_vec ? v_last : 0) * kV), a.inner, a.inner_mul, a.inner_shift);
+            const bool uniform   = __all_sync(0xffffffffu, g0 == g1);   // (the tile loop is uniform: all 32 lanes are here)
             if (v0 >= num_vec)
                 continue;
-            const int64_t v_last = min(v0 + (kBcUnroll - 1) * 32, num_vec - 1 - ((num_vec - 1 - v0) & 31));
-            const uint32_t g0    = fast_div((uint32_t) (v0 * kV), a.inner, a.inner_mul, a.inner_shift);
-            const uint32_t g1    = fast_div((uint32_t) (v_last * kV), a.inner, a.inner_mul, a.inner_shift);
-            if (g0 == g1)
+            if (uniform)
             {
                 const Enc4 e     = load_enc(a, (int64_t) g0);
                 const Divisor dv = make_divisor(e.delta);
@@ -150,33 +153,52 @@ __global__ void __launch_bounds__(kBcThreads)
                     }
                     stg_stream(reinterpret_cast<uint4*>(out) + v0 + u * 32, Elem<T>::pack(f));
                 }
+                continue;
             }
-            else
+            // a run ends inside this warp's chunk: the encoding and the divisor set-up are redone only where the run changes
+            // between two of a thread's vectors (only that short set-up diverges, the arithmetic below stays converged)
+            uint32_t g_cur = 0xffffffffu;
+            Enc4 e {};
+            Divisor dv {};
+            bool ok = false, pos = false;
+            float moff = 0.0f;
+#pragma unroll
+            for (int u = 0; u < kBcUnroll; ++u)
             {
-#pragma unroll
-                for (int u = 0; u < kBcUnroll; ++u)
+                const int64_t v = v0 + u * 32;
+                if (v >= num_vec)
+                    continue;
+                const uint32_t g = fast_div((uint32_t) (v * kV), a.inner, a.inner_mul, a.inner_shift);
+                if (g != g_cur)
                 {
-                    const int64_t v = v0 + u * 32;
-                    if (v >= num_vec)
-                        continue;
-                    float f[kV];
-                    Elem<T>::unpack(raw[u], f);
-                    const Enc4 e     = load_enc(a, (int64_t) fast_div((uint32_t) (v * kV), a.inner, a.inner_mul, a.inner_shift));
-                    const Divisor dv = make_divisor(e.delta);
-                    if (qdq_fast_ok(e, dv))
-                    {
-#pragma unroll
-                        for (int k = 0; k < kV; ++k)
-                            f[k] = qdq_fast(f[k], e, dv);
-                    }
-                    else
-                    {
-#pragma unroll
-                        for (int k = 0; k < kV; ++k)
-                            f[k] = qdq_exact(f[k], e);
-                    }
-                    stg_stream(reinterpret_cast<uint4*>(out) + v, Elem<T>::pack(f));
+                    g_cur = g;
+                    e     = load_enc(a, (int64_t) g);
+                    dv    = make_divisor(e.delta);
+                    ok    = qdq_fast_ok(e, dv);
+                    pos   = ok && qdq_pos_ok(e, dv);
+                    moff  = __fsub_rn(12582912.0f, e.offset);
                 }
+                float f[kV];
+                Elem<T>::unpack(raw[u], f);
+                if (pos)
+                {
+#pragma unroll
+                    for (int k = 0; k < kV; ++k)
+                        f[k] = qdq_fast_pos(f[k], e, dv, moff);
+                }
+                else if (ok)
+                {
+#pragma unroll
+                    for (int k = 0; k < kV; ++k)
+                        f[k] = qdq_fast(f[k], e, dv);
+                }
+                else
+                {
+#pragma unroll
+                    for (int k = 0; k < kV; ++k)
+                        f[k] = qdq_exact(f[k], e);
+                }
+                stg_stream(reinterpret_cast<uint4*>(out) + v, Elem<T>::pack(f));
             }
         }
         if (blockIdx.x == 0)

@@ -75,7 +75,8 @@ class _Cuda(_Oracle):
 
     def fill(self, bw, mn, mx):
         from aimet_b200 import ops
-        got = tuple(ops.fill_encoding_info(bw, mn, mx))
+        e = ops.fill_encoding_info(bw, mn, mx)
+        got = (e.min, e.max, e.delta, e.offset, e.bw)
         assert got[:4] == tuple(super().fill(bw, mn, mx))[:4]
         return got
 
