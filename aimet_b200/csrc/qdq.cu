@@ -738,10 +738,23 @@ int ab_qdq_per_channel_fwd(const void* in, void* out, int64_t num_channel, int64
     const bool run_bf16 = dtype == AB_BF16 && num_element_per_channel % 8 == 0;
     const bool run_fp32 = dtype == AB_F32 && num_element_per_channel % 4 == 0 && num_element_per_channel >= 512 &&
                           num_element <= (int64_t) 8 << 20;
-    if (fast && (run_bf16 || run_fp32) && num_element < (int64_t) 0x7fff0000 &&
-        num_element <= num_channel * num_element_per_channel)
-        return launch_run_qdq(in, out, num_element, num_element_per_channel, params, params + num_channel,
-                              params + 2 * num_channel, params + 3 * num_channel, dtype, st);
+    if (fast && (run_bf16 || run_fp32) && num_element <= num_channel * num_element_per_channel)
+    {
+        // the run kernel indexes with 32 bits: a tensor of 2^31 elements or more goes in slices of whole channels
+        const int64_t channels_per_launch = std::max<int64_t>(1, (int64_t) 0x7fff0000 / num_element_per_channel);
+        const int64_t slice               = channels_per_launch * num_element_per_channel;
+        const size_t es                   = dtype == AB_BF16 ? 2 : 4;
+        for (int64_t e0 = 0, c0 = 0; e0 < num_element; e0 += slice, c0 += channels_per_launch)
+        {
+            const int rc = launch_run_qdq(static_cast<const char*>(in) + e0 * es, static_cast<char*>(out) + e0 * es,
+                                          std::min(slice, num_element - e0), num_element_per_channel, params + c0,
+                                          params + num_channel + c0, params + 2 * num_channel + c0,
+                                          params + 3 * num_channel + c0, dtype, st);
+            if (rc != AB_OK)
+                return rc;
+        }
+        return AB_OK;
+    }
     if (fast)
     {
         // CUTLASS-style fast divmod constants, exact for dividends below 2^31

@@ -64,10 +64,9 @@ class ParamPlan:
         self._signature = None
 
     # ---- construction / validation ---------------------------------------------------------------------------
-    def _scan(self):
-        sim = self._sim()
+    def _scan(self, wrappers=None):
         found = []
-        for _, wrapper in sim.quant_wrappers():
+        for wrapper in (wrappers if wrappers is not None else [w for _, w in self._sim().quant_wrappers()]):
             if not isinstance(wrapper, StaticGridQuantWrapper):
                 continue
             for name, param in wrapper.get_named_parameters():
@@ -76,9 +75,10 @@ class ParamPlan:
                     found.append((wrapper, name, param, q))
         return found
 
-    def ensure(self):
-        """(Re)build the plan when the set of eligible quantizers, their flags or their parameters' shapes changed."""
-        found = self._scan()
+    def ensure(self, wrappers=None):
+        """(Re)build the plan when the set of eligible quantizers, their flags or their parameters' shapes changed.
+        `wrappers`: the sim's wrappers, when the caller has just walked the model anyway."""
+        found = self._scan(wrappers)
         signature = tuple((id(q), id(q._cppOp[0]), _key(p, q), tuple(p.shape)) for _, _, p, q in found)   # pylint: disable=protected-access
         if signature == self._signature:
             return
@@ -121,7 +121,15 @@ class ParamPlan:
     def refresh(self, only=None, stamp=None):
         """Refresh the encodings of the planned quantizers (`only(entry) -> bool` selects a subset) from the current
         parameter values. Returns the number of quantizers refreshed."""
-        done = 0
+        launched = self.launch(only)
+        self.stamp(launched, stamp)
+        return sum(len(run) for _, run in launched)
+
+    def launch(self, only=None):
+        """The device half of `refresh`: the native calls are enqueued, the quantizers are not touched yet. The caller may
+        do unrelated host work (which may reset the very quantizers: prepare_sim_for_compute_encodings) while the device
+        derives the encodings, and must then hand the result to `stamp`."""
+        launched = []
         for g in self.groups:
             runs, run = [], []
             for e in g.entries:                       # consecutive records by construction
@@ -137,12 +145,17 @@ class ParamPlan:
             if run:
                 runs.append(run)
             for run in runs:
-                self._refresh_run(g, run, run[0].first, stamp)
-                done += len(run)
-        return done
+                self._launch_run(g, run, run[0].first)
+                launched.append((g, run))
+        return launched
+
+    def stamp(self, launched, stamp=None):
+        """The host half of `refresh`: the quantizers of the launched runs now own the device-resident encodings."""
+        for g, run in launched:
+            self._stamp_run(g, run, stamp)
 
     @staticmethod
-    def _refresh_run(g, run, start, stamp):
+    def _launch_run(g, run, start):
         code, bw, sym, strict, unsigned_sym = g.key[:5]
         tensors, segs = [], []
         for e in run:
@@ -153,6 +166,9 @@ class ParamPlan:
             segs.append(e.count)
         ops.stats_refresh_multi_impl(tensors, segs, g.block.arena, g.block.first, code, bw, sym, strict, unsigned_sym,
                                      g.enc, g.qdq4, g.params, first_record=start)
+
+    @staticmethod
+    def _stamp_run(g, run, stamp):
         for e in run:
             q = e.q
             q._enc_dev = g.enc[e.first:e.first + e.count]                      # pylint: disable=protected-access

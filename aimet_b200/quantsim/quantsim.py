@@ -282,28 +282,33 @@ class QuantizationSimModel:
     # ---- calibration -------------------------------------------------------------------------------------------
     @staticmethod
     def prepare_sim_for_compute_encodings(sim: "QuantizationSimModel"):
-        if any(isinstance(layer, LearnedGridQuantWrapper) for _, layer in sim.quant_wrappers()):
+        wrappers = [layer for _, layer in sim.quant_wrappers()]      # ONE walk over the model for everything below
+        if any(isinstance(layer, LearnedGridQuantWrapper) for layer in wrappers):
             raise RuntimeError("the wrappers have already been replaced by range-learning wrappers; their encodings are "
                                "trainable parameters now and are not re-calibrated")
-        sim._bind_activation_states()   # pylint: disable=protected-access
         plan = sim._plan()              # pylint: disable=protected-access
+        launched = None
         if plan is not None:
-            plan.ensure()
-            plan.mark_reset_pending()   # their records are reset block-wide by the refresh below, not one launch each
+            # The parameters are known now: derive all their encodings in one native call instead of four launches per
+            # weight inside the first forward (the wrappers find them ready; same values either way). The call is enqueued
+            # FIRST -- it resets the planned records block-wide itself -- so the device works through the 26 561 grid
+            # searches while the host does the per-wrapper bookkeeping below; the quantizers are stamped at the end.
+            plan.ensure(wrappers)
+            plan.mark_reset_pending()   # their records are reset block-wide by that call, not one launch each
+            with torch.no_grad():
+                launched = plan.launch()
+        sim._bind_activation_states(wrappers)   # pylint: disable=protected-access
         if getattr(sim, "_act_block", None) is not None:
             sim._act_block.reset()      # all activation records in one launch  # pylint: disable=protected-access
             for q in sim._act_block_quantizers:   # pylint: disable=protected-access
                 q._reset_done_blockwide = True    # pylint: disable=protected-access
-        for _, layer in sim.quant_wrappers():
+        for layer in wrappers:
             layer.reset_encodings()
             layer.set_mode(QcQuantizeOpMode.ANALYSIS)
-        if plan is not None:
-            # The parameters are known now: derive all their encodings in one native call instead of four launches per
-            # weight inside the first forward (the wrappers find them ready; same values either way).
-            with torch.no_grad():
-                plan.refresh()
+        if launched is not None:
+            plan.stamp(launched)
         if sim._quant_scheme == QuantScheme.post_training_percentile:   # pylint: disable=protected-access
-            for _, layer in sim.quant_wrappers():                       # reference :397-400
+            for layer in wrappers:                                      # reference :397-400
                 layer.set_percentile_value(sim._percentile_value)       # pylint: disable=protected-access
 
     def set_percentile_value(self, percentile_value: float):
@@ -312,10 +317,10 @@ class QuantizationSimModel:
             raise ValueError("Percentile value must be in range [90, 100]")
         self._percentile_value = percentile_value
 
-    def activation_quantizers(self):
+    def activation_quantizers(self, wrappers=None):
         """Enabled per-tensor activation quantizers in a deterministic (module, input/output, index) order."""
         out = []
-        for _, layer in self.quant_wrappers():
+        for layer in (wrappers if wrappers is not None else [w for _, w in self.quant_wrappers()]):
             if not isinstance(layer, StaticGridQuantWrapper):
                 continue
             for q in layer.input_quantizers + layer.output_quantizers:
@@ -323,7 +328,7 @@ class QuantizationSimModel:
                     out.append(q)
         return out
 
-    def _bind_activation_states(self):
+    def _bind_activation_states(self, wrappers=None):
         """Give all activation quantizers ONE contiguous block of device statistics records, so that range injection,
         the ordered replay and the final grid search are single launches over the whole model."""
         from ..state import StateArena
@@ -334,7 +339,7 @@ class QuantizationSimModel:
             return
         if device.type != "cuda":
             return
-        quantizers = [q for q in self.activation_quantizers() if isinstance(q._cppOp[0], AimetTensorQuantizer)]   # pylint: disable=protected-access
+        quantizers = [q for q in self.activation_quantizers(wrappers) if isinstance(q._cppOp[0], AimetTensorQuantizer)]   # pylint: disable=protected-access
         if not quantizers:
             return
         block = getattr(self, "_act_block", None)
@@ -346,8 +351,9 @@ class QuantizationSimModel:
 
     @staticmethod
     def compute_layer_encodings_for_sim(sim: "QuantizationSimModel"):
-        sim._compute_activation_encodings_batched()   # pylint: disable=protected-access
-        for _, layer in sim.quant_wrappers():
+        wrappers = [layer for _, layer in sim.quant_wrappers()]
+        sim._compute_activation_encodings_batched(wrappers)   # pylint: disable=protected-access
+        for layer in wrappers:
             layer.compute_encoding()
             layer.set_mode(QcQuantizeOpMode.ACTIVE)
         sim.replace_wrappers_for_quantize_dequantize()
@@ -426,7 +432,7 @@ class QuantizationSimModel:
         for q, initialized in zip(self._act_block_quantizers, rec["initialized"].tolist()):
             q._cppOp[0]._range_fixed = bool(initialized)   # pylint: disable=protected-access
 
-    def _compute_activation_encodings_batched(self):
+    def _compute_activation_encodings_batched(self, wrappers=None):
         """All per-tensor grid searches are enqueued first and read back with ONE device->host copy (the reference does
         one blocking native call per quantizer). Quantizers that are not backed by the native op are left to the
         generic path in layer.compute_encoding()."""
@@ -434,7 +440,7 @@ class QuantizationSimModel:
         from ..tensor_quantizer_op import AimetTensorQuantizer
         from .tensor_quantizer import StaticGridPerTensorQuantizer
         pending = []
-        for _, layer in self.quant_wrappers():
+        for layer in (wrappers if wrappers is not None else [w for _, w in self.quant_wrappers()]):
             for q in layer.input_quantizers + list(layer.param_quantizers.values()) + layer.output_quantizers:
                 if not isinstance(q, StaticGridPerTensorQuantizer) or not q.enabled or q.is_encoding_frozen or \
                         q.bitwidth == 32 or (q._has_encoding() and not q._stats_dirty):   # pylint: disable=protected-access

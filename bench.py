@@ -703,6 +703,23 @@ def run_ours(args):
     # ---- the same job once more with CUDA events around every statistics call (roofline of the dominant kernel) ----
     roofline = measure_roofline(sim, job, resident, steps, barrier, device, rank)
 
+    # ---- for orientation only: the same job with the model's convolutions allowed TF32 (torch's own GPU default; the
+    # headline keeps them in plain fp32 like the reference's CPU forward). The quantsim kernels are unchanged, so this shows
+    # how much of the step is the model's forward and how much is the path this repo owns ----
+    forward_tf32 = None
+    if world == 1 and not args.no_other_configs:
+        torch.backends.cudnn.allow_tf32 = True
+        try:
+            t_steps = min(steps, 16)
+            job(resident, min(t_steps, 3))
+            t_ms, _ = timed_job(resident, t_steps)
+            forward_tf32 = {"value": round(BATCH * t_steps / (t_ms / 1e3), 2), "unit": UNIT, "steps": t_steps,
+                            "ms_per_step": round(t_ms / t_steps, 3),
+                            "note": "NOT the headline: complete job with torch.backends.cudnn.allow_tf32 = True for the "
+                                    "model's convolutions; statistics / QDQ / grid-search kernels identical"}
+        finally:
+            torch.backends.cudnn.allow_tf32 = False
+
     # BASELINE configs[2] (MobileNet-v2 QAT) at this N: under DistributedDataParallel when N > 1, so EVERY rank runs it
     # (a rank that dropped out would hang the others: an error here is fatal at N > 1)
     qat_leg = None
@@ -741,6 +758,8 @@ def run_ours(args):
             "encodings_sha256": sha_timed, "parity": parity, "parity_checked": parity.get("parity_checked"),
             "strong_scaling": strong,
             "roofline": roofline, "clocks": clocks}
+    if forward_tf32 is not None:
+        line["forward_tf32"] = forward_tf32
 
     if world == 1 and not args.no_kernels:
         try:

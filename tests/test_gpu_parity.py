@@ -463,11 +463,15 @@ def test_large_tensor_properties(ops, oracle):
     assert (r["run_min"], r["run_max"]) == (mn, mx)
 
 
-def test_per_channel_more_than_2_31_elements(ops, oracle):
+@pytest.mark.parametrize("whole_vectors", [False, True])
+def test_per_channel_more_than_2_31_elements(ops, oracle, whole_vectors):
     """The reference's `int` element counts overflow at 2^31 elements; the C ABI takes int64_t and the fast per-channel
-    kernel keeps only the tile base in 64 bits. Spot-checked against the oracle at the start, across 2^31 and at the end."""
+    kernel keeps only the tile base in 64 bits (ragged channel length), the bf16 run kernel goes in slices of whole channels
+    (channel length a whole number of vectors). Spot-checked against the oracle at the start, across 2^31 and at the end."""
     c = 2050
     per = (2**31 + 2**20) // c + 3            # ragged channel length, total just above 2^31
+    if whole_vectors:
+        per = (per + 7) // 8 * 8
     n = c * per
     assert n > 2**31
     g = torch.Generator(device="cuda").manual_seed(11)
