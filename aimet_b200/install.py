@@ -14,7 +14,7 @@ import sys
 import types
 
 from . import libpymo as _pymo
-from .tensor_quantizer_op import AimetTensorQuantizer
+from . import tensor_quantizer_op as _atq
 
 _IN_SCOPE = ["ComputationMode", "QuantizationMode", "RoundingMode", "TensorQuantizerOpMode", "TfEncoding",
              "TensorQuantizer", "EncodingAnalyzerForPython", "TensorQuantizationSimForPython", "PtrToInt64",
@@ -30,7 +30,9 @@ def install(extra_pymo_names=None):
     out-of-scope bindings -- SVD, BN fold, QnnDatatype ... -- that some of its modules import at load time; take them
     from the reference's own pure-python `aimet_common.py_libpymo`)."""
     atq = types.ModuleType("aimet_common.AimetTensorQuantizer")
-    atq.AimetTensorQuantizer = AimetTensorQuantizer
+    # The reference's Python makes one native call per weight channel: it gets the class that queues and batches them
+    # (same methods, same results; AB_DEFER_DROPIN=0 registers the plain one-call-one-launch class instead).
+    atq.AimetTensorQuantizer = _atq.DeferredAimetTensorQuantizer if _atq.DEFER_DROPIN else _atq.AimetTensorQuantizer
     atq.__all__ = ["AimetTensorQuantizer"]
     sys.modules["aimet_common.AimetTensorQuantizer"] = atq
 

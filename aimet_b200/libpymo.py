@@ -65,9 +65,17 @@ def encoding_epoch() -> int:
     return _ENCODING_EPOCH[0]
 
 
+_FIELDS = ("min", "max", "delta", "offset", "bw")
+
+
 class TfEncoding:
-    """DlQuantization::TfEncoding (Quantization.hpp:113-120): read/write fields min, max, delta, offset, bw."""
-    __slots__ = ("min", "max", "delta", "offset", "bw")
+    """DlQuantization::TfEncoding (Quantization.hpp:113-120): read/write fields min, max, delta, offset, bw.
+
+    An encoding handed out by a DEFERRED getEncoding (tensor_quantizer_op.DeferredAimetTensorQuantizer) has its five
+    slots unset and `_lazy` pointing at the queue that owes the result: the first read of any field lands in
+    `__getattr__`, which has the queue executed (one batched launch + one read-back for every encoding it owes) and the
+    slots filled. An ordinary encoding never reaches `__getattr__`."""
+    __slots__ = _FIELDS + ("_lazy",)
 
     def __init__(self):
         _set = object.__setattr__
@@ -76,9 +84,24 @@ class TfEncoding:
         _set(self, "delta", 0.0)
         _set(self, "offset", 0.0)
         _set(self, "bw", 0)
+        _set(self, "_lazy", None)
         _ENCODING_EPOCH[0] += 1
 
+    def __getattr__(self, name):
+        # only reached when the slot is unset
+        if name in _FIELDS:
+            try:
+                lazy = object.__getattribute__(self, "_lazy")
+            except AttributeError:
+                lazy = None
+            if lazy is not None:
+                lazy.resolve()
+                return object.__getattribute__(self, name)
+        raise AttributeError(name)
+
     def __setattr__(self, name, value):
+        if getattr(self, "_lazy", None) is not None:
+            self._lazy.resolve()          # the other fields must exist before one of them is overwritten
         object.__setattr__(self, name, value)
         _ENCODING_EPOCH[0] += 1
 
@@ -91,8 +114,26 @@ class TfEncoding:
         _set(e, "delta", float(delta))
         _set(e, "offset", float(offset))
         _set(e, "bw", int(bw))
+        _set(e, "_lazy", None)
         _ENCODING_EPOCH[0] += 1
         return e
+
+    @classmethod
+    def _deferred(cls, lazy):
+        """An encoding whose values `lazy.resolve()` will fill in (see the class docstring)."""
+        e = cls.__new__(cls)
+        object.__setattr__(e, "_lazy", lazy)
+        _ENCODING_EPOCH[0] += 1
+        return e
+
+    def _fill(self, row):
+        _set = object.__setattr__
+        _set(self, "min", row[0])
+        _set(self, "max", row[1])
+        _set(self, "delta", row[2])
+        _set(self, "offset", row[3])
+        _set(self, "bw", int(row[4]))
+        _set(self, "_lazy", None)
 
     @classmethod
     def _from_c(cls, c):
@@ -105,7 +146,8 @@ class TfEncoding:
         return (self.min, self.max, self.delta, self.offset, self.bw)
 
     def __setstate__(self, s):
-        for k, v in zip(self.__slots__, s):
+        object.__setattr__(self, "_lazy", None)
+        for k, v in zip(_FIELDS, s):
             object.__setattr__(self, k, v)
         _ENCODING_EPOCH[0] += 1
 

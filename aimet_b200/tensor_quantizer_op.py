@@ -12,6 +12,9 @@ Differences a caller can observe, all deliberate:
   * `updateStats` never synchronises: statistics are device resident; the only host round trip is in `getEncoding`
     / `getStatsHistogram`.
 """
+import os
+import threading
+
 import torch
 
 from . import libpymo
@@ -211,6 +214,252 @@ class AimetTensorQuantizer:
         self._pc_cache = (key, dev, encodings)
         return dev
 
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the same class with its native calls DEFERRED and batched -- for callers that drive it one channel at a time
+# ---------------------------------------------------------------------------------------------------------------------
+class _DeferredCalls:
+    """FIFO of native calls that have been asked for but not issued yet (one queue per thread).
+
+    The reference's Python drives a per-channel weight quantizer one channel at a time (aimet_torch/v1/tensor_quantizer.py:
+    296-305, 567-570; qc_quantize_op.py:231-243): C x resetEncodingStats, C x updateStats(slice c), C x getEncoding -- for
+    ResNet-50 26 560 channels, twice per calibration job, each call a launch or two and, for getEncoding, a blocking
+    read-back. Queued instead, consecutive calls of one kind on consecutive records become ONE launch (a block-wide reset,
+    a segmented statistics launch over the slices of one weight, one grid-search launch) and all encodings owed come back
+    in ONE copy; `flush` runs when somebody reads a field of an encoding that is still owed, before any native call that
+    is not queued, and when the queue is long. Results are those of the one-by-one calls: same kernels' arithmetic, calls
+    on a record issued in their original order."""
+    LIMIT = 1 << 16
+
+    def __init__(self):
+        self.lock = threading.RLock()
+        self.entries = []
+        self.stream = None
+        self.last_update = None   # (arena, record, tensor, code) of the latest updateStats, issued or queued
+
+    def resolve(self):
+        self.flush()
+
+    def push(self, entry, stream):
+        with self.lock:
+            if self.entries and stream != self.stream:
+                self.flush()          # queued work belongs to the stream that was current when it was asked for
+            self.stream = stream
+            self.entries.append(entry)
+            if len(self.entries) >= self.LIMIT:
+                self.flush()
+
+    @staticmethod
+    def _continues(prev, t, k=1):
+        """Is `t` the slice that follows `prev` k slices further on in the same storage (same length, dtype)?"""
+        return (t.dtype == prev.dtype and t.numel() == prev.numel() and
+                t.data_ptr() == prev.data_ptr() + k * prev.numel() * prev.element_size() and
+                t.untyped_storage().data_ptr() == prev.untyped_storage().data_ptr())
+
+    def flush(self):
+        with self.lock:
+            entries, self.entries = self.entries, []
+            if not entries:
+                return
+            n = len(entries)
+            owed = {}                                     # device -> number of encodings owed
+            for e in entries:
+                if e[0] == "S":
+                    owed[e[1].device] = owed.get(e[1].device, 0) + 1
+            outs = {d: [torch.empty((c, 5), dtype=torch.float64, device=d), 0, []] for d, c in owed.items()}
+            i = 0
+            while i < n:
+                e = entries[i]
+                kind, arena, rec = e[0], e[1], e[2]
+                j = i + 1
+                if kind == "R":
+                    while j < n and entries[j][0] == "R" and entries[j][1] is arena and entries[j][2] == rec + (j - i):
+                        j += 1
+                    ops.stats_reset_impl(arena, rec, j - i)
+                elif kind == "U":
+                    t0, code = e[3], e[4]
+                    while j < n:
+                        f = entries[j]
+                        if not (f[0] == "U" and f[1] is arena and f[2] == rec + (j - i) and f[4] == code and
+                                self._continues(t0, f[3], j - i)):
+                            break
+                        j += 1
+                    for f in entries[i:j]:
+                        if f[3]._version != f[5]:   # pylint: disable=protected-access
+                            raise RuntimeError("aimet_b200: a tensor handed to updateStats was modified in place before its "
+                                               "deferred statistics ran; set AB_DEFER_DROPIN=0")
+                    if j - i == 1:
+                        ops.stats_update_impl(t0, arena, rec, code, None, 0, 0)
+                    else:
+                        whole = t0.new_empty(0).set_(t0.untyped_storage(), t0.storage_offset(), ((j - i) * t0.numel(),), (1,))
+                        ops.stats_update_segmented_impl(whole, arena, rec, j - i, t0.numel(), code)
+                else:
+                    key = e[3]
+                    while j < n and entries[j][0] == "S" and entries[j][1] is arena and \
+                            entries[j][2] == rec + (j - i) and entries[j][3] == key:
+                        j += 1
+                    out, at, fills = outs[arena.device]
+                    code, bw, sym, strict, unsigned, percentile = key
+                    ops.compute_encodings_into(arena, rec, j - i, code, bw, sym, strict, unsigned, out[at:at + (j - i)],
+                                               percentile=percentile)
+                    fills.extend(f[4] for f in entries[i:j])
+                    outs[arena.device][1] = at + (j - i)
+                i = j
+            for out, _, fills in outs.values():
+                for enc, row in zip(fills, out.cpu().tolist()):       # the one read-back
+                    enc._fill(row)                                    # pylint: disable=protected-access
+
+
+_TLS = threading.local()
+
+
+def _calls() -> _DeferredCalls:
+    q = getattr(_TLS, "queue", None)
+    if q is None:
+        q = _TLS.queue = _DeferredCalls()
+    return q
+
+
+def flush_deferred_calls():
+    """Issue whatever the calling thread's DeferredAimetTensorQuantizer objects have queued."""
+    _calls().flush()
+
+
+class _RecordPool:
+    """Statistics records for objects that ask for them one at a time: carved 256 at a time (one reset launch per 256, not
+    one per object), so that objects created together -- the channels of one weight -- sit on consecutive records."""
+    BLOCK = 256
+    _pools = {}
+    _lock = threading.Lock()
+
+    def __init__(self, device):
+        self.device = device
+        self.block, self.used = None, 0
+        self.free = []
+
+    @classmethod
+    def take(cls, device):
+        with cls._lock:
+            pool = cls._pools.get(device)
+            if pool is None:
+                pool = cls._pools[device] = _RecordPool(device)
+            if pool.free:
+                block, index = pool.free.pop()
+                recycled = True
+            else:
+                if pool.block is None or pool.used == cls.BLOCK:
+                    pool.block, pool.used = StateArena.for_device(device).allocate(cls.BLOCK), 0
+                block, index, recycled = pool.block, pool.used, False
+                pool.used += 1
+        if recycled:
+            ops.stats_reset_impl(block.arena, block.first + index, 1)
+        return block, index
+
+    @classmethod
+    def give_back(cls, block, index):
+        pool = cls._pools.get(block.device)
+        if pool is not None:
+            pool.free.append((block, index))     # list.append is atomic; the record is reset when it is handed out again
+
+
+class DeferredAimetTensorQuantizer(AimetTensorQuantizer):
+    """AimetTensorQuantizer for callers that make one native call per channel -- the class `aimet_b200.install` registers
+    for the reference's own Python. Same methods, same results; resetEncodingStats, updateStats on the slices of one
+    tensor, and getEncoding are queued and issued in batches (see _DeferredCalls). The encodings getEncoding returns are
+    complete TfEncoding objects from the caller's point of view: the first read of a field has the queue executed."""
+
+    def _ensure_state(self, device):
+        if self._block is None or self._block.device != device:
+            self._release_record()
+            self._block, self._index = _RecordPool.take(device)
+            self._pooled = True
+
+    def _release_record(self):
+        if getattr(self, "_pooled", False) and self._block is not None:
+            _RecordPool.give_back(self._block, self._index)
+            self._pooled = False
+
+    def __del__(self):
+        try:
+            self._release_record()
+        except Exception:   # pylint: disable=broad-except  (interpreter shutdown)
+            pass
+
+    def _bind(self, block, index, group=None):
+        _calls().flush()
+        self._release_record()
+        super()._bind(block, index, group)
+
+    def resetEncodingStats(self):
+        self._reset_host_state()
+        if self._block is not None:
+            _calls().push(("R", self._block.arena, self._block.first + self._index), ops._stream(self._block.arena))   # pylint: disable=protected-access
+
+    def updateStats(self, input, use_cuda):   # pylint: disable=redefined-builtin
+        t, _ = _to_device_tensor(input)
+        queue = _calls()
+        deferrable = self._code != ops.QUANTIZATION_ENTROPY and t.is_contiguous() and t.numel() > 0 and \
+            not torch.cuda.is_current_stream_capturing()
+        if not deferrable:
+            queue.flush()
+            queue.last_update = None
+            super().updateStats(t, use_cuda)
+            return
+        self._is_encoding_valid = True
+        self._ensure_state(t.device)
+        arena, rec = self._block.arena, self._block.first + self._index
+        self._updates += 1
+        last = queue.last_update
+        queue.last_update = (arena, rec, t, self._code)
+        # A call is queued only when it CONTINUES the previous one -- the next record, the next slice of the same storage:
+        # the caller is walking over the channels of one tensor and control has not gone back to the model in between, so
+        # nothing can have written to that tensor. A call that starts something new (an activation: the model may overwrite
+        # it in place as soon as this method returns) is issued at once.
+        if last is not None and last[0] is arena and last[1] + 1 == rec and last[3] == self._code and \
+                queue._continues(last[2], t):   # pylint: disable=protected-access
+            queue.push(("U", arena, rec, t, self._code, t._version), ops._stream(t))   # pylint: disable=protected-access
+            return
+        queue.flush()
+        ops.stats_update_impl(t, arena, rec, self._code, None, 0, ops.STATS_RANGE_FIXED if self._range_fixed else 0)
+        if ops.keeps_histogram(self._code) and not self._range_fixed and self._updates >= 2:
+            self._poll_range_fixed()
+
+    def getEncoding(self, bitwidth, use_symmetric_encodings, use_strict_symmetric, use_unsigned_symmetric):
+        if not self._is_encoding_valid or self._block is None:
+            return libpymo.TfEncoding(), self._is_encoding_valid
+        queue = _calls()
+        if self._code == ops.QUANTIZATION_ENTROPY or torch.cuda.is_current_stream_capturing():
+            queue.flush()
+            return super().getEncoding(bitwidth, use_symmetric_encodings, use_strict_symmetric, use_unsigned_symmetric)
+        if use_symmetric_encodings and self._code == ops.QUANTIZATION_TF:
+            assert not (use_strict_symmetric and use_unsigned_symmetric)   # TfEncodingAnalyzer.cpp:85-86
+        enc = libpymo.TfEncoding._deferred(queue)   # pylint: disable=protected-access
+        key = (self._code, int(bitwidth), bool(use_symmetric_encodings), bool(use_strict_symmetric),
+               bool(use_unsigned_symmetric), self._percentile)
+        queue.push(("S", self._block.arena, self._block.first + self._index, key, enc), ops._stream(self._block.arena))   # pylint: disable=protected-access
+        return enc, True
+
+    # everything else reads encodings (which flushes by itself) or the record: issue what is queued first
+    def quantizeDequantize(self, input, encoding, rounding_mode, use_cuda):   # pylint: disable=redefined-builtin
+        _calls().flush()
+        return super().quantizeDequantize(input, encoding, rounding_mode, use_cuda)
+
+    def quantize(self, input, encoding, rounding_mode, use_cuda, shift_to_signed):   # pylint: disable=redefined-builtin
+        _calls().flush()
+        return super().quantize(input, encoding, rounding_mode, use_cuda, shift_to_signed)
+
+    def quantizeDequantizePerChannel(self, input, encodings, num_channel, num_element, num_element_per_channel,   # pylint: disable=redefined-builtin
+                                     rounding_mode, use_cuda):
+        _calls().flush()
+        return super().quantizeDequantizePerChannel(input, encodings, num_channel, num_element, num_element_per_channel,
+                                                    rounding_mode, use_cuda)
+
+    def getStatsHistogram(self):
+        _calls().flush()
+        return super().getStatsHistogram()
+
+
+DEFER_DROPIN = os.environ.get("AB_DEFER_DROPIN", "1") != "0"
 
 _SEED = [0]
 

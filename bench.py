@@ -807,25 +807,39 @@ def reference_python_leg(steps=2):
     under baseline/_ref: its ConnectedGraph, wrappers and per-channel loops -- 26 560 updateStats + 53 163 getEncoding calls
     per ResNet-50 job) on top of aimet_b200's drop-ins for its two native modules, in a process of its own
     (tests/ref_python_driver.py --backend native; parity of that path: tests/test_gpu_reference_python.py). Reported next to
-    the headline, which goes through this repo's host layer (batched per-channel calls, device-resident encodings)."""
+    the headline, which goes through this repo's host layer (batched per-channel calls, device-resident encodings).
+    `aimet_b200.install` registers the drop-in that queues the per-channel calls and issues them in batches
+    (tensor_quantizer_op.DeferredAimetTensorQuantizer); `call_by_call` is the same job with one launch per call."""
     driver = os.path.join(ROOT, "tests", "ref_python_driver.py")
     if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "aimet_torch")):
         return {"unavailable": "baseline/_ref not staged (tools/make_ref_python.py needs the reference checkout)"}
-    try:
+
+    def drive(defer):
         res = subprocess.run([sys.executable, driver, "--backend", "native", "--model", "resnet50", "--config", "per_channel",
                               "--scheme", "tf_enhanced", "--batch", str(BATCH), "--image", str(IMAGE[1]), "--steps", str(steps),
                               "--warmup", "1"], cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
-                             timeout=600)
+                             timeout=600, env=dict(os.environ, AB_DEFER_DROPIN="1" if defer else "0"))
         if res.returncode != 0:
-            return {"error": res.stderr[-400:]}
-        r = json.loads(res.stdout.strip().splitlines()[-1])
+            raise RuntimeError(res.stderr[-400:])
+        return json.loads(res.stdout.strip().splitlines()[-1])
+
+    try:
+        r = drive(True)
         n = r["native"]
-        return {"api": "reference_python", "value": n["img_s"], "unit": UNIT, "steps": steps, "images_per_step": BATCH,
-                "seconds": n["seconds"], "aimet_b200_launches": n["aimet_b200_launches"],
-                "num_activation_encodings": n["num_activation_encodings"], "num_param_encodings": n["num_param_encodings"],
-                "encodings_sha256": n["encodings_sha256"], "quantsim_module": r["quantsim_module"],
-                "note": "complete job of `steps` batches; one native call per weight CHANNEL and a device->host read per "
-                        "getEncoding, as the reference's Python makes them"}
+        out = {"api": "reference_python", "value": n["img_s"], "unit": UNIT, "steps": steps, "images_per_step": BATCH,
+               "seconds": n["seconds"], "aimet_b200_launches": n["aimet_b200_launches"],
+               "num_activation_encodings": n["num_activation_encodings"], "num_param_encodings": n["num_param_encodings"],
+               "encodings_sha256": n["encodings_sha256"], "quantsim_module": r["quantsim_module"],
+               "note": "complete job of `steps` batches; the reference's Python makes one native call per weight CHANNEL "
+                       "(reset, updateStats, getEncoding); the registered drop-in queues them and issues consecutive calls "
+                       "on consecutive records as one launch, all owed encodings come back in one read"}
+        try:
+            p = drive(False)["native"]
+            out["call_by_call"] = {"value": p["img_s"], "seconds": p["seconds"], "aimet_b200_launches": p["aimet_b200_launches"],
+                                   "encodings_sha256_equal": p["encodings_sha256"] == n["encodings_sha256"]}
+        except Exception as exc:   # pylint: disable=broad-except
+            out["call_by_call"] = {"error": str(exc)[:200]}
+        return out
     except Exception as exc:   # pylint: disable=broad-except
         return {"error": str(exc)[:300]}
 

@@ -140,3 +140,87 @@ def test_device_prefetcher_yields_every_batch_in_order():
         for got, h in zip(seen, host):
             assert torch.allclose(got, (h * 2.0).sum(dim=(1, 2, 3)), rtol=1e-5, atol=1e-4)
     assert list(DevicePrefetcher([], torch.device("cuda", 0))) == []
+
+
+# ---- the deferring variant of the drop-in (what aimet_b200.install registers for the reference's own Python) -----------------
+def _drive_per_channel(cls, weight, scheme, sym, rounds=2):
+    """The reference's per-channel loops (v1/tensor_quantizer.py:296-305, 567-570; qc_quantize_op.py:231-243) on `cls`."""
+    from aimet_b200 import libpymo
+    ops_ = [cls(scheme) for _ in range(weight.shape[0])]
+    result = []
+    for r in range(rounds):
+        for op in ops_:
+            op.resetEncodingStats()
+        for c, op in enumerate(ops_):
+            op.updateStats(weight.select(0, c).contiguous(memory_format=torch.contiguous_format), True)
+        if r == 1:                                        # a second batch on the same records, no reset in between
+            for c, op in enumerate(ops_):
+                op.updateStats(weight.select(0, c).contiguous() * 0.5, True)     # fresh tensors: not slices of one storage
+        encs = [op.getEncoding(8, sym, False, False) for op in ops_]
+        assert all(valid for _, valid in encs)
+        result.append([(e.min, e.max, e.delta, e.offset, e.bw) for e, _ in encs])
+    hist = ops_[3].getStatsHistogram() if scheme != libpymo.QuantizationMode.QUANTIZATION_TF else None
+    return result, hist, ops_
+
+
+@pytest.mark.parametrize("scheme_name", ["QUANTIZATION_TF_ENHANCED", "QUANTIZATION_TF"])
+@pytest.mark.parametrize("shape", [(300, 147), (64, 1024)])
+def test_deferred_dropin_equals_the_call_by_call_class(scheme_name, shape):
+    from aimet_b200 import libpymo
+    from aimet_b200 import tensor_quantizer_op as atq
+    scheme = getattr(libpymo.QuantizationMode, scheme_name)
+    w = (torch.randn(shape, generator=torch.Generator().manual_seed(5)) * 0.2).cuda()
+    w[7] = 0.0                                             # an all-zero channel (no range on the first batch)
+    for sym in (False, True):
+        plain, hist_p, _ = _drive_per_channel(atq.AimetTensorQuantizer, w, scheme, sym)
+        before = dict(atq.ops.LAUNCHES)
+        lazy, hist_l, keep = _drive_per_channel(atq.DeferredAimetTensorQuantizer, w, scheme, sym)
+        issued = sum(atq.ops.LAUNCHES[k] - before[k] for k in before)
+        assert lazy == plain and hist_l == hist_p
+        assert issued < 0.5 * 7 * shape[0], issued         # 7 calls per channel; only round 2's fresh tensors launch one by one
+        del keep
+
+
+def test_deferred_dropin_encoding_objects_and_hazards(oracle):
+    from aimet_b200 import libpymo
+    from aimet_b200 import tensor_quantizer_op as atq
+    from oracle.bindings import OracleTfe
+    import pickle
+    mode = libpymo.QuantizationMode.QUANTIZATION_TF_ENHANCED
+    x = torch.randn(4, 4096, generator=torch.Generator().manual_seed(1)).cuda()
+    ops_ = [atq.DeferredAimetTensorQuantizer(mode) for _ in range(4)]
+    assert ops_[0].getEncoding(8, False, False, False)[1] is False          # nothing queued for an op without statistics
+    for c, op in enumerate(ops_):
+        op.updateStats(x[c], True)
+    encs = [op.getEncoding(8, False, False, False)[0] for op in ops_]
+    assert all(e._lazy is not None for e in encs)                            # owed, not computed yet
+    o = OracleTfe(oracle)
+    o.update(x[2].cpu().numpy())
+    assert (encs[2].min, encs[2].max, encs[2].delta, encs[2].offset, encs[2].bw) == o.compute(8)
+    assert all(e._lazy is None for e in encs)                                # one read resolved them all
+    # writing a field of an owed encoding resolves it first; an owed encoding pickles like any other
+    e2 = ops_[1].getEncoding(8, False, False, False)[0]
+    e2.max = 9.0
+    assert e2.max == 9.0 and e2.min == encs[1].min and e2.bw == 8
+    e3 = pickle.loads(pickle.dumps(ops_[1].getEncoding(8, False, False, False)[0]))
+    assert (e3.min, e3.max) == (encs[1].min, encs[1].max)
+    # a queued slice whose storage is written before the queue runs is an error, not a silently different histogram
+    for op in ops_:
+        op.resetEncodingStats()
+    for c, op in enumerate(ops_):
+        op.updateStats(x[c], True)
+    x.mul_(2.0)
+    with pytest.raises(RuntimeError, match="modified in place"):
+        atq.flush_deferred_calls()
+    # a lone large tensor (an activation) is never queued: its statistics are issued by the call itself
+    act = torch.randn(1 << 20, device="cuda")
+    original = act.cpu().numpy()
+    a = atq.DeferredAimetTensorQuantizer(mode)
+    before = atq.ops.LAUNCHES["hist"]
+    a.updateStats(act, True)
+    assert atq.ops.LAUNCHES["hist"] == before + 1
+    act.zero_()                                                              # the model may overwrite it right away
+    o = OracleTfe(oracle)
+    o.update(original)
+    e = a.getEncoding(8, False, False, False)[0]
+    assert (e.min, e.max, e.delta, e.offset, e.bw) == o.compute(8)
