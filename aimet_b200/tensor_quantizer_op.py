@@ -235,26 +235,21 @@ class _DeferredCalls:
         self.lock = threading.RLock()
         self.entries = []
         self.stream = None
-        self.last_update = None   # (arena, record, tensor, code) of the latest updateStats, issued or queued
+        self.last_update = None   # (arena, record, code, where, tensor) of the latest updateStats, issued or queued
 
     def resolve(self):
         self.flush()
 
-    def push(self, entry, stream):
+    def push(self, entry, device_index):
+        stream = _current_raw_stream(device_index)
         with self.lock:
-            if self.entries and stream != self.stream:
-                self.flush()          # queued work belongs to the stream that was current when it was asked for
-            self.stream = stream
+            if stream != self.stream:
+                if self.entries:
+                    self.flush()      # queued work belongs to the stream that was current when it was asked for
+                self.stream = stream
             self.entries.append(entry)
             if len(self.entries) >= self.LIMIT:
                 self.flush()
-
-    @staticmethod
-    def _continues(prev, t, k=1):
-        """Is `t` the slice that follows `prev` k slices further on in the same storage (same length, dtype)?"""
-        return (t.dtype == prev.dtype and t.numel() == prev.numel() and
-                t.data_ptr() == prev.data_ptr() + k * prev.numel() * prev.element_size() and
-                t.untyped_storage().data_ptr() == prev.untyped_storage().data_ptr())
 
     def flush(self):
         with self.lock:
@@ -277,11 +272,11 @@ class _DeferredCalls:
                         j += 1
                     ops.stats_reset_impl(arena, rec, j - i)
                 elif kind == "U":
-                    t0, code = e[3], e[4]
+                    t0, code, where = e[3], e[4], e[6]          # where = (data pointer, bytes, storage pointer, dtype)
                     while j < n:
                         f = entries[j]
                         if not (f[0] == "U" and f[1] is arena and f[2] == rec + (j - i) and f[4] == code and
-                                self._continues(t0, f[3], j - i)):
+                                f[6] == (where[0] + (j - i) * where[1], where[1], where[2], where[3])):
                             break
                         j += 1
                     for f in entries[i:j]:
@@ -311,6 +306,7 @@ class _DeferredCalls:
 
 
 _TLS = threading.local()
+_current_raw_stream = torch._C._cuda_getCurrentRawStream   # pylint: disable=protected-access  (0.1 us; no Stream object)
 
 
 def _calls() -> _DeferredCalls:
@@ -373,6 +369,7 @@ class DeferredAimetTensorQuantizer(AimetTensorQuantizer):
             self._release_record()
             self._block, self._index = _RecordPool.take(device)
             self._pooled = True
+            self._clean = True        # handed out reset
 
     def _release_record(self):
         if getattr(self, "_pooled", False) and self._block is not None:
@@ -392,8 +389,11 @@ class DeferredAimetTensorQuantizer(AimetTensorQuantizer):
 
     def resetEncodingStats(self):
         self._reset_host_state()
-        if self._block is not None:
-            _calls().push(("R", self._block.arena, self._block.first + self._index), ops._stream(self._block.arena))   # pylint: disable=protected-access
+        # a record that has not been touched since its last reset (or since the pool handed it out) is not reset again:
+        # the reference's Python resets every channel up to four times per calibration job
+        if self._block is not None and not getattr(self, "_clean", False):
+            self._clean = True
+            _calls().push(("R", self._block.arena, self._block.first + self._index), self._block.arena.device.index)
 
     def updateStats(self, input, use_cuda):   # pylint: disable=redefined-builtin
         t, _ = _to_device_tensor(input)
@@ -404,20 +404,24 @@ class DeferredAimetTensorQuantizer(AimetTensorQuantizer):
             queue.flush()
             queue.last_update = None
             super().updateStats(t, use_cuda)
+            self._clean = False
             return
         self._is_encoding_valid = True
         self._ensure_state(t.device)
+        self._clean = False
         arena, rec = self._block.arena, self._block.first + self._index
         self._updates += 1
+        nbytes = t.numel() * t.element_size()
+        where = (t.data_ptr(), nbytes, t.untyped_storage().data_ptr(), t.dtype)
         last = queue.last_update
-        queue.last_update = (arena, rec, t, self._code)
+        queue.last_update = (arena, rec, self._code, where, t)      # (t: keeps the storage, hence the pointers, alive)
         # A call is queued only when it CONTINUES the previous one -- the next record, the next slice of the same storage:
         # the caller is walking over the channels of one tensor and control has not gone back to the model in between, so
         # nothing can have written to that tensor. A call that starts something new (an activation: the model may overwrite
         # it in place as soon as this method returns) is issued at once.
-        if last is not None and last[0] is arena and last[1] + 1 == rec and last[3] == self._code and \
-                queue._continues(last[2], t):   # pylint: disable=protected-access
-            queue.push(("U", arena, rec, t, self._code, t._version), ops._stream(t))   # pylint: disable=protected-access
+        if last is not None and last[0] is arena and last[1] + 1 == rec and last[2] == self._code and \
+                where == (last[3][0] + nbytes, last[3][1], last[3][2], last[3][3]):
+            queue.push(("U", arena, rec, t, self._code, t._version, where), t.device.index)   # pylint: disable=protected-access
             return
         queue.flush()
         ops.stats_update_impl(t, arena, rec, self._code, None, 0, ops.STATS_RANGE_FIXED if self._range_fixed else 0)
@@ -436,7 +440,7 @@ class DeferredAimetTensorQuantizer(AimetTensorQuantizer):
         enc = libpymo.TfEncoding._deferred(queue)   # pylint: disable=protected-access
         key = (self._code, int(bitwidth), bool(use_symmetric_encodings), bool(use_strict_symmetric),
                bool(use_unsigned_symmetric), self._percentile)
-        queue.push(("S", self._block.arena, self._block.first + self._index, key, enc), ops._stream(self._block.arena))   # pylint: disable=protected-access
+        queue.push(("S", self._block.arena, self._block.first + self._index, key, enc), self._block.arena.device.index)
         return enc, True
 
     # everything else reads encodings (which flushes by itself) or the record: issue what is queued first
