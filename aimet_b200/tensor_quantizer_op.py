@@ -218,6 +218,16 @@ class AimetTensorQuantizer:
 # ---------------------------------------------------------------------------------------------------------------------
 # the same class with its native calls DEFERRED and batched -- for callers that drive it one channel at a time
 # ---------------------------------------------------------------------------------------------------------------------
+class _FailedCalls:
+    """Stands in for the queue of an encoding whose deferred calls failed."""
+
+    def __init__(self, exc):
+        self.exc = exc
+
+    def resolve(self):
+        raise RuntimeError("aimet_b200: the deferred native calls this encoding depends on failed") from self.exc
+
+
 class _DeferredCalls:
     """FIFO of native calls that have been asked for but not issued yet (one queue per thread).
 
@@ -256,53 +266,66 @@ class _DeferredCalls:
             entries, self.entries = self.entries, []
             if not entries:
                 return
-            n = len(entries)
-            owed = {}                                     # device -> number of encodings owed
-            for e in entries:
-                if e[0] == "S":
-                    owed[e[1].device] = owed.get(e[1].device, 0) + 1
-            outs = {d: [torch.empty((c, 5), dtype=torch.float64, device=d), 0, []] for d, c in owed.items()}
-            i = 0
-            while i < n:
-                e = entries[i]
-                kind, arena, rec = e[0], e[1], e[2]
-                j = i + 1
-                if kind == "R":
-                    while j < n and entries[j][0] == "R" and entries[j][1] is arena and entries[j][2] == rec + (j - i):
-                        j += 1
-                    ops.stats_reset_impl(arena, rec, j - i)
-                elif kind == "U":
-                    t0, code, where = e[3], e[4], e[6]          # where = (data pointer, bytes, storage pointer, dtype)
-                    while j < n:
-                        f = entries[j]
-                        if not (f[0] == "U" and f[1] is arena and f[2] == rec + (j - i) and f[4] == code and
-                                f[6] == (where[0] + (j - i) * where[1], where[1], where[2], where[3])):
-                            break
-                        j += 1
-                    for f in entries[i:j]:
-                        if f[3]._version != f[5]:   # pylint: disable=protected-access
-                            raise RuntimeError("aimet_b200: a tensor handed to updateStats was modified in place before its "
-                                               "deferred statistics ran; set AB_DEFER_DROPIN=0")
-                    if j - i == 1:
-                        ops.stats_update_impl(t0, arena, rec, code, None, 0, 0)
-                    else:
-                        whole = t0.new_empty(0).set_(t0.untyped_storage(), t0.storage_offset(), ((j - i) * t0.numel(),), (1,))
-                        ops.stats_update_segmented_impl(whole, arena, rec, j - i, t0.numel(), code)
+            try:
+                self._issue(entries)
+            except BaseException as exc:
+                # the encodings this queue still owes can never be computed now: reading one must say so
+                failed = _FailedCalls(exc)
+                for e in entries:
+                    if e[0] == "S" and getattr(e[4], "_lazy", None) is not None:
+                        object.__setattr__(e[4], "_lazy", failed)
+                raise
+
+    @staticmethod
+    def _issue(entries):
+        """Issue the entries in order, runs of one kind on consecutive records as one launch each."""
+        n = len(entries)
+        owed = {}                                     # device -> number of encodings owed
+        for e in entries:
+            if e[0] == "S":
+                owed[e[1].device] = owed.get(e[1].device, 0) + 1
+        outs = {d: [torch.empty((c, 5), dtype=torch.float64, device=d), 0, []] for d, c in owed.items()}
+        i = 0
+        while i < n:
+            e = entries[i]
+            kind, arena, rec = e[0], e[1], e[2]
+            j = i + 1
+            if kind == "R":
+                while j < n and entries[j][0] == "R" and entries[j][1] is arena and entries[j][2] == rec + (j - i):
+                    j += 1
+                ops.stats_reset_impl(arena, rec, j - i)
+            elif kind == "U":
+                t0, code, where = e[3], e[4], e[6]          # where = (data pointer, bytes, storage pointer, dtype)
+                while j < n:
+                    f = entries[j]
+                    if not (f[0] == "U" and f[1] is arena and f[2] == rec + (j - i) and f[4] == code and
+                            f[6] == (where[0] + (j - i) * where[1], where[1], where[2], where[3])):
+                        break
+                    j += 1
+                for f in entries[i:j]:
+                    if f[3]._version != f[5]:   # pylint: disable=protected-access
+                        raise RuntimeError("aimet_b200: a tensor handed to updateStats was modified in place before its "
+                                           "deferred statistics ran; set AB_DEFER_DROPIN=0")
+                if j - i == 1:
+                    ops.stats_update_impl(t0, arena, rec, code, None, 0, 0)
                 else:
-                    key = e[3]
-                    while j < n and entries[j][0] == "S" and entries[j][1] is arena and \
-                            entries[j][2] == rec + (j - i) and entries[j][3] == key:
-                        j += 1
-                    out, at, fills = outs[arena.device]
-                    code, bw, sym, strict, unsigned, percentile = key
-                    ops.compute_encodings_into(arena, rec, j - i, code, bw, sym, strict, unsigned, out[at:at + (j - i)],
-                                               percentile=percentile)
-                    fills.extend(f[4] for f in entries[i:j])
-                    outs[arena.device][1] = at + (j - i)
-                i = j
-            for out, _, fills in outs.values():
-                for enc, row in zip(fills, out.cpu().tolist()):       # the one read-back
-                    enc._fill(row)                                    # pylint: disable=protected-access
+                    whole = t0.new_empty(0).set_(t0.untyped_storage(), t0.storage_offset(), ((j - i) * t0.numel(),), (1,))
+                    ops.stats_update_segmented_impl(whole, arena, rec, j - i, t0.numel(), code)
+            else:
+                key = e[3]
+                while j < n and entries[j][0] == "S" and entries[j][1] is arena and \
+                        entries[j][2] == rec + (j - i) and entries[j][3] == key:
+                    j += 1
+                out, at, fills = outs[arena.device]
+                code, bw, sym, strict, unsigned, percentile = key
+                ops.compute_encodings_into(arena, rec, j - i, code, bw, sym, strict, unsigned, out[at:at + (j - i)],
+                                           percentile=percentile)
+                fills.extend(f[4] for f in entries[i:j])
+                outs[arena.device][1] = at + (j - i)
+            i = j
+        for out, _, fills in outs.values():
+            for enc, row in zip(fills, out.cpu().tolist()):       # the one read-back
+                enc._fill(row)                                    # pylint: disable=protected-access
 
 
 _TLS = threading.local()

@@ -209,9 +209,12 @@ def test_deferred_dropin_encoding_objects_and_hazards(oracle):
         op.resetEncodingStats()
     for c, op in enumerate(ops_):
         op.updateStats(x[c], True)
+    owed = ops_[3].getEncoding(8, False, False, False)[0]
     x.mul_(2.0)
     with pytest.raises(RuntimeError, match="modified in place"):
         atq.flush_deferred_calls()
+    with pytest.raises(RuntimeError, match="deferred native calls"):
+        _ = owed.min                                                         # can never be computed: says so
     # a lone large tensor (an activation) is never queued: its statistics are issued by the call itself
     act = torch.randn(1 << 20, device="cuda")
     original = act.cpu().numpy()
