@@ -288,34 +288,44 @@ class ShardedCalibrator:
             self._range_round(done=True)
         self.batcher.flush()
         sink = self.sink
-        used = torch.tensor([sink.used], device=self.device, dtype=torch.int64)
-        if self.world > 1:
-            _all_reduce(used, dist.ReduceOp.MAX, self.group)
-        rows = int(used.item())
-        if rows == 0:
-            return
-        # one buffer per rank: the log rows, then their (local batch, record) tags and this rank's "was called" flags
-        tag_words = 2 * rows + q_count
-        tag_rows = (tag_words + LOG_WORDS - 1) // LOG_WORDS
-        payload = torch.zeros((rows + tag_rows, LOG_WORDS), dtype=torch.int32, device=self.device)
+        # Everything the replay needs besides the counts themselves -- how many rows each rank logged, their (local batch,
+        # record) tags, which records were called -- is known on the HOST the moment the last forward has been issued, while
+        # the device is still tens of milliseconds behind. That exchange, its read-back and the replay plan therefore run on
+        # a side stream that does not wait for the forwards; the main stream gets one gather of the rows and the fold launch
+        # queued behind the last forward, with no host synchronisation in between.
+        main = torch.cuda.current_stream(self.device)
+        side = getattr(self, "_side", None)
+        if side is None:
+            side = self._side = torch.cuda.Stream(self.device)
+        with torch.cuda.stream(side):
+            used = torch.tensor([sink.used], dtype=torch.int64).to(self.device)
+            if self.world > 1:
+                _all_reduce(used, dist.ReduceOp.MAX, self.group)
+            rows = int(used.item())
+            if rows == 0:
+                return
+            tags = torch.full((rows, 2), -1, dtype=torch.int32)
+            if sink.used:
+                tags[:sink.used] = torch.tensor(sink.meta, dtype=torch.int32).view(-1, 2)
+            called = torch.tensor([int(q._cppOp[0]._is_encoding_valid) for q in self.quantizers], dtype=torch.int32)   # pylint: disable=protected-access
+            mine = torch.cat([tags.view(-1), called]).to(self.device)
+            tail = (_all_gather(mine, self.group) if self.world > 1 else mine.unsqueeze(0)).cpu()   # read-back, side stream only
+            meta = tail[:, :2 * rows].reshape(self.world, rows, 2)
+            called_anywhere = tail[:, 2 * rows:].max(dim=0).values.tolist()
+            entry_rows, record_begin = replay_plan(meta, q_count)    # rows of rank w sit at w * rows + r in the gathered log
+            entry_rows, record_begin = entry_rows.to(self.device), record_begin.to(self.device)
+            updated = torch.tensor(called_anywhere, dtype=torch.int32).to(self.device)
+            for t in (entry_rows, record_begin, updated):
+                t.record_stream(main)
+            ready = side.record_event()
+        main.wait_event(ready)
+        payload = torch.zeros((rows, LOG_WORDS), dtype=torch.int32, device=self.device)
         payload[:sink.used] = sink.rows[:sink.used]
-        tags = torch.full((rows, 2), -1, dtype=torch.int32)
-        if sink.used:
-            tags[:sink.used] = torch.tensor(sink.meta, dtype=torch.int32).view(-1, 2)
-        called = torch.tensor([int(q._cppOp[0]._is_encoding_valid) for q in self.quantizers], dtype=torch.int32)   # pylint: disable=protected-access
-        payload[rows:].view(-1)[:tag_words] = torch.cat([tags.view(-1), called]).to(self.device, non_blocking=True)
         gathered = _all_gather(payload, self.group) if self.world > 1 else payload.unsqueeze(0)
-        tail = gathered[:, rows:].reshape(self.world, -1)[:, :tag_words].cpu()                 # the read-back of the merge
-        meta = tail[:, :2 * rows].reshape(self.world, rows, 2)
-        called_anywhere = tail[:, 2 * rows:].max(dim=0).values.tolist()
-        entry_rows, record_begin = replay_plan(meta, q_count)
-        # rows of rank w sit at w * (rows + tag_rows) + r in the gathered buffer
-        stride = rows + tag_rows
-        entry_rows = (entry_rows // rows) * stride + entry_rows % rows
-        ops.stats_fold_log_impl(self.block.arena, self.block.first, q_count, gathered.view(-1, LOG_WORDS),
-                                entry_rows.to(self.device), record_begin.to(self.device))
+        ops.stats_fold_log_impl(self.block.arena, self.block.first, q_count, gathered.view(-1, LOG_WORDS), entry_rows,
+                                record_begin)
         flags = self.block.bytes_view().view(torch.int32).view(q_count, -1)
-        flags[:, field_index("stats_updated", 4)] = torch.tensor(called_anywhere, dtype=torch.int32).to(self.device)
+        flags[:, field_index("stats_updated", 4)] = updated
         for q, u in zip(self.quantizers, called_anywhere):
             q._cppOp[0]._is_encoding_valid = bool(u)   # pylint: disable=protected-access
             q._stats_dirty = True                      # pylint: disable=protected-access
