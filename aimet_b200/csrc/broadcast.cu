@@ -86,7 +86,8 @@ __device__ __forceinline__ float qdq_exact(float x, const Enc4& e)
 // kSimple: the encoding index is the run index itself (a.linear) and a run is a whole number of 128-bit vectors, so no
 // vector straddles a run boundary -- blockwise and per-channel encodings with block sizes that are multiples of 4 (fp32) /
 // 8 (bf16) elements. The per-vector work is then one multiply-high, four loads and the divisor set-up.
-// kShared (with kSimple): runs at least as long as the 32 * kBcUnroll vectors a thread's chunk spans -- see the first branch.
+// kShared: linear encodings with runs at least as long as the 32 * kBcUnroll vectors a thread's chunk spans; with kSimple the
+// run is a whole number of vectors, without it a run may end inside a vector (handled where it happens) -- first branch.
 template <typename T, bool kSimple, bool kShared = false>
 __global__ void __launch_bounds__(kBcThreads)
     broadcast_fast_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t count, BroadcastArgs a)
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(kBcThreads)
     const int64_t num_vec   = count / kV;
     const int64_t num_tiles = (num_vec + kBcThreads * kBcUnroll - 1) / (kBcThreads * kBcUnroll);
     const uint32_t inner    = (uint32_t) a.inner;
-    if constexpr (kSimple && kShared)
+    if constexpr (kShared)
     {
         // Long runs that are whole numbers of vectors (per-channel weights, blocks): every WARP takes kBcUnroll consecutive rows of
         // 32 vectors, so a thread's vectors lie within 32 * kBcUnroll * kV consecutive elements -- inside ONE run whenever
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(kBcThreads)
         // instructions per bf16 element), and takes the shorter QDQ form where the grid allows it. A warp whose chunk does
         // straddle a run end redoes the set-up only where the run changes.
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        constexpr bool ragged = !kSimple;      // runs may end inside a vector (a.linear still holds: index == run index)
         for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
         {
             const int64_t v0 = tile * (kBcThreads * kBcUnroll) + (int64_t) warp * (32 * kBcUnroll) + lane;
@@ -113,9 +115,11 @@ __global__ void __launch_bounds__(kBcThreads)
                 if (v0 + u * 32 < num_vec)
                     raw[u] = ldg_stream(reinterpret_cast<const uint4*>(in) + v0 + u * 32);
             // does every lane's chunk lie inside one run? (the common case: a single fetch + set-up per thread, no per-vector index)
+            // (first element of the first vector, LAST element of the last one: a ragged run length may split a vector)
             const int64_t v_last = min(v0 + (kBcUnroll - 1) * 32, num_vec - 1 - ((num_vec - 1 - v0) & 31));
             const uint32_t g0    = fast_div((uint32_t) ((v0 < num_vec ? v0 : 0) * kV), a.inner, a.inner_mul, a.inner_shift);
-            const uint32_t g1    = fast_div((uint32_t) ((v0 < num_vec ? v_last : 0) * kV), a.inner, a.inner_mul, a.inner_shift);
+            const uint32_t g1    = fast_div((uint32_t) ((v0 < num_vec ? v_last : 0) * kV + (kV - 1)), a.inner, a.inner_mul,
+                                            a.inner_shift);
             const bool uniform   = __all_sync(0xffffffffu, g0 == g1);   // (the tile loop is uniform: all 32 lanes are here)
             if (v0 >= num_vec)
                 continue;
@@ -169,6 +173,26 @@ __global__ void __launch_bounds__(kBcThreads)
                 if (v >= num_vec)
                     continue;
                 const uint32_t g = fast_div((uint32_t) (v * kV), a.inner, a.inner_mul, a.inner_shift);
+                if (ragged && (uint32_t) (v * kV) - g * inner + kV > inner)
+                {
+                    // the run ends inside this vector (run length not a whole number of vectors): element by element
+                    float f[kV];
+                    Elem<T>::unpack(raw[u], f);
+                    uint32_t r = (uint32_t) (v * kV) - g * inner, gg = g;
+                    Enc4 ee    = load_enc(a, (int64_t) gg);
+#pragma unroll
+                    for (int k = 0; k < kV; ++k)
+                    {
+                        f[k] = qdq_exact(f[k], ee);
+                        if (++r == inner && k + 1 < kV)
+                        {
+                            r  = 0;
+                            ee = load_enc(a, (int64_t) ++gg);
+                        }
+                    }
+                    stg_stream(reinterpret_cast<uint4*>(out) + v, Elem<T>::pack(f));
+                    continue;
+                }
                 if (g != g_cur)
                 {
                     g_cur = g;
@@ -329,6 +353,9 @@ int launch(const void* in, void* out, int64_t count, const BroadcastArgs& a, boo
         if (a.linear && a.inner % kV == 0 && a.inner >= (int64_t) 32 * kBcUnroll * kV)
             broadcast_fast_kernel<T, true, true>
                 <<<grid_size((const void*) broadcast_fast_kernel<T, true, true>, tiles), kBcThreads, 0, st>>>(x, y, count, a);
+        else if (a.linear && a.inner >= (int64_t) 32 * kBcUnroll * kV)       // long runs of a ragged length
+            broadcast_fast_kernel<T, false, true>
+                <<<grid_size((const void*) broadcast_fast_kernel<T, false, true>, tiles), kBcThreads, 0, st>>>(x, y, count, a);
         else if (a.linear && a.inner % kV == 0)
             broadcast_fast_kernel<T, true><<<grid_size((const void*) broadcast_fast_kernel<T, true>, tiles), kBcThreads, 0, st>>>(
                 x, y, count, a);

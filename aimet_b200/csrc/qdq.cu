@@ -735,7 +735,7 @@ int ab_qdq_per_channel_fwd(const void* in, void* out, int64_t num_channel, int64
     // fp32: the staged kernel below is the faster one on large tensors (0.93-0.95 against 0.89-0.92 from 256 MB up), the run
     // kernel on small ones, where the staging barriers cost more than they save (16 MB: 6.9 against 8.2 us) -- and weights,
     // the tensors that are quantized per channel, are small.
-    const bool run_bf16 = dtype == AB_BF16 && num_element_per_channel % 8 == 0;
+    const bool run_bf16 = dtype == AB_BF16 && (num_element_per_channel % 8 == 0 || num_element_per_channel >= 1024);
     const bool run_fp32 = dtype == AB_F32 && num_element_per_channel % 4 == 0 && num_element_per_channel >= 512 &&
                           num_element <= (int64_t) 8 << 20;
     if (fast && (run_bf16 || run_fp32) && num_element <= num_channel * num_element_per_channel)

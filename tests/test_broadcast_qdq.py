@@ -15,6 +15,8 @@ CASES = [
     ((5, 3, 4), (3, 1)),                  # fewer leading dimensions
     ((7, 3), (7, 3)),                     # nothing broadcast
     ((130, 2, 3), (130, 1, 3)),           # run length 3 < one 128-bit vector
+    ((7, 2051), (7, 1)),                  # long runs of a ragged length: runs end inside 128-bit vectors
+    ((3, 5, 1029), (3, 5, 1)),            # the same, blockwise layout
 ]
 
 
