@@ -238,7 +238,8 @@ class _DeferredCalls:
     a segmented statistics launch over the slices of one weight, one grid-search launch) and all encodings owed come back
     in ONE copy; `flush` runs when somebody reads a field of an encoding that is still owed, before any native call that
     is not queued, and when the queue is long. Results are those of the one-by-one calls: same kernels' arithmetic, calls
-    on a record issued in their original order."""
+    on a record issued in their original order. Every entry ends with the object that asked for it: an object with work
+    in the queue stays alive, so its record cannot go back to the pool (and to somebody else) before that work has run."""
     LIMIT = 1 << 16
 
     def __init__(self):
@@ -416,7 +417,7 @@ class DeferredAimetTensorQuantizer(AimetTensorQuantizer):
         # the reference's Python resets every channel up to four times per calibration job
         if self._block is not None and not getattr(self, "_clean", False):
             self._clean = True
-            _calls().push(("R", self._block.arena, self._block.first + self._index), self._block.arena.device.index)
+            _calls().push(("R", self._block.arena, self._block.first + self._index, self), self._block.arena.device.index)
 
     def updateStats(self, input, use_cuda):   # pylint: disable=redefined-builtin
         t, _ = _to_device_tensor(input)
@@ -444,7 +445,7 @@ class DeferredAimetTensorQuantizer(AimetTensorQuantizer):
         # it in place as soon as this method returns) is issued at once.
         if last is not None and last[0] is arena and last[1] + 1 == rec and last[2] == self._code and \
                 where == (last[3][0] + nbytes, last[3][1], last[3][2], last[3][3]):
-            queue.push(("U", arena, rec, t, self._code, t._version, where), t.device.index)   # pylint: disable=protected-access
+            queue.push(("U", arena, rec, t, self._code, t._version, where, self), t.device.index)   # pylint: disable=protected-access
             return
         queue.flush()
         ops.stats_update_impl(t, arena, rec, self._code, None, 0, ops.STATS_RANGE_FIXED if self._range_fixed else 0)
@@ -463,7 +464,7 @@ class DeferredAimetTensorQuantizer(AimetTensorQuantizer):
         enc = libpymo.TfEncoding._deferred(queue)   # pylint: disable=protected-access
         key = (self._code, int(bitwidth), bool(use_symmetric_encodings), bool(use_strict_symmetric),
                bool(use_unsigned_symmetric), self._percentile)
-        queue.push(("S", self._block.arena, self._block.first + self._index, key, enc), self._block.arena.device.index)
+        queue.push(("S", self._block.arena, self._block.first + self._index, key, enc, self), self._block.arena.device.index)
         return enc, True
 
     # everything else reads encodings (which flushes by itself) or the record: issue what is queued first
