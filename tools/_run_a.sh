@@ -1,12 +1,11 @@
 set -x
-(time timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -6) > gpurun_out/pytest_gpu_final.log 2>&1
-tail -5 gpurun_out/pytest_gpu_final.log
-(time python bench.py > gpurun_out/bench_final_n1.json 2> gpurun_out/bench_final_n1.err) 2> gpurun_out/bench_final_n1.time
-tail -3 gpurun_out/bench_final_n1.time; tail -3 gpurun_out/bench_final_n1.err
-(time python bench.py --impl reference --steps 4 --warmup 1 > gpurun_out/bench_final_reference_arm.json 2> gpurun_out/bench_final_reference_arm.err) 2> gpurun_out/bench_final_reference_arm.time
-tail -3 gpurun_out/bench_final_reference_arm.time
-CMD="python bench.py --steps 4 --warmup 2 --no-kernels --no-cpu-baseline --no-reference-python --no-parity --no-strong --no-other-configs"
-$CMD > gpurun_out/ncu_plain_final.log 2>&1 &&
-ncu --nvtx --nvtx-include "timed/" --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_launches_final2.csv $CMD > gpurun_out/ncu_launches_final2.log 2>&1
-echo ncu rc=$?
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+(time timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -4) > gpurun_out/pytest_gpu_final2.log 2>&1
+tail -3 gpurun_out/pytest_gpu_final2.log
+python tools/profile_kernels.py pc > /dev/null 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:"broadcast_fast_kernel|per_channel_fast_kernel" -s 2 -c 4 -o gpurun_out/r2_run_kernel -f python tools/profile_kernels.py pc > gpurun_out/ncu_run_kernel.log 2>&1
+echo rc=$?
+ncu -i gpurun_out/r2_run_kernel.ncu-rep --page raw --csv > gpurun_out/r2_run_kernel_raw.csv 2>/dev/null
+S="--no-cpu-baseline --no-reference-python --no-other-configs"
+python bench.py $S > gpurun_out/bench_final2_n1.json 2> gpurun_out/bench_final2_n1.err; tail -2 gpurun_out/bench_final2_n1.err
+python -c "
+import json; d=json.loads(open('gpurun_out/bench_final2_n1.json').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'], d['parity']['equals_oracle_checked_golden'])"
