@@ -238,92 +238,120 @@ class _DeferredCalls:
     a segmented statistics launch over the slices of one weight, one grid-search launch) and all encodings owed come back
     in ONE copy; `flush` runs when somebody reads a field of an encoding that is still owed, before any native call that
     is not queued, and when the queue is long. Results are those of the one-by-one calls: same kernels' arithmetic, calls
-    on a record issued in their original order. Every entry ends with the object that asked for it: an object with work
-    in the queue stays alive, so its record cannot go back to the pool (and to somebody else) before that work has run."""
+    on a record issued in their original order. Every run keeps the objects that asked for it: an object with work in the
+    queue stays alive, so its record cannot go back to the pool (and to somebody else) before that work has run.
+
+    The queue is a list of RUNS, extended as the calls come in:
+        ["R", arena, first record, n, objects]
+        ["U", arena, first record, n, objects, scheme code, (pointer, bytes, storage pointer, dtype) of slice 0, tensors, versions]
+        ["S", arena, first record, n, objects, (scheme code, bw, sym, strict, unsigned, percentile), encodings]"""
     LIMIT = 1 << 16
 
     def __init__(self):
         self.lock = threading.RLock()
-        self.entries = []
+        self.runs = []
+        self.calls = 0
         self.stream = None
         self.last_update = None   # (arena, record, code, where, tensor) of the latest updateStats, issued or queued
 
     def resolve(self):
         self.flush()
 
-    def push(self, entry, device_index):
+    def _tail(self, kind, arena, rec, device_index):
+        """The run a call of `kind` on record `rec` may extend, or None. Lock held."""
         stream = _current_raw_stream(device_index)
+        if stream != self.stream:
+            if self.runs:
+                self.flush()          # queued work belongs to the stream that was current when it was asked for
+            self.stream = stream
+        if self.calls >= self.LIMIT:
+            self.flush()
+        self.calls += 1
+        if self.runs:
+            run = self.runs[-1]
+            if run[0] == kind and run[1] is arena and run[2] + run[3] == rec:
+                return run
+        return None
+
+    def push_reset(self, arena, rec, obj):
         with self.lock:
-            if stream != self.stream:
-                if self.entries:
-                    self.flush()      # queued work belongs to the stream that was current when it was asked for
-                self.stream = stream
-            self.entries.append(entry)
-            if len(self.entries) >= self.LIMIT:
-                self.flush()
+            run = self._tail("R", arena, rec, arena.device.index)
+            if run is None:
+                self.runs.append(["R", arena, rec, 1, [obj]])
+            else:
+                run[3] += 1
+                run[4].append(obj)
+
+    def push_update(self, arena, rec, obj, code, where, tensor):
+        with self.lock:
+            run = self._tail("U", arena, rec, arena.device.index)
+            if run is not None and run[5] == code and \
+                    where == (run[6][0] + run[3] * run[6][1], run[6][1], run[6][2], run[6][3]):
+                run[3] += 1
+                run[4].append(obj)
+                run[7].append(tensor)
+                run[8].append(tensor._version)   # pylint: disable=protected-access
+            else:
+                self.runs.append(["U", arena, rec, 1, [obj], code, where, [tensor], [tensor._version]])   # pylint: disable=protected-access
+
+    def push_search(self, arena, rec, obj, key, enc):
+        with self.lock:
+            run = self._tail("S", arena, rec, arena.device.index)
+            if run is not None and run[5] == key:
+                run[3] += 1
+                run[4].append(obj)
+                run[6].append(enc)
+            else:
+                self.runs.append(["S", arena, rec, 1, [obj], key, [enc]])
 
     def flush(self):
         with self.lock:
-            entries, self.entries = self.entries, []
-            if not entries:
+            runs, self.runs, self.calls = self.runs, [], 0
+            if not runs:
                 return
             try:
-                self._issue(entries)
+                self._issue(runs)
             except BaseException as exc:
                 # the encodings this queue still owes can never be computed now: reading one must say so
                 failed = _FailedCalls(exc)
-                for e in entries:
-                    if e[0] == "S" and getattr(e[4], "_lazy", None) is not None:
-                        object.__setattr__(e[4], "_lazy", failed)
+                for run in runs:
+                    if run[0] == "S":
+                        for enc in run[6]:
+                            if getattr(enc, "_lazy", None) is not None:
+                                object.__setattr__(enc, "_lazy", failed)
                 raise
 
     @staticmethod
-    def _issue(entries):
-        """Issue the entries in order, runs of one kind on consecutive records as one launch each."""
-        n = len(entries)
+    def _issue(runs):
+        """Issue the runs in order, one launch each; one read-back per device for every encoding owed."""
         owed = {}                                     # device -> number of encodings owed
-        for e in entries:
-            if e[0] == "S":
-                owed[e[1].device] = owed.get(e[1].device, 0) + 1
+        for run in runs:
+            if run[0] == "S":
+                owed[run[1].device] = owed.get(run[1].device, 0) + run[3]
         outs = {d: [torch.empty((c, 5), dtype=torch.float64, device=d), 0, []] for d, c in owed.items()}
-        i = 0
-        while i < n:
-            e = entries[i]
-            kind, arena, rec = e[0], e[1], e[2]
-            j = i + 1
+        for run in runs:
+            kind, arena, first, n = run[0], run[1], run[2], run[3]
             if kind == "R":
-                while j < n and entries[j][0] == "R" and entries[j][1] is arena and entries[j][2] == rec + (j - i):
-                    j += 1
-                ops.stats_reset_impl(arena, rec, j - i)
+                ops.stats_reset_impl(arena, first, n)
             elif kind == "U":
-                t0, code, where = e[3], e[4], e[6]          # where = (data pointer, bytes, storage pointer, dtype)
-                while j < n:
-                    f = entries[j]
-                    if not (f[0] == "U" and f[1] is arena and f[2] == rec + (j - i) and f[4] == code and
-                            f[6] == (where[0] + (j - i) * where[1], where[1], where[2], where[3])):
-                        break
-                    j += 1
-                for f in entries[i:j]:
-                    if f[3]._version != f[5]:   # pylint: disable=protected-access
+                code, tensors, versions = run[5], run[7], run[8]
+                for t, version in zip(tensors, versions):
+                    if t._version != version:   # pylint: disable=protected-access
                         raise RuntimeError("aimet_b200: a tensor handed to updateStats was modified in place before its "
                                            "deferred statistics ran; set AB_DEFER_DROPIN=0")
-                if j - i == 1:
-                    ops.stats_update_impl(t0, arena, rec, code, None, 0, 0)
+                t0 = tensors[0]
+                if n == 1:
+                    ops.stats_update_impl(t0, arena, first, code, None, 0, 0)
                 else:
-                    whole = t0.new_empty(0).set_(t0.untyped_storage(), t0.storage_offset(), ((j - i) * t0.numel(),), (1,))
-                    ops.stats_update_segmented_impl(whole, arena, rec, j - i, t0.numel(), code)
+                    whole = t0.new_empty(0).set_(t0.untyped_storage(), t0.storage_offset(), (n * t0.numel(),), (1,))
+                    ops.stats_update_segmented_impl(whole, arena, first, n, t0.numel(), code)
             else:
-                key = e[3]
-                while j < n and entries[j][0] == "S" and entries[j][1] is arena and \
-                        entries[j][2] == rec + (j - i) and entries[j][3] == key:
-                    j += 1
-                out, at, fills = outs[arena.device]
-                code, bw, sym, strict, unsigned, percentile = key
-                ops.compute_encodings_into(arena, rec, j - i, code, bw, sym, strict, unsigned, out[at:at + (j - i)],
+                code, bw, sym, strict, unsigned, percentile = run[5]
+                slot = outs[arena.device]
+                ops.compute_encodings_into(arena, first, n, code, bw, sym, strict, unsigned, slot[0][slot[1]:slot[1] + n],
                                            percentile=percentile)
-                fills.extend(f[4] for f in entries[i:j])
-                outs[arena.device][1] = at + (j - i)
-            i = j
+                slot[2].extend(run[6])
+                slot[1] += n
         for out, _, fills in outs.values():
             for enc, row in zip(fills, out.cpu().tolist()):       # the one read-back
                 enc._fill(row)                                    # pylint: disable=protected-access
@@ -417,7 +445,7 @@ class DeferredAimetTensorQuantizer(AimetTensorQuantizer):
         # the reference's Python resets every channel up to four times per calibration job
         if self._block is not None and not getattr(self, "_clean", False):
             self._clean = True
-            _calls().push(("R", self._block.arena, self._block.first + self._index, self), self._block.arena.device.index)
+            _calls().push_reset(self._block.arena, self._block.first + self._index, self)
 
     def updateStats(self, input, use_cuda):   # pylint: disable=redefined-builtin
         t, _ = _to_device_tensor(input)
@@ -445,7 +473,7 @@ class DeferredAimetTensorQuantizer(AimetTensorQuantizer):
         # it in place as soon as this method returns) is issued at once.
         if last is not None and last[0] is arena and last[1] + 1 == rec and last[2] == self._code and \
                 where == (last[3][0] + nbytes, last[3][1], last[3][2], last[3][3]):
-            queue.push(("U", arena, rec, t, self._code, t._version, where, self), t.device.index)   # pylint: disable=protected-access
+            queue.push_update(arena, rec, self, self._code, where, t)
             return
         queue.flush()
         ops.stats_update_impl(t, arena, rec, self._code, None, 0, ops.STATS_RANGE_FIXED if self._range_fixed else 0)
@@ -464,7 +492,7 @@ class DeferredAimetTensorQuantizer(AimetTensorQuantizer):
         enc = libpymo.TfEncoding._deferred(queue)   # pylint: disable=protected-access
         key = (self._code, int(bitwidth), bool(use_symmetric_encodings), bool(use_strict_symmetric),
                bool(use_unsigned_symmetric), self._percentile)
-        queue.push(("S", self._block.arena, self._block.first + self._index, key, enc, self), self._block.arena.device.index)
+        queue.push_search(self._block.arena, self._block.first + self._index, self, key, enc)
         return enc, True
 
     # everything else reads encodings (which flushes by itself) or the record: issue what is queued first

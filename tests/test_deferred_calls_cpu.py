@@ -36,6 +36,7 @@ class _Recorder:
 def queue(monkeypatch):
     rec = _Recorder()
     monkeypatch.setattr(atq, "ops", rec)
+    monkeypatch.setattr(atq, "_current_raw_stream", lambda device_index: 0)
     return atq._DeferredCalls(), rec          # pylint: disable=protected-access
 
 
@@ -43,8 +44,8 @@ def _where(t):
     return (t.data_ptr(), t.numel() * t.element_size(), t.untyped_storage().data_ptr(), t.dtype)
 
 
-def _update(arena, rec, t, code=1):
-    return ("U", arena, rec, t, code, t._version, _where(t), None)   # pylint: disable=protected-access
+def _update(q, arena, rec, t, code=1, where=None):
+    q.push_update(arena, rec, None, code, where or _where(t), t)
 
 
 def test_runs_are_coalesced_and_order_is_kept(queue):
@@ -53,15 +54,21 @@ def test_runs_are_coalesced_and_order_is_kept(queue):
     w = torch.arange(40, dtype=torch.float32).view(5, 8)
     key = (1, 8, True, False, False, None)
     encs = [libpymo.TfEncoding._deferred(q) for _ in range(6)]       # pylint: disable=protected-access
-    entries = [("R", arena, 10, None), ("R", arena, 11, None), ("R", arena, 12, None), ("R", arena, 20, None),
-               ("R", other, 21, None),                                # another arena: its own launch
-               _update(arena, 11, w[1]), _update(arena, 12, w[2]), _update(arena, 13, w[3]),
-               _update(arena, 14, w[0]),                              # next record, but not the next slice
-               ("S", arena, 10, key, encs[0], None), ("S", arena, 11, key, encs[1], None),
-               ("S", arena, 12, (1, 4, True, False, False, None), encs[2], None),   # other arguments: its own launch
-               ("R", arena, 10, None),
-               ("S", arena, 10, key, encs[3], None), ("S", arena, 30, key, encs[4], None), ("S", arena, 31, key, encs[5], None)]
-    q.entries = list(entries)
+    for r in (10, 11, 12, 20):
+        q.push_reset(arena, r, None)
+    q.push_reset(other, 21, None)                                     # another arena: its own launch
+    _update(q, arena, 11, w[1])
+    _update(q, arena, 12, w[2])
+    _update(q, arena, 13, w[3])
+    _update(q, arena, 14, w[0])                                       # next record, but not the next slice
+    q.push_search(arena, 10, None, key, encs[0])
+    q.push_search(arena, 11, None, key, encs[1])
+    q.push_search(arena, 12, None, (1, 4, True, False, False, None), encs[2])   # other arguments: its own launch
+    q.push_reset(arena, 10, None)
+    q.push_search(arena, 10, None, key, encs[3])
+    q.push_search(arena, 30, None, key, encs[4])
+    q.push_search(arena, 31, None, key, encs[5])
+    assert len(q.runs) == 10 and rec.calls == []
     q.flush()
     kinds = [c[:3] if c[0] != "segmented" else c[:4] for c in rec.calls]
     assert kinds == [("reset", 10, 3), ("reset", 20, 1), ("reset", 21, 1), ("segmented", 11, 3, 8), ("update", 14, 8),
@@ -70,15 +77,15 @@ def test_runs_are_coalesced_and_order_is_kept(queue):
     # every encoding got its own row, whichever launch computed it
     assert [(e.min, e.max, e.bw) for e in encs] == [(-10, 10, 8), (-11, 11, 8), (-12, 12, 4), (-10, 10, 8), (-30, 30, 8),
                                                    (-31, 31, 8)]
-    assert all(e._lazy is None for e in encs) and not q.entries      # pylint: disable=protected-access
+    assert all(e._lazy is None for e in encs) and not q.runs         # pylint: disable=protected-access
 
 
 def test_reading_an_owed_encoding_runs_the_queue(queue):
     q, rec = queue
     arena = torch.zeros(1)
     e = libpymo.TfEncoding._deferred(q)                              # pylint: disable=protected-access
-    q.entries.append(("R", arena, 3, None))
-    q.entries.append(("S", arena, 3, (1, 8, False, False, False, None), e, None))
+    q.push_reset(arena, 3, None)
+    q.push_search(arena, 3, None, (1, 8, False, False, False, None), e)
     assert rec.calls == []
     assert e.offset == -7.0                                          # first read of any field
     assert [c[0] for c in rec.calls] == ["reset", "search"] and e.delta == 0.5
@@ -88,10 +95,23 @@ def test_adjacent_addresses_in_different_storages_are_not_merged(queue):
     q, rec = queue
     arena = torch.zeros(1)
     a, b = torch.zeros(8), torch.zeros(8)
-    fake = ("U", arena, 6, b, 1, b._version, (_where(a)[0] + 32, 32, b.untyped_storage().data_ptr(), b.dtype), None)   # pylint: disable=protected-access
-    q.entries = [_update(arena, 5, a), fake]
+    _update(q, arena, 5, a)
+    _update(q, arena, 6, b, where=(_where(a)[0] + 32, 32, b.untyped_storage().data_ptr(), b.dtype))   # adjacent address
     q.flush()
     assert [c[0] for c in rec.calls] == ["update", "update"]
+
+
+def test_a_stream_change_or_a_long_queue_flushes(queue, monkeypatch):
+    q, rec = queue
+    arena = torch.zeros(1)
+    q.push_reset(arena, 0, None)
+    monkeypatch.setattr(atq, "_current_raw_stream", lambda device_index: 7)
+    q.push_reset(arena, 1, None)                                     # asked for on another stream: what was queued goes first
+    assert rec.calls == [("reset", 0, 1)] and len(q.runs) == 1
+    monkeypatch.setattr(q, "LIMIT", 4)
+    for r in range(2, 8):
+        q.push_reset(arena, r, None)
+    assert rec.calls[1] == ("reset", 1, 4) and q.runs[0][2:4] == [5, 3]     # flushed when the 5th call came in
 
 
 def test_a_tensor_written_before_the_flush_is_an_error_and_marks_what_is_owed(queue):
@@ -99,10 +119,12 @@ def test_a_tensor_written_before_the_flush_is_an_error_and_marks_what_is_owed(qu
     arena = torch.zeros(1)
     w = torch.zeros(3, 8)
     e = libpymo.TfEncoding._deferred(q)                              # pylint: disable=protected-access
-    q.entries = [_update(arena, 0, w[0]), _update(arena, 1, w[1]), ("S", arena, 0, (1, 8, False, False, False, None), e, None)]
+    _update(q, arena, 0, w[0])
+    _update(q, arena, 1, w[1])
+    q.push_search(arena, 0, None, (1, 8, False, False, False, None), e)
     w.add_(1.0)
     with pytest.raises(RuntimeError, match="modified in place"):
         q.flush()
-    assert rec.calls == [] and not q.entries
+    assert rec.calls == [] and not q.runs
     with pytest.raises(RuntimeError, match="deferred native calls"):
         _ = e.min
