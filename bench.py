@@ -15,7 +15,10 @@ that the headline (`"scaling": "strong"`).
 
 Also on the line: `encodings_sha256` + `parity` (ranks agree; the sharded result equals a single-process run over the same
 global batches), `kernels` (driver-run QDQ / STE / min-max / histogram GB/s sweep with the reference C++ single-core times),
-`roofline` (dominant kernel, CUDA events in the workload), `cpu_baseline`, `clocks`.
+`roofline` (dominant kernel, CUDA events in the workload), `cpu_baseline`, `clocks`, `other_configs` (BASELINE's other
+configurations, short), `reference_python_api` (the reference's unmodified Python on the drop-ins; `call_by_call` = the same
+without the deferred call queue) and `forward_tf32` (orientation only: the same job with the model's convolutions allowed
+TF32 -- the headline keeps the forward in plain fp32).
 
 One JSON line on stdout (rank 0). See README / DESIGN.md for the key meanings.
 """
