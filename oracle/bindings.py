@@ -381,6 +381,26 @@ class Reference:
         n = self.L.ref_quantize_packed(_f(x), x.size, out.ctypes.data_as(C.c_void_p), mn, mx, bw, int(shift_to_signed))
         return None if n < 0 else out[:n]
 
+    def tq_qdq_per_channel_tensor(self, x4, axis, bw, strict, mode=QUANTIZATION_TF):
+        """TensorQuantizer::quantizeDequantizePerChannelTensor on a 4-D tensor -> (output, [C][5] encodings) or None"""
+        x4 = np.ascontiguousarray(x4, dtype=np.float32)
+        shape = (C.c_uint32 * 4)(*x4.shape)
+        out = np.empty_like(x4)
+        enc = np.zeros((x4.shape[axis], 5), np.float64)
+        n = self.L.ref_tq_qdq_per_channel_tensor(mode, _f(x4), shape, axis, bw, int(strict), _f(out), _d(enc))
+        return None if n < 0 else (out, enc)
+
+    def tq_packed_per_channel_tensor(self, x4, axis, bw, strict, mode=QUANTIZATION_TF):
+        """TensorQuantizer::quantizePerChannelTensorPacked -> (bytes, encodings) or None"""
+        x4 = np.ascontiguousarray(x4, dtype=np.float32)
+        shape = (C.c_uint32 * 4)(*x4.shape)
+        out = np.zeros(x4.size * max(bw, 8) // 8 + 8, dtype=np.uint8)
+        enc = np.zeros((x4.shape[axis], 5), np.float64)
+        self.L.ref_tq_packed_per_channel_tensor.restype = C.c_int64
+        n = self.L.ref_tq_packed_per_channel_tensor(mode, _f(x4), shape, axis, bw, int(strict),
+                                                    out.ctypes.data_as(C.c_void_p), _d(enc))
+        return None if n < 0 else (out[:n], enc)
+
     def qdq_per_channel(self, x, num_channel, num_per_channel, emin, emax, edelta, eoffset):
         x = np.ascontiguousarray(x, dtype=np.float32)
         out = np.empty_like(x)

@@ -207,6 +207,48 @@ int ref_tq_partial(void* h, int bw, double* enc5, int sym, int unsigned_sym, int
     put(e, enc5);
     return 0;
 }
+// ---- TensorQuantizer's per-channel 4-D helpers (TensorQuantizer.cpp:189-326): slice on `axis`, one encoding per slice from
+//      its data, quantize-dequantize / pack every slice, concat. enc_out: [shape4[axis]][5]. Return -1 if the reference threw.
+int ref_tq_qdq_per_channel_tensor(int quant_mode, const float* in, const uint32_t* shape4, uint32_t axis, int bw, int strict,
+                                  float* out, double* enc_out)
+{
+    try
+    {
+        TensorQuantizer tq(static_cast<QuantizationMode>(quant_mode), ROUND_NEAREST);
+        std::vector<uint32_t> shape(shape4, shape4 + 4);
+        std::vector<TfEncoding> encodings;
+        tq.quantizeDequantizePerChannelTensor(in, shape, axis, out, encodings, (uint8_t) bw, ROUND_NEAREST, false, strict != 0);
+        for (size_t i = 0; i < encodings.size(); ++i)
+            put(encodings[i], enc_out + 5 * i);
+        return (int) encodings.size();
+    }
+    catch (const std::exception&)
+    {
+        return -1;
+    }
+}
+
+int64_t ref_tq_packed_per_channel_tensor(int quant_mode, const float* in, const uint32_t* shape4, uint32_t axis, int bw,
+                                         int strict, uint8_t* out, double* enc_out)
+{
+    try
+    {
+        TensorQuantizer tq(static_cast<QuantizationMode>(quant_mode), ROUND_NEAREST);
+        std::vector<uint32_t> shape(shape4, shape4 + 4);
+        std::vector<TfEncoding> encodings;
+        std::vector<uint8_t> packed;
+        tq.quantizePerChannelTensorPacked(in, shape, axis, packed, encodings, (uint8_t) bw, ROUND_NEAREST, false, strict != 0);
+        for (size_t i = 0; i < encodings.size(); ++i)
+            put(encodings[i], enc_out + 5 * i);
+        std::copy(packed.begin(), packed.end(), out);
+        return (int64_t) packed.size();
+    }
+    catch (const std::exception&)
+    {
+        return -1;
+    }
+}
+
 // The input the reference's own fixture builds (DlQuantization/test/TestTensorQuantizer.cpp:92-103):
 // std::normal_distribution<float>(mean, stddev) driven by std::mt19937(seed). libstdc++-specific, hence generated here.
 // ---- the entropy scheme's raw histogram: updateTensorHistogram on a TensorProfilingParams the test owns

@@ -364,3 +364,29 @@ def test_quantizer_packed_and_dequantize_per_channel(be):                       
     exp = [-39.7647, -1.01961, 0, 1.01961, 2.03922, -49.9608, 80.0392, 1.01961, 30.1176, 9.88235, 24.9412, 2.82353,
            1.88235, -49.8824, 70.1176, 0.941176]
     assert np.abs(back - np.array(exp)).max() <= 1e-4
+
+
+# ---- the composition above against the reference's per-channel 4-D helpers RUN LIVE (oracle/_ref) -----------------------
+@pytest.mark.parametrize("strict", [False, True])
+@pytest.mark.parametrize("axis", [0, 1, 2, 3])
+def test_per_channel_composition_equals_the_reference_live(oracle, reference, axis, strict):
+    """TensorQuantizer::quantizeDequantizePerChannelTensor / quantizePerChannelTensorPacked (TensorQuantizer.cpp:189-216)
+    on random 4-D tensors: encodings, dequantized output and packed bytes of the composition the tests above use
+    (axis to the front, one TF encoding per slice, per-slice QDQ / packed grid, back) are the reference's, bit for bit."""
+    if not hasattr(reference.L, "ref_tq_qdq_per_channel_tensor"):
+        pytest.skip("oracle/_ref built before this entry point existed")
+    be = _Oracle(oracle)
+    rng = np.random.default_rng(40 + axis)
+    for shape in ((3, 5, 4, 6), (2, 7, 1, 9)):
+        x = (rng.standard_normal(shape) * rng.uniform(0.5, 6.0)).astype(np.float32)
+        x[(0,) * 4] = 0.0
+        rows, encs = per_channel(be, x, axis, 8, strict)
+        out_ref, enc_ref = reference.tq_qdq_per_channel_tensor(x, axis, 8, strict)
+        assert [tuple(e[:4]) for e in encs] == [tuple(r[:4]) for r in enc_ref.tolist()]
+        mine = concat(be.qdq_rows(rows, encs, 8), shape, axis)
+        assert np.array_equal(mine.view(np.uint32), out_ref.reshape(-1).view(np.uint32))
+        packed_ref, enc_ref2 = reference.tq_packed_per_channel_tensor(x, axis, 8, strict)
+        assert np.array_equal(enc_ref2, enc_ref)
+        mine_packed = concat([be.packed(r, e[0], e[1], 8, strict) for r, e in zip(rows, encs)], shape, axis)
+        assert np.array_equal(mine_packed, packed_ref)
+    assert reference.tq_qdq_per_channel_tensor(np.zeros((2, 2, 2, 2), np.float32), 1, 4, False) is None   # bw < 8: throws
