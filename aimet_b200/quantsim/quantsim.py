@@ -352,10 +352,20 @@ class QuantizationSimModel:
     @staticmethod
     def compute_layer_encodings_for_sim(sim: "QuantizationSimModel"):
         wrappers = [layer for _, layer in sim.quant_wrappers()]
-        sim._compute_activation_encodings_batched(wrappers)   # pylint: disable=protected-access
+        # The grid searches of all activation quantizers are enqueued and their read-back started; the per-wrapper host work
+        # that does not need those results (every other quantizer's compute_encoding -- an early exit for parameters whose
+        # encodings exist --, the mode switch) runs while the device is still working through the forwards; only then does
+        # the host wait for the copy.
+        finish, handled = sim._compute_activation_encodings_batched(wrappers)   # pylint: disable=protected-access
         for layer in wrappers:
-            layer.compute_encoding()
+            if handled:
+                for q in layer.input_quantizers + list(layer.param_quantizers.values()) + layer.output_quantizers:
+                    if id(q) not in handled:
+                        q.compute_encoding()
+            else:
+                layer.compute_encoding()
             layer.set_mode(QcQuantizeOpMode.ACTIVE)
+        finish()
         sim.replace_wrappers_for_quantize_dequantize()
 
     def replace_wrappers_for_quantize_dequantize(self):
@@ -433,9 +443,10 @@ class QuantizationSimModel:
             q._cppOp[0]._range_fixed = bool(initialized)   # pylint: disable=protected-access
 
     def _compute_activation_encodings_batched(self, wrappers=None):
-        """All per-tensor grid searches are enqueued first and read back with ONE device->host copy (the reference does
-        one blocking native call per quantizer). Quantizers that are not backed by the native op are left to the
-        generic path in layer.compute_encoding()."""
+        """All per-tensor grid searches are enqueued first and read back with ONE device->host copy per device (the
+        reference does one blocking native call per quantizer). Returns (finish, handled): `handled` holds the ids of the
+        quantizers whose searches are in flight, `finish()` waits for the copy and gives them their encodings. Quantizers
+        that are not backed by the native op are left to the generic path (compute_encoding())."""
         from .. import libpymo, ops
         from ..tensor_quantizer_op import AimetTensorQuantizer
         from .tensor_quantizer import StaticGridPerTensorQuantizer
@@ -449,10 +460,11 @@ class QuantizationSimModel:
                 if isinstance(op, AimetTensorQuantizer) and op._is_encoding_valid and op._block is not None:   # pylint: disable=protected-access
                     pending.append((q, op))
         if not pending:
-            return
+            return (lambda: None), set()
         by_device = defaultdict(list)
         for q, op in pending:
             by_device[op._block.device].append((q, op))   # pylint: disable=protected-access
+        in_flight = []
         for device, items in by_device.items():
             out = torch.empty((len(items), 5), dtype=torch.float64, device=device)
             first_q, first_op = items[0]
@@ -469,12 +481,25 @@ class QuantizationSimModel:
                 ops.compute_encodings_into(op._block.arena, op._block.first + op._index, 1, op._code, q.bitwidth,   # pylint: disable=protected-access
                                            q.use_symmetric_encodings, q.use_strict_symmetric,
                                            q.use_unsigned_symmetric, out[row:row + 1], percentile=op._percentile)   # pylint: disable=protected-access
-            rows = out.cpu().tolist()
-            for (q, _), r in zip(items, rows):
-                q._encoding = [libpymo.TfEncoding._from_values(r[0], r[1], r[2], r[3], int(r[4]))]   # pylint: disable=protected-access
-                q.is_unsigned_symmetric = q.use_symmetric_encodings and q.use_unsigned_symmetric and \
-                    r[0] >= 0 and r[1] >= 0
-                q._stats_dirty = False   # pylint: disable=protected-access
+            host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+            with torch.cuda.device(device):
+                host.copy_(out, non_blocking=True)
+                event = torch.cuda.Event()
+                event.record()
+            in_flight.append((items, host, event, out))
+        # a quantizer whose search is in flight must not be recomputed by the loop that runs meanwhile
+        for q, _ in pending:
+            q._stats_dirty = False   # pylint: disable=protected-access
+
+        def finish():
+            for items, host, event, _ in in_flight:
+                event.synchronize()
+                for (q, _), r in zip(items, host.tolist()):
+                    q._encoding = [libpymo.TfEncoding._from_values(r[0], r[1], r[2], r[3], int(r[4]))]   # pylint: disable=protected-access
+                    q.is_unsigned_symmetric = q.use_symmetric_encodings and q.use_unsigned_symmetric and \
+                        r[0] >= 0 and r[1] >= 0
+
+        return finish, {id(q) for q, _ in pending}
 
     # ---- export ------------------------------------------------------------------------------------------------
     def get_activation_param_encodings(self):
