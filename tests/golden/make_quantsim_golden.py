@@ -30,6 +30,11 @@ CASES = {
                                  (2, 3, 64, 64), True),
     "resnet50_perchannel_tfe": (torchvision.models.resnet50, CFG + "default_config_per_channel.json",
                                 QuantScheme.post_training_tf_enhanced, (2, 3, 64, 64), False),
+    "mobilenet_v2_perchannel_tfe": (torchvision.models.mobilenet_v2, CFG + "default_config_per_channel.json",
+                                    QuantScheme.post_training_tf_enhanced, (2, 3, 64, 64), False),
+    "resnet18_perchannel_tf": (torchvision.models.resnet18, CFG + "default_config_per_channel.json",
+                               QuantScheme.post_training_tf, (2, 3, 64, 64), False),
+    "vgg11_default_tfe": (torchvision.models.vgg11, None, QuantScheme.post_training_tf_enhanced, (2, 3, 64, 64), True),
 }
 
 

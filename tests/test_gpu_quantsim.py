@@ -30,7 +30,8 @@ def run(name, factory):
 
 
 @pytest.mark.parametrize("name", ["resnet18_default_tfe", "resnet18_perchannel_tfe", "resnet18_default_tf",
-                                  "mobilenet_v2_default_tfe", "resnet50_perchannel_tfe", "resnet18_percentile"])
+                                  "mobilenet_v2_default_tfe", "resnet50_perchannel_tfe", "resnet18_percentile",
+                                  "mobilenet_v2_perchannel_tfe", "resnet18_perchannel_tf", "vgg11_default_tfe"])
 def test_cuda_ops_and_oracle_give_identical_encodings_json(oracle, name):
     from aimet_b200 import AimetTensorQuantizer
     from tests.oracle_backend import OracleTensorQuantizer

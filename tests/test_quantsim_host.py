@@ -21,6 +21,9 @@ CASES = {
     "resnet18_default_tf": (torchvision.models.resnet18, "default", "tf", (4, 3, 64, 64)),
     "mobilenet_v2_default_tfe": (torchvision.models.mobilenet_v2, "default", "tf_enhanced", (2, 3, 64, 64)),
     "resnet50_perchannel_tfe": (torchvision.models.resnet50, "per_channel", "tf_enhanced", (2, 3, 64, 64)),
+    "mobilenet_v2_perchannel_tfe": (torchvision.models.mobilenet_v2, "per_channel", "tf_enhanced", (2, 3, 64, 64)),
+    "resnet18_perchannel_tf": (torchvision.models.resnet18, "per_channel", "tf", (2, 3, 64, 64)),
+    "vgg11_default_tfe": (torchvision.models.vgg11, "default", "tf_enhanced", (2, 3, 64, 64)),
 }
 
 
